@@ -1,0 +1,75 @@
+"""ctypes binding of libmegreader_b200.so — the only way host code reaches the CUDA kernels.
+
+Fails loudly: there is no CPU fallback and no alternative backend.  If the library is missing
+or a symbol is absent the import of any op raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libmegreader_b200.so")
+
+_lib = None
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_f32 = ctypes.c_float
+c_p = ctypes.c_void_p
+
+# name -> argtypes (restype is int status unless listed in _RESTYPES)
+_SIGS = {
+    "mr_status_string": [c_int],
+    "mr_last_cuda_error": [],
+    "mr_abi_version": [],
+    "mr_launch_count": [],
+    "mr_launch_count_reset": [],
+    "mr_ctc2d_forward_f32": [c_p] * 4 + [c_i64] * 8 + [c_int, c_p, c_p, c_p],
+    "mr_ctc2d_forward_f64": [c_p] * 4 + [c_i64] * 8 + [c_int, c_p, c_p, c_p],
+    "mr_ctc2d_backward_f32": [c_p, c_i64] + [c_p] * 6 + [c_i64] * 8 + [c_int, c_p, c_p],
+    "mr_ctc2d_backward_f64": [c_p, c_i64] + [c_p] * 6 + [c_i64] * 8 + [c_int, c_p, c_p],
+    "mr_ctc2d_forward_train_f32": [c_p] * 4 + [c_i64] * 8 + [c_int, c_p, c_p, c_p],
+    "mr_ctc2d_backward_apply_f32": [c_p, c_i64, c_p, c_p] + [c_i64] * 4 + [c_int, c_p, c_p],
+}
+_RESTYPES = {
+    "mr_status_string": ctypes.c_char_p,
+    "mr_last_cuda_error": ctypes.c_char_p,
+    "mr_launch_count": c_i64,
+    "mr_launch_count_reset": None,
+}
+
+
+class MegReaderB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise MegReaderB200Error(
+                "megreader_b200: %s is missing - build it with `python -m megreader_b200.build` "
+                "(there is no CPU or library fallback)" % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        for name, args in _SIGS.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported: fail loudly
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = L
+    return _lib
+
+
+def check(status, what=""):
+    if status != 0:
+        L = lib()
+        msg = L.mr_status_string(status).decode()
+        if status == 6:
+            msg += ": " + L.mr_last_cuda_error().decode()
+        raise MegReaderB200Error("%s%s" % (what + ": " if what else "", msg))
+
+
+def launch_count():
+    return int(lib().mr_launch_count())
+
+
+def reset_launch_count():
+    lib().mr_launch_count_reset()

@@ -1,0 +1,38 @@
+#include "common.cuh"
+#include <mutex>
+#include <string>
+
+namespace mr {
+std::atomic<int64_t> g_launch_count{0};
+static std::mutex g_err_mu;
+static std::string g_err;
+void set_cuda_error(cudaError_t e, const char *where) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err = std::string(where) + ": " + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
+}
+}  // namespace mr
+
+extern "C" {
+const char *mr_status_string(int s) {
+    switch (s) {
+        case MR_OK: return "ok";
+        case MR_ERR_NULL_POINTER: return "null pointer argument";
+        case MR_ERR_BLANK_RANGE: return "blank must be in label range";
+        case MR_ERR_TARGET_TOO_LONG: return "max target length out of range (2*S+1 must be <= 1024)";
+        case MR_ERR_BAD_SHAPE: return "bad shape / size argument";
+        case MR_ERR_UNSUPPORTED: return "shape not supported by this build (on-chip staging does not fit)";
+        case MR_ERR_CUDA: return "CUDA runtime error (see mr_last_cuda_error)";
+        case MR_ERR_NO_DEVICE: return "no CUDA device";
+        default: return "unknown status";
+    }
+}
+const char *mr_last_cuda_error(void) {
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(mr::g_err_mu);
+    copy = mr::g_err;
+    return copy.c_str();
+}
+int mr_abi_version(void) { return 1; }
+int64_t mr_launch_count(void) { return mr::g_launch_count.load(); }
+void mr_launch_count_reset(void) { mr::g_launch_count.store(0); }
+}

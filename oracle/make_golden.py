@@ -1,0 +1,79 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (build container only).
+
+Run:  python -m oracle.make_golden            (from the repo root; needs /root/reference)
+
+2D-CTC: the reference's CUDA op cannot run here (no GPU, does not build on torch 2.11), so the
+golden vectors come from the reference's own pure-Python CTCLoss2D (decoders/ctc_loss2d.py:86-154)
+with (mask + classify) == log_probs, on cases where it does not numerically saturate
+(valid while every per-state height-sum stays above fp32 tiny, i.e. loss <~ 60).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def ctc2d_case(seed, T, H, N, C, S, Lmax, peak):
+    g = torch.Generator().manual_seed(seed)
+    tl = torch.randint(1, Lmax + 1, (N,), generator=g)
+    targets = torch.zeros(N, S, dtype=torch.long)
+    for b in range(N):
+        targets[b, :tl[b]] = torch.randint(1, C, (int(tl[b]),), generator=g)
+    il = torch.full((N,), T, dtype=torch.long)
+    mask_logit = torch.randn(T, H, N, generator=g)
+    cls_logit = torch.randn(T, H, N, C, generator=g)
+    if peak > 0:
+        # push the classifier toward a monotone alignment of the target so the loss stays small
+        for b in range(N):
+            L = int(tl[b])
+            for t in range(T):
+                k = min(L - 1, t * L // T)
+                cls_logit[t, :, b, targets[b, k]] += peak
+    mask = mask_logit.log_softmax(1)
+    classify = cls_logit.log_softmax(3)
+    return mask, classify, targets, il, tl
+
+
+def make_ctc2d():
+    m = ref_loader.load("decoders.ctc_loss2d")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = m.CTCLoss2D(blank=0, reduction="none")
+    cases = [  # name, seed, T, H, N, C, S, Lmax, peak
+        ("doc", 1, 32, 8, 16, 20, 20, 6, 4.0),      # docstring shape decoders/ctc_loss2d.py:37-45 (short targets)
+        ("small", 2, 8, 4, 4, 6, 5, 3, 0.0),
+        ("cfg3", 3, 32, 8, 8, 38, 32, 5, 5.0),      # res50-ppm-2d-ctc.yaml shape, peaked
+        ("h1", 4, 12, 1, 3, 7, 6, 4, 2.0),          # H=1 degenerates to 1D CTC
+        ("rep", 5, 16, 3, 4, 5, 8, 6, 3.0),         # tiny alphabet -> repeated labels (have_three false)
+    ]
+    for name, seed, T, H, N, C, S, Lmax, peak in cases:
+        mask, classify, targets, il, tl = ctc2d_case(seed, T, H, N, C, S, Lmax, peak)
+        classify.requires_grad_(True)
+        loss = ref(mask, classify, targets, il, tl)
+        # autograd of the reference python loss = TRUE derivative -exp(G + nll - lp); the CUDA op's K3
+        # returns exp(lp) + that on in-target classes, which tests check.
+        (ref_grad,) = torch.autograd.grad(loss.sum(), classify)
+        classify = classify.detach()
+        lp = (mask.unsqueeze(-1) + classify).contiguous()
+        np.savez_compressed(
+            os.path.join(GOLD, "ctc2d_pyref_%s.npz" % name),
+            log_probs=lp.numpy(), targets=targets.numpy(), input_lengths=il.numpy(),
+            target_lengths=tl.numpy(), ref_nll=loss.detach().numpy(),
+            ref_autograd=ref_grad.numpy())
+        print("ctc2d", name, "ref nll", loss.detach().numpy()[:4])
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["ctc2d"]
+    if "ctc2d" in which:
+        make_ctc2d()
