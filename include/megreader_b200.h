@@ -75,8 +75,8 @@ int mr_ctc2d_backward_f64(const double *grad_out, int64_t grad_out_stride, const
                           double *grad, void *stream);
 
 /* Training pair used by CTCLoss2DFunction (ops/ctc_2d/ctc_loss_2d.py:7-37) when log_probs.requires_grad:
- * the forward keeps no log_alpha; it writes nll [N] and a per-(t,class) factor `gfac` [N,T,C] such that
- *   grad[t,h,b,c] = exp(log_probs[t,h,b,c]) * gfac[b,t,c] * grad_out[b]        (same values as K3),
+ * the forward keeps no log_alpha; it writes nll [N] and a per-(t,class) factor `gfac` [T,N,C] such that
+ *   grad[t,h,b,c] = exp(log_probs[t,h,b,c]) * gfac[t,b,c] * grad_out[b]        (same values as K3),
  * which mr_ctc2d_backward_apply streams out.  Total HBM traffic 3*|log_probs| instead of
  * 3*|log_probs| + 2*|log_alpha|. */
 int mr_ctc2d_forward_train_f32(const float *log_probs, const int64_t *targets, const int64_t *input_lengths,
@@ -86,6 +86,39 @@ int mr_ctc2d_forward_train_f32(const float *log_probs, const int64_t *targets, c
 int mr_ctc2d_backward_apply_f32(const float *grad_out, int64_t grad_out_stride, const float *log_probs,
                                 const float *gfac, int64_t T, int64_t H, int64_t N, int64_t C, int fast_math,
                                 float *grad, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Deformable convolution v1 / v2  (replaces pybind module assets.ops.dcn.deform_conv_cuda:
+ * assets/ops/dcn/src/deform_conv_cuda.cpp:681-695).  fp32, NCHW contiguous input [B,C,H,W] and weight
+ * [Cout, C/group, kh, kw].  offset / mask (and their gradients) are addressed per sample as
+ * base + b*bstride (elements) and then FLAT with (Ho, Wo) strides, as the reference kernels do
+ * (deform_conv_cuda_kernel.cu:599-609) — the caller's tensors may have a larger spatial size.
+ * mask == NULL selects DCNv1 (deform_conv_forward_cuda & co., deform_conv_cuda.cpp:151-484).
+ * `workspace` is caller-allocated scratch for the column matrix: at least
+ * mr_dcn_workspace_bytes(1, ...) bytes; with room for nb samples the op processes nb samples per launch.
+ * The GEMMs are cuBLAS SGEMM (plain fp32); the first call per device creates a cuBLAS handle (which
+ * allocates cuBLAS's own workspace).
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mr_dcn_workspace_bytes(int64_t nb, int64_t C, int64_t kh, int64_t kw, int64_t Ho, int64_t Wo);
+
+/* modulated_deform_conv_cuda_forward (deform_conv_cuda.cpp:486-564) / deform_conv_forward_cuda (:151-258).
+ * Writes output [B,Cout,Ho,Wo] (+bias when bias != NULL). */
+int mr_dcn_forward_f32(const float *input, const float *weight, const float *bias, const float *offset,
+                       int64_t offset_bstride, const float *mask, int64_t mask_bstride, float *output,
+                       float *workspace, int64_t workspace_bytes, int B, int C, int H, int W, int Cout, int kh, int kw,
+                       int sh, int sw, int ph, int pw, int dh, int dw, int group, int dg, void *stream);
+
+/* modulated_deform_conv_cuda_backward (deform_conv_cuda.cpp:566-679) / deform_conv_backward_input_cuda (:260-371)
+ * + deform_conv_backward_parameters_cuda (:373-484).  grad_input / grad_weight / grad_bias are ACCUMULATED into
+ * (the caller zero-fills them, functions/deform_conv.py:150-154); grad_offset / grad_mask entries are assigned with
+ * the flat (Ho,Wo) layout.  Any of the five gradient pointers may be NULL to skip it.  weight_grad_scale is the
+ * `scale` of deform_conv_backward_parameters_cuda (1 for DCNv2). */
+int mr_dcn_backward_f32(const float *input, const float *weight, const float *offset, int64_t offset_bstride,
+                        const float *mask, int64_t mask_bstride, const float *grad_output, float *grad_input,
+                        float *grad_weight, float *grad_bias, float *grad_offset, int64_t grad_offset_bstride,
+                        float *grad_mask, int64_t grad_mask_bstride, float weight_grad_scale, float *workspace,
+                        int64_t workspace_bytes, int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw,
+                        int ph, int pw, int dh, int dw, int group, int dg, void *stream);
 
 #ifdef __cplusplus
 }

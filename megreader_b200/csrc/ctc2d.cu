@@ -100,102 +100,174 @@ __device__ __forceinline__ StateCtx make_ctx(const Geo &q, int b0, int Gv, const
 // Contract forward: log_alpha + nll.  One CTA = G consecutive samples, thread = (sample, state).
 // The [H, G*C] slab of log_probs for column t is prefetched kStages-1 columns ahead with cp.async;
 // it feeds both Q[t] and the expansion, so HBM sees every byte of log_probs exactly once.
+// All per-thread addressing (copy plan, output pointer, gather offset) is hoisted out of the column
+// loop: the first version of this kernel spent 60 % of its issue slots on index arithmetic
+// (profiles/ctc2d_r1a_summary.md).
 // ------------------------------------------------------------------------------------------------
-template <typename real, bool STAGED>
-__device__ __forceinline__ void load_slab(const Geo &q, const real *__restrict__ lp, real *dst, int t, int b0, int Gv) {
-    if (!STAGED) return;
-    const int rowElems = q.G * q.C;
-    const int n_el = Gv * q.C;
-    const int nvec = n_el / q.vec;
-    const int rem = n_el - nvec * q.vec;
-    const int per_row = nvec + rem;
-    for (int i = threadIdx.x; i < q.H * per_row; i += blockDim.x) {
-        const int h = i / per_row, j = i - h * per_row;
-        const real *src = lp + ((int64_t)(t * q.H + h) * q.N + b0) * q.C;
-        real *d = dst + h * rowElems;
-        if (j < nvec) {
-            if (q.vec > 1) cp_async16(d + j * q.vec, src + j * q.vec);
-            else if (sizeof(real) == 8) cp_async8(d + j, src + j);
-            else cp_async4(d + j, src + j);
-        } else {
-            const int e = nvec * q.vec + (j - nvec);
-            if (sizeof(real) == 8) cp_async8(d + e, src + e);
-            else cp_async4(d + e, src + e);
-        }
-    }
-}
+constexpr int kPlan = 4;  // cp.async chunks per thread per column held in registers
 
-template <typename real, bool FAST, bool STAGED>
+template <typename real, bool FAST, bool STAGED, int HT>
 __global__ void ctc2d_alpha_kernel(Geo q, const real *__restrict__ lp, const int64_t *__restrict__ tg,
                                    const int64_t *__restrict__ il, const int64_t *__restrict__ tl,
                                    real *__restrict__ nll, real *__restrict__ la) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const real NINF = Lim<real>::ninf();
+    const int H = HT > 0 ? HT : q.H;
     const int tid = threadIdx.x, nth = blockDim.x;
     const int b0 = blockIdx.x * q.G;
     const int Gv = min(q.G, q.N - b0);
     const int rowElems = q.G * q.C;
-    const int slabElems = q.H * rowElems;
+    const int slabElems = H * rowElems;
     real *slab = reinterpret_cast<real *>(smem_raw);
     real *Qs = slab + (STAGED ? kStages * slabElems : 0);
     real *As = Qs + rowElems;
     real *fin = As + q.G * q.SS;
+    const int64_t strideH = (int64_t)q.N * q.C;
+    const int64_t strideT = strideH * H;
+    const real *lp_cta = lp + (int64_t)b0 * q.C;
 
     const StateCtx c = make_ctx(q, b0, Gv, tg, il, tl);
     if (tid < 2 * q.G) fin[tid] = NINF;
     real R = NINF;
 
+    // ---- copy plan: which chunks of a column slab this thread fetches (same for every column)
+    int64_t pl_src[kPlan];
+    int pl_dst[kPlan], pl_kind[kPlan];  // 0 none, 1 element, 2 16-byte vector
+    bool plan_ok = false;
+    const int n_el = Gv * q.C;
+    const int nvec = n_el / q.vec, rem = n_el - nvec * q.vec, per_row = nvec + rem;
+    if (STAGED) {
+        plan_ok = H * per_row <= kPlan * nth;
+#pragma unroll
+        for (int m = 0; m < kPlan; ++m) {
+            const int i = tid + m * nth;
+            pl_kind[m] = 0; pl_src[m] = 0; pl_dst[m] = 0;
+            if (i < H * per_row) {
+                const int h = i / per_row, j = i - h * per_row;
+                const int e = j < nvec ? j * q.vec : nvec * q.vec + (j - nvec);
+                pl_kind[m] = (j < nvec && q.vec > 1) ? 2 : 1;
+                pl_src[m] = h * strideH + e;
+                pl_dst[m] = h * rowElems + e;
+            }
+        }
+    }
+    auto fetch = [&](int t, real *dst) {
+        const real *base = lp_cta + t * strideT;
+        if (plan_ok) {
+#pragma unroll
+            for (int m = 0; m < kPlan; ++m) {
+                if (pl_kind[m] == 2) cp_async16(dst + pl_dst[m], base + pl_src[m]);
+                else if (pl_kind[m] == 1) {
+                    if (sizeof(real) == 8) cp_async8(dst + pl_dst[m], base + pl_src[m]);
+                    else cp_async4(dst + pl_dst[m], base + pl_src[m]);
+                }
+            }
+        } else {
+            for (int i = tid; i < H * per_row; i += nth) {
+                const int h = i / per_row, j = i - h * per_row;
+                const int e = j < nvec ? j * q.vec : nvec * q.vec + (j - nvec);
+                const real *src = base + h * strideH + e;
+                real *d = dst + h * rowElems + e;
+                if (j < nvec && q.vec > 1) cp_async16(d, src);
+                else if (sizeof(real) == 8) cp_async8(d, src);
+                else cp_async4(d, src);
+            }
+        }
+    };
+
     if (STAGED) {
         for (int st = 0; st < kStages - 1; ++st) {
-            if (st < q.T) load_slab<real, STAGED>(q, lp, slab + st * slabElems, st, b0, Gv);
+            if (st < q.T) fetch(st, slab + st * slabElems);
             cp_async_commit();
         }
     }
+    const int gc = c.g * q.C + c.cur;                      // gather offset of l'_s inside a slab row
+    real *out = la + ((int64_t)c.b * q.T * H) * q.SS + c.s;  // log_alpha[b, 0, 0, s]
+    const int outT = H * q.SS;
+    const real *arow = As + tid;                            // tid == g*SS + s for active threads
+
     for (int t = 0; t < q.T; ++t) {
         if (STAGED) cp_async_wait<kStages - 2>();
-        __syncthreads();  // slab[t] landed; As/fin of step t-1 visible; slab[t-1] free for reuse
+        __syncthreads();  // slab[t] landed; As/fin of column t-1 visible; slab[t-1] free for reuse
         if (STAGED) {
             const int tn = t + kStages - 1;
-            if (tn < q.T) load_slab<real, STAGED>(q, lp, slab + (tn % kStages) * slabElems, tn, b0, Gv);
+            if (tn < q.T) fetch(tn, slab + (tn % kStages) * slabElems);
             cp_async_commit();
         }
-        const real *sl = STAGED ? slab + (t % kStages) * slabElems : lp + ((int64_t)t * q.H * q.N + b0) * q.C;
-        const int64_t hstride = STAGED ? rowElems : (int64_t)q.N * q.C;
-
         if (c.active) {
             if (t == 0) {
                 R = (c.s == 0 || (c.s == 1 && c.L > 0)) ? (real)0 : NINF;  // K1 :84-111
             } else if (t < c.Tb && c.in_range) {                           // K1 :128-173
-                const real *a = As + c.g * q.SS + c.s;
-                const real a1 = a[0];
-                const real a2 = c.s > 0 ? a[-1] : NINF;
-                const real a3 = c.skip_fwd ? a[-2] : NINF;
-                R = lse3<FAST>(a1, a2, a3);
+                R = lse3<FAST>(arow[0], c.s > 0 ? arow[-1] : NINF, c.skip_fwd ? arow[-2] : NINF);
             } else {
                 R = NINF;                                                  // K1 :174-182
             }
-            real *out = la + (((int64_t)c.b * q.T + t) * q.H) * q.SS + c.s;
-            const real *src = sl + c.g * q.C + c.cur;
-#pragma unroll 4
-            for (int h = 0; h < q.H; ++h) __stcs(out + (int64_t)h * q.SS, src[h * hstride] + R);
         }
-        // Q[t][g][c] = LSE_h lp[t,h,b,c]
-        for (int idx = tid; idx < Gv * q.C; idx += nth) {
-            const real *p = sl + idx;
-            real m = NINF;
-            for (int h = 0; h < q.H; ++h) m = fmax(m, p[h * hstride]);
-            real v = m;
-            if (m != NINF) {
-                real sum = 0;
-                for (int h = 0; h < q.H; ++h) sum += ex<FAST>(p[h * hstride] - m);
-                v = m + lg<FAST>(sum);
+        if (STAGED) {
+            const real *sl = slab + (t % kStages) * slabElems;
+            if (c.active) {
+                const real *src = sl + gc;
+#pragma unroll
+                for (int h = 0; h < (HT > 0 ? HT : 1); ++h) {
+                    if (HT > 0) __stcs(out + h * q.SS, src[h * rowElems] + R);
+                }
+                if (HT == 0)
+                    for (int h = 0; h < H; ++h) __stcs(out + h * q.SS, src[h * rowElems] + R);
             }
-            Qs[idx] = v;
+            // Q[t][g][c] = LSE_h lp[t,h,b,c]
+            for (int idx = tid; idx < n_el; idx += nth) {
+                const real *p = sl + idx;
+                real v;
+                if (HT > 0) {
+                    real x[HT > 0 ? HT : 1];
+#pragma unroll
+                    for (int h = 0; h < (HT > 0 ? HT : 1); ++h) x[h] = p[h * rowElems];
+                    real m = x[0];
+#pragma unroll
+                    for (int h = 1; h < (HT > 0 ? HT : 1); ++h) m = fmax(m, x[h]);
+                    v = m;
+                    if (m != NINF) {
+                        real sum = 0;
+#pragma unroll
+                        for (int h = 0; h < (HT > 0 ? HT : 1); ++h) sum += ex<FAST>(x[h] - m);
+                        v = m + lg<FAST>(sum);
+                    }
+                } else {
+                    real m = NINF;
+                    for (int h = 0; h < H; ++h) m = fmax(m, p[h * rowElems]);
+                    v = m;
+                    if (m != NINF) {
+                        real sum = 0;
+                        for (int h = 0; h < H; ++h) sum += ex<FAST>(p[h * rowElems] - m);
+                        v = m + lg<FAST>(sum);
+                    }
+                }
+                Qs[idx] = v;
+            }
+        } else {
+            const real *sl = lp_cta + t * strideT;
+            if (c.active) {
+                const real *src = sl + gc;
+                for (int h = 0; h < H; ++h) __stcs(out + h * q.SS, src[h * strideH] + R);
+            }
+            for (int idx = tid; idx < n_el; idx += nth) {
+                const real *p = sl + idx;
+                real m = NINF;
+                for (int h = 0; h < H; ++h) m = fmax(m, p[h * strideH]);
+                real v = m;
+                if (m != NINF) {
+                    real sum = 0;
+                    for (int h = 0; h < H; ++h) sum += ex<FAST>(p[h * strideH] - m);
+                    v = m + lg<FAST>(sum);
+                }
+                Qs[idx] = v;
+            }
         }
+        out += outT;
         __syncthreads();
         if (c.active) {
-            const real a = R + Qs[c.g * q.C + c.cur];
-            As[c.g * q.SS + c.s] = a;
+            const real a = R + Qs[gc];
+            As[tid] = a;
             if (t == c.Tb - 1) {  // K1 :189-209 reads LSE_h alpha[Tb-1, h, 2L] and [.., 2L-1]
                 if (c.s == 2 * c.L) fin[2 * c.g] = a;
                 else if (c.s == 2 * c.L - 1) fin[2 * c.g + 1] = a;
@@ -212,7 +284,7 @@ __global__ void ctc2d_alpha_kernel(Geo q, const real *__restrict__ lp, const int
 //   P2  forward sweep R[t] (kept in smem), nll; backward sweep Rb[t] fused with the per-class
 //       accumulation  acc[t][g][c] += exp(R + Rb + nll)   and the "class present" flag
 //   P3  MODE_GRAD: re-stream log_probs (L2) and write grad = exp(lp) * fac * go
-//       MODE_FAC : write fac [N,T,C] (+ nll)
+//       MODE_FAC : write fac [T,N,C] (+ nll)
 // ------------------------------------------------------------------------------------------------
 enum { MODE_GRAD = 0, MODE_FAC = 1 };
 
@@ -247,81 +319,127 @@ __device__ __forceinline__ void st_cs(real *p, const VecT<real, VE> &v) {
     __stcs(reinterpret_cast<R *>(p), t);
 }
 
-template <typename real, bool FAST, int VE>
-__device__ __forceinline__ void phase_q(const Geo &q, const real *__restrict__ lp, real *Qall, int b0, int Gv) {
-    const int rowElems = q.G * q.C;
-    const int n_el = Gv * q.C;
-    const int nvec = (n_el + VE - 1) / VE;  // VE > 1 only when n_el % VE == 0 for every CTA
+// LSE over the H rows of one vector column, H processed in register chunks of 8.
+template <typename real, bool FAST, int VE, int HT>
+__device__ __forceinline__ void lse_rows(const real *base, int64_t hs, int H, real *dst) {
     const real NINF = Lim<real>::ninf();
-    for (int i = threadIdx.x; i < q.T * nvec; i += blockDim.x) {
-        const int t = i / nvec, j = i - t * nvec;
-        const real *base = lp + ((int64_t)t * q.H * q.N + b0) * q.C + j * VE;
-        const int64_t hs = (int64_t)q.N * q.C;
-        real m[VE], sum[VE];
+    real m[VE], sum[VE];
 #pragma unroll
-        for (int k = 0; k < VE; ++k) { m[k] = NINF; sum[k] = 0; }
-        for (int h0 = 0; h0 < q.H; h0 += 8) {
-            VecT<real, VE> x[8];
+    for (int k = 0; k < VE; ++k) { m[k] = NINF; sum[k] = 0; }
+    for (int h0 = 0; h0 < H; h0 += 8) {
+        VecT<real, VE> x[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                if (h0 + u < q.H) x[u] = ld_nc<real, VE>(base + (h0 + u) * hs);
-                else {
+        for (int u = 0; u < 8; ++u) {
+            if ((HT > 0 && h0 + u < HT) || (HT == 0 && h0 + u < H)) x[u] = ld_nc<real, VE>(base + (h0 + u) * hs);
+            else {
 #pragma unroll
-                    for (int k = 0; k < VE; ++k) x[u].v[k] = NINF;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < VE; ++k) {
-                real cm = x[0].v[k];
-#pragma unroll
-                for (int u = 1; u < 8; ++u) cm = fmax(cm, x[u].v[k]);
-                const real nm = fmax(m[k], cm);
-                if (nm != NINF) {
-                    real sacc = (m[k] == NINF) ? (real)0 : sum[k] * ex<FAST>(m[k] - nm);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) sacc += ex<FAST>(x[u].v[k] - nm);
-                    sum[k] = sacc;
-                    m[k] = nm;
-                }
+                for (int k = 0; k < VE; ++k) x[u].v[k] = NINF;
             }
         }
-#pragma unroll
-        for (int k = 0; k < VE; ++k)
-            Qall[t * rowElems + j * VE + k] = (m[k] == NINF) ? NINF : m[k] + lg<FAST>(sum[k]);
-    }
-}
-
-template <typename real, bool FAST, int VE>
-__device__ __forceinline__ void phase_grad(const Geo &q, const real *__restrict__ lp, const real *Fs,
-                                           real *__restrict__ grad, int b0, int Gv) {
-    const int rowElems = q.G * q.C;
-    const int n_el = Gv * q.C;
-    const int nvec = (n_el + VE - 1) / VE;
-    const int64_t rows = (int64_t)q.T * q.H;
-    for (int64_t i = threadIdx.x; i < rows * nvec; i += blockDim.x) {
-        const int64_t r = i / nvec;
-        const int j = (int)(i - r * nvec);
-        const int t = (int)(r / q.H);
-        const int64_t off = (r * q.N + b0) * q.C + j * VE;
-        VecT<real, VE> x = ld_cs<real, VE>(lp + off);
-        const real *f = Fs + t * rowElems + j * VE;
-        VecT<real, VE> o;
 #pragma unroll
         for (int k = 0; k < VE; ++k) {
-            const real fk = f[k];
-            o.v[k] = (fk == (real)0) ? (real)0 : ex<FAST>(x.v[k]) * fk;
+            real cm = x[0].v[k];
+#pragma unroll
+            for (int u = 1; u < 8; ++u) cm = fmax(cm, x[u].v[k]);
+            const real nm = fmax(m[k], cm);
+            if (nm != NINF) {
+                real sacc = (m[k] == NINF) ? (real)0 : sum[k] * ex<FAST>(m[k] - nm);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sacc += ex<FAST>(x[u].v[k] - nm);
+                sum[k] = sacc;
+                m[k] = nm;
+            }
         }
-        st_cs<real, VE>(grad + off, o);
+    }
+#pragma unroll
+    for (int k = 0; k < VE; ++k) dst[k] = (m[k] == NINF) ? NINF : m[k] + lg<FAST>(sum[k]);
+}
+
+template <typename real, bool FAST, int VE, int HT>
+__device__ __forceinline__ void phase_q(const Geo &q, const real *__restrict__ lp, real *Qall, int b0, int Gv) {
+    const int H = HT > 0 ? HT : q.H;
+    const int rowElems = q.G * q.C;
+    const int nvec = (Gv * q.C + VE - 1) / VE;  // VE > 1 only when Gv*C % VE == 0 for every CTA
+    const int64_t hs = (int64_t)q.N * q.C;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const real *cta = lp + (int64_t)b0 * q.C;
+    if (nvec <= nth) {  // thread-fixed vector column, stride over t: no per-item division
+        const int tpr = nth / nvec;
+        const int t0 = tid / nvec, j = tid - t0 * nvec;
+        if (t0 < tpr)
+            for (int t = t0; t < q.T; t += tpr)
+                lse_rows<real, FAST, VE, HT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
+    } else {
+        for (int i = tid; i < q.T * nvec; i += nth) {
+            const int t = i / nvec, j = i - t * nvec;
+            lse_rows<real, FAST, VE, HT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
+        }
     }
 }
 
-template <typename real, bool FAST, int MODE>
+template <typename real, bool FAST, int VE, int HT>
+__device__ __forceinline__ void grad_rows(const real *src, real *dst, int64_t hs, int H, const real *f) {
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < VE; ++k) any |= (f[k] != (real)0);
+    if (HT > 0) {
+        VecT<real, VE> x[HT > 0 ? HT : 1];
+        if (any) {
+#pragma unroll
+            for (int h = 0; h < (HT > 0 ? HT : 1); ++h) x[h] = ld_cs<real, VE>(src + h * hs);
+        }
+#pragma unroll
+        for (int h = 0; h < (HT > 0 ? HT : 1); ++h) {
+            VecT<real, VE> o;
+#pragma unroll
+            for (int k = 0; k < VE; ++k) o.v[k] = (f[k] == (real)0) ? (real)0 : ex<FAST>(x[h].v[k]) * f[k];
+            st_cs<real, VE>(dst + h * hs, o);
+        }
+    } else {
+        for (int h = 0; h < H; ++h) {
+            VecT<real, VE> x = ld_cs<real, VE>(src + h * hs);
+            VecT<real, VE> o;
+#pragma unroll
+            for (int k = 0; k < VE; ++k) o.v[k] = (f[k] == (real)0) ? (real)0 : ex<FAST>(x.v[k]) * f[k];
+            st_cs<real, VE>(dst + h * hs, o);
+        }
+    }
+}
+
+template <typename real, bool FAST, int VE, int HT>
+__device__ __forceinline__ void phase_grad(const Geo &q, const real *__restrict__ lp, const real *Fs,
+                                           real *__restrict__ grad, int b0, int Gv) {
+    const int H = HT > 0 ? HT : q.H;
+    const int rowElems = q.G * q.C;
+    const int nvec = (Gv * q.C + VE - 1) / VE;
+    const int64_t hs = (int64_t)q.N * q.C;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int64_t cta = (int64_t)b0 * q.C;
+    if (nvec <= nth) {
+        const int tpr = nth / nvec;
+        const int t0 = tid / nvec, j = tid - t0 * nvec;
+        if (t0 < tpr)
+            for (int t = t0; t < q.T; t += tpr) {
+                const int64_t off = cta + (int64_t)t * H * hs + j * VE;
+                grad_rows<real, FAST, VE, HT>(lp + off, grad + off, hs, H, Fs + t * rowElems + j * VE);
+            }
+    } else {
+        for (int i = tid; i < q.T * nvec; i += nth) {
+            const int t = i / nvec, j = i - t * nvec;
+            const int64_t off = cta + (int64_t)t * H * hs + j * VE;
+            grad_rows<real, FAST, VE, HT>(lp + off, grad + off, hs, H, Fs + t * rowElems + j * VE);
+        }
+    }
+}
+
+template <typename real, bool FAST, int MODE, int HT>
 __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_t *__restrict__ tg,
                                 const int64_t *__restrict__ il, const int64_t *__restrict__ tl,
                                 const real *__restrict__ grad_out, int64_t go_stride,
                                 real *__restrict__ nll_out, real *__restrict__ fac_out, real *__restrict__ grad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const real NINF = Lim<real>::ninf();
+    constexpr int V16 = 16 / (int)sizeof(real);
     const int tid = threadIdx.x, nth = blockDim.x;
     const int b0 = blockIdx.x * q.G;
     const int Gv = min(q.G, q.N - b0);
@@ -338,29 +456,35 @@ __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_
     for (int i = tid; i < q.T * rowElems; i += nth) { acc[i] = 0; pres[i] = 0; }
     if (tid < 2 * q.G) fin[tid] = NINF;
 
-    if (q.vec == 4) phase_q<real, FAST, (sizeof(real) == 4 ? 4 : 1)>(q, lp, Qall, b0, Gv);
-    else if (q.vec == 2) phase_q<real, FAST, (sizeof(real) == 8 ? 2 : 1)>(q, lp, Qall, b0, Gv);
-    else phase_q<real, FAST, 1>(q, lp, Qall, b0, Gv);
+    if (q.vec > 1) phase_q<real, FAST, V16, HT>(q, lp, Qall, b0, Gv);
+    else phase_q<real, FAST, 1, HT>(q, lp, Qall, b0, Gv);
     __syncthreads();
 
+    const int gc = c.g * q.C + c.cur;
     // ---- forward sweep (same recurrence as ctc2d_alpha_kernel), one barrier per column
     real R = NINF;
-    for (int t = 0; t < q.T; ++t) {
-        if (c.active) {
-            if (t == 0) R = (c.s == 0 || (c.s == 1 && c.L > 0)) ? (real)0 : NINF;
-            else if (t < c.Tb && c.in_range) {
-                const real *a = As + ((t - 1) & 1) * rowStates + c.g * q.SS + c.s;
-                R = lse3<FAST>(a[0], c.s > 0 ? a[-1] : NINF, c.skip_fwd ? a[-2] : NINF);
-            } else R = NINF;
-            Ra[t * rowStates + c.g * q.SS + c.s] = R;
-            const real a = R + Qall[t * rowElems + c.g * q.C + c.cur];
-            As[(t & 1) * rowStates + c.g * q.SS + c.s] = a;
-            if (t == c.Tb - 1) {
-                if (c.s == 2 * c.L) fin[2 * c.g] = a;
-                else if (c.s == 2 * c.L - 1) fin[2 * c.g + 1] = a;
+    {
+        real *ra = Ra + tid;
+        const real *qp = Qall + gc;
+        for (int t = 0; t < q.T; ++t) {
+            if (c.active) {
+                if (t == 0) R = (c.s == 0 || (c.s == 1 && c.L > 0)) ? (real)0 : NINF;
+                else if (t < c.Tb && c.in_range) {
+                    const real *a = As + ((t - 1) & 1) * rowStates + tid;
+                    R = lse3<FAST>(a[0], c.s > 0 ? a[-1] : NINF, c.skip_fwd ? a[-2] : NINF);
+                } else R = NINF;
+                *ra = R;
+                const real a = R + *qp;
+                As[(t & 1) * rowStates + tid] = a;
+                if (t == c.Tb - 1) {
+                    if (c.s == 2 * c.L) fin[2 * c.g] = a;
+                    else if (c.s == 2 * c.L - 1) fin[2 * c.g + 1] = a;
+                }
             }
+            ra += rowStates;
+            qp += rowElems;
+            __syncthreads();
         }
-        __syncthreads();
     }
     real *nlls = fin + 2 * q.G;
     if (c.active && c.s == 0) {
@@ -372,74 +496,76 @@ __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_
     const real my_nll = c.active ? nlls[c.g] : (real)0;
 
     // ---- backward sweep (K2 :283-366) fused with K3's per-class collection (:460-497)
-    real Rb = NINF;
-    for (int t = q.T - 1; t >= 0; --t) {
-        if (c.active) {
-            if (t == c.Tb - 1) {
-                Rb = (c.s == 2 * c.L || (c.L > 0 && c.s == 2 * c.L - 1)) ? (real)0 : NINF;
-            } else if (t < c.Tb - 1 && c.in_range) {
-                const real *bq = As + ((t + 1) & 1) * rowStates + c.g * q.SS + c.s;
-                Rb = lse3<FAST>(bq[0], c.s < 2 * c.L ? bq[1] : NINF, c.skip_bwd ? bq[2] : NINF);
-            } else Rb = NINF;
-            As[(t & 1) * rowStates + c.g * q.SS + c.s] = Rb + Qall[t * rowElems + c.g * q.C + c.cur];
-            if (c.in_range && t < c.Tb) {
-                const real v = Ra[t * rowStates + c.g * q.SS + c.s] + Rb;
-                if (v != NINF) {
-                    const int o = t * rowElems + c.g * q.C + c.cur;
-                    pres[o] = 1;
-                    atomicAdd(acc + o, ex<FAST>(v + my_nll));
+    {
+        real Rb = NINF;
+        const real *ra = Ra + (q.T - 1) * rowStates + tid;
+        int o = (q.T - 1) * rowElems + gc;
+        for (int t = q.T - 1; t >= 0; --t) {
+            if (c.active) {
+                if (t == c.Tb - 1) {
+                    Rb = (c.s == 2 * c.L || (c.L > 0 && c.s == 2 * c.L - 1)) ? (real)0 : NINF;
+                } else if (t < c.Tb - 1 && c.in_range) {
+                    const real *bq = As + ((t + 1) & 1) * rowStates + tid;
+                    Rb = lse3<FAST>(bq[0], c.s < 2 * c.L ? bq[1] : NINF, c.skip_bwd ? bq[2] : NINF);
+                } else Rb = NINF;
+                As[(t & 1) * rowStates + tid] = Rb + Qall[o];
+                if (c.in_range && t < c.Tb) {
+                    const real v = *ra + Rb;
+                    if (v != NINF) {
+                        pres[o] = 1;
+                        atomicAdd(acc + o, ex<FAST>(v + my_nll));
+                    }
                 }
             }
+            ra -= rowStates;
+            o -= rowElems;
+            __syncthreads();
         }
-        __syncthreads();
     }
 
     // ---- factor: (1 - acc) [* go] where the class is present and t < Tb, else 0 (K3 :501-515)
-    for (int i = tid; i < q.T * Gv * q.C; i += nth) {
-        const int t = i / (Gv * q.C);
-        const int r = i - t * (Gv * q.C);
-        const int g = r / q.C;
-        const int o = t * rowElems + r;
-        real f = 0;
-        if (pres[o] && t < il[b0 + g]) {
-            f = (real)1 - acc[o];
-            if (MODE == MODE_GRAD) f *= grad_out[(int64_t)(b0 + g) * go_stride];
+    for (int e = tid; e < Gv * q.C; e += nth) {
+        const int g = e / q.C;
+        const int cc = e - g * q.C;
+        const int64_t Tb = il[b0 + g];
+        const real gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + g) * go_stride] : (real)1;
+        real *fo = (MODE == MODE_FAC) ? fac_out + (int64_t)(b0 + g) * q.C + cc : nullptr;
+        for (int t = 0; t < q.T; ++t) {
+            const int o = t * rowElems + e;
+            real f = 0;
+            if (pres[o] && t < Tb) f = ((real)1 - acc[o]) * gs;
+            if (MODE == MODE_FAC) fo[(int64_t)t * q.N * q.C] = f;
+            else acc[o] = f;
         }
-        if (MODE == MODE_FAC) fac_out[((int64_t)(b0 + g) * q.T + t) * q.C + (r - g * q.C)] = f;
-        else acc[o] = f;
     }
     if (MODE == MODE_GRAD) {
         __syncthreads();
-        if (q.vec == 4) phase_grad<real, FAST, (sizeof(real) == 4 ? 4 : 1)>(q, lp, acc, grad, b0, Gv);
-        else if (q.vec == 2) phase_grad<real, FAST, (sizeof(real) == 8 ? 2 : 1)>(q, lp, acc, grad, b0, Gv);
-        else phase_grad<real, FAST, 1>(q, lp, acc, grad, b0, Gv);
+        if (q.vec > 1) phase_grad<real, FAST, V16, HT>(q, lp, acc, grad, b0, Gv);
+        else phase_grad<real, FAST, 1, HT>(q, lp, acc, grad, b0, Gv);
     }
 }
 
-// Training backward: grad[t,h,b,c] = exp(lp) * gfac[b,t,c] * go[b].  Pure streaming; thread = 16-byte vector.
-template <bool FAST, int VE>
-__global__ void ctc2d_apply_kernel(const float *__restrict__ lp, const float *__restrict__ fac,
-                                   const float *__restrict__ go, int64_t go_stride, int T, int H, int N, int C,
-                                   float *__restrict__ grad) {
-    const int64_t row = (int64_t)N * C;           // one (t,h) row
+// Training backward: grad[t,h,b,c] = exp(lp) * gfac[t,b,c] * go[b].  Pure streaming.  blockIdx.y = t, thread = one
+// 16-byte vector column of the [N*C] row; the factor is formed once and reused for the H rows.
+template <bool FAST, int VE, int HT>
+__global__ void __launch_bounds__(256)
+ctc2d_apply_kernel(const float *__restrict__ lp, const float *__restrict__ fac, const float *__restrict__ go,
+                   int64_t go_stride, int T, int Hrt, int N, int C, float *__restrict__ grad) {
+    const int H = HT > 0 ? HT : Hrt;
+    const int64_t row = (int64_t)N * C;
     const int64_t nvec_row = row / VE;
-    const int64_t total = (int64_t)T * H * nvec_row;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / nvec_row;
-        const int64_t j = (i - r * nvec_row) * VE;
-        const int t = (int)(r / H);
-        const int64_t off = r * row + j;
-        VecT<float, VE> x = ld_cs<float, VE>(lp + off);
-        VecT<float, VE> o;
+    const int t = blockIdx.y;
+    for (int64_t jv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; jv < nvec_row; jv += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = jv * VE;
+        VecT<float, VE> fv = ld_nc<float, VE>(fac + (int64_t)t * row + j);
+        float f[VE];
 #pragma unroll
         for (int k = 0; k < VE; ++k) {
-            const int64_t e = j + k;
-            const int b = (int)(e / C);
-            const int cc = (int)(e - (int64_t)b * C);
-            const float f = __ldg(fac + ((int64_t)b * T + t) * C + cc) * __ldg(go + (int64_t)b * go_stride);
-            o.v[k] = (f == 0.f) ? 0.f : ex<FAST>(x.v[k]) * f;
+            const int b = (int)((j + k) / C);
+            f[k] = fv.v[k] * __ldg(go + (int64_t)b * go_stride);
         }
-        st_cs<float, VE>(grad + off, o);
+        const int64_t off = (int64_t)t * H * row + j;
+        grad_rows<float, FAST, VE, HT>(lp + off, grad + off, row, H, f);
     }
 }
 
@@ -505,7 +631,8 @@ int launch_alpha(const real *lp, const int64_t *tg, const int64_t *il, const int
     q.vec = pick_vec<real>(lp, N, C, G);
     const int threads = (int)round_up((int64_t)G * q.SS, 32);
     const int grid = (int)ceil_div(N, G);
-    auto kern = staged ? ctc2d_alpha_kernel<real, FAST, true> : ctc2d_alpha_kernel<real, FAST, false>;
+    auto kern = staged ? (H == 8 ? ctc2d_alpha_kernel<real, FAST, true, 8> : ctc2d_alpha_kernel<real, FAST, true, 0>)
+                       : ctc2d_alpha_kernel<real, FAST, false, 0>;
     if (smem > 48 * 1024)
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ctc2d_alpha attr");
     kern<<<grid, threads, smem, st>>>(q, lp, tg, il, tl, nll, la);
@@ -534,7 +661,7 @@ int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_
     if (MODE == MODE_GRAD && ((uintptr_t)grad % 16) != 0) q.vec = 1;
     const int threads = (int)round_up((int64_t)G * q.SS, 32);
     const int grid = (int)ceil_div(N, G);
-    auto kern = ctc2d_dp_kernel<real, FAST, MODE>;
+    auto kern = (H == 8) ? ctc2d_dp_kernel<real, FAST, MODE, 8> : ctc2d_dp_kernel<real, FAST, MODE, 0>;
     if (smem > 48 * 1024)
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ctc2d_dp attr");
     kern<<<grid, threads, smem, st>>>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad);
@@ -615,19 +742,21 @@ int mr_ctc2d_backward_apply_f32(const float *go, int64_t go_stride, const float 
     if (N == 0 || T == 0 || H == 0) return MR_OK;
     if (!go || !lp || !gfac || !grad) return MR_ERR_NULL_POINTER;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool v4 = ((uintptr_t)lp % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((N * C) % 4 == 0);
-    const int64_t nvec = T * H * (N * C / (v4 ? 4 : 1));
+    const bool v4 = ((uintptr_t)lp % 16 == 0) && ((uintptr_t)grad % 16 == 0) && ((uintptr_t)gfac % 16 == 0) && ((N * C) % 4 == 0);
+    const int64_t nvec_row = N * C / (v4 ? 4 : 1);
     const int threads = 256;
-    int64_t blocks = ceil_div(nvec, threads);
-    const int64_t cap = 148 * 16;
-    if (blocks > cap) blocks = cap;
+    int64_t bx = ceil_div(nvec_row, threads);
+    if (bx > 65535) bx = 65535;
+    if (T > 65535) return MR_ERR_BAD_SHAPE;
+    dim3 grid((unsigned)bx, (unsigned)T);
+#define MR_APPLY(FASTV, VEV, HTV) ctc2d_apply_kernel<FASTV, VEV, HTV><<<grid, threads, 0, st>>>(lp, gfac, go, go_stride, (int)T, (int)H, (int)N, (int)C, grad)
     if (v4) {
-        if (fast_math) ctc2d_apply_kernel<true, 4><<<(int)blocks, threads, 0, st>>>(lp, gfac, go, go_stride, (int)T, (int)H, (int)N, (int)C, grad);
-        else ctc2d_apply_kernel<false, 4><<<(int)blocks, threads, 0, st>>>(lp, gfac, go, go_stride, (int)T, (int)H, (int)N, (int)C, grad);
+        if (H == 8) { if (fast_math) MR_APPLY(true, 4, 8); else MR_APPLY(false, 4, 8); }
+        else { if (fast_math) MR_APPLY(true, 4, 0); else MR_APPLY(false, 4, 0); }
     } else {
-        if (fast_math) ctc2d_apply_kernel<true, 1><<<(int)blocks, threads, 0, st>>>(lp, gfac, go, go_stride, (int)T, (int)H, (int)N, (int)C, grad);
-        else ctc2d_apply_kernel<false, 1><<<(int)blocks, threads, 0, st>>>(lp, gfac, go, go_stride, (int)T, (int)H, (int)N, (int)C, grad);
+        if (fast_math) MR_APPLY(true, 1, 0); else MR_APPLY(false, 1, 0);
     }
+#undef MR_APPLY
     return check_launch("ctc2d_apply_kernel");
 }
 

@@ -92,11 +92,11 @@ def ctc2d_backward(grad_out, log_probs, targets, input_lengths, target_lengths, 
 
 
 def ctc2d_forward_train(log_probs, targets, input_lengths, target_lengths, BLANK):
-    """-> (nll[N], gfac[N,T,C]) — training forward without log_alpha (float32)."""
+    """-> (nll[N], gfac[T,N,C]) — training forward without log_alpha (float32)."""
     T, H, N, C, S = _check_inputs(log_probs, targets, input_lengths, target_lengths, BLANK)
     il, tl = _c(input_lengths), _c(target_lengths)
     nll = torch.empty((N,), dtype=log_probs.dtype, device=log_probs.device)
-    gfac = torch.empty((N, T, C), dtype=log_probs.dtype, device=log_probs.device)
+    gfac = torch.empty((T, N, C), dtype=log_probs.dtype, device=log_probs.device)
     with torch.cuda.device(log_probs.device):
         _lib.check(_lib.lib().mr_ctc2d_forward_train_f32(
             log_probs.data_ptr(), targets.data_ptr(), il.data_ptr(), tl.data_ptr(), T, H, N, C, S,

@@ -108,3 +108,57 @@ def ctc2d_fwd_bwd(grad_out, log_probs, targets, input_lengths, target_lengths, b
     fn(ptr(go), ptr(lp), ptr(tg), ptr(il), ptr(tl), I64(T), I64(H), I64(N), I64(C), I64(S), I64(blank),
        ptr(nll), ptr(la), ptr(lb), ptr(gr))
     return nll, la, gr
+
+
+# ---------------------------------------------------------------- DCN (oracle/dcn_oracle.c)
+I32 = ctypes.c_int
+
+
+def _dcn_out(H, W, kh, kw, sh, sw, ph, pw, dh, dw):
+    return ((H + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1, (W + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1)
+
+
+def dcn_forward(inp, weight, bias, offset, mask, stride=1, padding=1, dilation=1, group=1, dg=1):
+    """Modulated (mask given) or v1 (mask None) deformable conv forward.  offset/mask may have a larger spatial
+    size than the output: they are indexed flat per sample with (Ho, Wo) strides like the reference kernels."""
+    x = np.ascontiguousarray(inp)
+    dt = x.dtype
+    B, C, H, W = x.shape
+    w = np.ascontiguousarray(weight, dtype=dt)
+    Cout, _, kh, kw = w.shape
+    off = np.ascontiguousarray(offset, dtype=dt)
+    msk = None if mask is None else np.ascontiguousarray(mask, dtype=dt)
+    Ho, Wo = _dcn_out(H, W, kh, kw, stride, stride, padding, padding, dilation, dilation)
+    out = np.empty((B, Cout, Ho, Wo), dt)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=dt)
+    fn = getattr(lib(), "dcn_forward_" + _suf(dt))
+    fn(ptr(x), ptr(w), ptr(b) if b is not None else None, ptr(off), I64(off[0].size),
+       ptr(msk) if msk is not None else None, I64(msk[0].size if msk is not None else 0),
+       I32(B), I32(C), I32(H), I32(W), I32(Cout), I32(kh), I32(kw), I32(stride), I32(stride), I32(padding),
+       I32(padding), I32(dilation), I32(dilation), I32(group), I32(dg), I32(1 if b is not None else 0), ptr(out))
+    return out
+
+
+def dcn_backward(inp, weight, bias, offset, mask, grad_output, stride=1, padding=1, dilation=1, group=1, dg=1):
+    """-> (grad_input, grad_weight, grad_bias|None, grad_offset, grad_mask|None); grad_offset/grad_mask have the
+    shape of offset/mask with the reference's flat (Ho,Wo) layout inside each sample slab (tail left zero)."""
+    x = np.ascontiguousarray(inp)
+    dt = x.dtype
+    B, C, H, W = x.shape
+    w = np.ascontiguousarray(weight, dtype=dt)
+    Cout, _, kh, kw = w.shape
+    off = np.ascontiguousarray(offset, dtype=dt)
+    msk = None if mask is None else np.ascontiguousarray(mask, dtype=dt)
+    go = np.ascontiguousarray(grad_output, dtype=dt)
+    gi, gw = np.zeros_like(x), np.zeros_like(w)
+    gb = None if bias is None else np.zeros((Cout,), dt)
+    goff = np.zeros_like(off)
+    gmsk = None if msk is None else np.zeros_like(msk)
+    fn = getattr(lib(), "dcn_backward_" + _suf(dt))
+    fn(ptr(x), ptr(w), ptr(off), I64(off[0].size), ptr(msk) if msk is not None else None,
+       I64(msk[0].size if msk is not None else 0), ptr(go),
+       I32(B), I32(C), I32(H), I32(W), I32(Cout), I32(kh), I32(kw), I32(stride), I32(stride), I32(padding),
+       I32(padding), I32(dilation), I32(dilation), I32(group), I32(dg), I32(1 if gb is not None else 0),
+       ptr(gi), ptr(gw), ptr(gb) if gb is not None else None, ptr(goff), I64(goff[0].size),
+       ptr(gmsk) if gmsk is not None else None, I64(gmsk[0].size if gmsk is not None else 0))
+    return gi, gw, gb, goff, gmsk
