@@ -88,6 +88,23 @@ int mr_ctc2d_backward_apply_f32(const float *grad_out, int64_t grad_out_stride, 
                                 float *grad, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 1D CTC head of the CRNN decoder (replaces the `log_softmax -> nn.CTCLoss(zero_infinity=True)` call,
+ * decoders/crnn.py:47-48,95-99; arithmetic restated in decoders/ctc_loss.py:65-122).  fp32.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[r,:] = log_softmax(x[r,:]) for `rows` rows of C classes (decoders/crnn.py:96). */
+int mr_log_softmax_rows_f32(const float *x, int64_t rows, int64_t C, float *out, void *stream);
+/* log_probs [T,N,C]; writes nll [N] (raw, may be +inf) and gfac [T,N,C] with aten's gradient convention:
+ * d nll_b / d log_probs[t,b,c] = exp(lp) * gfac   (0 for t >= input_length, and for nll=+inf when zero_infinity). */
+int mr_ctc1d_forward_train_f32(const float *log_probs, const int64_t *targets, const int64_t *input_lengths,
+                               const int64_t *target_lengths, int64_t T, int64_t N, int64_t C, int64_t S,
+                               int64_t tg_stride_n, int64_t tg_stride_s, int64_t blank, int zero_infinity,
+                               int fast_math, float *nll, float *gfac, void *stream);
+/* grad_logits [T,N,C] = scale[b] * log_softmax_backward(exp(lp) * gfac): the CTC gradient pushed through the
+ * log_softmax, scale[b] = upstream gradient of nll_b (1 / (N * target_length) for the 'mean' reduction). */
+int mr_ctc1d_backward_logits_f32(const float *log_probs, const float *gfac, const float *scale, int64_t T, int64_t N,
+                                 int64_t C, float *grad_logits, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Deformable convolution v1 / v2  (replaces pybind module assets.ops.dcn.deform_conv_cuda:
  * assets/ops/dcn/src/deform_conv_cuda.cpp:681-695).  fp32, NCHW contiguous input [B,C,H,W] and weight
  * [Cout, C/group, kh, kw].  offset / mask (and their gradients) are addressed per sample as

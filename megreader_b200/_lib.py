@@ -29,6 +29,9 @@ _SIGS = {
     "mr_ctc2d_backward_f64": [c_p, c_i64] + [c_p] * 6 + [c_i64] * 8 + [c_int, c_p, c_p],
     "mr_ctc2d_forward_train_f32": [c_p] * 4 + [c_i64] * 8 + [c_int, c_p, c_p, c_p],
     "mr_ctc2d_backward_apply_f32": [c_p, c_i64, c_p, c_p] + [c_i64] * 4 + [c_int, c_p, c_p],
+    "mr_log_softmax_rows_f32": [c_p, c_i64, c_i64, c_p, c_p],
+    "mr_ctc1d_forward_train_f32": [c_p] * 4 + [c_i64] * 7 + [c_int, c_int, c_p, c_p, c_p],
+    "mr_ctc1d_backward_logits_f32": [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p],
     "mr_dcn_workspace_bytes": [c_i64] * 6,
     "mr_dcn_forward_f32": [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64] + [c_int] * 15 + [c_p],
     "mr_dcn_backward_f32": [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_f32,

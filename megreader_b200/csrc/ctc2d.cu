@@ -56,6 +56,7 @@ struct Geo {
     int G;                  // samples per CTA
     int vec;                // elements per 16-byte vector usable on log_probs rows (1 = scalar path)
     int blank;
+    int zero_inf;           // MODE_FAC_STD: zero the factor of samples whose nll is +inf (zero_infinity=True)
     int64_t tg_sn, tg_ss;
 };
 
@@ -286,7 +287,7 @@ __global__ void ctc2d_alpha_kernel(Geo q, const real *__restrict__ lp, const int
 //   P3  MODE_GRAD: re-stream log_probs (L2) and write grad = exp(lp) * fac * go
 //       MODE_FAC : write fac [T,N,C] (+ nll)
 // ------------------------------------------------------------------------------------------------
-enum { MODE_GRAD = 0, MODE_FAC = 1 };
+enum { MODE_GRAD = 0, MODE_FAC = 1, MODE_FAC_STD = 2 };  // FAC_STD: torch.nn.CTCLoss gradient convention (1D CTC)
 
 template <typename real, int VE> struct alignas(sizeof(real) * VE) VecT { real v[VE]; };
 
@@ -490,7 +491,7 @@ __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_
     if (c.active && c.s == 0) {
         const real v = -lse2<FAST>(fin[2 * c.g], fin[2 * c.g + 1]);
         nlls[c.g] = v;
-        if (MODE == MODE_FAC) nll_out[c.b] = v;
+        if (MODE != MODE_GRAD) nll_out[c.b] = v;
     }
     __syncthreads();
     const real my_nll = c.active ? nlls[c.g] : (real)0;
@@ -529,12 +530,16 @@ __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_
         const int cc = e - g * q.C;
         const int64_t Tb = il[b0 + g];
         const real gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + g) * go_stride] : (real)1;
-        real *fo = (MODE == MODE_FAC) ? fac_out + (int64_t)(b0 + g) * q.C + cc : nullptr;
+        real *fo = (MODE != MODE_GRAD) ? fac_out + (int64_t)(b0 + g) * q.C + cc : nullptr;
+        const bool dead = (MODE == MODE_FAC_STD) && q.zero_inf && (nlls[g] == -NINF);
         for (int t = 0; t < q.T; ++t) {
             const int o = t * rowElems + e;
             real f = 0;
-            if (pres[o] && t < Tb) f = ((real)1 - acc[o]) * gs;
-            if (MODE == MODE_FAC) fo[(int64_t)t * q.N * q.C] = f;
+            if (MODE == MODE_FAC_STD) {
+                // aten ctc_loss backward: (exp(lp) - exp(lcab + nll - lp)) * gr for EVERY class, t < Tb
+                if (t < Tb && !dead) f = (real)1 - acc[o];
+            } else if (pres[o] && t < Tb) f = ((real)1 - acc[o]) * gs;
+            if (MODE != MODE_GRAD) fo[(int64_t)t * q.N * q.C] = f;
             else acc[o] = f;
         }
     }
@@ -566,6 +571,41 @@ ctc2d_apply_kernel(const float *__restrict__ lp, const float *__restrict__ fac, 
         }
         const int64_t off = (int64_t)t * H * row + j;
         grad_rows<float, FAST, VE, HT>(lp + off, grad + off, row, H, f);
+    }
+}
+
+// ---- 1D CTC helpers: one warp per (t, b) row of C classes ----
+__global__ void rows_log_softmax_kernel(const float *__restrict__ x, int64_t rows, int C, float *__restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float *p = x + r * C;
+    float m = -INFINITY;
+    for (int c = lane; c < C; c += 32) m = fmaxf(m, p[c]);
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(p[c] - m);
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    const float lse = m + logf(sum);
+    for (int c = lane; c < C; c += 32) out[r * C + c] = p[c] - lse;
+}
+
+// grad_logits[r,c] = scale[b] * (g - p * sum_c g),  g = p * fac,  p = exp(lp)   (CTC grad folded through log_softmax)
+__global__ void ctc1d_grad_rows_kernel(const float *__restrict__ lp, const float *__restrict__ fac,
+                                       const float *__restrict__ scale, int64_t rows, int N, int C,
+                                       float *__restrict__ grad) {
+    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const int b = (int)(r % N);
+    const float sc = scale[b];
+    const float *l = lp + r * C, *f = fac + r * C;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(l[c]) * f[c];
+    for (int s = 16; s > 0; s >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, s);
+    for (int c = lane; c < C; c += 32) {
+        const float p = expf(l[c]);
+        grad[r * C + c] = sc * (p * f[c] - p * sum);
     }
 }
 
@@ -606,6 +646,7 @@ int launch_alpha(const real *lp, const int64_t *tg, const int64_t *il, const int
                  int64_t N, int64_t C, int64_t S, int64_t tg_sn, int64_t tg_ss, int64_t blank, real *nll, real *la,
                  cudaStream_t st) {
     Geo q;
+    q.zero_inf = 0;
     q.T = (int)T; q.H = (int)H; q.N = (int)N; q.C = (int)C; q.S = (int)S; q.SS = (int)(2 * S + 1);
     q.blank = (int)blank; q.tg_sn = tg_sn; q.tg_ss = tg_ss;
     int G = 288 / q.SS;
@@ -642,8 +683,9 @@ int launch_alpha(const real *lp, const int64_t *tg, const int64_t *il, const int
 template <typename real, bool FAST, int MODE>
 int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const real *go,
               int64_t go_stride, int64_t T, int64_t H, int64_t N, int64_t C, int64_t S, int64_t tg_sn,
-              int64_t tg_ss, int64_t blank, real *nll, real *fac, real *grad, cudaStream_t st) {
+              int64_t tg_ss, int64_t blank, real *nll, real *fac, real *grad, cudaStream_t st, int zero_inf = 0) {
     Geo q;
+    q.zero_inf = zero_inf;
     q.T = (int)T; q.H = (int)H; q.N = (int)N; q.C = (int)C; q.S = (int)S; q.SS = (int)(2 * S + 1);
     q.blank = (int)blank; q.tg_sn = tg_sn; q.tg_ss = tg_ss;
     int G = 160 / q.SS;  // fewer samples per CTA than the alpha kernel: the sweeps are latency-bound,
@@ -758,6 +800,42 @@ int mr_ctc2d_backward_apply_f32(const float *go, int64_t go_stride, const float 
     }
 #undef MR_APPLY
     return check_launch("ctc2d_apply_kernel");
+}
+
+
+/* ---------------- 1D CTC (CRNN head): log_softmax rows -> DP (H = 1) -> gradient w.r.t. the logits ------------- */
+
+int mr_log_softmax_rows_f32(const float *x, int64_t rows, int64_t C, float *out, void *stream) {
+    if (rows < 0 || C <= 0) return MR_ERR_BAD_SHAPE;
+    if (rows == 0) return MR_OK;
+    if (!x || !out) return MR_ERR_NULL_POINTER;
+    const int wpb = 8;
+    rows_log_softmax_kernel<<<(unsigned)ceil_div(rows, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(x, rows, (int)C, out);
+    return check_launch("rows_log_softmax_kernel");
+}
+
+int mr_ctc1d_forward_train_f32(const float *log_probs, const int64_t *tg, const int64_t *il, const int64_t *tl,
+                               int64_t T, int64_t N, int64_t C, int64_t S, int64_t tg_sn, int64_t tg_ss, int64_t blank,
+                               int zero_infinity, int fast_math, float *nll, float *gfac, void *stream) {
+    int rc = check_common(log_probs, tg, il, tl, T, 1, N, C, S, blank);
+    if (rc) return rc;
+    if (N == 0) return MR_OK;
+    if (T == 0) return MR_ERR_BAD_SHAPE;
+    if (!nll || !gfac) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    return fast_math ? launch_dp<float, true, MODE_FAC_STD>(log_probs, tg, il, tl, nullptr, 0, T, 1, N, C, S, tg_sn, tg_ss, blank, nll, gfac, nullptr, st, zero_infinity)
+                     : launch_dp<float, false, MODE_FAC_STD>(log_probs, tg, il, tl, nullptr, 0, T, 1, N, C, S, tg_sn, tg_ss, blank, nll, gfac, nullptr, st, zero_infinity);
+}
+
+int mr_ctc1d_backward_logits_f32(const float *log_probs, const float *gfac, const float *scale, int64_t T, int64_t N,
+                                 int64_t C, float *grad_logits, void *stream) {
+    if (T < 0 || N < 0 || C <= 0) return MR_ERR_BAD_SHAPE;
+    if (T == 0 || N == 0) return MR_OK;
+    if (!log_probs || !gfac || !scale || !grad_logits) return MR_ERR_NULL_POINTER;
+    const int wpb = 8;
+    ctc1d_grad_rows_kernel<<<(unsigned)ceil_div(T * N, wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        log_probs, gfac, scale, T * N, (int)N, (int)C, grad_logits);
+    return check_launch("ctc1d_grad_rows_kernel");
 }
 
 }  // extern "C"

@@ -72,8 +72,46 @@ def make_ctc2d():
         print("ctc2d", name, "ref nll", loss.detach().numpy()[:4])
 
 
+def make_crnn():
+    """cfg 1 exactly (crnn.yaml): reference crnn_backbone + CRNNDecoder(nn.CTCLoss), N=4, 3x32x100, fp32, CPU."""
+    from tests.weights import crnn_batch, fill_state_dict
+    ref_loader.install()
+    import backbones as rb
+    import decoders as rd
+    torch.manual_seed(0)
+    bb = fill_state_dict(rb.crnn_backbone(), "bb.")
+    dec = fill_state_dict(rd.CRNNDecoder(in_channels=512, inner_channels=256), "dec.")
+    for name, (N, W) in {"cfg1": (4, 100), "w128": (3, 128)}.items():
+        T = W // 4 + 1
+        x, labels, lengths = crnn_batch(0, N, W, 8, T)
+        bb.train(); dec.train()
+        bb.zero_grad(); dec.zero_grad()
+        tx = torch.from_numpy(x)
+        feat = bb(tx)
+        loss, pred = dec(feat, targets=torch.from_numpy(labels), lengths=torch.from_numpy(lengths), train=True)
+        loss.mean().backward()
+        grads = {"grad." + k: v.grad.numpy().copy() for k, v in list(bb.named_parameters()) + list(dec.named_parameters())
+                 if k in ("cnn.0.0.0.weight", "cnn.2.1.weight", "cnn.6.1.bias", "cnn.6.0.bias",
+                          "rnn.1.embedding.weight", "rnn.1.embedding.bias", "rnn.0.rnn.bias_hh_l0_reverse")}
+        gnorm = {"gnorm." + k: np.float64(v.grad.double().norm().item())
+                 for k, v in list(bb.named_parameters()) + list(dec.named_parameters())}
+        bn_after = {"bn." + k: v.numpy().copy() for k, v in bb.state_dict().items() if "running" in k and k.startswith("cnn.2")}
+        # eval-mode forward AFTER the training forward (running stats updated once), like eval.py would see
+        bb.eval(); dec.eval()
+        with torch.no_grad():
+            prob = dec(bb(tx), train=False)                       # (N, C, 1, T) softmax
+        # re-load pristine weights for the next case (BN running stats were updated)
+        np.savez_compressed(os.path.join(GOLD, "crnn_ref_%s.npz" % name), x=x[:, :1], labels=labels, lengths=lengths,
+                            feature=feat.detach().numpy(), loss=np.float64(loss.item()), log_probs=pred.detach().numpy(),
+                            eval_prob=prob.numpy(), **grads, **gnorm, **bn_after)
+        print("crnn", name, "loss", loss.item(), "feat", tuple(feat.shape), "pred", tuple(pred.shape))
+        fill_state_dict(bb, "bb."); fill_state_dict(dec, "dec.")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["ctc2d"]
     if "ctc2d" in which:
         make_ctc2d()
+    if "crnn" in which:
+        make_crnn()
