@@ -142,10 +142,12 @@ def run_ours(args):
         host.append((x.pin_memory(), y.pin_memory(), l.pin_memory()))
     dev_batches = [tuple(t.to(dev) for t in hb) for hb in host]
 
+    from megreader_b200 import crnn_engine
+    crnn_engine.set_compute_dtype(torch.bfloat16)          # BASELINE.json cfg 2: bf16 compute, fp32 master weights
+
     def step(x, y, l):
         opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss, _ = model(x, y, l)
+        loss, _ = model(x, y, l)
         loss.mean().backward()
         opt.step()
         return loss
@@ -226,7 +228,9 @@ def run_ours(args):
     if rank == 0:
         out["ctc2d"], out["roofline"] = bench_ctc2d(dev)
         out["cpu_baseline"] = cpu_arm(steps=3, warmup=1, sample_n=16)
-        out["stages"] = {"conv/BN/pool": "library (cuDNN via ATen) in this revision", "BiLSTM+Linear": "library (cuDNN/cuBLAS)",
+        out["stages"] = {"conv": "megreader_b200 im2col/col2im kernels + cuBLAS bf16 GEMM (plain library GEMM)",
+                         "bias+ReLU+MaxPool, BatchNorm": "megreader_b200 CUDA (fused NHWC kernels)",
+                         "BiLSTM+Linear": "megreader_b200 cell kernels + cuBLAS GEMMs",
                          "log_softmax+CTC": "megreader_b200 CUDA", "Adam": "library (torch fused)",
                          "allreduce": "NCCL via DDP" if world > 1 else "n/a"}
         print(json.dumps(out), flush=True)
@@ -249,10 +253,6 @@ def bench_ctc2d(dev, N=16384, iters=10):
     d_il = torch.from_numpy(np.tile(il, rep)).to(dev)
     d_tl = torch.from_numpy(np.tile(tl, rep)).to(dev)
     go = 1.0 / d_tl.float()
-    nll = torch.empty(N, device=dev)
-    gfac = torch.empty(T, N, C, device=dev)
-    grad = torch.empty_like(d_lp)
-
     def fwd():
         return ctc2d.ctc2d_forward_train(d_lp, d_tg, d_il, d_tl, 0)
 
@@ -268,7 +268,6 @@ def bench_ctc2d(dev, N=16384, iters=10):
         torch.cuda.synchronize()
         tf += a.elapsed_time(b); tb += b.elapsed_time(c)
     tf, tb = tf / iters * 1e-3, tb / iters * 1e-3
-    del nll, gfac, grad
     lp_b, idx_b = T * H * C * 4, 8 * S + 16
     fwd_bytes, bwd_bytes = lp_b + T * C * 4 + idx_b + 4, 2 * lp_b + T * C * 4 + 4
     pk = peaks()
@@ -285,12 +284,30 @@ def bench_ctc2d(dev, N=16384, iters=10):
 
 
 # ---------------------------------------------------------------------------------------------- CPU / reference arm
-def cpu_arm(steps, warmup, sample_n):
+def usable_cores():
+    """Host threads this process can really use: affinity mask and cgroup CPU quota (os.cpu_count() reports the
+    whole machine inside a quota-limited container and oversubscribing it is 100x slower), capped at 32 because
+    the ATen CPU kernels of this small model stop scaling there."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
+def cpu_arm(steps, warmup, sample_n, budget_s=25.0):
     """The reference's own CPU path for this workload, restated by oracle/crnn_port.py (validated bit-for-bit against
     the unmodified reference modules in the build container): fp32, all host cores, same model/optimizer."""
     from oracle import crnn_port
     from tests.weights import fill_state_dict
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     bb = fill_state_dict(crnn_port.CRNNBackbonePort(), "bb.").train()
     dec = fill_state_dict(crnn_port.CRNNDecoderPort(), "dec.").train()
@@ -303,11 +320,19 @@ def cpu_arm(steps, warmup, sample_n):
         loss.mean().backward()
         opt.step()
         return loss
+    tw = time.perf_counter()
     for _ in range(warmup):
         step()
+        if time.perf_counter() - tw > budget_s / 2:
+            break
     t0 = time.perf_counter()
+    done = 0
     for _ in range(steps):
         step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    steps = done
     dt = time.perf_counter() - t0
     return {"value": sample_n * steps / dt, "unit": "lines/s", "cores": cores, "kind": "port",
             "sample": "%d steps of a %d-line batch (3x32x256 fp32) of the same train step, torch CPU fp32, %d threads"

@@ -137,6 +137,52 @@ int mr_dcn_backward_f32(const float *input, const float *weight, const float *of
                         int64_t workspace_bytes, int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw,
                         int ph, int pw, int dh, int dw, int group, int dg, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * CRNN training engine building blocks (replace the ATen / cuDNN composition behind backbones/crnn.py:46-59 and
+ * decoders/crnn.py:8-24,80-104).  Activations are NHWC ("rows" = N*H*W pixels x C channels); dtype codes:
+ * 0 = float32, 1 = bfloat16.  Vector kernels need C % 4 == 0 (fp32) / C % 8 == 0 (bf16).
+ * ---------------------------------------------------------------------------------------------- */
+int mr_nchw_to_nhwc(const float *x, int N, int C, int H, int W, int Cp, int dtype, void *y, void *stream);
+int mr_nhwc_to_nchw(const void *x, int N, int C, int H, int W, int Cp, int dtype, float *y, void *stream);
+/* stride-1 convolution lowering: col [N*Ho*Wo, Kp], column (i*kw + j)*C + c; columns >= kh*kw*C are zero. */
+int mr_im2col_nhwc(const void *x, int N, int H, int W, int C, int kh, int kw, int ph, int pw, int Kp, int dtype,
+                   void *col, void *stream);
+int mr_col2im_nhwc(const void *dcol, int N, int H, int W, int C, int kh, int kw, int ph, int pw, int Kp, int dtype,
+                   void *dx, void *stream);
+/* conv epilogue fused with nn.MaxPool2d(k, s, p): y = maxpool(relu(x + bias)); idx = first arg-max (uint8). */
+int mr_bias_relu_pool_fwd(const void *x, const float *bias, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                          int ph, int pw, int dtype, void *y, unsigned char *idx, void *stream);
+int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *idx, int N, int H, int W, int C, int kh,
+                          int kw, int sh, int sw, int ph, int pw, int dtype, void *dz, void *stream);
+int mr_bias_act(const void *x, const float *bias, int64_t rows, int C, int relu, int dtype, void *y, void *stream);
+/* nn.BatchNorm2d in training mode over (x + bias): batch stats, running-stat update, normalise; `sums` = scratch of
+ * 2*C doubles.  mr_bn_apply is the eval-mode affine transform with given mean / invstd. */
+int mr_bn_train_fwd(const void *x, const float *bias, const float *gamma, const float *beta, float *running_mean,
+                    float *running_var, float momentum, float eps, int64_t rows, int C, int dtype, void *y, float *mean,
+                    float *invstd, double *sums, void *stream);
+int mr_bn_apply(const void *x, const float *bias, const float *mean, const float *invstd, const float *gamma,
+                const float *beta, int64_t rows, int C, int dtype, void *y, void *stream);
+int mr_bn_train_bwd(const void *dy, const void *x, const float *bias, const float *mean, const float *invstd,
+                    const float *gamma, int64_t rows, int C, int dtype, void *dx, float *dgamma, float *dbeta,
+                    double *sums, void *stream);
+/* out[c] (= or +=) sum_r a[r,c] (bias gradients); `sums` = scratch of 2*C doubles. */
+int mr_colsum(const void *a, int64_t rows, int C, int dtype, float *out, int accumulate, double *sums, void *stream);
+/* nn.LSTM cell, gate order i,f,g,o.  fwd: gates [B,4H] pre-activations in, activations out (in place). */
+int mr_lstm_cell_fwd(void *gates, const float *b_ih, const float *b_hh, const float *c_prev, float *c_out, void *h_out,
+                     int64_t ldh, void *h_state, int B, int H, int dtype, void *stream);
+int mr_lstm_cell_bwd(const void *gates, const float *c, const float *c_prev, const void *dh_out, int64_t ldh,
+                     const void *dh_rec, float *dc, void *dgates, int B, int H, int dtype, void *stream);
+/* torch.optim.Adam step over one flat fp32 buffer (training/optimizer_scheduler.py:17-22 builds torch.optim.Adam). */
+int mr_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 int64_t step, float grad_scale, void *bf16_shadow, void *stream);
+int mr_cast(const void *x, int src_dtype, int64_t n, int dst_dtype, void *y, void *stream);
+/* Row-major C[M,N] = alpha * op(A) op(B) + beta * C, fp32 accumulate (plain library GEMM: cuBLAS). */
+int mr_gemm(const void *A, const void *B, void *C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+            int64_t ldc, int transA, int transB, int in_dtype, int out_dtype, float alpha, float beta, void *stream);
+int mr_gemm_batched(const void *A, const void *B, void *C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                    int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transA, int transB,
+                    int in_dtype, int out_dtype, float alpha, float beta, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,23 @@ _SIGS = {
     "mr_log_softmax_rows_f32": [c_p, c_i64, c_i64, c_p, c_p],
     "mr_ctc1d_forward_train_f32": [c_p] * 4 + [c_i64] * 7 + [c_int, c_int, c_p, c_p, c_p],
     "mr_ctc1d_backward_logits_f32": [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_p, c_p],
+    "mr_nchw_to_nhwc": [c_p] + [c_int] * 6 + [c_p, c_p],
+    "mr_nhwc_to_nchw": [c_p] + [c_int] * 6 + [c_p, c_p],
+    "mr_im2col_nhwc": [c_p] + [c_int] * 10 + [c_p, c_p],
+    "mr_col2im_nhwc": [c_p] + [c_int] * 10 + [c_p, c_p],
+    "mr_bias_relu_pool_fwd": [c_p, c_p] + [c_int] * 11 + [c_p, c_p, c_p],
+    "mr_bias_relu_pool_bwd": [c_p, c_p, c_p] + [c_int] * 11 + [c_p, c_p],
+    "mr_bias_act": [c_p, c_p, c_i64, c_int, c_int, c_int, c_p, c_p],
+    "mr_bn_train_fwd": [c_p] * 6 + [c_f32, c_f32, c_i64, c_int, c_int] + [c_p] * 5,
+    "mr_bn_apply": [c_p] * 6 + [c_i64, c_int, c_int, c_p, c_p],
+    "mr_bn_train_bwd": [c_p] * 6 + [c_i64, c_int, c_int] + [c_p] * 5,
+    "mr_colsum": [c_p, c_i64, c_int, c_int, c_p, c_int, c_p, c_p],
+    "mr_lstm_cell_fwd": [c_p] * 6 + [c_i64, c_p, c_int, c_int, c_int, c_p],
+    "mr_lstm_cell_bwd": [c_p] * 4 + [c_i64, c_p, c_p, c_p, c_int, c_int, c_int, c_p],
+    "mr_adam_step": [c_p] * 4 + [c_i64] + [c_f32] * 4 + [c_i64, c_f32, c_p, c_p],
+    "mr_cast": [c_p, c_int, c_i64, c_int, c_p, c_p],
+    "mr_gemm": [c_p] * 3 + [c_i64] * 6 + [c_int] * 4 + [c_f32, c_f32, c_p],
+    "mr_gemm_batched": [c_p] * 3 + [c_i64] * 9 + [c_int] * 5 + [c_f32, c_f32, c_p],
     "mr_dcn_workspace_bytes": [c_i64] * 6,
     "mr_dcn_forward_f32": [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64] + [c_int] * 15 + [c_p],
     "mr_dcn_backward_f32": [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_f32,

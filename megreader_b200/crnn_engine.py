@@ -1,16 +1,35 @@
 """Execution engine behind the CRNN surfaces (refapi/backbones/crnn.py, refapi/decoders/crnn.py).
 
-The nn.Modules only own parameters (reference names / shapes); the arithmetic is dispatched
-here.  Stage status (DESIGN.md §kernels keeps this table current):
-    conv stack / BN / pools   : library (ATen -> cuDNN) in this revision
-    BiLSTM + Linear           : library (ATen -> cuDNN / cuBLAS) in this revision
-    log_softmax + 1D CTC loss : megreader_b200 CUDA (csrc/ctc2d.cu, H = 1 path)
-CUDA only: there is no CPU execution path.
+The nn.Modules only own parameters (reference names / shapes).  The arithmetic of
+    backbones/crnn.py:46-59   7 x (conv [+BN | +ReLU] [+MaxPool])
+    decoders/crnn.py:8-24     2 x (bidirectional LSTM + Linear)
+    decoders/crnn.py:95-99    log_softmax -> CTC (mean, zero_infinity)
+runs here as two hand-orchestrated autograd Functions over megreader_b200's CUDA kernels: activations stay NHWC
+in the compute dtype (fp32 for parity runs, bf16 for throughput; fp32 accumulation and fp32 master weights in both),
+every convolution is im2col (csrc/nn_kernels.cu) + one dense GEMM (csrc/gemm.cu), bias+ReLU+MaxPool and BatchNorm are
+single fused passes, the LSTM is one input-projection GEMM per direction plus a per-step recurrent GEMM and a fused
+cell kernel, and the loss is the fused log_softmax+CTC of csrc/ctc2d.cu.  CUDA only: there is no CPU path.
 """
 import torch
 import torch.nn.functional as F
 
 from . import ctc1d
+from . import nnops as ops
+
+_COMPUTE_DTYPE = torch.float32
+
+
+def set_compute_dtype(dtype):
+    """torch.float32 (default; parity with the reference within 1e-4) or torch.bfloat16 (BASELINE.json cfg 2)."""
+    global _COMPUTE_DTYPE
+    ops.code(dtype)
+    _COMPUTE_DTYPE = dtype
+
+
+def compute_dtype():
+    if torch.is_autocast_enabled() and torch.get_autocast_gpu_dtype() == torch.bfloat16:
+        return torch.bfloat16
+    return _COMPUTE_DTYPE
 
 
 def _require_cuda(t, what):
@@ -18,18 +37,262 @@ def _require_cuda(t, what):
         raise NotImplementedError("megreader_b200.%s: CUDA tensors only (no CPU fallback)" % what)
 
 
+def _vn(dtype):
+    return 4 if dtype == torch.float32 else 8
+
+
+# ------------------------------------------------------------------------------------------------ backbone
+def _conv_layers(module):
+    """[(conv, bn|None, pool|None)] in order, read off the reference-shaped Sequential (backbones/crnn.py:15-43)."""
+    out = []
+    for blk in module.cnn:
+        conv = bn = pool = None
+        for m in blk.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                conv = m
+            elif isinstance(m, torch.nn.BatchNorm2d):
+                bn = m
+            elif isinstance(m, torch.nn.MaxPool2d):
+                pool = m
+        out.append((conv, bn, pool))
+    return out
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+def _weight_matrix(w, Cp, Kp, dtype):
+    """conv weight [Cout, Cin, kh, kw] fp32 -> GEMM operand [Cout, Kp] in `dtype`, column = (i*kw + j)*Cp + c."""
+    Cout, Cin, kh, kw = w.shape
+    m = w.detach().permute(0, 2, 3, 1)
+    if Cp != Cin:
+        m = F.pad(m, (0, Cp - Cin))
+    m = m.reshape(Cout, kh * kw * Cp)
+    if Kp != m.size(1):
+        m = F.pad(m, (0, Kp - m.size(1)))
+    return ops.cast(m.contiguous(), dtype)
+
+
+def _weight_grad(dWm, Cin, Cp, kh, kw):
+    Cout = dWm.size(0)
+    return dWm[:, :kh * kw * Cp].reshape(Cout, kh, kw, Cp)[..., :Cin].permute(0, 3, 1, 2).contiguous()
+
+
+class _BackboneFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module, training, dtype, *params):
+        layers = _conv_layers(module)
+        vn = _vn(dtype)
+        N, Cin, H, W = x.shape
+        Cp = -(-Cin // vn) * vn
+        a = ops.nchw_to_nhwc(x.contiguous().float(), Cp, dtype)
+        saved = []
+        for (conv, bn, pool) in layers:
+            kh, kw = conv.kernel_size
+            ph, pw = conv.padding
+            assert conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1
+            C = a.size(3)
+            K = kh * kw * C
+            Kp = -(-K // vn) * vn
+            Wm = _weight_matrix(conv.weight, C, Kp, dtype)
+            col, Ho, Wo = ops.im2col(a, kh, kw, ph, pw, Kp)
+            z = ops.gemm(col, Wm, transB=True)                      # [P, Cout] raw conv output (no bias yet)
+            Cout = Wm.size(0)
+            rec = {"col": col if training else None, "Wm": Wm, "in_shape": tuple(a.shape), "k": (kh, kw), "p": (ph, pw),
+                   "Cin": conv.in_channels, "out_hw": (Ho, Wo)}
+            if bn is not None:
+                if training:
+                    mom = bn.momentum if bn.momentum is not None else 0.1
+                    y, mean, invstd = ops.bn_train_fwd(z, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                       mom, bn.eps)
+                    bn.num_batches_tracked += 1
+                    rec.update(z=z, mean=mean, invstd=invstd, kind="bn")
+                else:
+                    invstd = torch.rsqrt(bn.running_var + bn.eps)
+                    y = ops.bn_apply(z, conv.bias, bn.running_mean, invstd, bn.weight, bn.bias)
+                a = y.view(N, Ho, Wo, Cout)
+            else:
+                assert pool is not None, "CRNN: every ReLU block is followed by a MaxPool (backbones/crnn.py:18-35)"
+                k, s, p = _pair(pool.kernel_size), _pair(pool.stride), _pair(pool.padding)
+                y, idx = ops.bias_relu_pool_fwd(z, conv.bias, N, Ho, Wo, Cout, k, s, p)
+                rec.update(y=y, idx=idx, pool=(k, s, p), kind="pool")
+                a = y
+            saved.append(rec)
+        ctx.saved = saved
+        ctx.layers = layers
+        ctx.dtype = dtype
+        ctx.N = N
+        feat = a                                                       # [N, Hf, Wf, 512] NHWC
+        ctx.feat_shape = tuple(feat.shape)
+        return feat.permute(0, 3, 1, 2)                                # (N, 512, Hf, Wf) view, channels-last memory
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        N, Hf, Wf, Cf = ctx.feat_shape
+        dtype = ctx.dtype
+        dy = ops.cast(dfeat.permute(0, 2, 3, 1).contiguous(), dtype).view(N * Hf * Wf, Cf)
+        grads = []
+        for li in range(len(ctx.layers) - 1, -1, -1):
+            conv, bn, pool = ctx.layers[li]
+            rec = ctx.saved[li]
+            Nn, H, W, C = rec["in_shape"]
+            Ho, Wo = rec["out_hw"]
+            Cout = rec["Wm"].size(0)
+            kh, kw = rec["k"]
+            ph, pw = rec["p"]
+            if rec["kind"] == "bn":
+                dz, dgamma, dbeta = ops.bn_train_bwd(dy, rec["z"], conv.bias, rec["mean"], rec["invstd"], bn.weight)
+            else:
+                k, s, p = rec["pool"]
+                dz = ops.bias_relu_pool_bwd(dy, rec["y"], rec["idx"], Nn, Ho, Wo, Cout, k, s, p)
+                dgamma = dbeta = None
+            dbias = ops.colsum(dz)
+            dWm = ops.gemm(dz, rec["col"], transA=True, out_dtype=torch.float32)          # [Cout, Kp]
+            dW = _weight_grad(dWm, rec["Cin"], C, kh, kw)
+            layer_grads = [dW, dbias] + ([dgamma, dbeta] if bn is not None else [])
+            grads = layer_grads + grads
+            if li > 0:
+                dcol = ops.gemm(dz, rec["Wm"])                                               # [P, Kp]
+                dy = ops.col2im(dcol, Nn, H, W, C, kh, kw, ph, pw).view(Nn * H * W, C)
+            rec.clear()
+        return (None, None, None, None) + tuple(grads)
+
+
+def _backbone_params(module):
+    ps = []
+    for conv, bn, _ in _conv_layers(module):
+        ps += [conv.weight, conv.bias]
+        if bn is not None:
+            ps += [bn.weight, bn.bias]
+    return ps
+
+
 def backbone_forward(module, x):
     """backbones/crnn.py:57-59."""
     _require_cuda(x, "crnn_backbone")
-    return module.cnn(x)
+    return _BackboneFn.apply(x, module, module.training and torch.is_grad_enabled(), compute_dtype(),
+                             *_backbone_params(module))
+
+
+# ------------------------------------------------------------------------------------------------ BiLSTM + Linear
+def _lstm_dir_params(rnn, d):
+    sfx = "_reverse" if d == 1 else ""
+    return [getattr(rnn, n + "_l0" + sfx) for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+
+
+def _bilstm_params(module):
+    return _lstm_dir_params(module.rnn, 0) + _lstm_dir_params(module.rnn, 1) + [module.embedding.weight,
+                                                                                 module.embedding.bias]
+
+
+def _bilstm_forward_impl(X, params, dtype, training):
+    """X [T, N, I] (compute dtype, contiguous) -> (out [T, N, nOut], saved dict)."""
+    T, N, I = X.shape
+    w_ih = [params[0], params[4]]
+    w_hh = [params[1], params[5]]
+    b_ih = [params[2], params[6]]
+    b_hh = [params[3], params[7]]
+    w_emb, b_emb = params[8], params[9]
+    H = w_hh[0].size(1)
+    dev = X.device
+    Wih = [ops.cast(w.detach(), dtype) for w in w_ih]
+    Whh = torch.stack([ops.cast(w.detach(), dtype) for w in w_hh])                 # [2, 4H, H]
+    X2 = X.view(T * N, I)
+    G = torch.empty((2, T, N, 4 * H), dtype=dtype, device=dev)
+    for d in range(2):
+        ops.gemm(X2, Wih[d], transB=True, out=G[d].view(T * N, 4 * H))               # input projection, all steps
+    Cst = torch.empty((2, T, N, H), dtype=torch.float32, device=dev)
+    Y = torch.empty((T, N, 2 * H), dtype=dtype, device=dev)
+    hst = torch.zeros((2, N, H), dtype=dtype, device=dev)
+    esz = G.element_size()
+    for s in range(T):
+        tf, tr = s, T - 1 - s
+        if s > 0:
+            # both directions in one strided-batched GEMM: G[d][t_d] += h_d W_hh_d^T
+            pC = G.data_ptr() + tf * N * 4 * H * esz
+            sC = (T + tr - tf) * N * 4 * H
+            ops.gemm_batched_raw(hst.data_ptr(), Whh.data_ptr(), pC, N, 4 * H, H, H, H, 4 * H, N * H, 4 * H * H, sC, 2,
+                                 False, True, dtype, dtype, 1.0, 1.0)
+        for d, t in ((0, tf), (1, tr)):
+            tp = t - 1 if d == 0 else t + 1
+            ops.lstm_cell_fwd(G[d, t], b_ih[d], b_hh[d], Cst[d, tp] if s > 0 else None, Cst[d, t],
+                              Y[t, :, d * H:(d + 1) * H], 2 * H, hst[d])
+    Wemb = ops.cast(w_emb.detach(), dtype)
+    nOut = Wemb.size(0)
+    out_dtype = dtype if nOut % _vn(dtype) == 0 else torch.float32   # the 38-class logits leave in fp32
+    E = ops.gemm(Y.view(T * N, 2 * H), Wemb, transB=True, out_dtype=out_dtype)
+    ops.bias_act(E, b_emb, relu=False, out=E)
+    saved = dict(X=X, G=G, C=Cst, Y=Y, Wih=Wih, Whh=Whh, Wemb=Wemb, H=H) if training else None
+    return E.view(T, N, nOut), saved
+
+
+def _bilstm_backward_impl(dE, sv, dtype):
+    """dE [T, N, nOut] -> (dX [T, N, I], grads for the 10 parameters in _bilstm_params order)."""
+    X, G, Cst, Y, H = sv["X"], sv["G"], sv["C"], sv["Y"], sv["H"]
+    T, N, I = X.shape
+    dev = X.device
+    dE2 = ops.cast(dE.reshape(T * N, -1), dtype)
+    Y2 = Y.view(T * N, 2 * H)
+    dWemb = ops.gemm(dE2, Y2, transA=True, out_dtype=torch.float32)
+    dbemb = ops.colsum(dE2)
+    dY = ops.gemm(dE2, sv["Wemb"])                                                   # [T*N, 2H]
+    dY3 = dY.view(T, N, 2 * H)
+    dG = torch.empty((2, T, N, 4 * H), dtype=dtype, device=dev)
+    dc = torch.zeros((2, N, H), dtype=torch.float32, device=dev)
+    dhr = torch.empty((2, N, H), dtype=dtype, device=dev)
+    esz = dG.element_size()
+    for s in range(T - 1, -1, -1):
+        tf, tr = s, T - 1 - s
+        for d, t in ((0, tf), (1, tr)):
+            tp = t - 1 if d == 0 else t + 1
+            ops.lstm_cell_bwd(G[d, t], Cst[d, t], Cst[d, tp] if s > 0 else None, dY3[t, :, d * H:(d + 1) * H], 2 * H,
+                              dhr[d] if s < T - 1 else None, dc[d], dG[d, t])
+        if s > 0:
+            # dh_rec_d = dG_d[t_d] W_hh_d   (both directions, one strided-batched GEMM)
+            pA = dG.data_ptr() + tf * N * 4 * H * esz
+            sA = (T + tr - tf) * N * 4 * H
+            ops.gemm_batched_raw(pA, sv["Whh"].data_ptr(), dhr.data_ptr(), N, H, 4 * H, 4 * H, H, H, sA, 4 * H * H, N * H,
+                                 2, False, False, dtype, dtype, 1.0, 0.0)
+    X2 = X.view(T * N, I)
+    grads = []
+    dX = torch.empty((T * N, I), dtype=dtype, device=dev)
+    for d in range(2):
+        dG2 = dG[d].view(T * N, 4 * H)
+        dWih = ops.gemm(dG2, X2, transA=True, out_dtype=torch.float32)
+        # dW_hh = sum_t dG[t]^T h_{t_prev}: forward dir pairs dG[1:] with Y[:-1], reverse dir dG[:-1] with Y[1:]
+        if d == 0:
+            A = dG[0, 1:].reshape((T - 1) * N, 4 * H)
+            Bm = Y[:T - 1].view((T - 1) * N, 2 * H)[:, :H]
+        else:
+            A = dG[1, :T - 1].reshape((T - 1) * N, 4 * H)
+            Bm = Y[1:].view((T - 1) * N, 2 * H)[:, H:]
+        dWhh = ops.gemm(A, Bm, transA=True, out_dtype=torch.float32) if T > 1 else torch.zeros(4 * H, H, device=dev)
+        db = ops.colsum(dG2)
+        grads += [dWih, dWhh, db, db.clone()]
+        ops.gemm(dG2, sv["Wih"][d], out=dX, beta=0.0 if d == 0 else 1.0)
+    return dX.view(T, N, I), grads + [dWemb, dbemb]
+
+
+class _BiLSTMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype, training, *params):
+        X = ops.cast(x.contiguous(), dtype)
+        out, sv = _bilstm_forward_impl(X, params, dtype, training)
+        ctx.sv, ctx.dtype, ctx.in_dtype = sv, dtype, x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dX, grads = _bilstm_backward_impl(dout.contiguous(), ctx.sv, ctx.dtype)
+        ctx.sv = None
+        return (dX.to(ctx.in_dtype), None, None) + tuple(grads)
 
 
 def bilstm_forward(module, x):
     """decoders/crnn.py:16-24: (T, N, nIn) -> LSTM -> Linear -> (T, N, nOut)."""
     _require_cuda(x, "BidirectionalLSTM")
-    recurrent, _ = module.rnn(x)
-    T, b, h = recurrent.size()
-    return module.embedding(recurrent.view(T * b, h)).view(T, b, -1)
+    return _BiLSTMFn.apply(x, compute_dtype(), torch.is_grad_enabled(), *_bilstm_params(module))
 
 
 def decoder_forward(module, feature, targets=None, lengths=None, train=False):
@@ -40,9 +303,7 @@ def decoder_forward(module, feature, targets=None, lengths=None, train=False):
         feature = module.fpn2rnn(feature)
         b, c, h, w = feature.size()
     assert h == 1, "the height of conv must be 1"
-    seq = feature.squeeze(2).permute(2, 0, 1)          # (W, N, C)
-    for r in module.rnn:
-        r.rnn.flatten_parameters()
+    seq = feature.squeeze(2).permute(2, 0, 1)          # (W, N, C) view; the BiLSTM entry makes it contiguous
     pred = module.rnn(seq)                             # (T, N, classes)
     if train:
         T = pred.size(0)
@@ -55,5 +316,5 @@ def decoder_forward(module, feature, targets=None, lengths=None, train=False):
                                                  zero_infinity=False, reduction="none")
             loss = nll / lengths.to(nll.device).to(nll.dtype)
         return loss, lp.to(torch.float64)              # decoders/crnn.py:96 hands float64 log-probs back
-    pred = pred.permute(1, 2, 0).unsqueeze(2)
+    pred = pred.float().permute(1, 2, 0).unsqueeze(2)
     return F.softmax(pred, dim=1)

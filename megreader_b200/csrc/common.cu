@@ -10,6 +10,21 @@ void set_cuda_error(cudaError_t e, const char *where) {
     std::lock_guard<std::mutex> lk(g_err_mu);
     g_err = std::string(where) + ": " + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
 }
+static std::mutex g_blas_mu;
+static cublasHandle_t g_blas[16] = {nullptr};
+int blas_handle(cublasHandle_t *h, cudaStream_t st) {
+    int dev = 0;
+    MR_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+    if (dev < 0 || dev >= 16) return MR_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lk(g_blas_mu);
+    if (!g_blas[dev]) {
+        if (cublasCreate(&g_blas[dev]) != CUBLAS_STATUS_SUCCESS) { set_cuda_error(cudaErrorUnknown, "cublasCreate"); return MR_ERR_CUDA; }
+        cublasSetMathMode(g_blas[dev], CUBLAS_DEFAULT_MATH);  // fp32 GEMMs stay plain fp32 (no TF32)
+    }
+    if (cublasSetStream(g_blas[dev], st) != CUBLAS_STATUS_SUCCESS) { set_cuda_error(cudaErrorUnknown, "cublasSetStream"); return MR_ERR_CUDA; }
+    *h = g_blas[dev];
+    return MR_OK;
+}
 }  // namespace mr
 
 extern "C" {

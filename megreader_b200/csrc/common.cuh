@@ -1,6 +1,7 @@
 // Shared helpers for the megreader_b200 C-ABI library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cublas_v2.h>
 #include <stdint.h>
 #include <atomic>
 #include "../../include/megreader_b200.h"
@@ -20,6 +21,11 @@ inline int check_launch(const char *where) {
 #define MR_CUDA_TRY(expr, where)                                            \
     do { cudaError_t _e = (expr);                                           \
          if (_e != cudaSuccess) { ::mr::set_cuda_error(_e, where); return MR_ERR_CUDA; } } while (0)
+
+// cuBLAS handle, one per device, created on first use (cuBLAS allocates its own workspace then); bound to `st`.
+int blas_handle(cublasHandle_t *h, cudaStream_t st);
+#define MR_BLAS_TRY(expr, where)                                                                        \
+    do { if ((expr) != CUBLAS_STATUS_SUCCESS) { ::mr::set_cuda_error(cudaErrorUnknown, where); return MR_ERR_CUDA; } } while (0)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

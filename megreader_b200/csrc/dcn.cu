@@ -19,9 +19,7 @@
 // Roofline: the gather/scatter kernels are HBM-bound on the column matrix (9*C*Ho*Wo*4 B per sample written,
 // then read by the GEMM); the GEMMs are plain fp32 library GEMMs (cuBLAS, no TF32: parity is 1e-4).
 #include "common.cuh"
-#include <cublas_v2.h>
 #include <math.h>
-#include <mutex>
 
 namespace {
 using namespace mr;
@@ -193,26 +191,6 @@ __global__ void dcn_bias_add_kernel(float *__restrict__ out, const float *__rest
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] += bias[(i / P) % Cout];
 }
-
-// ---- cuBLAS handle (one per device, created on first use; cuBLAS allocates its own small workspace) ----
-std::mutex g_blas_mu;
-cublasHandle_t g_blas[16] = {nullptr};
-int blas_handle(cublasHandle_t *h, cudaStream_t st) {
-    int dev = 0;
-    MR_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
-    if (dev < 0 || dev >= 16) return MR_ERR_NO_DEVICE;
-    std::lock_guard<std::mutex> lk(g_blas_mu);
-    if (!g_blas[dev]) {
-        if (cublasCreate(&g_blas[dev]) != CUBLAS_STATUS_SUCCESS) { set_cuda_error(cudaErrorUnknown, "cublasCreate"); return MR_ERR_CUDA; }
-        cublasSetMathMode(g_blas[dev], CUBLAS_DEFAULT_MATH);  // plain fp32 (no TF32): parity bar is 1e-4
-    }
-    if (cublasSetStream(g_blas[dev], st) != CUBLAS_STATUS_SUCCESS) { set_cuda_error(cudaErrorUnknown, "cublasSetStream"); return MR_ERR_CUDA; }
-    *h = g_blas[dev];
-    return MR_OK;
-}
-#define MR_BLAS_TRY(expr, where) \
-    do { if ((expr) != CUBLAS_STATUS_SUCCESS) { set_cuda_error(cudaErrorUnknown, where); return MR_ERR_CUDA; } \
-    } while (0)
 
 int fill_geo(DcnGeo &g, int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh,
              int dw, int group, int dg) {

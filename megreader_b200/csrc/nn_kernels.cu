@@ -1,0 +1,745 @@
+// NHWC building blocks of the CRNN training engine (sm_100a): layout conversion, im2col / col2im, fused
+// bias+ReLU+max-pool (forward and backward), training-mode BatchNorm (stats / apply / backward), column sums,
+// LSTM cell (forward / backward), fused Adam.  All HBM-bound streaming kernels: 16-byte vector accesses along the
+// channel dimension, fp32 accumulation, no atomics on the data path except the per-channel partial sums.
+//
+// Why these exist: with the ATen/cuDNN composition of the reference's modules (backbones/crnn.py:46-55,
+// decoders/crnn.py:8-24) the tensor-core convolutions are ~12 % of a B200 training step; NCHW max-pool forward /
+// backward, NCHW<->NHWC transposes, BatchNorm and the per-timestep LSTM glue are the other 88 %
+// (profiles/r1_library_step_launches.md).  Keeping activations NHWC end to end and fusing the elementwise chains
+// removes that traffic.
+//
+// dtype codes: 0 = float32, 1 = bfloat16.  "rows" = N*H*W pixels, C = channels (innermost).
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace {
+using namespace mr;
+typedef __nv_bfloat16 bf16;
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vector of T
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); uint4 raw; };
+template <typename T> __device__ __forceinline__ void unpack(const uint4 &r, float *f) {
+    constexpr int N = 16 / sizeof(T);
+    const T *p = reinterpret_cast<const T *>(&r);
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = to_f<T>(p[i]);
+}
+template <typename T> __device__ __forceinline__ uint4 pack(const float *f) {
+    constexpr int N = 16 / sizeof(T);
+    uint4 r;
+    T *p = reinterpret_cast<T *>(&r);
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = from_f<T>(f[i]);
+    return r;
+}
+
+inline int grid1d(int64_t work, int block, int per_sm = 16) {
+    int64_t b = ceil_div(work, block);
+    const int64_t cap = (int64_t)148 * per_sm;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---------------------------------------------------------------- NCHW fp32 -> NHWC (channel-padded) T
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ x, int N, int C, int HW, int Cp, T *__restrict__ y) {
+    const int64_t total = (int64_t)N * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / HW;
+        const int64_t p = i - n * HW;
+        const float *src = x + n * C * HW + p;
+        T *dst = y + i * Cp;
+        for (int c = 0; c < Cp; ++c) dst[c] = from_f<T>(c < C ? src[(int64_t)c * HW] : 0.f);
+    }
+}
+
+// NHWC T [rows, C] -> NCHW fp32 (used for the gradient w.r.t. the input image and generic layout exits)
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ x, int N, int C, int HW, int Cp, float *__restrict__ y) {
+    const int64_t total = (int64_t)N * C * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i % HW;
+        const int64_t nc = i / HW;
+        const int64_t n = nc / C, c = nc - n * C;
+        y[i] = to_f<T>(x[(n * HW + p) * Cp + c]);
+    }
+}
+
+// ---------------------------------------------------------------- im2col / col2im (stride 1)
+struct ConvGeo { int N, H, W, C, kh, kw, ph, pw, Ho, Wo, K, Kp; };
+
+// col[p][(i*kw + j)*C + c] = x[n, ho+i-ph, wo+j-pw, c]  (0 outside), columns K..Kp zero.  Vector path: C % VN == 0.
+template <typename T>
+__global__ void im2col_vec_kernel(ConvGeo g, const T *__restrict__ x, T *__restrict__ col) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = g.C / VN;                       // vectors per tap
+    const int kvec = g.Kp / VN;                    // vectors per column row
+    const int64_t total = (int64_t)g.N * g.Ho * g.Wo * kvec;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int kv = (int)(idx % kvec);
+        const int64_t p = idx / kvec;
+        const int wo = (int)(p % g.Wo);
+        const int64_t r = p / g.Wo;
+        const int ho = (int)(r % g.Ho);
+        const int n = (int)(r / g.Ho);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        const int tap = kv / cv;
+        if (tap < g.kh * g.kw) {
+            const int c0 = (kv - tap * cv) * VN;
+            const int i = tap / g.kw, j = tap - i * g.kw;
+            const int h = ho + i - g.ph, w = wo + j - g.pw;
+            if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+                v = __ldg(reinterpret_cast<const uint4 *>(x + (((int64_t)n * g.H + h) * g.W + w) * g.C + c0));
+        }
+        reinterpret_cast<uint4 *>(col)[idx] = v;
+    }
+}
+template <typename T>
+__global__ void im2col_scalar_kernel(ConvGeo g, const T *__restrict__ x, T *__restrict__ col) {
+    const int64_t total = (int64_t)g.N * g.Ho * g.Wo * g.Kp;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % g.Kp);
+        const int64_t p = idx / g.Kp;
+        const int wo = (int)(p % g.Wo);
+        const int64_t r = p / g.Wo;
+        const int ho = (int)(r % g.Ho);
+        const int n = (int)(r / g.Ho);
+        T v = from_f<T>(0.f);
+        if (k < g.K) {
+            const int tap = k / g.C, c = k - tap * g.C;
+            const int i = tap / g.kw, j = tap - i * g.kw;
+            const int h = ho + i - g.ph, w = wo + j - g.pw;
+            if (h >= 0 && h < g.H && w >= 0 && w < g.W) v = x[(((int64_t)n * g.H + h) * g.W + w) * g.C + c];
+        }
+        col[idx] = v;
+    }
+}
+
+// dx[n,h,w,c] = sum_{i,j} dcol[(n, h-i+ph, w-j+pw)][(i*kw+j)*C + c]   (gather form, no atomics)
+template <typename T>
+__global__ void col2im_vec_kernel(ConvGeo g, const T *__restrict__ dcol, T *__restrict__ dx) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = g.C / VN;
+    const int64_t total = (int64_t)g.N * g.H * g.W * cv;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(idx % cv) * VN;
+        const int64_t p = idx / cv;
+        const int w = (int)(p % g.W);
+        const int64_t r = p / g.W;
+        const int h = (int)(r % g.H);
+        const int n = (int)(r / g.H);
+        float acc[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+        for (int i = 0; i < g.kh; ++i) {
+            const int ho = h - i + g.ph;
+            if (ho < 0 || ho >= g.Ho) continue;
+            for (int j = 0; j < g.kw; ++j) {
+                const int wo = w - j + g.pw;
+                if (wo < 0 || wo >= g.Wo) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(
+                    dcol + (((int64_t)n * g.Ho + ho) * g.Wo + wo) * g.Kp + (i * g.kw + j) * g.C + c0));
+                float f[VN];
+                unpack<T>(v, f);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) acc[e] += f[e];
+            }
+        }
+        reinterpret_cast<uint4 *>(dx)[idx] = pack<T>(acc);
+    }
+}
+
+// ---------------------------------------------------------------- bias + ReLU (+ max-pool) on a GEMM output
+struct PoolGeo { int N, H, W, C, kh, kw, sh, sw, ph, pw, Ho, Wo; };
+
+// y[n,ho,wo,c] = max over window of relu(x + bias) ; idx = first arg-max in (i,j) scan order (ATen's strict '>').
+// Padded positions never win (ATen pads with -inf).  x is the raw GEMM output [N*H*W, C].
+template <typename T>
+__global__ void bias_relu_pool_fwd_kernel(PoolGeo g, const T *__restrict__ x, const float *__restrict__ bias,
+                                          T *__restrict__ y, unsigned char *__restrict__ idx) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = g.C / VN;
+    const int64_t total = (int64_t)g.N * g.Ho * g.Wo * cv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(t % cv) * VN;
+        const int64_t p = t / cv;
+        const int wo = (int)(p % g.Wo);
+        const int64_t r = p / g.Wo;
+        const int ho = (int)(r % g.Ho);
+        const int n = (int)(r / g.Ho);
+        float best[VN];
+        int bi[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+        for (int i = 0; i < g.kh; ++i) {
+            const int h = ho * g.sh - g.ph + i;
+            if (h < 0 || h >= g.H) continue;
+            for (int j = 0; j < g.kw; ++j) {
+                const int w = wo * g.sw - g.pw + j;
+                if (w < 0 || w >= g.W) continue;
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(x + (((int64_t)n * g.H + h) * g.W + w) * g.C + c0));
+                float f[VN];
+                unpack<T>(v, f);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    // round through T so that the compared values are what an unfused bias+ReLU would have stored
+                    const float a = to_f<T>(from_f<T>(fmaxf(f[e] + bias[c0 + e], 0.f)));
+                    if (a > best[e]) { best[e] = a; bi[e] = i * g.kw + j; }
+                }
+            }
+        }
+        reinterpret_cast<uint4 *>(y)[t] = pack<T>(best);
+        unsigned char *ip = idx + t * VN;
+#pragma unroll
+        for (int e = 0; e < VN; ++e) ip[e] = (unsigned char)bi[e];
+    }
+}
+
+// dz[n,h,w,c] (gradient w.r.t. the raw GEMM output) = sum over windows that contain (h,w) whose arg-max is (h,w)
+// and whose pooled value is > 0 (ReLU') of dy[window].
+template <typename T>
+__global__ void bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y,
+                                          const unsigned char *__restrict__ idx, T *__restrict__ dz) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = g.C / VN;
+    const int64_t total = (int64_t)g.N * g.H * g.W * cv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(t % cv) * VN;
+        const int64_t p = t / cv;
+        const int w = (int)(p % g.W);
+        const int64_t r = p / g.W;
+        const int h = (int)(r % g.H);
+        const int n = (int)(r / g.H);
+        float acc[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+        for (int i = 0; i < g.kh; ++i) {
+            const int hn = h + g.ph - i;
+            if (hn < 0 || hn % g.sh) continue;
+            const int ho = hn / g.sh;
+            if (ho >= g.Ho) continue;
+            for (int j = 0; j < g.kw; ++j) {
+                const int wn = w + g.pw - j;
+                if (wn < 0 || wn % g.sw) continue;
+                const int wo = wn / g.sw;
+                if (wo >= g.Wo) continue;
+                const int64_t q = (((int64_t)n * g.Ho + ho) * g.Wo + wo) * g.C + c0;
+                float fy[VN], fd[VN];
+                unpack<T>(__ldg(reinterpret_cast<const uint4 *>(y + q)), fy);
+                unpack<T>(__ldg(reinterpret_cast<const uint4 *>(dy + q)), fd);
+                const unsigned char *ip = idx + q;
+#pragma unroll
+                for (int e = 0; e < VN; ++e)
+                    if (ip[e] == i * g.kw + j && fy[e] > 0.f) acc[e] += fd[e];
+            }
+        }
+        reinterpret_cast<uint4 *>(dz)[t] = pack<T>(acc);
+    }
+}
+
+// plain bias (+ optional ReLU) on [rows, C], and its backward mask
+template <typename T>
+__global__ void bias_act_kernel(const T *__restrict__ x, const float *__restrict__ bias, int64_t rows, int C, int relu,
+                                T *__restrict__ y) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = C / VN;
+    const int64_t total = rows * cv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(t % cv) * VN;
+        float f[VN];
+        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(x) + t), f);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            f[e] += bias[c0 + e];
+            if (relu) f[e] = fmaxf(f[e], 0.f);
+        }
+        reinterpret_cast<uint4 *>(y)[t] = pack<T>(f);
+    }
+}
+
+template <typename T>
+__global__ void bias_act_scalar_kernel(const T *__restrict__ x, const float *__restrict__ bias, int64_t total, int C,
+                                       int relu, T *__restrict__ y) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        float f = to_f<T>(x[t]) + bias[t % C];
+        if (relu) f = fmaxf(f, 0.f);
+        y[t] = from_f<T>(f);
+    }
+}
+
+// ---------------------------------------------------------------- per-channel reductions over rows
+// sums[0][c] += sum_r f(x[r,c] (+bias[c]));  sums[1][c] += sum_r g(...)   MODE 0: (x+b, (x+b)^2)   [BN statistics]
+//                                                                          MODE 1: (dy, dy*xhat)      [BN backward]
+//                                                                          MODE 2: (dy, -)            [bias gradient]
+// xhat = (x + bias - mean) * invstd.  One CTA = 32 channel-vectors x 8 row lanes; double atomics at the end.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+col_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, const float *__restrict__ bias,
+                  const float *__restrict__ mean, const float *__restrict__ invstd, int64_t rows, int C,
+                  int64_t rows_per_cta, double *__restrict__ sums) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = C / VN;
+    const int lane_c = threadIdx.x & 31, lane_r = threadIdx.x >> 5;   // 32 x 8
+    const int v = blockIdx.x * 32 + lane_c;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = min(rows, r0 + rows_per_cta);
+    float s0[VN], s1[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) s0[e] = s1[e] = 0.f;
+    if (v < cv) {
+        float bb[VN], mm[VN], is[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            bb[e] = bias ? bias[v * VN + e] : 0.f;
+            mm[e] = (MODE == 1) ? mean[v * VN + e] : 0.f;
+            is[e] = (MODE == 1) ? invstd[v * VN + e] : 0.f;
+        }
+        for (int64_t r = r0 + lane_r; r < r1; r += 8) {
+            float fa[VN];
+            unpack<T>(__ldg(reinterpret_cast<const uint4 *>(a + r * C) + v), fa);
+            if (MODE == 0) {
+#pragma unroll
+                for (int e = 0; e < VN; ++e) { const float x = fa[e] + bb[e]; s0[e] += x; s1[e] += x * x; }
+            } else if (MODE == 1) {
+                float fb[VN];
+                unpack<T>(__ldg(reinterpret_cast<const uint4 *>(b + r * C) + v), fb);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) { s0[e] += fa[e]; s1[e] += fa[e] * ((fb[e] + bb[e] - mm[e]) * is[e]); }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VN; ++e) s0[e] += fa[e];
+            }
+        }
+    }
+    __shared__ float red[2][8][32][VN + 1];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) { red[0][lane_r][lane_c][e] = s0[e]; red[1][lane_r][lane_c][e] = s1[e]; }
+    __syncthreads();
+    if (lane_r == 0 && v < cv) {
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { t0 += red[0][k][lane_c][e]; t1 += red[1][k][lane_c][e]; }
+            atomicAdd(sums + v * VN + e, (double)t0);
+            if (MODE != 2) atomicAdd(sums + C + v * VN + e, (double)t1);
+        }
+    }
+}
+
+// BatchNorm finalize (one thread per channel): mean / invstd from the sums, running-stat update (momentum, unbiased
+// variance for running_var like ATen), num_batches_tracked is bumped by the host.
+__global__ void bn_finalize_kernel(const double *__restrict__ sums, int64_t rows, int C, float eps, float momentum,
+                                   float *__restrict__ mean, float *__restrict__ invstd,
+                                   float *__restrict__ running_mean, float *__restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double m = sums[c] / (double)rows;
+    double var = sums[C + c] / (double)rows - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        const double unbiased = rows > 1 ? var * (double)rows / (double)(rows - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+}
+
+// y = (x + bias - mean) * invstd * gamma + beta
+template <typename T>
+__global__ void bn_apply_kernel(const T *__restrict__ x, const float *__restrict__ bias, const float *__restrict__ mean,
+                                const float *__restrict__ invstd, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, int64_t rows, int C, T *__restrict__ y) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = C / VN;
+    const int64_t total = rows * cv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(t % cv) * VN;
+        float f[VN];
+        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(x) + t), f);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            const int c = c0 + e;
+            f[e] = (f[e] + (bias ? bias[c] : 0.f) - mean[c]) * (invstd[c] * gamma[c]) + beta[c];
+        }
+        reinterpret_cast<uint4 *>(y)[t] = pack<T>(f);
+    }
+}
+
+// dx = gamma * invstd * (dy - sum_dy/rows - xhat * sum_dy_xhat/rows)
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ bias,
+                                    const float *__restrict__ mean, const float *__restrict__ invstd,
+                                    const float *__restrict__ gamma, const double *__restrict__ sums, int64_t rows,
+                                    int C, T *__restrict__ dx) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = C / VN;
+    const int64_t total = rows * cv;
+    const float inv_rows = 1.f / (float)rows;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(t % cv) * VN;
+        float fd[VN], fx[VN];
+        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(dy) + t), fd);
+        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(x) + t), fx);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            const int c = c0 + e;
+            const float xhat = (fx[e] + (bias ? bias[c] : 0.f) - mean[c]) * invstd[c];
+            fd[e] = gamma[c] * invstd[c] * (fd[e] - (float)sums[c] * inv_rows - xhat * (float)sums[C + c] * inv_rows);
+        }
+        reinterpret_cast<uint4 *>(dx)[t] = pack<T>(fd);
+    }
+}
+
+__global__ void sums_to_float_kernel(const double *__restrict__ s, int n, float scale, float *__restrict__ out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (accumulate ? out[i] : 0.f) + scale * (float)s[i];
+}
+
+// ---------------------------------------------------------------- LSTM cell (gate order i, f, g, o like ATen)
+// gates_pre [B, 4H] (T): x-projection + h_{t-1} W_hh^T already summed by the GEMMs; bias_ih + bias_hh added here.
+// Writes the activated gates back in place (saved for backward), c_t [B,H] fp32, h_t [B,H] (T) into `h_out` (row
+// stride ldh, so it lands directly in the [T, B, 2H] output of the bidirectional layer).
+template <typename T>
+__global__ void lstm_cell_fwd_kernel(T *__restrict__ gates, const float *__restrict__ b_ih, const float *__restrict__ b_hh,
+                                     const float *__restrict__ c_prev, float *__restrict__ c_out, T *__restrict__ h_out,
+                                     int64_t ldh, T *__restrict__ h_state, int B, int H) {
+    const int64_t total = (int64_t)B * H;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / H), j = (int)(t - (int64_t)b * H);
+        T *gp = gates + (int64_t)b * 4 * H;
+        const float gi = to_f<T>(gp[j]) + b_ih[j] + b_hh[j];
+        const float gf = to_f<T>(gp[H + j]) + b_ih[H + j] + b_hh[H + j];
+        const float gg = to_f<T>(gp[2 * H + j]) + b_ih[2 * H + j] + b_hh[2 * H + j];
+        const float go = to_f<T>(gp[3 * H + j]) + b_ih[3 * H + j] + b_hh[3 * H + j];
+        const float i_ = 1.f / (1.f + expf(-gi)), f_ = 1.f / (1.f + expf(-gf)), g_ = tanhf(gg), o_ = 1.f / (1.f + expf(-go));
+        const float c = f_ * (c_prev ? c_prev[t] : 0.f) + i_ * g_;
+        const float h = o_ * tanhf(c);
+        gp[j] = from_f<T>(i_); gp[H + j] = from_f<T>(f_); gp[2 * H + j] = from_f<T>(g_); gp[3 * H + j] = from_f<T>(o_);
+        c_out[t] = c;
+        const T hv = from_f<T>(h);
+        h_out[(int64_t)b * ldh + j] = hv;
+        h_state[t] = hv;
+    }
+}
+
+// dh_total = dh_out[t] (from the layer output gradient, row stride ldh) + dh_rec (from step t+1, may be NULL).
+// Produces the pre-activation gate gradients dgates [B,4H] (T) and dc_prev (fp32, in place over dc).
+template <typename T>
+__global__ void lstm_cell_bwd_kernel(const T *__restrict__ gates, const float *__restrict__ c, const float *__restrict__ c_prev,
+                                     const T *__restrict__ dh_out, int64_t ldh, const T *__restrict__ dh_rec,
+                                     float *__restrict__ dc, T *__restrict__ dgates, int B, int H) {
+    const int64_t total = (int64_t)B * H;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(t / H), j = (int)(t - (int64_t)b * H);
+        const T *gp = gates + (int64_t)b * 4 * H;
+        const float i_ = to_f<T>(gp[j]), f_ = to_f<T>(gp[H + j]), g_ = to_f<T>(gp[2 * H + j]), o_ = to_f<T>(gp[3 * H + j]);
+        const float dh = to_f<T>(dh_out[(int64_t)b * ldh + j]) + (dh_rec ? to_f<T>(dh_rec[t]) : 0.f);
+        const float tc = tanhf(c[t]);
+        const float dct = dc[t] + dh * o_ * (1.f - tc * tc);
+        const float cp = c_prev ? c_prev[t] : 0.f;
+        T *dg = dgates + (int64_t)b * 4 * H;
+        dg[j] = from_f<T>(dct * g_ * i_ * (1.f - i_));
+        dg[H + j] = from_f<T>(dct * cp * f_ * (1.f - f_));
+        dg[2 * H + j] = from_f<T>(dct * i_ * (1.f - g_ * g_));
+        dg[3 * H + j] = from_f<T>(dh * tc * o_ * (1.f - o_));
+        dc[t] = dct * f_;
+    }
+}
+
+// ---------------------------------------------------------------- fused Adam over one flat fp32 buffer
+// torch.optim.Adam semantics (no amsgrad, no weight decay): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+// p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).  Optionally refreshes a bf16 shadow copy of the parameters.
+__global__ void adam_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
+                            int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale,
+                            bf16 *__restrict__ shadow) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float pi = p[i] - (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+        p[i] = pi;
+        if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+    }
+}
+
+// small-C fallback of the column sum (C not a multiple of the vector width, e.g. the 38 classes of the last Linear)
+template <typename T>
+__global__ void colsum_scalar_kernel(const T *__restrict__ a, int64_t rows, int C, double *__restrict__ sums) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = 0.f;
+        for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) acc += to_f<T>(a[r * C + c]);
+        atomicAdd(sums + c, (double)acc);
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI *__restrict__ x, int64_t n, TO *__restrict__ y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = from_f<TO>(to_f<TI>(x[i]));
+}
+
+#define DISPATCH(dtype, CALL)                                   \
+    do { if ((dtype) == 0) { using T = float; CALL; }           \
+         else if ((dtype) == 1) { using T = bf16; CALL; }       \
+         else return MR_ERR_BAD_SHAPE; } while (0)
+
+int vec_ok(int dtype, int C) { return C % (dtype == 0 ? 4 : 8) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int mr_nchw_to_nhwc(const float *x, int N, int C, int H, int W, int Cp, int dtype, void *y, void *stream) {
+    if (N < 0 || C <= 0 || H <= 0 || W <= 0 || Cp < C) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!x || !y) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH(dtype, (nchw_to_nhwc_kernel<T><<<grid1d((int64_t)N * H * W, 256), 256, 0, st>>>(x, N, C, H * W, Cp, (T *)y)));
+    return check_launch("nchw_to_nhwc_kernel");
+}
+
+int mr_nhwc_to_nchw(const void *x, int N, int C, int H, int W, int Cp, int dtype, float *y, void *stream) {
+    if (N < 0 || C <= 0 || H <= 0 || W <= 0 || Cp < C) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!x || !y) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH(dtype, (nhwc_to_nchw_kernel<T><<<grid1d((int64_t)N * C * H * W, 256), 256, 0, st>>>((const T *)x, N, C, H * W, Cp, y)));
+    return check_launch("nhwc_to_nchw_kernel");
+}
+
+static int conv_geo(ConvGeo &g, int N, int H, int W, int C, int kh, int kw, int ph, int pw, int Kp) {
+    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || kh <= 0 || kw <= 0 || ph < 0 || pw < 0) return MR_ERR_BAD_SHAPE;
+    g.N = N; g.H = H; g.W = W; g.C = C; g.kh = kh; g.kw = kw; g.ph = ph; g.pw = pw;
+    g.Ho = H + 2 * ph - kh + 1; g.Wo = W + 2 * pw - kw + 1; g.K = kh * kw * C; g.Kp = Kp;
+    if (g.Ho <= 0 || g.Wo <= 0 || Kp < g.K) return MR_ERR_BAD_SHAPE;
+    return MR_OK;
+}
+
+/* col [N*Ho*Wo, Kp] from NHWC x; stride-1 convolution geometry (all the CRNN stack uses, backbones/crnn.py:8-10). */
+int mr_im2col_nhwc(const void *x, int N, int H, int W, int C, int kh, int kw, int ph, int pw, int Kp, int dtype,
+                   void *col, void *stream) {
+    ConvGeo g;
+    int rc = conv_geo(g, N, H, W, C, kh, kw, ph, pw, Kp);
+    if (rc) return rc;
+    if (N == 0) return MR_OK;
+    if (!x || !col) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t P = (int64_t)N * g.Ho * g.Wo;
+    if (vec_ok(dtype, C) && vec_ok(dtype, Kp)) {
+        const int vn = dtype == 0 ? 4 : 8;
+        DISPATCH(dtype, (im2col_vec_kernel<T><<<grid1d(P * (Kp / vn), 256, 32), 256, 0, st>>>(g, (const T *)x, (T *)col)));
+    } else {
+        DISPATCH(dtype, (im2col_scalar_kernel<T><<<grid1d(P * Kp, 256, 32), 256, 0, st>>>(g, (const T *)x, (T *)col)));
+    }
+    return check_launch("im2col_kernel");
+}
+
+/* dx NHWC [N,H,W,C] from dcol [N*Ho*Wo, Kp]  (adjoint of mr_im2col_nhwc). */
+int mr_col2im_nhwc(const void *dcol, int N, int H, int W, int C, int kh, int kw, int ph, int pw, int Kp, int dtype,
+                   void *dx, void *stream) {
+    ConvGeo g;
+    int rc = conv_geo(g, N, H, W, C, kh, kw, ph, pw, Kp);
+    if (rc) return rc;
+    if (N == 0) return MR_OK;
+    if (!dcol || !dx) return MR_ERR_NULL_POINTER;
+    if (!vec_ok(dtype, C) || !vec_ok(dtype, Kp)) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vn = dtype == 0 ? 4 : 8;
+    DISPATCH(dtype, (col2im_vec_kernel<T><<<grid1d((int64_t)N * H * W * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dcol, (T *)dx)));
+    return check_launch("col2im_kernel");
+}
+
+static int pool_geo(PoolGeo &g, int N, int H, int W, int C, int kh, int kw, int sh, int sw, int ph, int pw) {
+    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || kh <= 0 || kw <= 0 || sh <= 0 || sw <= 0 || ph < 0 || pw < 0 || kh * kw > 255)
+        return MR_ERR_BAD_SHAPE;
+    g.N = N; g.H = H; g.W = W; g.C = C; g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.ph = ph; g.pw = pw;
+    g.Ho = (H + 2 * ph - kh) / sh + 1; g.Wo = (W + 2 * pw - kw) / sw + 1;   /* floor mode, nn.MaxPool2d default */
+    if (g.Ho <= 0 || g.Wo <= 0) return MR_ERR_BAD_SHAPE;
+    return MR_OK;
+}
+
+/* y = maxpool(relu(x + bias)), idx = arg-max inside the window (uint8). */
+int mr_bias_relu_pool_fwd(const void *x, const float *bias, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                          int ph, int pw, int dtype, void *y, unsigned char *idx, void *stream) {
+    PoolGeo g;
+    int rc = pool_geo(g, N, H, W, C, kh, kw, sh, sw, ph, pw);
+    if (rc) return rc;
+    if (N == 0) return MR_OK;
+    if (!x || !bias || !y || !idx) return MR_ERR_NULL_POINTER;
+    if (!vec_ok(dtype, C)) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vn = dtype == 0 ? 4 : 8;
+    DISPATCH(dtype, (bias_relu_pool_fwd_kernel<T><<<grid1d((int64_t)N * g.Ho * g.Wo * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)x, bias, (T *)y, idx)));
+    return check_launch("bias_relu_pool_fwd_kernel");
+}
+
+int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *idx, int N, int H, int W, int C, int kh,
+                          int kw, int sh, int sw, int ph, int pw, int dtype, void *dz, void *stream) {
+    PoolGeo g;
+    int rc = pool_geo(g, N, H, W, C, kh, kw, sh, sw, ph, pw);
+    if (rc) return rc;
+    if (N == 0) return MR_OK;
+    if (!dy || !y || !idx || !dz) return MR_ERR_NULL_POINTER;
+    if (!vec_ok(dtype, C)) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vn = dtype == 0 ? 4 : 8;
+    DISPATCH(dtype, (bias_relu_pool_bwd_kernel<T><<<grid1d((int64_t)N * H * W * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz)));
+    return check_launch("bias_relu_pool_bwd_kernel");
+}
+
+int mr_bias_act(const void *x, const float *bias, int64_t rows, int C, int relu, int dtype, void *y, void *stream) {
+    if (rows < 0 || C <= 0) return MR_ERR_BAD_SHAPE;
+    if (rows == 0) return MR_OK;
+    if (!x || !bias || !y) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!vec_ok(dtype, C)) {
+        DISPATCH(dtype, (bias_act_scalar_kernel<T><<<grid1d(rows * C, 256, 32), 256, 0, st>>>((const T *)x, bias, rows * C, C, relu, (T *)y)));
+        return check_launch("bias_act_scalar_kernel");
+    }
+    const int vn = dtype == 0 ? 4 : 8;
+    DISPATCH(dtype, (bias_act_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)x, bias, rows, C, relu, (T *)y)));
+    return check_launch("bias_act_kernel");
+}
+
+static int launch_reduce(int mode, int dtype, const void *a, const void *b, const float *bias, const float *mean,
+                         const float *invstd, int64_t rows, int C, double *sums, cudaStream_t st) {
+    if (!vec_ok(dtype, C)) return MR_ERR_UNSUPPORTED;
+    const int vn = dtype == 0 ? 4 : 8;
+    const int cv = C / vn;
+    const int gx = (int)ceil_div(cv, 32);
+    int64_t gy = (148 * 8) / gx;
+    if (gy < 1) gy = 1;
+    int64_t rpc = ceil_div(rows, gy);
+    if (rpc < 64) rpc = 64;
+    gy = ceil_div(rows, rpc);
+    MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st), "memset sums");
+    dim3 grid(gx, (unsigned)gy);
+#define RL(MODEV) DISPATCH(dtype, (col_reduce_kernel<T, MODEV><<<grid, 256, 0, st>>>((const T *)a, (const T *)b, bias, mean, invstd, rows, C, rpc, sums)))
+    if (mode == 0) RL(0); else if (mode == 1) RL(1); else RL(2);
+#undef RL
+    return check_launch("col_reduce_kernel");
+}
+
+/* Training-mode BatchNorm over [rows, C] of (x + bias): batch statistics, running-stat update, normalisation.
+ * `sums` is a caller-provided scratch of 2*C doubles.  mean / invstd [C] are saved for the backward. */
+int mr_bn_train_fwd(const void *x, const float *bias, const float *gamma, const float *beta, float *running_mean,
+                    float *running_var, float momentum, float eps, int64_t rows, int C, int dtype, void *y, float *mean,
+                    float *invstd, double *sums, void *stream) {
+    if (rows <= 0 || C <= 0) return MR_ERR_BAD_SHAPE;
+    if (!x || !gamma || !beta || !y || !mean || !invstd || !sums) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_reduce(0, dtype, x, nullptr, bias, nullptr, nullptr, rows, C, sums, st);
+    if (rc) return rc;
+    bn_finalize_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums, rows, C, eps, momentum, mean, invstd, running_mean, running_var);
+    rc = check_launch("bn_finalize_kernel");
+    if (rc) return rc;
+    const int vn = dtype == 0 ? 4 : 8;
+    DISPATCH(dtype, (bn_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, (T *)y)));
+    return check_launch("bn_apply_kernel");
+}
+
+/* Inference BatchNorm with given statistics (eval branch): y = (x + bias - mean) * invstd * gamma + beta. */
+int mr_bn_apply(const void *x, const float *bias, const float *mean, const float *invstd, const float *gamma,
+                const float *beta, int64_t rows, int C, int dtype, void *y, void *stream) {
+    if (rows < 0 || C <= 0) return MR_ERR_BAD_SHAPE;
+    if (rows == 0) return MR_OK;
+    if (!x || !mean || !invstd || !gamma || !beta || !y) return MR_ERR_NULL_POINTER;
+    if (!vec_ok(dtype, C)) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vn = dtype == 0 ? 4 : 8;
+    DISPATCH(dtype, (bn_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, (T *)y)));
+    return check_launch("bn_apply_kernel");
+}
+
+/* BatchNorm backward: dx (gradient w.r.t. x + bias), dgamma, dbeta (fp32, assigned). */
+int mr_bn_train_bwd(const void *dy, const void *x, const float *bias, const float *mean, const float *invstd,
+                    const float *gamma, int64_t rows, int C, int dtype, void *dx, float *dgamma, float *dbeta,
+                    double *sums, void *stream) {
+    if (rows <= 0 || C <= 0) return MR_ERR_BAD_SHAPE;
+    if (!dy || !x || !mean || !invstd || !gamma || !dx || !dgamma || !dbeta || !sums) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_reduce(1, dtype, dy, x, bias, mean, invstd, rows, C, sums, st);
+    if (rc) return rc;
+    sums_to_float_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums, C, 1.f, dbeta, 0);
+    sums_to_float_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums + C, C, 1.f, dgamma, 0);
+    rc = check_launch("sums_to_float_kernel");
+    if (rc) return rc;
+    const int vn = dtype == 0 ? 4 : 8;
+    DISPATCH(dtype, (bn_bwd_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)dy, (const T *)x, bias, mean, invstd, gamma, sums, rows, C, (T *)dx)));
+    return check_launch("bn_bwd_apply_kernel");
+}
+
+/* out[c] (= or +=) sum_r a[r, c]  — bias gradients. */
+int mr_colsum(const void *a, int64_t rows, int C, int dtype, float *out, int accumulate, double *sums, void *stream) {
+    if (rows < 0 || C <= 0) return MR_ERR_BAD_SHAPE;
+    if (!a || !out || !sums) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!vec_ok(dtype, C)) {
+        MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * C, st), "memset sums");
+        DISPATCH(dtype, (colsum_scalar_kernel<T><<<grid1d(rows, 256, 4), 256, 0, st>>>((const T *)a, rows, C, sums)));
+        int rc0 = check_launch("colsum_scalar_kernel");
+        if (rc0) return rc0;
+        sums_to_float_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums, C, 1.f, out, accumulate);
+        return check_launch("sums_to_float_kernel");
+    }
+    int rc = launch_reduce(2, dtype, a, nullptr, nullptr, nullptr, nullptr, rows, C, sums, st);
+    if (rc) return rc;
+    sums_to_float_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums, C, 1.f, out, accumulate);
+    return check_launch("sums_to_float_kernel");
+}
+
+int mr_lstm_cell_fwd(void *gates, const float *b_ih, const float *b_hh, const float *c_prev, float *c_out, void *h_out,
+                     int64_t ldh, void *h_state, int B, int H, int dtype, void *stream) {
+    if (B <= 0 || H <= 0) return MR_ERR_BAD_SHAPE;
+    if (!gates || !b_ih || !b_hh || !c_out || !h_out || !h_state) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH(dtype, (lstm_cell_fwd_kernel<T><<<grid1d((int64_t)B * H, 256), 256, 0, st>>>((T *)gates, b_ih, b_hh, c_prev, c_out, (T *)h_out, ldh, (T *)h_state, B, H)));
+    return check_launch("lstm_cell_fwd_kernel");
+}
+
+int mr_lstm_cell_bwd(const void *gates, const float *c, const float *c_prev, const void *dh_out, int64_t ldh,
+                     const void *dh_rec, float *dc, void *dgates, int B, int H, int dtype, void *stream) {
+    if (B <= 0 || H <= 0) return MR_ERR_BAD_SHAPE;
+    if (!gates || !c || !dh_out || !dc || !dgates) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH(dtype, (lstm_cell_bwd_kernel<T><<<grid1d((int64_t)B * H, 256), 256, 0, st>>>((const T *)gates, c, c_prev, (const T *)dh_out, ldh, (const T *)dh_rec, dc, (T *)dgates, B, H)));
+    return check_launch("lstm_cell_bwd_kernel");
+}
+
+int mr_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 int64_t step, float grad_scale, void *bf16_shadow, void *stream) {
+    if (n < 0 || step < 1) return MR_ERR_BAD_SHAPE;
+    if (n == 0) return MR_OK;
+    if (!p || !g || !m || !v) return MR_ERR_NULL_POINTER;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    adam_kernel<<<grid1d(n, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s, grad_scale, (bf16 *)bf16_shadow);
+    return check_launch("adam_kernel");
+}
+
+int mr_cast(const void *x, int src_dtype, int64_t n, int dst_dtype, void *y, void *stream) {
+    if (n < 0) return MR_ERR_BAD_SHAPE;
+    if (n == 0) return MR_OK;
+    if (!x || !y) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid1d(n, 256);
+    if (src_dtype == 0 && dst_dtype == 1) cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float *)x, n, (bf16 *)y);
+    else if (src_dtype == 1 && dst_dtype == 0) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16 *)x, n, (float *)y);
+    else if (src_dtype == 0 && dst_dtype == 0) cast_kernel<float, float><<<g, 256, 0, st>>>((const float *)x, n, (float *)y);
+    else if (src_dtype == 1 && dst_dtype == 1) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16 *)x, n, (bf16 *)y);
+    else return MR_ERR_BAD_SHAPE;
+    return check_launch("cast_kernel");
+}
+
+}  // extern "C"

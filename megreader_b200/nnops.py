@@ -1,0 +1,171 @@
+"""Thin torch-tensor wrappers over the C-ABI building blocks (include/megreader_b200.h, csrc/nn_kernels.cu,
+csrc/gemm.cu).  No arithmetic happens in Python; these only allocate outputs and pass pointers."""
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+
+
+def code(dtype):
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("megreader_b200: compute dtype must be float32 or bfloat16, got %s" % dtype)
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _chk(rc, what):
+    _lib.check(rc, what)
+
+
+def nchw_to_nhwc(x, Cp, dtype):
+    N, C, H, W = x.shape
+    y = torch.empty((N, H, W, Cp), dtype=dtype, device=x.device)
+    _chk(_lib.lib().mr_nchw_to_nhwc(_p(x), N, C, H, W, Cp, code(dtype), _p(y), _st()), "nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x, C):
+    N, H, W, Cp = x.shape
+    y = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    _chk(_lib.lib().mr_nhwc_to_nchw(_p(x), N, C, H, W, Cp, code(x.dtype), _p(y), _st()), "nhwc_to_nchw")
+    return y
+
+
+def im2col(x, kh, kw, ph, pw, Kp):
+    N, H, W, C = x.shape
+    Ho, Wo = H + 2 * ph - kh + 1, W + 2 * pw - kw + 1
+    col = torch.empty((N * Ho * Wo, Kp), dtype=x.dtype, device=x.device)
+    _chk(_lib.lib().mr_im2col_nhwc(_p(x), N, H, W, C, kh, kw, ph, pw, Kp, code(x.dtype), _p(col), _st()), "im2col")
+    return col, Ho, Wo
+
+
+def col2im(dcol, N, H, W, C, kh, kw, ph, pw):
+    dx = torch.empty((N, H, W, C), dtype=dcol.dtype, device=dcol.device)
+    _chk(_lib.lib().mr_col2im_nhwc(_p(dcol), N, H, W, C, kh, kw, ph, pw, dcol.size(1), code(dcol.dtype), _p(dx), _st()),
+         "col2im")
+    return dx
+
+
+def pool_out(H, W, k, s, p):
+    return (H + 2 * p[0] - k[0]) // s[0] + 1, (W + 2 * p[1] - k[1]) // s[1] + 1
+
+
+def bias_relu_pool_fwd(z, bias, N, H, W, C, k, s, p):
+    Ho, Wo = pool_out(H, W, k, s, p)
+    y = torch.empty((N, Ho, Wo, C), dtype=z.dtype, device=z.device)
+    idx = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=z.device)
+    _chk(_lib.lib().mr_bias_relu_pool_fwd(_p(z), _p(bias), N, H, W, C, k[0], k[1], s[0], s[1], p[0], p[1], code(z.dtype),
+                                          _p(y), _p(idx), _st()), "bias_relu_pool_fwd")
+    return y, idx
+
+
+def bias_relu_pool_bwd(dy, y, idx, N, H, W, C, k, s, p):
+    dz = torch.empty((N * H * W, C), dtype=dy.dtype, device=dy.device)
+    _chk(_lib.lib().mr_bias_relu_pool_bwd(_p(dy), _p(y), _p(idx), N, H, W, C, k[0], k[1], s[0], s[1], p[0], p[1],
+                                          code(dy.dtype), _p(dz), _st()), "bias_relu_pool_bwd")
+    return dz
+
+
+def bias_act(x, bias, relu=False, out=None):
+    rows, C = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    _chk(_lib.lib().mr_bias_act(_p(x), _p(bias), rows, C, int(relu), code(x.dtype), _p(y), _st()), "bias_act")
+    return y
+
+
+def _sums(C, dev):
+    return torch.empty((2 * C,), dtype=torch.float64, device=dev)
+
+
+def bn_train_fwd(z, bias, gamma, beta, running_mean, running_var, momentum, eps):
+    rows, C = z.shape
+    y = torch.empty_like(z)
+    mean = torch.empty((C,), dtype=torch.float32, device=z.device)
+    invstd = torch.empty_like(mean)
+    _chk(_lib.lib().mr_bn_train_fwd(_p(z), _p(bias), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                                    float(momentum), float(eps), rows, C, code(z.dtype), _p(y), _p(mean), _p(invstd),
+                                    _p(_sums(C, z.device)), _st()), "bn_train_fwd")
+    return y, mean, invstd
+
+
+def bn_apply(z, bias, mean, invstd, gamma, beta):
+    rows, C = z.shape
+    y = torch.empty_like(z)
+    _chk(_lib.lib().mr_bn_apply(_p(z), _p(bias), _p(mean), _p(invstd), _p(gamma), _p(beta), rows, C, code(z.dtype), _p(y),
+                                _st()), "bn_apply")
+    return y
+
+
+def bn_train_bwd(dy, z, bias, mean, invstd, gamma):
+    rows, C = z.shape
+    dx = torch.empty_like(z)
+    dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
+    dbeta = torch.empty_like(dgamma)
+    _chk(_lib.lib().mr_bn_train_bwd(_p(dy), _p(z), _p(bias), _p(mean), _p(invstd), _p(gamma), rows, C, code(z.dtype),
+                                    _p(dx), _p(dgamma), _p(dbeta), _p(_sums(C, z.device)), _st()), "bn_train_bwd")
+    return dx, dgamma, dbeta
+
+
+def colsum(a, out=None, accumulate=False):
+    rows, C = a.shape
+    if out is None:
+        out = torch.empty((C,), dtype=torch.float32, device=a.device)
+    _chk(_lib.lib().mr_colsum(_p(a), rows, C, code(a.dtype), _p(out), int(accumulate), _p(_sums(C, a.device)), _st()),
+         "colsum")
+    return out
+
+
+def cast(x, dtype):
+    if x.dtype == dtype and x.is_contiguous():
+        return x
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    _chk(_lib.lib().mr_cast(_p(x), code(x.dtype), x.numel(), code(dtype), _p(y), _st()), "cast")
+    return y
+
+
+def gemm(A, B, transA=False, transB=False, out=None, out_dtype=None, alpha=1.0, beta=0.0):
+    """Row-major out[M,N] = alpha * op(A) op(B) + beta * out.  A, B: 2-D, unit inner stride (row stride = ld)."""
+    assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1 and A.dtype == B.dtype
+    M, K = (A.size(1), A.size(0)) if transA else (A.size(0), A.size(1))
+    Kb, N = (B.size(1), B.size(0)) if transB else (B.size(0), B.size(1))
+    assert K == Kb, (A.shape, B.shape, transA, transB)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype or A.dtype, device=A.device)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    _chk(_lib.lib().mr_gemm(_p(A), _p(B), _p(out), M, N, K, A.stride(0), B.stride(0), out.stride(0), int(transA),
+                            int(transB), code(A.dtype), code(out.dtype), float(alpha), float(beta), _st()), "gemm")
+    return out
+
+
+def gemm_batched_raw(pA, pB, pC, M, N, K, lda, ldb, ldc, sA, sB, sC, batch, transA, transB, in_dtype, out_dtype,
+                     alpha=1.0, beta=0.0):
+    _chk(_lib.lib().mr_gemm_batched(pA, pB, pC, M, N, K, lda, ldb, ldc, sA, sB, sC, batch, int(transA), int(transB),
+                                    code(in_dtype), code(out_dtype), float(alpha), float(beta), _st()), "gemm_batched")
+
+
+def lstm_cell_fwd(gates, b_ih, b_hh, c_prev, c_out, h_out, ldh, h_state):
+    B, H4 = gates.shape
+    _chk(_lib.lib().mr_lstm_cell_fwd(_p(gates), _p(b_ih), _p(b_hh), _p(c_prev), _p(c_out), _p(h_out), ldh, _p(h_state), B,
+                                     H4 // 4, code(gates.dtype), _st()), "lstm_cell_fwd")
+
+
+def lstm_cell_bwd(gates, c, c_prev, dh_out, ldh, dh_rec, dc, dgates):
+    B, H4 = gates.shape
+    _chk(_lib.lib().mr_lstm_cell_bwd(_p(gates), _p(c), _p(c_prev), _p(dh_out), ldh, _p(dh_rec), _p(dc), _p(dgates), B,
+                                     H4 // 4, code(gates.dtype), _st()), "lstm_cell_bwd")
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None):
+    _chk(_lib.lib().mr_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                 int(step), float(grad_scale), _p(shadow), _st()), "adam_step")

@@ -31,7 +31,7 @@ def test_ctc1d_vs_reference_call(cuda, zero_inf):
     rng = np.random.RandomState(0)
     T, N, C, S = 26, 6, 38, 32
     logits = torch.from_numpy(rng.standard_normal((T, N, C)).astype(np.float32) * 2)
-    lengths = torch.tensor([3, 8, 1, 12, 5, 13])       # 13 -> 2*13+1 = 27 > T: infeasible -> inf / zero_infinity
+    lengths = torch.tensor([3, 8, 1, 12, 5, 30])       # 30 labels in T=26 columns: infeasible -> inf / zero_infinity
     labels = torch.zeros(N, S, dtype=torch.int32)
     for b in range(N):
         labels[b, :lengths[b]] = torch.from_numpy(rng.randint(2, C, size=int(lengths[b])))
@@ -71,7 +71,7 @@ def test_crnn_train_step_vs_reference_golden(cuda, api, name):
         if key.startswith("grad."):
             got = params[key[5:]].grad.cpu().numpy()
             scale = max(1e-6, float(np.abs(g[key]).max()))
-            np.testing.assert_allclose(got, g[key], rtol=2e-3, atol=2e-4 * scale, err_msg=key)
+            np.testing.assert_allclose(got, g[key], rtol=2e-3, atol=max(2e-4 * scale, 1e-6), err_msg=key)  # conv bias before BN: grad == 0 up to noise
         elif key.startswith("gnorm."):
             np.testing.assert_allclose(params[key[6:]].grad.double().norm().item(), float(g[key]), rtol=2e-3, err_msg=key)
         elif key.startswith("bn."):
