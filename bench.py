@@ -131,9 +131,10 @@ def run_ours(args):
     torch.manual_seed(0)
     net = build_model(dev)
     model = net
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)   # optimizer_scheduler.py:17-22, lr crnn.yaml
+    params = list(net.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)   # optimizer_scheduler.py:17-22, lr crnn.yaml
+    from megreader_b200 import crnn_engine, dp
+    crnn_engine.set_compute_dtype(torch.bfloat16)          # BASELINE.json cfg 2: bf16 compute, fp32 master weights
 
     n_host = 3
     host = []
@@ -141,14 +142,13 @@ def run_ours(args):
         x, y, l = synth_batch(100 * rank + i, BATCH_PER_GPU)
         host.append((x.pin_memory(), y.pin_memory(), l.pin_memory()))
     dev_batches = [tuple(t.to(dev) for t in hb) for hb in host]
+    static = tuple(torch.empty_like(t) for t in dev_batches[0])
 
-    from megreader_b200 import crnn_engine
-    crnn_engine.set_compute_dtype(torch.bfloat16)          # BASELINE.json cfg 2: bf16 compute, fp32 master weights
-
-    def step(x, y, l):
+    def eager_step(x, y, l):
         opt.zero_grad(set_to_none=True)
         loss, _ = model(x, y, l)
         loss.mean().backward()
+        dp.allreduce_mean_grads_(params)                   # NCCL all-reduce(mean) of one flat 33 MB bucket
         opt.step()
         return loss
 
@@ -157,6 +157,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # warm up eagerly (cuBLAS workspaces, allocator), then capture ONE whole training step in a CUDA graph:
+    # ~1000 small launches per step would otherwise be bound by host launch overhead.
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(3):
+            eager_step(*dev_batches[i % n_host])
+    torch.cuda.current_stream().wait_stream(side)
+    barrier()
+    graph = torch.cuda.CUDAGraph()
+    _lib.reset_launch_count()
+    with torch.cuda.graph(graph):
+        static_loss = eager_step(*static)
+    launches_per_step = _lib.launch_count()
+
+    def step(x, y, l):
+        for dst, src in zip(static, (x, y, l)):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return static_loss
+
     # ---- device-resident arm ("value")
     for i in range(args.warmup):
         step(*dev_batches[i % n_host])
@@ -164,14 +185,13 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    _lib.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         loss = step(*dev_batches[i % n_host])
     e1.record()
     barrier()
-    launches = _lib.launch_count()
+    launches = launches_per_step * args.steps          # kernels of this library inside the replayed graphs
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     final_loss = float(loss.mean().item())
@@ -231,8 +251,9 @@ def run_ours(args):
         out["stages"] = {"conv": "megreader_b200 im2col/col2im kernels + cuBLAS bf16 GEMM (plain library GEMM)",
                          "bias+ReLU+MaxPool, BatchNorm": "megreader_b200 CUDA (fused NHWC kernels)",
                          "BiLSTM+Linear": "megreader_b200 cell kernels + cuBLAS GEMMs",
-                         "log_softmax+CTC": "megreader_b200 CUDA", "Adam": "library (torch fused)",
-                         "allreduce": "NCCL via DDP" if world > 1 else "n/a"}
+                         "log_softmax+CTC": "megreader_b200 CUDA", "Adam": "library (torch fused, capturable)",
+                         "allreduce": "NCCL all-reduce of one flat bucket" if world > 1 else "n/a",
+                         "launch": "whole step captured in one CUDA graph"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
