@@ -183,6 +183,14 @@ int mr_gemm_batched(const void *A, const void *B, void *C, int64_t M, int64_t N,
                     int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, int batch, int transA, int transB,
                     int in_dtype, int out_dtype, float alpha, float beta, void *stream);
 
+/* Hand-written Blackwell GEMM (tcgen05.mma + TMEM accumulators + TMA operand staging), bf16 in / fp32 accumulate.
+ * Same storage convention as mr_gemm; supported forms (transA,transB) = (0,1) and (1,0); optional per-column bias
+ * and ReLU in the epilogue; beta = 1 accumulates atomically into fp32 C and enables split-K.  Returns
+ * MR_ERR_UNSUPPORTED for shapes / alignments it does not cover (the caller then uses mr_gemm). */
+int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                    int64_t ldc, int transA, int transB, int out_dtype, const float *bias, int relu, float beta,
+                    int splits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,377 @@
+// Blackwell-native dense GEMM: bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, cta_group::1, UMMA 128xBNx16),
+// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through a 4..6-stage mbarrier ring.
+//
+//   C[M,N] (row-major, bf16 or fp32)  (+)=  op(A)[M,K] * op(B)[K,N]
+//     A_MN = 0: A stored [M,K] row-major (K-major operand)        A_MN = 1: A stored [K,M] row-major (MN-major operand)
+//     B_MN = 0: B stored [N,K] row-major (K-major operand)        B_MN = 1: B stored [K,N] row-major (MN-major operand)
+//   i.e. (0,0) is the "NT" form used for conv forward / dgrad / Linear layers, (1,1) is the "TN" form of weight
+//   gradients  dW[Cout, K] = dZ[P, Cout]^T * col[P, K].
+//   Epilogue: optional per-column bias, optional ReLU, fp32 or bf16 store, or fp32 atomic accumulation (split-K).
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (TMEM -> registers -> global), each owning the 32 TMEM lanes its warp id
+// (mod 4) may touch.  One 128 x BN output tile per CTA (grid = tiles x split-K); K loops over 64-element blocks.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+using namespace mr;
+typedef __nv_bfloat16 bf16;
+
+constexpr int BM = 128;
+constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle atom
+constexpr int UMMA_K = 16;
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, px;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
+// shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=SWIZZLE_128B(2) [61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor for kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), majors (15,16), N>>3 (17..22), M>>4 (24..28)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct GemmArgs {
+    int M, N, K;
+    int64_t ldc;
+    void *C;
+    const float *bias;
+    int relu, out_bf16, atomic;     // atomic: fp32 atomicAdd into C (split-K)
+    int kblocks_per_split;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;      // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+};
+
+template <int BN, int STAGES, int A_MN, int B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024 B
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb_total = (g.K + BK - 1) / BK;
+    const int kb_lo = blockIdx.z * g.kblocks_per_split;
+    const int kb_hi = min(kb_total, kb_lo + g.kblocks_per_split);
+    const int nkb = kb_hi - kb_lo;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(empty + s, ph ^ 1);
+                unsigned char *a_dst = smem + s * L::STAGE_BYTES;
+                unsigned char *b_dst = a_dst + L::A_BYTES;
+                mbar_expect_tx(full + s, L::STAGE_BYTES);
+                const int k0 = (kb_lo + i) * BK;
+                if (A_MN == 0) tma_load_2d(&tmA, full + s, a_dst, k0, m0);                 // box {64 k, 128 m}
+                else {                                                                       // 2 boxes {64 m, 64 k}
+                    tma_load_2d(&tmA, full + s, a_dst, m0, k0);
+                    tma_load_2d(&tmA, full + s, a_dst + BK * 128, m0 + 64, k0);
+                }
+                if (B_MN == 0) tma_load_2d(&tmB, full + s, b_dst, k0, n0);                 // box {64 k, BN n}
+                else {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tmB, full + s, b_dst + j * BK * 128, n0 + 64 * j, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            const uint32_t ph = (i / STAGES) & 1;
+            mbar_wait(full + s, ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // K-major: 8-row groups 1024 B apart (SBO), advance 32 B per UMMA_K inside the 128 B atom.
+                    // MN-major: 64-element M/N atoms BK*128 B apart (LBO), 8-row K groups 1024 B apart (SBO),
+                    //           advance 16 rows * 128 B per UMMA_K.
+                    const uint64_t ad = A_MN == 0 ? make_desc(a_addr + k * 32, 16, 1024)
+                                                  : make_desc(a_addr + k * 2048, BK * 128, 1024);
+                    const uint64_t bd = B_MN == 0 ? make_desc(b_addr + k * 32, 16, 1024)
+                                                  : make_desc(b_addr + k * 2048, BK * 128, 1024);
+                    umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0);
+                }
+                umma_commit(empty + s);                       // frees the smem slot when these MMAs retire
+                if (i == nkb - 1) umma_commit(tmem_full);     // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                               // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        float *Cf = (float *)g.C;
+        bf16 *Ch = (bf16 *)g.C;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0;
+            }
+            const int nbase = n0 + c * 32;
+            if (row < g.M && nbase < g.N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(r[j]);
+                    if (g.bias && nbase + j < g.N) v[j] += g.bias[nbase + j];
+                    if (g.relu) v[j] = fmaxf(v[j], 0.f);
+                }
+                const bool full32 = nbase + 32 <= g.N;
+                if (g.atomic) {
+                    float *dst = Cf + (int64_t)row * g.ldc + nbase;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (full32 || nbase + j < g.N) atomicAdd(dst + j, v[j]);
+                } else if (g.out_bf16) {
+                    bf16 *dst = Ch + (int64_t)row * g.ldc + nbase;
+                    if (full32 && ((uintptr_t)dst % 16 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                            *reinterpret_cast<uint4 *>(dst + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nbase + j < g.N) dst[j] = __float2bfloat16_rn(v[j]);
+                    }
+                } else {
+                    float *dst = Cf + (int64_t)row * g.ldc + nbase;
+                    if (full32 && ((uintptr_t)dst % 16 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nbase + j < g.N) dst[j] = v[j];
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- host: tensor maps through the driver entry point
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 tensor, `inner` contiguous elements per row, `outer` rows, row pitch ld elements; box {box_inner, box_outer}
+int make_map(CUtensorMap *m, const void *base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return MR_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled"); return MR_ERR_CUDA; }
+    return MR_OK;
+}
+
+template <int BN, int STAGES, int A_MN, int B_MN>
+int launch(const CUtensorMap &ta, const CUtensorMap &tb, const GemmArgs &g, int splits, cudaStream_t st) {
+    using L = SmemLayout<BN, STAGES>;
+    auto kern = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm_tcgen05 smem attr");
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)splits);
+    kern<<<grid, 192, L::TOTAL, st>>>(ta, tb, g);
+    return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+/* bf16 GEMM on tcgen05/TMA.  transA = 0: A stored [M,K] (lda >= K); transA = 1: A stored [K,M] (lda >= M).
+ * transB = 1: B stored [N,K] (ldb >= K);  transB = 0: B stored [K,N] (ldb >= N).   [same convention as mr_gemm]
+ * Supported operand forms: (transA, transB) = (0, 1) "NT" and (1, 0) "TN".  lda, ldb multiples of 8, bases 16-byte
+ * aligned.  out_dtype 0 = fp32, 1 = bf16.  beta must be 0 or 1; beta = 1 (fp32 only) accumulates atomically and allows
+ * split-K (splits > 1).  Returns MR_ERR_UNSUPPORTED for anything else so that the caller can route to mr_gemm. */
+int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                    int64_t ldc, int transA, int transB, int out_dtype, const float *bias, int relu, float beta,
+                    int splits, void *stream) {
+    if (M < 0 || N < 0 || K < 0) return MR_ERR_BAD_SHAPE;
+    if (M == 0 || N == 0) return MR_OK;
+    if (!A || !B || !C) return MR_ERR_NULL_POINTER;
+    const bool nt = (transA == 0 && transB == 1), tn = (transA == 1 && transB == 0);
+    if (!nt && !tn) return MR_ERR_UNSUPPORTED;
+    if (lda % 8 || ldb % 8 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return MR_ERR_UNSUPPORTED;
+    if (beta != 0.f && (beta != 1.f || out_dtype != 0)) return MR_ERR_UNSUPPORTED;
+    if (K == 0 || M > (1LL << 31) - 256 || N > (1LL << 31) - 256 || K > (1LL << 31) - 256) return MR_ERR_UNSUPPORTED;
+    if (splits < 1) splits = 1;
+    if (splits > 1 && beta != 1.f) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int BN = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    CUtensorMap ta, tb;
+    int rc;
+    if (nt) {
+        rc = make_map(&ta, A, K, M, lda, BK, BM);
+        if (rc) return rc;
+        rc = make_map(&tb, B, K, N, ldb, BK, BN);
+    } else {
+        rc = make_map(&ta, A, M, K, lda, 64, BK);
+        if (rc) return rc;
+        rc = make_map(&tb, B, N, K, ldb, 64, BK);
+    }
+    if (rc) return rc;
+    GemmArgs g;
+    g.M = (int)M; g.N = (int)N; g.K = (int)K; g.ldc = ldc; g.C = C; g.bias = bias; g.relu = relu;
+    g.out_bf16 = out_dtype == 1; g.atomic = beta == 1.f;
+    const int kb_total = (int)ceil_div(K, BK);
+    if (splits > kb_total) splits = kb_total;
+    g.kblocks_per_split = (int)ceil_div(kb_total, splits);
+    splits = (int)ceil_div(kb_total, g.kblocks_per_split);
+#define MR_LAUNCH(BNV, STV)                                                              \
+    (nt ? launch<BNV, STV, 0, 0>(ta, tb, g, splits, st) : launch<BNV, STV, 1, 1>(ta, tb, g, splits, st))
+    if (BN == 256) return MR_LAUNCH(256, 4);
+    if (BN == 128) return MR_LAUNCH(128, 6);
+    return MR_LAUNCH(64, 8);
+#undef MR_LAUNCH
+}
+
+}  // extern "C"

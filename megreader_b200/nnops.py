@@ -169,3 +169,20 @@ def lstm_cell_bwd(gates, c, c_prev, dh_out, ldh, dh_rec, dc, dgates):
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None):
     _chk(_lib.lib().mr_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                  int(step), float(grad_scale), _p(shadow), _st()), "adam_step")
+
+
+def gemm_tc(A, B, transA=False, transB=True, out=None, out_dtype=None, bias=None, relu=False, beta=0.0, splits=1):
+    """Hand-written tcgen05/TMA bf16 GEMM (csrc/gemm_tcgen05.cu).  Same storage convention as gemm(); forms NT / TN.
+    Raises MegReaderB200Error(MR_ERR_UNSUPPORTED) for shapes it does not cover."""
+    assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1
+    assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
+    M, K = (A.size(1), A.size(0)) if transA else (A.size(0), A.size(1))
+    Kb, N = (B.size(1), B.size(0)) if transB else (B.size(0), B.size(1))
+    assert K == Kb, (A.shape, B.shape, transA, transB)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype or torch.bfloat16, device=A.device)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    _chk(_lib.lib().mr_gemm_tcgen05(_p(A), _p(B), _p(out), M, N, K, A.stride(0), B.stride(0), out.stride(0), int(transA),
+                                    int(transB), code(out.dtype), _p(bias), int(relu), float(beta), int(splits), _st()),
+         "gemm_tcgen05")
+    return out
