@@ -191,6 +191,15 @@ int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N,
                     int64_t ldc, int transA, int transB, int out_dtype, const float *bias, int relu, float beta,
                     int splits, void *stream);
 
+/* Implicit-GEMM stride-1 convolution (nn.Conv2d of backbones/crnn.py:46-49) on NHWC bf16, tcgen05 + TMA + gathered
+ * activation tiles: y[N*Ho*Wo, Cout] = conv(x[N,H,W,C], Wm[Cout, kh*kw*C]) (+bias, ReLU); C % 64 == 0.  With
+ * flipped/transposed weights and padding (k-1-p) the same entry computes the input gradient. */
+int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, int W, int C, int Cout, int kh, int kw,
+                          int ph, int pw, int out_dtype, const float *bias, int relu, void *stream);
+/* Implicit-GEMM weight gradient: dWm[Cout, kh*kw*C] fp32 += dz[N,Ho,Wo,Cout]^T (*) x[N,H,W,C] (atomic, split-K). */
+int mr_conv_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int H, int W, int C, int Cout, int kh, int kw,
+                          int ph, int pw, int splits, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,73 @@ struct GemmArgs {
     int kblocks_per_split;
 };
 
+// Epilogue shared by the GEMM and convolution kernels: warps 2..5, TMEM -> registers -> (bias, ReLU) -> global.
+template <int BN>
+__device__ __forceinline__ void epilogue_store(const GemmArgs &g, uint32_t tmem_base, uint64_t *tmem_full, int m0, int n0,
+                                               int warp, int lane, bool have_acc) {
+        const int q = warp & 3;                               // TMEM lane quarter this warp may access
+        const int row = m0 + q * 32 + lane;
+        const int nkb = have_acc ? 1 : 0;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        float *Cf = (float *)g.C;
+        bf16 *Ch = (bf16 *)g.C;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0;
+            }
+            const int nbase = n0 + c * 32;
+            if (row < g.M && nbase < g.N) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = __uint_as_float(r[j]);
+                    if (g.bias && nbase + j < g.N) v[j] += g.bias[nbase + j];
+                    if (g.relu) v[j] = fmaxf(v[j], 0.f);
+                }
+                const bool full32 = nbase + 32 <= g.N;
+                if (g.atomic) {
+                    float *dst = Cf + (int64_t)row * g.ldc + nbase;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (full32 || nbase + j < g.N) atomicAdd(dst + j, v[j]);
+                } else if (g.out_bf16) {
+                    bf16 *dst = Ch + (int64_t)row * g.ldc + nbase;
+                    if (full32 && ((uintptr_t)dst % 16 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk;
+                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
+                            *reinterpret_cast<uint4 *>(dst + j) = pk;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nbase + j < g.N) dst[j] = __float2bfloat16_rn(v[j]);
+                    }
+                } else {
+                    float *dst = Cf + (int64_t)row * g.ldc + nbase;
+                    if (full32 && ((uintptr_t)dst % 16 == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (nbase + j < g.N) dst[j] = v[j];
+                    }
+                }
+            }
+        }
+}
+
 template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;      // 16 KB
@@ -209,66 +276,254 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;                               // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
-        if (nkb > 0) {
-            mbar_wait(tmem_full, 0);
+        epilogue_store<BN>(g, tmem_base, tmem_full, m0, n0, warp, lane, nkb > 0);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// =====================================================================================================
+// Implicit-GEMM convolution, stride 1, NHWC bf16  (backbones/crnn.py:46-49 nn.Conv2d; also its input gradient)
+//
+//   y[p, co] = sum_{tap, c} x[pixel(p) shifted by tap, c] * Wm[co, tap*C + c]          p = (n, ho, wo) flattened
+//
+// The im2col matrix never exists in HBM: warps 2..5 (one thread per output pixel of the 128-row tile) gather the
+// 128-byte channel chunk of each row with zero-filling cp.async straight into the 128B-swizzled K-major smem tile
+// that tcgen05.mma reads (chunk j of row r lands at r*128 + ((j ^ (r & 7)) << 4)); the weight tile comes by TMA.
+// The same kernel computes the input gradient: dgrad of a stride-1 convolution is a convolution of dz with the
+// flipped / transposed weights and padding (k-1-p).  Requires C % 64 == 0.
+// =====================================================================================================
+struct ConvArgs {
+    const bf16 *x;
+    int N, H, W, C, kh, kw, ph, pw, Ho, Wo;
+    GemmArgs g;        // M = N*Ho*Wo, N = Cout, K = kh*kw*C
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    const GemmArgs &g = a.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int cchunks = a.C / BK;
+    const int nkb = a.kh * a.kw * cchunks;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1 + 128); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {                                   // weight tiles by TMA
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+                mbar_expect_tx(full + s, L::B_BYTES);
+                tma_load_2d(&tmB, full + s, smem + s * L::STAGE_BYTES + L::A_BYTES, i * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(full + s, (i / STAGES) & 1);
             tc_fence_after();
-        }
-        float *Cf = (float *)g.C;
-        bf16 *Ch = (bf16 *)g.C;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-            else {
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0;
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
+                              (i | k) != 0);
+                umma_commit(empty + s);
+                if (i == nkb - 1) umma_commit(tmem_full);
             }
-            const int nbase = n0 + c * 32;
-            if (row < g.M && nbase < g.N) {
-                float v[32];
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ activation gather (one thread = one tile row)
+        const int r = threadIdx.x - 64;
+        const int64_t p = (int64_t)m0 + r;
+        const bool valid = p < g.M;
+        int n = 0, ho = 0, wo = 0;
+        if (valid) {
+            wo = (int)(p % a.Wo);
+            const int64_t t = p / a.Wo;
+            ho = (int)(t % a.Ho);
+            n = (int)(t / a.Ho);
+        }
+        const uint32_t row_off = (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+        constexpr int D = 3;                                  // cp.async groups in flight per thread
+        int tap = 0, cc = 0, ti = 0, tj = 0;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+            const int h = ho + ti - a.ph, w = wo + tj - a.pw;
+            const bool ok = valid && h >= 0 && h < a.H && w >= 0 && w < a.W;
+            const bf16 *src = ok ? a.x + ((((int64_t)n * a.H + h) * a.W + w) * a.C + cc * BK) : a.x;
+            const uint32_t dst = smem_u32(smem + s * L::STAGE_BYTES) + row_off;
+            const uint32_t nbytes = ok ? 16u : 0u;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = __uint_as_float(r[j]);
-                    if (g.bias && nbase + j < g.N) v[j] += g.bias[nbase + j];
-                    if (g.relu) v[j] = fmaxf(v[j], 0.f);
-                }
-                const bool full32 = nbase + 32 <= g.N;
-                if (g.atomic) {
-                    float *dst = Cf + (int64_t)row * g.ldc + nbase;
+            for (int j = 0; j < 8; ++j) cp_async16_zfill(dst + (((uint32_t)j ^ sw) << 4), src + j * 8, nbytes);
+            cp_async_commit();
+            if (i >= D - 1) {
+                cp_async_wait<D - 1>();
+                fence_proxy_async();                          // generic-proxy smem writes -> visible to tcgen05
+                mbar_arrive(full + (i - (D - 1)) % STAGES);
+            }
+            if (++cc == cchunks) { cc = 0; ++tap; if (++tj == a.kw) { tj = 0; ++ti; } }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (int i = (nkb >= D - 1 ? nkb - (D - 1) : 0); i < nkb; ++i) mbar_arrive(full + i % STAGES);
+        epilogue_store<BN>(g, tmem_base, tmem_full, m0, n0, warp, lane, nkb > 0);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// =====================================================================================================
+// Implicit-GEMM weight gradient:  dW[co, tap*C + c] += sum_p dz[p, co] * x[pixel(p) shifted by tap, c]
+// Both operands are MN-major and come by 4-D TMA: the reduction dimension (pixels) is tiled in row segments
+// {RB w, 1 h, 1 n}; the tap shift is a signed coordinate offset and TMA zero-fills what falls outside the image, so
+// padding needs no special case.  Split-K over the row segments, fp32 atomics into dW (pre-zeroed by the caller).
+// =====================================================================================================
+struct WgradArgs {
+    int N, H, W, C, kh, kw, ph, pw, Ho, Wo, Cout;
+    int wboxes;                 // ceil(Wo / RB)
+    int kb_total, kblocks_per_split;
+    GemmArgs g;                 // M = Cout, N = kh*kw*C, C = dW, atomic = 1
+};
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+template <int BN, int RB, int STAGES>
+struct WgradSmem {
+    static constexpr int A_BYTES = 2 * RB * 128;              // 128 output channels = 2 atoms of [RB rows][128 B]
+    static constexpr int B_BYTES = (BN / 64) * RB * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int RB, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid_constant__ CUtensorMap tmX, WgradArgs a) {
+    using L = WgradSmem<BN, RB, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    const GemmArgs &g = a.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb_lo = blockIdx.z * a.kblocks_per_split;
+    const int kb_hi = min(a.kb_total, kb_lo + a.kblocks_per_split);
+    const int nkb = kb_hi - kb_lo;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDz);
+        tma_prefetch_desc(&tmX);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // the BN/64 column atoms of this tile: (tap, channel offset) each
+            int at_i[BN / 64], at_j[BN / 64], at_c[BN / 64];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (full32 || nbase + j < g.N) atomicAdd(dst + j, v[j]);
-                } else if (g.out_bf16) {
-                    bf16 *dst = Ch + (int64_t)row * g.ldc + nbase;
-                    if (full32 && ((uintptr_t)dst % 16 == 0)) {
+            for (int q = 0; q < BN / 64; ++q) {
+                const int col = n0 + 64 * q;
+                const int tap = col / a.C;
+                at_c[q] = col - tap * a.C;
+                at_i[q] = tap / a.kw;
+                at_j[q] = tap - at_i[q] * a.kw;
+            }
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+                int kb = kb_lo + i;
+                const int wb = kb % a.wboxes; kb /= a.wboxes;
+                const int ho = kb % a.Ho;
+                const int n = kb / a.Ho;
+                unsigned char *a_dst = smem + s * L::STAGE_BYTES;
+                unsigned char *b_dst = a_dst + L::A_BYTES;
+                mbar_expect_tx(full + s, L::STAGE_BYTES);
+                tma_load_4d(&tmDz, full + s, a_dst, m0, wb * RB, ho, n);
+                tma_load_4d(&tmDz, full + s, a_dst + RB * 128, m0 + 64, wb * RB, ho, n);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            uint4 pk;
-                            __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[j + 2 * e], v[j + 2 * e + 1]);
-                            *reinterpret_cast<uint4 *>(dst + j) = pk;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (nbase + j < g.N) dst[j] = __float2bfloat16_rn(v[j]);
-                    }
-                } else {
-                    float *dst = Cf + (int64_t)row * g.ldc + nbase;
-                    if (full32 && ((uintptr_t)dst % 16 == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (nbase + j < g.N) dst[j] = v[j];
-                    }
+                for (int q = 0; q < BN / 64; ++q) {
+                    if (n0 + 64 * q < g.N)
+                        tma_load_4d(&tmX, full + s, b_dst + q * RB * 128, at_c[q], wb * RB + at_j[q] - a.pw, ho + at_i[q] - a.ph, n);
+                    else   // column atom beyond kh*kw*C: keep the transaction count with an all-out-of-bounds box
+                        tma_load_4d(&tmX, full + s, b_dst + q * RB * 128, 0, -RB - 8, 0, n);
                 }
             }
         }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(full + s, (i / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < RB / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_desc(a_addr + k * 2048, RB * 128, 1024), make_desc(b_addr + k * 2048, RB * 128, 1024),
+                              idesc, (i | k) != 0);
+                umma_commit(empty + s);
+                if (i == nkb - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        epilogue_store<BN>(g, tmem_base, tmem_full, m0, n0, warp, lane, nkb > 0);
         tc_fence_before();
     }
     __syncthreads();
@@ -323,13 +578,56 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const GemmArgs &g, int 
     return check_launch("gemm_tcgen05_kernel");
 }
 
+// 4-D bf16 NHWC tensor map {C, W, H, N}, box {64, box_w, 1, 1}
+int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_t H, int64_t N, int box_w) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return MR_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(4d)"); return MR_ERR_CUDA; }
+    return MR_OK;
+}
+
+template <int BN, int STAGES>
+int launch_conv(const CUtensorMap &tb, const ConvArgs &a, cudaStream_t st) {
+    using L = SmemLayout<BN, STAGES>;
+    auto kern = conv_fprop_tcgen05_kernel<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_fprop smem attr");
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(a.g.M, BM), (unsigned)ceil_div(a.g.N, BN), 1);
+    kern<<<grid, 192, L::TOTAL, st>>>(tb, a);
+    return check_launch("conv_fprop_tcgen05_kernel");
+}
+
+template <int BN, int RB, int STAGES>
+int launch_wgrad(const CUtensorMap &tdz, const CUtensorMap &tx, const WgradArgs &a, int splits, cudaStream_t st) {
+    using L = WgradSmem<BN, RB, STAGES>;
+    auto kern = conv_wgrad_tcgen05_kernel<BN, RB, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_wgrad smem attr");
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(a.g.M, BM), (unsigned)ceil_div(a.g.N, BN), (unsigned)splits);
+    kern<<<grid, 192, L::TOTAL, st>>>(tdz, tx, a);
+    return check_launch("conv_wgrad_tcgen05_kernel");
+}
+
 }  // namespace
 
 extern "C" {
 
 /* bf16 GEMM on tcgen05/TMA.  transA = 0: A stored [M,K] (lda >= K); transA = 1: A stored [K,M] (lda >= M).
  * transB = 1: B stored [N,K] (ldb >= K);  transB = 0: B stored [K,N] (ldb >= N).   [same convention as mr_gemm]
- * Supported operand forms: (transA, transB) = (0, 1) "NT" and (1, 0) "TN".  lda, ldb multiples of 8, bases 16-byte
+ * Supported operand forms: (transA, transB) = (0, 1) "NT", (0, 0) "NN" and (1, 0) "TN".  lda, ldb multiples of 8, bases 16-byte
  * aligned.  out_dtype 0 = fp32, 1 = bf16.  beta must be 0 or 1; beta = 1 (fp32 only) accumulates atomically and allows
  * split-K (splits > 1).  Returns MR_ERR_UNSUPPORTED for anything else so that the caller can route to mr_gemm. */
 int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
@@ -338,8 +636,8 @@ int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N,
     if (M < 0 || N < 0 || K < 0) return MR_ERR_BAD_SHAPE;
     if (M == 0 || N == 0) return MR_OK;
     if (!A || !B || !C) return MR_ERR_NULL_POINTER;
-    const bool nt = (transA == 0 && transB == 1), tn = (transA == 1 && transB == 0);
-    if (!nt && !tn) return MR_ERR_UNSUPPORTED;
+    const bool nt = (transA == 0 && transB == 1), tn = (transA == 1 && transB == 0), nn = (transA == 0 && transB == 0);
+    if (!nt && !tn && !nn) return MR_ERR_UNSUPPORTED;
     if (lda % 8 || ldb % 8 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return MR_ERR_UNSUPPORTED;
     if (beta != 0.f && (beta != 1.f || out_dtype != 0)) return MR_ERR_UNSUPPORTED;
     if (K == 0 || M > (1LL << 31) - 256 || N > (1LL << 31) - 256 || K > (1LL << 31) - 256) return MR_ERR_UNSUPPORTED;
@@ -353,6 +651,10 @@ int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N,
         rc = make_map(&ta, A, K, M, lda, BK, BM);
         if (rc) return rc;
         rc = make_map(&tb, B, K, N, ldb, BK, BN);
+    } else if (nn) {
+        rc = make_map(&ta, A, K, M, lda, BK, BM);
+        if (rc) return rc;
+        rc = make_map(&tb, B, N, K, ldb, 64, BK);
     } else {
         rc = make_map(&ta, A, M, K, lda, 64, BK);
         if (rc) return rc;
@@ -367,11 +669,78 @@ int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N,
     g.kblocks_per_split = (int)ceil_div(kb_total, splits);
     splits = (int)ceil_div(kb_total, g.kblocks_per_split);
 #define MR_LAUNCH(BNV, STV)                                                              \
-    (nt ? launch<BNV, STV, 0, 0>(ta, tb, g, splits, st) : launch<BNV, STV, 1, 1>(ta, tb, g, splits, st))
+    (nt ? launch<BNV, STV, 0, 0>(ta, tb, g, splits, st)                                  \
+        : (nn ? launch<BNV, STV, 0, 1>(ta, tb, g, splits, st) : launch<BNV, STV, 1, 1>(ta, tb, g, splits, st)))
     if (BN == 256) return MR_LAUNCH(256, 4);
     if (BN == 128) return MR_LAUNCH(128, 6);
     return MR_LAUNCH(64, 8);
 #undef MR_LAUNCH
+}
+
+/* Implicit-GEMM stride-1 convolution on NHWC bf16:  y[N*Ho*Wo, Cout] = conv(x[N,H,W,C], Wm[Cout, kh*kw*C]) (+bias, ReLU).
+ * C % 64 == 0, Wm row pitch = kh*kw*C.  With flipped/transposed weights and padding (k-1-p) it is the input gradient. */
+int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, int W, int C, int Cout, int kh, int kw,
+                          int ph, int pw, int out_dtype, const float *bias, int relu, void *stream) {
+    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || ph < 0 || pw < 0) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!x || !Wm || !y) return MR_ERR_NULL_POINTER;
+    if (C % 64 || ((uintptr_t)x % 16) || ((uintptr_t)Wm % 16)) return MR_ERR_UNSUPPORTED;
+    ConvArgs a;
+    a.x = (const bf16 *)x; a.N = N; a.H = H; a.W = W; a.C = C; a.kh = kh; a.kw = kw; a.ph = ph; a.pw = pw;
+    a.Ho = H + 2 * ph - kh + 1; a.Wo = W + 2 * pw - kw + 1;
+    if (a.Ho <= 0 || a.Wo <= 0) return MR_ERR_BAD_SHAPE;
+    const int64_t P = (int64_t)N * a.Ho * a.Wo, K = (int64_t)kh * kw * C;
+    if (P > (1LL << 31) - 256) return MR_ERR_UNSUPPORTED;
+    a.g.M = (int)P; a.g.N = Cout; a.g.K = (int)K; a.g.ldc = Cout; a.g.C = y; a.g.bias = bias; a.g.relu = relu;
+    a.g.out_bf16 = out_dtype == 1; a.g.atomic = 0; a.g.kblocks_per_split = 0;
+    const int BN = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
+    CUtensorMap tb;
+    int rc = make_map(&tb, Wm, K, Cout, K, BK, BN);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (BN == 256) return launch_conv<256, 4>(tb, a, st);
+    if (BN == 128) return launch_conv<128, 6>(tb, a, st);
+    return launch_conv<64, 8>(tb, a, st);
+}
+
+/* Implicit-GEMM weight gradient: dWm[Cout, kh*kw*C] (fp32, ACCUMULATED atomically: zero it first) from
+ * dz[N,Ho,Wo,Cout] and x[N,H,W,C] (NHWC bf16, stride-1 geometry).  C % 64 == 0 and Cout % 8 == 0. */
+int mr_conv_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int H, int W, int C, int Cout, int kh, int kw,
+                          int ph, int pw, int splits, void *stream) {
+    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || ph < 0 || pw < 0) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!dz || !x || !dWm) return MR_ERR_NULL_POINTER;
+    if (C % 64 || Cout % 8 || ((uintptr_t)x % 16) || ((uintptr_t)dz % 16)) return MR_ERR_UNSUPPORTED;
+    WgradArgs a;
+    a.N = N; a.H = H; a.W = W; a.C = C; a.kh = kh; a.kw = kw; a.ph = ph; a.pw = pw; a.Cout = Cout;
+    a.Ho = H + 2 * ph - kh + 1; a.Wo = W + 2 * pw - kw + 1;
+    if (a.Ho <= 0 || a.Wo <= 0) return MR_ERR_BAD_SHAPE;
+    const int K = kh * kw * C;
+    const bool rb80 = (a.Wo > 64 && a.Wo <= 80);
+    const int RB = rb80 ? 80 : 64;
+    a.wboxes = (int)ceil_div(a.Wo, RB);
+    a.kb_total = N * a.Ho * a.wboxes;
+    if (splits < 1) splits = 1;
+    if (splits > a.kb_total) splits = a.kb_total;
+    a.kblocks_per_split = (int)ceil_div(a.kb_total, splits);
+    splits = (int)ceil_div(a.kb_total, a.kblocks_per_split);
+    a.g.M = Cout; a.g.N = K; a.g.K = 0; a.g.ldc = K; a.g.C = dWm; a.g.bias = nullptr; a.g.relu = 0; a.g.out_bf16 = 0;
+    a.g.atomic = 1; a.g.kblocks_per_split = a.kblocks_per_split;
+    CUtensorMap tdz, tx;
+    int rc = make_map_nhwc(&tdz, dz, Cout, a.Wo, a.Ho, N, RB);
+    if (rc) return rc;
+    rc = make_map_nhwc(&tx, x, C, W, H, N, RB);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int BN = K > 128 ? 256 : (K > 64 ? 128 : 64);
+    if (rb80) {
+        if (BN == 256) return launch_wgrad<256, 80, 3>(tdz, tx, a, splits, st);
+        if (BN == 128) return launch_wgrad<128, 80, 4>(tdz, tx, a, splits, st);
+        return launch_wgrad<64, 80, 6>(tdz, tx, a, splits, st);
+    }
+    if (BN == 256) return launch_wgrad<256, 64, 4>(tdz, tx, a, splits, st);
+    if (BN == 128) return launch_wgrad<128, 64, 6>(tdz, tx, a, splits, st);
+    return launch_wgrad<64, 64, 8>(tdz, tx, a, splits, st);
 }
 
 }  // extern "C"

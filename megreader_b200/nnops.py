@@ -186,3 +186,29 @@ def gemm_tc(A, B, transA=False, transB=True, out=None, out_dtype=None, bias=None
                                     int(transB), code(out.dtype), _p(bias), int(relu), float(beta), int(splits), _st()),
          "gemm_tcgen05")
     return out
+
+
+def conv_fprop_tc(x, Wm, kh, kw, ph, pw, out_dtype=torch.bfloat16, bias=None, relu=False):
+    """Implicit-GEMM conv (csrc/gemm_tcgen05.cu): x NHWC bf16 [N,H,W,C], Wm [Cout, kh*kw*C] bf16 -> [N*Ho*Wo, Cout]."""
+    N, H, W, C = x.shape
+    Cout = Wm.size(0)
+    assert x.is_contiguous() and Wm.is_contiguous() and Wm.size(1) == kh * kw * C
+    Ho, Wo = H + 2 * ph - kh + 1, W + 2 * pw - kw + 1
+    y = torch.empty((N * Ho * Wo, Cout), dtype=out_dtype, device=x.device)
+    _chk(_lib.lib().mr_conv_fprop_tcgen05(_p(x), _p(Wm), _p(y), N, H, W, C, Cout, kh, kw, ph, pw, code(out_dtype), _p(bias),
+                                          int(relu), _st()), "conv_fprop_tcgen05")
+    return y, Ho, Wo
+
+
+def conv_wgrad_tc(dz, x, kh, kw, ph, pw, splits=0):
+    """dWm [Cout, kh*kw*C] fp32 from dz [N,Ho,Wo,Cout] and x [N,H,W,C] (NHWC bf16)."""
+    N, H, W, C = x.shape
+    Cout = dz.size(-1)
+    K = kh * kw * C
+    dWm = torch.zeros((Cout, K), dtype=torch.float32, device=x.device)
+    if splits <= 0:
+        tiles = ((Cout + 127) // 128) * ((K + 255) // 256)
+        splits = max(1, -(-288 // tiles))
+    _chk(_lib.lib().mr_conv_wgrad_tcgen05(_p(dz), _p(x), _p(dWm), N, H, W, C, Cout, kh, kw, ph, pw, int(splits), _st()),
+         "conv_wgrad_tcgen05")
+    return dWm
