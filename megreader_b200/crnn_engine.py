@@ -17,6 +17,9 @@ from . import ctc1d
 from . import nnops as ops
 
 _COMPUTE_DTYPE = torch.float32
+# bf16 mode: convolutions with C % 64 == 0 run as tcgen05 implicit GEMMs (csrc/gemm_tcgen05.cu); False routes them
+# through im2col + cuBLAS (kept for A/B comparison in benchmarks)
+USE_TCGEN05 = __import__("os").environ.get("MEGREADER_B200_TCGEN05", "1") != "0"
 
 
 def set_compute_dtype(dtype):
@@ -96,11 +99,17 @@ class _BackboneFn(torch.autograd.Function):
             K = kh * kw * C
             Kp = -(-K // vn) * vn
             Wm = _weight_matrix(conv.weight, C, Kp, dtype)
-            col, Ho, Wo = ops.im2col(a, kh, kw, ph, pw, Kp)
-            z = ops.gemm(col, Wm, transB=True)                      # [P, Cout] raw conv output (no bias yet)
+            implicit = USE_TCGEN05 and dtype == torch.bfloat16 and C % 64 == 0
+            if implicit:
+                # tcgen05 implicit GEMM: activation tiles are gathered straight into swizzled smem, no im2col in HBM
+                z, Ho, Wo = ops.conv_fprop_tc(a, Wm, kh, kw, ph, pw)
+                col = None
+            else:
+                col, Ho, Wo = ops.im2col(a, kh, kw, ph, pw, Kp)
+                z = ops.gemm(col, Wm, transB=True)                  # [P, Cout] raw conv output (no bias yet)
             Cout = Wm.size(0)
-            rec = {"col": col if training else None, "Wm": Wm, "in_shape": tuple(a.shape), "k": (kh, kw), "p": (ph, pw),
-                   "Cin": conv.in_channels, "out_hw": (Ho, Wo)}
+            rec = {"col": col if training else None, "x": a if (training and implicit) else None, "Wm": Wm,
+                   "in_shape": tuple(a.shape), "k": (kh, kw), "p": (ph, pw), "Cin": conv.in_channels, "out_hw": (Ho, Wo)}
             if bn is not None:
                 if training:
                     mom = bn.momentum if bn.momentum is not None else 0.1
@@ -148,13 +157,23 @@ class _BackboneFn(torch.autograd.Function):
                 dz = ops.bias_relu_pool_bwd(dy, rec["y"], rec["idx"], Nn, Ho, Wo, Cout, k, s, p)
                 dgamma = dbeta = None
             dbias = ops.colsum(dz)
-            dWm = ops.gemm(dz, rec["col"], transA=True, out_dtype=torch.float32)          # [Cout, Kp]
+            if rec["x"] is not None:
+                dz4 = dz.view(Nn, Ho, Wo, Cout)
+                dWm = ops.conv_wgrad_tc(dz4, rec["x"], kh, kw, ph, pw)                     # [Cout, K] fp32
+            else:
+                dWm = ops.gemm(dz, rec["col"], transA=True, out_dtype=torch.float32)      # [Cout, Kp]
             dW = _weight_grad(dWm, rec["Cin"], C, kh, kw)
             layer_grads = [dW, dbias] + ([dgamma, dbeta] if bn is not None else [])
             grads = layer_grads + grads
             if li > 0:
-                dcol = ops.gemm(dz, rec["Wm"])                                               # [P, Kp]
-                dy = ops.col2im(dcol, Nn, H, W, C, kh, kw, ph, pw).view(Nn * H * W, C)
+                if rec["x"] is not None and Cout % 64 == 0:
+                    # input gradient = convolution of dz with the flipped, transposed weights, padding k-1-p
+                    Wd = ops.cast(conv.weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(C, kh * kw * Cout)
+                                  .contiguous(), dtype)
+                    dy, _, _ = ops.conv_fprop_tc(dz4, Wd, kh, kw, kh - 1 - ph, kw - 1 - pw)
+                else:
+                    dcol = ops.gemm(dz, rec["Wm"])                                           # [P, Kp]
+                    dy = ops.col2im(dcol, Nn, H, W, C, kh, kw, ph, pw).view(Nn * H * W, C)
             rec.clear()
         return (None, None, None, None) + tuple(grads)
 

@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 
 GEOS = [  # N, H, W, C, Cout, k, pad       (CRNN layer geometries at small batch + edge cases)
     (3, 16, 128, 64, 128, 3, 1), (2, 8, 64, 128, 256, 3, 1), (2, 4, 65, 256, 512, 3, 1), (3, 2, 66, 512, 512, 2, 0),
-    (5, 5, 7, 64, 64, 3, 1), (1, 9, 33, 128, 72, 3, 1),
+    (5, 5, 7, 64, 64, 3, 1), (1, 9, 33, 128, 192, 3, 1),
 ]
 
 
