@@ -152,8 +152,11 @@ int mr_col2im_nhwc(const void *dcol, int N, int H, int W, int C, int kh, int kw,
 /* conv epilogue fused with nn.MaxPool2d(k, s, p): y = maxpool(relu(x + bias)); idx = first arg-max (uint8). */
 int mr_bias_relu_pool_fwd(const void *x, const float *bias, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
                           int ph, int pw, int dtype, void *y, unsigned char *idx, void *stream);
+/* backward also returns the conv-bias gradient dbias[C] = column sums of dz (fused; `sums` = scratch of C doubles);
+ * dbias may be NULL. */
 int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *idx, int N, int H, int W, int C, int kh,
-                          int kw, int sh, int sw, int ph, int pw, int dtype, void *dz, void *stream);
+                          int kw, int sh, int sw, int ph, int pw, int dtype, void *dz, float *dbias, double *sums,
+                          void *stream);
 int mr_bias_act(const void *x, const float *bias, int64_t rows, int C, int relu, int dtype, void *y, void *stream);
 /* nn.BatchNorm2d in training mode over (x + bias): batch stats, running-stat update, normalise; `sums` = scratch of
  * 2*C doubles.  mr_bn_apply is the eval-mode affine transform with given mean / invstd. */
@@ -162,16 +165,21 @@ int mr_bn_train_fwd(const void *x, const float *bias, const float *gamma, const 
                     float *invstd, double *sums, void *stream);
 int mr_bn_apply(const void *x, const float *bias, const float *mean, const float *invstd, const float *gamma,
                 const float *beta, int64_t rows, int C, int dtype, void *y, void *stream);
+/* backward: `sums` = scratch of 3*C doubles; dbias (nullable) = column sums of dx (gradient of the conv bias). */
 int mr_bn_train_bwd(const void *dy, const void *x, const float *bias, const float *mean, const float *invstd,
                     const float *gamma, int64_t rows, int C, int dtype, void *dx, float *dgamma, float *dbeta,
-                    double *sums, void *stream);
+                    float *dbias, double *sums, void *stream);
 /* out[c] (= or +=) sum_r a[r,c] (bias gradients); `sums` = scratch of 2*C doubles. */
 int mr_colsum(const void *a, int64_t rows, int C, int dtype, float *out, int accumulate, double *sums, void *stream);
-/* nn.LSTM cell, gate order i,f,g,o.  fwd: gates [B,4H] pre-activations in, activations out (in place). */
-int mr_lstm_cell_fwd(void *gates, const float *b_ih, const float *b_hh, const float *c_prev, float *c_out, void *h_out,
-                     int64_t ldh, void *h_state, int B, int H, int dtype, void *stream);
-int mr_lstm_cell_bwd(const void *gates, const float *c, const float *c_prev, const void *dh_out, int64_t ldh,
-                     const void *dh_rec, float *dc, void *dgates, int B, int H, int dtype, void *stream);
+/* nn.LSTM cell, gate order i,f,g,o; one launch advances `ndir` (1 or 2) directions of a bidirectional layer; the
+ * per-direction arguments are HOST arrays of `ndir` device pointers.  fwd: gates [B,4H] pre-activations in,
+ * activations out (in place); c_prev[d] may be NULL (first step).  bwd: c_prev[d] / dh_rec[d] may be NULL. */
+int mr_lstm_cell_fwd(void *const *gates, const float *const *b_ih, const float *const *b_hh, const float *const *c_prev,
+                     float *const *c_out, void *const *h_out, int64_t ldh, void *const *h_state, int ndir, int B, int H,
+                     int dtype, void *stream);
+int mr_lstm_cell_bwd(const void *const *gates, const float *const *c, const float *const *c_prev,
+                     const void *const *dh_out, int64_t ldh, const void *const *dh_rec, float *const *dc,
+                     void *const *dgates, int ndir, int B, int H, int dtype, void *stream);
 /* torch.optim.Adam step over one flat fp32 buffer (training/optimizer_scheduler.py:17-22 builds torch.optim.Adam). */
 int mr_adam_step(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
                  int64_t step, float grad_scale, void *bf16_shadow, void *stream);

@@ -37,14 +37,14 @@ _SIGS = {
     "mr_im2col_nhwc": [c_p] + [c_int] * 10 + [c_p, c_p],
     "mr_col2im_nhwc": [c_p] + [c_int] * 10 + [c_p, c_p],
     "mr_bias_relu_pool_fwd": [c_p, c_p] + [c_int] * 11 + [c_p, c_p, c_p],
-    "mr_bias_relu_pool_bwd": [c_p, c_p, c_p] + [c_int] * 11 + [c_p, c_p],
+    "mr_bias_relu_pool_bwd": [c_p, c_p, c_p] + [c_int] * 11 + [c_p, c_p, c_p, c_p],
     "mr_bias_act": [c_p, c_p, c_i64, c_int, c_int, c_int, c_p, c_p],
     "mr_bn_train_fwd": [c_p] * 6 + [c_f32, c_f32, c_i64, c_int, c_int] + [c_p] * 5,
     "mr_bn_apply": [c_p] * 6 + [c_i64, c_int, c_int, c_p, c_p],
-    "mr_bn_train_bwd": [c_p] * 6 + [c_i64, c_int, c_int] + [c_p] * 5,
+    "mr_bn_train_bwd": [c_p] * 6 + [c_i64, c_int, c_int] + [c_p] * 6,
     "mr_colsum": [c_p, c_i64, c_int, c_int, c_p, c_int, c_p, c_p],
-    "mr_lstm_cell_fwd": [c_p] * 6 + [c_i64, c_p, c_int, c_int, c_int, c_p],
-    "mr_lstm_cell_bwd": [c_p] * 4 + [c_i64, c_p, c_p, c_p, c_int, c_int, c_int, c_p],
+    "mr_lstm_cell_fwd": [c_p] * 6 + [c_i64, c_p, c_int, c_int, c_int, c_int, c_p],
+    "mr_lstm_cell_bwd": [c_p] * 4 + [c_i64, c_p, c_p, c_p, c_int, c_int, c_int, c_int, c_p],
     "mr_adam_step": [c_p] * 4 + [c_i64] + [c_f32] * 4 + [c_i64, c_f32, c_p, c_p],
     "mr_cast": [c_p, c_int, c_i64, c_int, c_p, c_p],
     "mr_gemm": [c_p] * 3 + [c_i64] * 6 + [c_int] * 4 + [c_f32, c_f32, c_p],

@@ -151,12 +151,11 @@ class _BackboneFn(torch.autograd.Function):
             kh, kw = rec["k"]
             ph, pw = rec["p"]
             if rec["kind"] == "bn":
-                dz, dgamma, dbeta = ops.bn_train_bwd(dy, rec["z"], conv.bias, rec["mean"], rec["invstd"], bn.weight)
+                dz, dgamma, dbeta, dbias = ops.bn_train_bwd(dy, rec["z"], conv.bias, rec["mean"], rec["invstd"], bn.weight)
             else:
                 k, s, p = rec["pool"]
-                dz = ops.bias_relu_pool_bwd(dy, rec["y"], rec["idx"], Nn, Ho, Wo, Cout, k, s, p)
+                dz, dbias = ops.bias_relu_pool_bwd(dy, rec["y"], rec["idx"], Nn, Ho, Wo, Cout, k, s, p)
                 dgamma = dbeta = None
-            dbias = ops.colsum(dz)
             if rec["x"] is not None:
                 dz4 = dz.view(Nn, Ho, Wo, Cout)
                 dWm = ops.conv_wgrad_tc(dz4, rec["x"], kh, kw, ph, pw)                     # [Cout, K] fp32
@@ -233,10 +232,10 @@ def _bilstm_forward_impl(X, params, dtype, training):
             sC = (T + tr - tf) * N * 4 * H
             ops.gemm_batched_raw(hst.data_ptr(), Whh.data_ptr(), pC, N, 4 * H, H, H, H, 4 * H, N * H, 4 * H * H, sC, 2,
                                  False, True, dtype, dtype, 1.0, 1.0)
-        for d, t in ((0, tf), (1, tr)):
-            tp = t - 1 if d == 0 else t + 1
-            ops.lstm_cell_fwd(G[d, t], b_ih[d], b_hh[d], Cst[d, tp] if s > 0 else None, Cst[d, t],
-                              Y[t, :, d * H:(d + 1) * H], 2 * H, hst[d])
+        ts, tps = (tf, tr), (tf - 1, tr + 1)
+        ops.lstm_cell_fwd([G[d, ts[d]] for d in (0, 1)], b_ih, b_hh,
+                          [Cst[d, tps[d]] if s > 0 else None for d in (0, 1)], [Cst[d, ts[d]] for d in (0, 1)],
+                          [Y[ts[d], :, d * H:(d + 1) * H] for d in (0, 1)], 2 * H, [hst[0], hst[1]])
     Wemb = ops.cast(w_emb.detach(), dtype)
     nOut = Wemb.size(0)
     out_dtype = dtype if nOut % _vn(dtype) == 0 else torch.float32   # the 38-class logits leave in fp32
@@ -263,10 +262,11 @@ def _bilstm_backward_impl(dE, sv, dtype):
     esz = dG.element_size()
     for s in range(T - 1, -1, -1):
         tf, tr = s, T - 1 - s
-        for d, t in ((0, tf), (1, tr)):
-            tp = t - 1 if d == 0 else t + 1
-            ops.lstm_cell_bwd(G[d, t], Cst[d, t], Cst[d, tp] if s > 0 else None, dY3[t, :, d * H:(d + 1) * H], 2 * H,
-                              dhr[d] if s < T - 1 else None, dc[d], dG[d, t])
+        ts, tps = (tf, tr), (tf - 1, tr + 1)
+        ops.lstm_cell_bwd([G[d, ts[d]] for d in (0, 1)], [Cst[d, ts[d]] for d in (0, 1)],
+                          [Cst[d, tps[d]] if s > 0 else None for d in (0, 1)],
+                          [dY3[ts[d], :, d * H:(d + 1) * H] for d in (0, 1)], 2 * H,
+                          [dhr[d] if s < T - 1 else None for d in (0, 1)], [dc[0], dc[1]], [dG[d, ts[d]] for d in (0, 1)])
         if s > 0:
             # dh_rec_d = dG_d[t_d] W_hh_d   (both directions, one strided-batched GEMM)
             pA = dG.data_ptr() + tf * N * 4 * H * esz

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
+#include <string.h>
 
 namespace {
 using namespace mr;
@@ -40,6 +41,39 @@ template <typename T> __device__ __forceinline__ uint4 pack(const float *f) {
 #pragma unroll
     for (int i = 0; i < N; ++i) p[i] = from_f<T>(f[i]);
     return r;
+}
+
+template <int VN> __device__ __forceinline__ void store_bytes(unsigned char *dst, const unsigned char *b);
+template <> __device__ __forceinline__ void store_bytes<8>(unsigned char *dst, const unsigned char *b) {
+    uint2 v; memcpy(&v, b, 8); *reinterpret_cast<uint2 *>(dst) = v;
+}
+template <> __device__ __forceinline__ void store_bytes<4>(unsigned char *dst, const unsigned char *b) {
+    unsigned v; memcpy(&v, b, 4); *reinterpret_cast<unsigned *>(dst) = v;
+}
+template <int VN> __device__ __forceinline__ void load_bytes(const unsigned char *src, unsigned char *b);
+template <> __device__ __forceinline__ void load_bytes<8>(const unsigned char *src, unsigned char *b) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src)); memcpy(b, &v, 8);
+}
+template <> __device__ __forceinline__ void load_bytes<4>(const unsigned char *src, unsigned char *b) {
+    const unsigned v = __ldg(reinterpret_cast<const unsigned *>(src)); memcpy(b, &v, 4);
+}
+
+// per-channel sums of values each thread accumulated for its (fixed) channel vector: block reduce, fp64 atomics
+template <int VN>
+__device__ __forceinline__ void block_channel_sum(const float *acc, int cv, double *sums, float (*red)[VN + 1]) {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) red[threadIdx.x][e] = acc[e];
+    __syncthreads();
+    if ((int)threadIdx.x < cv) {
+        const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int cvec = (int)(gtid % cv);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            float t = 0.f;
+            for (int k = threadIdx.x; k < (int)blockDim.x; k += cv) t += red[k][e];
+            atomicAdd(sums + cvec * VN + e, (double)t);
+        }
+    }
 }
 
 inline int grid1d(int64_t work, int block, int per_sm = 16) {
@@ -168,8 +202,15 @@ __global__ void bias_relu_pool_fwd_kernel(PoolGeo g, const T *__restrict__ x, co
     constexpr int VN = 16 / sizeof(T);
     const int cv = g.C / VN;
     const int64_t total = (int64_t)g.N * g.Ho * g.Wo * cv;
+    float bb[VN];
+    int c_cached = -1;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int c0 = (int)(t % cv) * VN;
+        if (c0 != c_cached) {          // invariant across the grid-stride loop when cv divides the block size
+#pragma unroll
+            for (int e = 0; e < VN; ++e) bb[e] = bias[c0 + e];
+            c_cached = c0;
+        }
         const int64_t p = t / cv;
         const int wo = (int)(p % g.Wo);
         const int64_t r = p / g.Wo;
@@ -191,26 +232,31 @@ __global__ void bias_relu_pool_fwd_kernel(PoolGeo g, const T *__restrict__ x, co
 #pragma unroll
                 for (int e = 0; e < VN; ++e) {
                     // round through T so that the compared values are what an unfused bias+ReLU would have stored
-                    const float a = to_f<T>(from_f<T>(fmaxf(f[e] + bias[c0 + e], 0.f)));
+                    const float a = to_f<T>(from_f<T>(fmaxf(f[e] + bb[e], 0.f)));
                     if (a > best[e]) { best[e] = a; bi[e] = i * g.kw + j; }
                 }
             }
         }
         reinterpret_cast<uint4 *>(y)[t] = pack<T>(best);
-        unsigned char *ip = idx + t * VN;
+        unsigned char ib[VN];
 #pragma unroll
-        for (int e = 0; e < VN; ++e) ip[e] = (unsigned char)bi[e];
+        for (int e = 0; e < VN; ++e) ib[e] = (unsigned char)bi[e];
+        store_bytes<VN>(idx + t * VN, ib);
     }
 }
 
 // dz[n,h,w,c] (gradient w.r.t. the raw GEMM output) = sum over windows that contain (h,w) whose arg-max is (h,w)
 // and whose pooled value is > 0 (ReLU') of dy[window].
 template <typename T>
-__global__ void bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y,
-                                          const unsigned char *__restrict__ idx, T *__restrict__ dz) {
+__global__ void __launch_bounds__(256)
+bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y,
+                          const unsigned char *__restrict__ idx, T *__restrict__ dz, double *__restrict__ bias_sums) {
     constexpr int VN = 16 / sizeof(T);
     const int cv = g.C / VN;
     const int64_t total = (int64_t)g.N * g.H * g.W * cv;
+    float bsum[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bsum[e] = 0.f;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int c0 = (int)(t % cv) * VN;
         const int64_t p = t / cv;
@@ -233,15 +279,27 @@ __global__ void bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, c
                 if (wo >= g.Wo) continue;
                 const int64_t q = (((int64_t)n * g.Ho + ho) * g.Wo + wo) * g.C + c0;
                 float fy[VN], fd[VN];
+                unsigned char ib[VN];
                 unpack<T>(__ldg(reinterpret_cast<const uint4 *>(y + q)), fy);
                 unpack<T>(__ldg(reinterpret_cast<const uint4 *>(dy + q)), fd);
-                const unsigned char *ip = idx + q;
+                load_bytes<VN>(idx + q, ib);
 #pragma unroll
                 for (int e = 0; e < VN; ++e)
-                    if (ip[e] == i * g.kw + j && fy[e] > 0.f) acc[e] += fd[e];
+                    if (ib[e] == i * g.kw + j && fy[e] > 0.f) acc[e] += fd[e];
             }
         }
-        reinterpret_cast<uint4 *>(dz)[t] = pack<T>(acc);
+        const uint4 packed = pack<T>(acc);
+        reinterpret_cast<uint4 *>(dz)[t] = packed;
+        if (bias_sums) {                 // sum what was actually stored (the rounded values), like a separate pass would
+            float fr[VN];
+            unpack<T>(packed, fr);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) bsum[e] += fr[e];
+        }
+    }
+    if (bias_sums) {                     // only launched with blockDim % cv == 0: the channel vector is thread-invariant
+        __shared__ float red[256][VN + 1];
+        block_channel_sum<VN>(bsum, cv, bias_sums, red);
     }
 }
 
@@ -354,7 +412,7 @@ __global__ void bn_finalize_kernel(const double *__restrict__ sums, int64_t rows
     }
 }
 
-// y = (x + bias - mean) * invstd * gamma + beta
+// y = (x + bias - mean) * invstd * gamma + beta  ==  x * sc + sh  per channel
 template <typename T>
 __global__ void bn_apply_kernel(const T *__restrict__ x, const float *__restrict__ bias, const float *__restrict__ mean,
                                 const float *__restrict__ invstd, const float *__restrict__ gamma,
@@ -362,41 +420,73 @@ __global__ void bn_apply_kernel(const T *__restrict__ x, const float *__restrict
     constexpr int VN = 16 / sizeof(T);
     const int cv = C / VN;
     const int64_t total = rows * cv;
+    float sc[VN], sh[VN];
+    int c_cached = -1;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int c0 = (int)(t % cv) * VN;
+        if (c0 != c_cached) {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const int c = c0 + e;
+                sc[e] = invstd[c] * gamma[c];
+                sh[e] = ((bias ? bias[c] : 0.f) - mean[c]) * sc[e] + beta[c];
+            }
+            c_cached = c0;
+        }
         float f[VN];
         unpack<T>(__ldg(reinterpret_cast<const uint4 *>(x) + t), f);
 #pragma unroll
-        for (int e = 0; e < VN; ++e) {
-            const int c = c0 + e;
-            f[e] = (f[e] + (bias ? bias[c] : 0.f) - mean[c]) * (invstd[c] * gamma[c]) + beta[c];
-        }
+        for (int e = 0; e < VN; ++e) f[e] = f[e] * sc[e] + sh[e];
         reinterpret_cast<uint4 *>(y)[t] = pack<T>(f);
     }
 }
 
 // dx = gamma * invstd * (dy - sum_dy/rows - xhat * sum_dy_xhat/rows)
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ bias,
-                                    const float *__restrict__ mean, const float *__restrict__ invstd,
-                                    const float *__restrict__ gamma, const double *__restrict__ sums, int64_t rows,
-                                    int C, T *__restrict__ dx) {
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ bias,
+                    const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+                    const double *__restrict__ sums, int64_t rows, int C, T *__restrict__ dx,
+                    double *__restrict__ bias_sums) {
     constexpr int VN = 16 / sizeof(T);
     const int cv = C / VN;
     const int64_t total = rows * cv;
     const float inv_rows = 1.f / (float)rows;
+    float A[VN], k1[VN], k2[VN], shf[VN], is[VN], bsum[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bsum[e] = 0.f;
+    int c_cached = -1;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int c0 = (int)(t % cv) * VN;
+        if (c0 != c_cached) {
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const int c = c0 + e;
+                is[e] = invstd[c];
+                A[e] = gamma[c] * is[e];
+                k1[e] = (float)sums[c] * inv_rows;
+                k2[e] = (float)sums[C + c] * inv_rows;
+                shf[e] = (bias ? bias[c] : 0.f) - mean[c];
+            }
+            c_cached = c0;
+        }
         float fd[VN], fx[VN];
         unpack<T>(__ldg(reinterpret_cast<const uint4 *>(dy) + t), fd);
         unpack<T>(__ldg(reinterpret_cast<const uint4 *>(x) + t), fx);
 #pragma unroll
-        for (int e = 0; e < VN; ++e) {
-            const int c = c0 + e;
-            const float xhat = (fx[e] + (bias ? bias[c] : 0.f) - mean[c]) * invstd[c];
-            fd[e] = gamma[c] * invstd[c] * (fd[e] - (float)sums[c] * inv_rows - xhat * (float)sums[C + c] * inv_rows);
+        for (int e = 0; e < VN; ++e) fd[e] = A[e] * (fd[e] - k1[e] - (fx[e] + shf[e]) * is[e] * k2[e]);
+        const uint4 packed = pack<T>(fd);
+        reinterpret_cast<uint4 *>(dx)[t] = packed;
+        if (bias_sums) {
+            float fr[VN];
+            unpack<T>(packed, fr);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) bsum[e] += fr[e];
         }
-        reinterpret_cast<uint4 *>(dx)[t] = pack<T>(fd);
+    }
+    if (bias_sums) {
+        __shared__ float red[256][VN + 1];
+        block_channel_sum<VN>(bsum, cv, bias_sums, red);
     }
 }
 
@@ -406,53 +496,68 @@ __global__ void sums_to_float_kernel(const double *__restrict__ s, int n, float 
 }
 
 // ---------------------------------------------------------------- LSTM cell (gate order i, f, g, o like ATen)
+// One launch handles up to two directions (blockIdx.y): the forward and the reverse direction of a bidirectional
+// layer advance in lock-step, so their cell updates share a launch.
 // gates_pre [B, 4H] (T): x-projection + h_{t-1} W_hh^T already summed by the GEMMs; bias_ih + bias_hh added here.
 // Writes the activated gates back in place (saved for backward), c_t [B,H] fp32, h_t [B,H] (T) into `h_out` (row
 // stride ldh, so it lands directly in the [T, B, 2H] output of the bidirectional layer).
+struct CellFwdDir { void *gates; const float *b_ih, *b_hh, *c_prev; float *c_out; void *h_out, *h_state; };
+struct CellFwdArgs { CellFwdDir d[2]; int64_t ldh; int B, H; };
+
 template <typename T>
-__global__ void lstm_cell_fwd_kernel(T *__restrict__ gates, const float *__restrict__ b_ih, const float *__restrict__ b_hh,
-                                     const float *__restrict__ c_prev, float *__restrict__ c_out, T *__restrict__ h_out,
-                                     int64_t ldh, T *__restrict__ h_state, int B, int H) {
-    const int64_t total = (int64_t)B * H;
+__global__ void lstm_cell_fwd_kernel(CellFwdArgs a) {
+    const CellFwdDir &q = a.d[blockIdx.y];
+    T *gates = (T *)q.gates;
+    T *h_out = (T *)q.h_out;
+    T *h_state = (T *)q.h_state;
+    const int H = a.H;
+    const int64_t total = (int64_t)a.B * H;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int b = (int)(t / H), j = (int)(t - (int64_t)b * H);
         T *gp = gates + (int64_t)b * 4 * H;
-        const float gi = to_f<T>(gp[j]) + b_ih[j] + b_hh[j];
-        const float gf = to_f<T>(gp[H + j]) + b_ih[H + j] + b_hh[H + j];
-        const float gg = to_f<T>(gp[2 * H + j]) + b_ih[2 * H + j] + b_hh[2 * H + j];
-        const float go = to_f<T>(gp[3 * H + j]) + b_ih[3 * H + j] + b_hh[3 * H + j];
+        const float gi = to_f<T>(gp[j]) + q.b_ih[j] + q.b_hh[j];
+        const float gf = to_f<T>(gp[H + j]) + q.b_ih[H + j] + q.b_hh[H + j];
+        const float gg = to_f<T>(gp[2 * H + j]) + q.b_ih[2 * H + j] + q.b_hh[2 * H + j];
+        const float go = to_f<T>(gp[3 * H + j]) + q.b_ih[3 * H + j] + q.b_hh[3 * H + j];
         const float i_ = 1.f / (1.f + expf(-gi)), f_ = 1.f / (1.f + expf(-gf)), g_ = tanhf(gg), o_ = 1.f / (1.f + expf(-go));
-        const float c = f_ * (c_prev ? c_prev[t] : 0.f) + i_ * g_;
+        const float c = f_ * (q.c_prev ? q.c_prev[t] : 0.f) + i_ * g_;
         const float h = o_ * tanhf(c);
         gp[j] = from_f<T>(i_); gp[H + j] = from_f<T>(f_); gp[2 * H + j] = from_f<T>(g_); gp[3 * H + j] = from_f<T>(o_);
-        c_out[t] = c;
+        q.c_out[t] = c;
         const T hv = from_f<T>(h);
-        h_out[(int64_t)b * ldh + j] = hv;
+        h_out[(int64_t)b * a.ldh + j] = hv;
         h_state[t] = hv;
     }
 }
 
 // dh_total = dh_out[t] (from the layer output gradient, row stride ldh) + dh_rec (from step t+1, may be NULL).
 // Produces the pre-activation gate gradients dgates [B,4H] (T) and dc_prev (fp32, in place over dc).
+struct CellBwdDir { const void *gates; const float *c, *c_prev; const void *dh_out, *dh_rec; float *dc; void *dgates; };
+struct CellBwdArgs { CellBwdDir d[2]; int64_t ldh; int B, H; };
+
 template <typename T>
-__global__ void lstm_cell_bwd_kernel(const T *__restrict__ gates, const float *__restrict__ c, const float *__restrict__ c_prev,
-                                     const T *__restrict__ dh_out, int64_t ldh, const T *__restrict__ dh_rec,
-                                     float *__restrict__ dc, T *__restrict__ dgates, int B, int H) {
-    const int64_t total = (int64_t)B * H;
+__global__ void lstm_cell_bwd_kernel(CellBwdArgs a) {
+    const CellBwdDir &q = a.d[blockIdx.y];
+    const T *gates = (const T *)q.gates;
+    const T *dh_out = (const T *)q.dh_out;
+    const T *dh_rec = (const T *)q.dh_rec;
+    T *dgates = (T *)q.dgates;
+    const int H = a.H;
+    const int64_t total = (int64_t)a.B * H;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int b = (int)(t / H), j = (int)(t - (int64_t)b * H);
         const T *gp = gates + (int64_t)b * 4 * H;
         const float i_ = to_f<T>(gp[j]), f_ = to_f<T>(gp[H + j]), g_ = to_f<T>(gp[2 * H + j]), o_ = to_f<T>(gp[3 * H + j]);
-        const float dh = to_f<T>(dh_out[(int64_t)b * ldh + j]) + (dh_rec ? to_f<T>(dh_rec[t]) : 0.f);
-        const float tc = tanhf(c[t]);
-        const float dct = dc[t] + dh * o_ * (1.f - tc * tc);
-        const float cp = c_prev ? c_prev[t] : 0.f;
+        const float dh = to_f<T>(dh_out[(int64_t)b * a.ldh + j]) + (dh_rec ? to_f<T>(dh_rec[t]) : 0.f);
+        const float tc = tanhf(q.c[t]);
+        const float dct = q.dc[t] + dh * o_ * (1.f - tc * tc);
+        const float cp = q.c_prev ? q.c_prev[t] : 0.f;
         T *dg = dgates + (int64_t)b * 4 * H;
         dg[j] = from_f<T>(dct * g_ * i_ * (1.f - i_));
         dg[H + j] = from_f<T>(dct * cp * f_ * (1.f - f_));
         dg[2 * H + j] = from_f<T>(dct * i_ * (1.f - g_ * g_));
         dg[3 * H + j] = from_f<T>(dh * tc * o_ * (1.f - o_));
-        dc[t] = dct * f_;
+        q.dc[t] = dct * f_;
     }
 }
 
@@ -499,6 +604,8 @@ int vec_ok(int dtype, int C) { return C % (dtype == 0 ? 4 : 8) == 0; }
 }  // namespace
 
 extern "C" {
+
+int mr_colsum(const void *a, int64_t rows, int C, int dtype, float *out, int accumulate, double *sums, void *stream);
 
 int mr_nchw_to_nhwc(const float *x, int N, int C, int H, int W, int Cp, int dtype, void *y, void *stream) {
     if (N < 0 || C <= 0 || H <= 0 || W <= 0 || Cp < C) return MR_ERR_BAD_SHAPE;
@@ -585,7 +692,8 @@ int mr_bias_relu_pool_fwd(const void *x, const float *bias, int N, int H, int W,
 }
 
 int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *idx, int N, int H, int W, int C, int kh,
-                          int kw, int sh, int sw, int ph, int pw, int dtype, void *dz, void *stream) {
+                          int kw, int sh, int sw, int ph, int pw, int dtype, void *dz, float *dbias, double *sums,
+                          void *stream) {
     PoolGeo g;
     int rc = pool_geo(g, N, H, W, C, kh, kw, sh, sw, ph, pw);
     if (rc) return rc;
@@ -594,8 +702,14 @@ int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *id
     if (!vec_ok(dtype, C)) return MR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int vn = dtype == 0 ? 4 : 8;
-    DISPATCH(dtype, (bias_relu_pool_bwd_kernel<T><<<grid1d((int64_t)N * H * W * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz)));
-    return check_launch("bias_relu_pool_bwd_kernel");
+    const bool fuse = dbias && sums && (256 % (C / vn) == 0);
+    if (fuse) MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * C, st), "memset sums");
+    DISPATCH(dtype, (bias_relu_pool_bwd_kernel<T><<<grid1d((int64_t)N * H * W * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, fuse ? sums : nullptr)));
+    rc = check_launch("bias_relu_pool_bwd_kernel");
+    if (rc || !dbias) return rc;
+    if (!fuse) return mr_colsum(dz, (int64_t)N * H * W, C, dtype, dbias, 0, sums, stream);
+    sums_to_float_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums, C, 1.f, dbias, 0);
+    return check_launch("sums_to_float_kernel");
 }
 
 int mr_bias_act(const void *x, const float *bias, int64_t rows, int C, int relu, int dtype, void *y, void *stream) {
@@ -665,7 +779,7 @@ int mr_bn_apply(const void *x, const float *bias, const float *mean, const float
 /* BatchNorm backward: dx (gradient w.r.t. x + bias), dgamma, dbeta (fp32, assigned). */
 int mr_bn_train_bwd(const void *dy, const void *x, const float *bias, const float *mean, const float *invstd,
                     const float *gamma, int64_t rows, int C, int dtype, void *dx, float *dgamma, float *dbeta,
-                    double *sums, void *stream) {
+                    float *dbias, double *sums, void *stream) {
     if (rows <= 0 || C <= 0) return MR_ERR_BAD_SHAPE;
     if (!dy || !x || !mean || !invstd || !gamma || !dx || !dgamma || !dbeta || !sums) return MR_ERR_NULL_POINTER;
     cudaStream_t st = (cudaStream_t)stream;
@@ -676,8 +790,15 @@ int mr_bn_train_bwd(const void *dy, const void *x, const float *bias, const floa
     rc = check_launch("sums_to_float_kernel");
     if (rc) return rc;
     const int vn = dtype == 0 ? 4 : 8;
-    DISPATCH(dtype, (bn_bwd_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)dy, (const T *)x, bias, mean, invstd, gamma, sums, rows, C, (T *)dx)));
-    return check_launch("bn_bwd_apply_kernel");
+    /* `sums` holds 2*C doubles of statistics + C more for the fused conv-bias gradient (sum of dx). */
+    const bool fuse = dbias && (256 % (C / vn) == 0);
+    if (fuse) MR_CUDA_TRY(cudaMemsetAsync(sums + 2 * C, 0, sizeof(double) * C, st), "memset sums");
+    DISPATCH(dtype, (bn_bwd_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)dy, (const T *)x, bias, mean, invstd, gamma, sums, rows, C, (T *)dx, fuse ? sums + 2 * C : nullptr)));
+    rc = check_launch("bn_bwd_apply_kernel");
+    if (rc || !dbias) return rc;
+    if (!fuse) return mr_colsum(dx, rows, C, dtype, dbias, 0, sums, stream);
+    sums_to_float_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums + 2 * C, C, 1.f, dbias, 0);
+    return check_launch("sums_to_float_kernel");
 }
 
 /* out[c] (= or +=) sum_r a[r, c]  — bias gradients. */
@@ -699,21 +820,40 @@ int mr_colsum(const void *a, int64_t rows, int C, int dtype, float *out, int acc
     return check_launch("sums_to_float_kernel");
 }
 
-int mr_lstm_cell_fwd(void *gates, const float *b_ih, const float *b_hh, const float *c_prev, float *c_out, void *h_out,
-                     int64_t ldh, void *h_state, int B, int H, int dtype, void *stream) {
-    if (B <= 0 || H <= 0) return MR_ERR_BAD_SHAPE;
-    if (!gates || !b_ih || !b_hh || !c_out || !h_out || !h_state) return MR_ERR_NULL_POINTER;
+/* ndir = 1 or 2 directions per launch; the per-direction pointers are arrays of length ndir. */
+int mr_lstm_cell_fwd(void *const *gates, const float *const *b_ih, const float *const *b_hh, const float *const *c_prev,
+                     float *const *c_out, void *const *h_out, int64_t ldh, void *const *h_state, int ndir, int B, int H,
+                     int dtype, void *stream) {
+    if (B <= 0 || H <= 0 || ndir < 1 || ndir > 2) return MR_ERR_BAD_SHAPE;
+    if (!gates || !b_ih || !b_hh || !c_prev || !c_out || !h_out || !h_state) return MR_ERR_NULL_POINTER;
+    CellFwdArgs a;
+    a.ldh = ldh; a.B = B; a.H = H;
+    for (int d = 0; d < ndir; ++d) {
+        if (!gates[d] || !b_ih[d] || !b_hh[d] || !c_out[d] || !h_out[d] || !h_state[d]) return MR_ERR_NULL_POINTER;
+        a.d[d].gates = gates[d]; a.d[d].b_ih = b_ih[d]; a.d[d].b_hh = b_hh[d]; a.d[d].c_prev = c_prev[d];
+        a.d[d].c_out = c_out[d]; a.d[d].h_out = h_out[d]; a.d[d].h_state = h_state[d];
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH(dtype, (lstm_cell_fwd_kernel<T><<<grid1d((int64_t)B * H, 256), 256, 0, st>>>((T *)gates, b_ih, b_hh, c_prev, c_out, (T *)h_out, ldh, (T *)h_state, B, H)));
+    dim3 grid(grid1d((int64_t)B * H, 256), ndir);
+    DISPATCH(dtype, (lstm_cell_fwd_kernel<T><<<grid, 256, 0, st>>>(a)));
     return check_launch("lstm_cell_fwd_kernel");
 }
 
-int mr_lstm_cell_bwd(const void *gates, const float *c, const float *c_prev, const void *dh_out, int64_t ldh,
-                     const void *dh_rec, float *dc, void *dgates, int B, int H, int dtype, void *stream) {
-    if (B <= 0 || H <= 0) return MR_ERR_BAD_SHAPE;
-    if (!gates || !c || !dh_out || !dc || !dgates) return MR_ERR_NULL_POINTER;
+int mr_lstm_cell_bwd(const void *const *gates, const float *const *c, const float *const *c_prev,
+                     const void *const *dh_out, int64_t ldh, const void *const *dh_rec, float *const *dc,
+                     void *const *dgates, int ndir, int B, int H, int dtype, void *stream) {
+    if (B <= 0 || H <= 0 || ndir < 1 || ndir > 2) return MR_ERR_BAD_SHAPE;
+    if (!gates || !c || !c_prev || !dh_out || !dh_rec || !dc || !dgates) return MR_ERR_NULL_POINTER;
+    CellBwdArgs a;
+    a.ldh = ldh; a.B = B; a.H = H;
+    for (int d = 0; d < ndir; ++d) {
+        if (!gates[d] || !c[d] || !dh_out[d] || !dc[d] || !dgates[d]) return MR_ERR_NULL_POINTER;
+        a.d[d].gates = gates[d]; a.d[d].c = c[d]; a.d[d].c_prev = c_prev[d]; a.d[d].dh_out = dh_out[d];
+        a.d[d].dh_rec = dh_rec[d]; a.d[d].dc = dc[d]; a.d[d].dgates = dgates[d];
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    DISPATCH(dtype, (lstm_cell_bwd_kernel<T><<<grid1d((int64_t)B * H, 256), 256, 0, st>>>((const T *)gates, c, c_prev, (const T *)dh_out, ldh, (const T *)dh_rec, dc, (T *)dgates, B, H)));
+    dim3 grid(grid1d((int64_t)B * H, 256), ndir);
+    DISPATCH(dtype, (lstm_cell_bwd_kernel<T><<<grid, 256, 0, st>>>(a)));
     return check_launch("lstm_cell_bwd_kernel");
 }
 

@@ -69,11 +69,14 @@ def bias_relu_pool_fwd(z, bias, N, H, W, C, k, s, p):
     return y, idx
 
 
-def bias_relu_pool_bwd(dy, y, idx, N, H, W, C, k, s, p):
+def bias_relu_pool_bwd(dy, y, idx, N, H, W, C, k, s, p, want_dbias=True):
+    """-> (dz [N*H*W, C], dbias [C] fp32 = column sums of dz, fused)."""
     dz = torch.empty((N * H * W, C), dtype=dy.dtype, device=dy.device)
+    dbias = torch.empty((C,), dtype=torch.float32, device=dy.device) if want_dbias else None
     _chk(_lib.lib().mr_bias_relu_pool_bwd(_p(dy), _p(y), _p(idx), N, H, W, C, k[0], k[1], s[0], s[1], p[0], p[1],
-                                          code(dy.dtype), _p(dz), _st()), "bias_relu_pool_bwd")
-    return dz
+                                          code(dy.dtype), _p(dz), _p(dbias), _p(_sums(C, dy.device)), _st()),
+         "bias_relu_pool_bwd")
+    return dz, dbias
 
 
 def bias_act(x, bias, relu=False, out=None):
@@ -111,9 +114,11 @@ def bn_train_bwd(dy, z, bias, mean, invstd, gamma):
     dx = torch.empty_like(z)
     dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
     dbeta = torch.empty_like(dgamma)
+    dbias = torch.empty_like(dgamma)
+    sums = torch.empty((3 * C,), dtype=torch.float64, device=z.device)
     _chk(_lib.lib().mr_bn_train_bwd(_p(dy), _p(z), _p(bias), _p(mean), _p(invstd), _p(gamma), rows, C, code(z.dtype),
-                                    _p(dx), _p(dgamma), _p(dbeta), _p(_sums(C, z.device)), _st()), "bn_train_bwd")
-    return dx, dgamma, dbeta
+                                    _p(dx), _p(dgamma), _p(dbeta), _p(dbias), _p(sums), _st()), "bn_train_bwd")
+    return dx, dgamma, dbeta, dbias
 
 
 def colsum(a, out=None, accumulate=False):
@@ -154,16 +159,24 @@ def gemm_batched_raw(pA, pB, pC, M, N, K, lda, ldb, ldc, sA, sB, sC, batch, tran
                                     code(in_dtype), code(out_dtype), float(alpha), float(beta), _st()), "gemm_batched")
 
 
+def _ptr_array(tensors):
+    import ctypes
+    return (ctypes.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else None) for t in tensors])
+
+
 def lstm_cell_fwd(gates, b_ih, b_hh, c_prev, c_out, h_out, ldh, h_state):
-    B, H4 = gates.shape
-    _chk(_lib.lib().mr_lstm_cell_fwd(_p(gates), _p(b_ih), _p(b_hh), _p(c_prev), _p(c_out), _p(h_out), ldh, _p(h_state), B,
-                                     H4 // 4, code(gates.dtype), _st()), "lstm_cell_fwd")
+    """Each argument: list (one entry per direction, 1 or 2) of tensors; c_prev entries may be None."""
+    B, H4 = gates[0].shape
+    _chk(_lib.lib().mr_lstm_cell_fwd(_ptr_array(gates), _ptr_array(b_ih), _ptr_array(b_hh), _ptr_array(c_prev),
+                                     _ptr_array(c_out), _ptr_array(h_out), ldh, _ptr_array(h_state), len(gates), B,
+                                     H4 // 4, code(gates[0].dtype), _st()), "lstm_cell_fwd")
 
 
 def lstm_cell_bwd(gates, c, c_prev, dh_out, ldh, dh_rec, dc, dgates):
-    B, H4 = gates.shape
-    _chk(_lib.lib().mr_lstm_cell_bwd(_p(gates), _p(c), _p(c_prev), _p(dh_out), ldh, _p(dh_rec), _p(dc), _p(dgates), B,
-                                     H4 // 4, code(gates.dtype), _st()), "lstm_cell_bwd")
+    B, H4 = gates[0].shape
+    _chk(_lib.lib().mr_lstm_cell_bwd(_ptr_array(gates), _ptr_array(c), _ptr_array(c_prev), _ptr_array(dh_out), ldh,
+                                     _ptr_array(dh_rec), _ptr_array(dc), _ptr_array(dgates), len(gates), B, H4 // 4,
+                                     code(gates[0].dtype), _st()), "lstm_cell_bwd")
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0, shadow=None):

@@ -63,8 +63,9 @@ def test_bias_relu_pool(cuda, ops, dtype, pool):
     torch.testing.assert_close(y.float().permute(0, 3, 1, 2), ref, rtol=0, atol=0)
     dy = torch.randn_like(ref).to(dtype)
     ref.backward(dy.float())
-    dz = ops.bias_relu_pool_bwd(dy.permute(0, 2, 3, 1).contiguous(), y, idx, N, H, W, C, k, s, p)
+    dz, dbias = ops.bias_relu_pool_bwd(dy.permute(0, 2, 3, 1).contiguous(), y, idx, N, H, W, C, k, s, p)
     torch.testing.assert_close(dz.float().view(N, H, W, C).permute(0, 3, 1, 2), zr.grad, **_tol(dtype))
+    torch.testing.assert_close(dbias, dz.float().sum(0), rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -86,7 +87,8 @@ def test_batchnorm_train(cuda, ops, dtype):
     torch.testing.assert_close(rv, rv_ref, rtol=1e-4, atol=1e-5)
     dy = torch.randn(rows, C, device=cuda).to(dtype)
     g = torch.autograd.grad(ref, zr, dy.float())[0]
-    dx, dgamma, dbeta = ops.bn_train_bwd(dy, z, bias, mean, invstd, gamma)
+    dx, dgamma, dbeta, dbias = ops.bn_train_bwd(dy, z, bias, mean, invstd, gamma)
+    torch.testing.assert_close(dbias, dx.float().sum(0), rtol=1e-3, atol=2e-2)
     torch.testing.assert_close(dx.float(), g, rtol=1e-3, atol=1e-4 if dtype == torch.float32 else 3e-2)
     xhat = (z.float() + bias - mean) * invstd
     torch.testing.assert_close(dbeta, dy.float().sum(0), rtol=1e-4, atol=1e-3)
