@@ -246,9 +246,11 @@ def run_ours(args):
         "gpu_launches": launches, "final_loss": final_loss, "clocks": clocks,
     }
     if rank == 0:
-        out["ctc2d"], out["roofline"] = bench_ctc2d(dev)
+        out["ctc2d"], ctc_roof = bench_ctc2d(dev)
+        out["roofline"] = bench_conv_roofline(dev)
+        out["roofline_ctc2d"] = ctc_roof
         out["cpu_baseline"] = cpu_arm(steps=3, warmup=1, sample_n=16)
-        out["stages"] = {"conv": "megreader_b200 im2col/col2im kernels + cuBLAS bf16 GEMM (plain library GEMM)",
+        out["stages"] = {"conv": "megreader_b200 tcgen05 implicit-GEMM kernels (fprop, dgrad, wgrad); conv0 (Cin=3): im2col kernel + cuBLAS",
                          "bias+ReLU+MaxPool, BatchNorm": "megreader_b200 CUDA (fused NHWC kernels)",
                          "BiLSTM+Linear": "megreader_b200 cell kernels + cuBLAS GEMMs",
                          "log_softmax+CTC": "megreader_b200 CUDA", "Adam": "library (torch fused, capturable)",
@@ -300,8 +302,34 @@ def bench_ctc2d(dev, N=16384, iters=10):
             "bound": "hbm", "achieved": N * fwd_bytes / tf / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": N * fwd_bytes / tf / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
             "alg_bytes_per_launch": N * fwd_bytes,
-            "note": "dominant HAND-WRITTEN kernel; the conv/LSTM stages of the CRNN step are library kernels in this revision"}
+            "note": "2D-CTC training forward (BASELINE.json metric, second half)"}
     return ctc, roof
+
+
+def bench_conv_roofline(dev, iters=10):
+    """Dominant kernel of the step: conv_fprop_tcgen05_kernel (implicit-GEMM conv, also used for dgrad) at its largest
+    shape (conv5: 512 x 4 x 65 x 512 -> 512 ch, 3x3), timed alone with CUDA events; inputs 136 MB + output 136 MB
+    exceed L2.  Algorithmic FLOPs = 2 * P * Cout * kh*kw*C per launch; peak = measured cuBLAS bf16 burst."""
+    from megreader_b200 import nnops
+    N, H, W, C, Cout, k, p = BATCH_PER_GPU, 4, 65, 512, 512, 3, 1
+    x = torch.randn(N, H, W, C, device=dev).bfloat16()
+    wm = (torch.randn(Cout, k * k * C, device=dev) / 68).bfloat16()
+    for _ in range(3):
+        nnops.conv_fprop_tc(x, wm, k, k, p, p)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        nnops.conv_fprop_tc(x, wm, k, k, p, p)
+    b.record()
+    torch.cuda.synchronize()
+    sec = a.elapsed_time(b) / iters * 1e-3
+    flops = 2.0 * N * H * W * Cout * k * k * C
+    pk = peaks()
+    return {"kernel": "conv_fprop_tcgen05_kernel<256,4> (implicit-GEMM 3x3 conv, conv5 shape, bf16 in / fp32 acc)",
+            "bound": "tensor", "achieved": flops / sec / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": flops / sec / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+            "alg_flops_per_launch": flops, "us_per_launch": sec * 1e6}
 
 
 # ---------------------------------------------------------------------------------------------- CPU / reference arm

@@ -310,10 +310,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int STAGES>
+// MT = number of 128-row sub-tiles per CTA (1 or 2).  MT = 2 shares every weight tile between two activation
+// sub-tiles (two TMEM accumulators): operand bytes per FLOP drop by a third, which matters because the first
+// version of this kernel was bound by L2 -> SM operand traffic (10 TB/s, profiles/conv_fprop_r1a_summary.md).
+template <int BN, int STAGES, int MT>
+struct ConvSmem {
+    static constexpr int A_BYTES = MT * BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, 1)
 conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
-    using L = SmemLayout<BN, STAGES>;
+    using L = ConvSmem<BN, STAGES, MT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
@@ -322,10 +334,10 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
     uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
     const GemmArgs &g = a.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.x * (BM * MT), n0 = blockIdx.y * BN;
     const int cchunks = a.C / BK;
     const int nkb = a.kh * a.kw * cchunks;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = (MT * BN) < 32 ? 32 : (MT * BN);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmB);
@@ -358,52 +370,66 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
                 const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                    umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
-                              (i | k) != 0);
+                for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(tmem_base + sub * BN, make_desc(a_addr + sub * (BM * BK * 2) + k * 32, 16, 1024),
+                                  make_desc(b_addr + k * 32, 16, 1024), idesc, (i | k) != 0);
+                }
                 umma_commit(empty + s);
                 if (i == nkb - 1) umma_commit(tmem_full);
             }
             __syncwarp();
         }
     } else {
-        // ------------------------------------------------------------ activation gather (one thread = one tile row)
+        // ------------------------------------------------------------ activation gather (one thread = MT tile rows)
         const int r = threadIdx.x - 64;
-        const int64_t p = (int64_t)m0 + r;
-        const bool valid = p < g.M;
-        int n = 0, ho = 0, wo = 0;
-        if (valid) {
-            wo = (int)(p % a.Wo);
-            const int64_t t = p / a.Wo;
-            ho = (int)(t % a.Ho);
-            n = (int)(t / a.Ho);
+        bool valid[MT];
+        int n[MT], ho[MT], wo[MT];
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {
+            const int64_t p = (int64_t)m0 + sub * BM + r;
+            valid[sub] = p < g.M;
+            n[sub] = ho[sub] = wo[sub] = 0;
+            if (valid[sub]) {
+                wo[sub] = (int)(p % a.Wo);
+                const int64_t t = p / a.Wo;
+                ho[sub] = (int)(t % a.Ho);
+                n[sub] = (int)(t / a.Ho);
+            }
         }
         const uint32_t row_off = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
         constexpr int D = 3;                                  // cp.async groups in flight per thread
-        int tap = 0, cc = 0, ti = 0, tj = 0;
+        static_assert(D - 1 < STAGES, "producer lookahead must be smaller than the ring");
+        int cc = 0, ti = 0, tj = 0;
         for (int i = 0; i < nkb; ++i) {
             const int s = i % STAGES;
             mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
-            const int h = ho + ti - a.ph, w = wo + tj - a.pw;
-            const bool ok = valid && h >= 0 && h < a.H && w >= 0 && w < a.W;
-            const bf16 *src = ok ? a.x + ((((int64_t)n * a.H + h) * a.W + w) * a.C + cc * BK) : a.x;
-            const uint32_t dst = smem_u32(smem + s * L::STAGE_BYTES) + row_off;
-            const uint32_t nbytes = ok ? 16u : 0u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cp_async16_zfill(dst + (((uint32_t)j ^ sw) << 4), src + j * 8, nbytes);
+            for (int sub = 0; sub < MT; ++sub) {
+                const int h = ho[sub] + ti - a.ph, w = wo[sub] + tj - a.pw;
+                const bool ok = valid[sub] && h >= 0 && h < a.H && w >= 0 && w < a.W;
+                const bf16 *src = ok ? a.x + ((((int64_t)n[sub] * a.H + h) * a.W + w) * a.C + cc * BK) : a.x;
+                const uint32_t dst = smem_u32(smem + s * L::STAGE_BYTES + sub * (BM * BK * 2)) + row_off;
+                const uint32_t nbytes = ok ? 16u : 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cp_async16_zfill(dst + (((uint32_t)j ^ sw) << 4), src + j * 8, nbytes);
+            }
             cp_async_commit();
             if (i >= D - 1) {
                 cp_async_wait<D - 1>();
                 fence_proxy_async();                          // generic-proxy smem writes -> visible to tcgen05
                 mbar_arrive(full + (i - (D - 1)) % STAGES);
             }
-            if (++cc == cchunks) { cc = 0; ++tap; if (++tj == a.kw) { tj = 0; ++ti; } }
+            if (++cc == cchunks) { cc = 0; if (++tj == a.kw) { tj = 0; ++ti; } }
         }
         cp_async_wait<0>();
         fence_proxy_async();
         for (int i = (nkb >= D - 1 ? nkb - (D - 1) : 0); i < nkb; ++i) mbar_arrive(full + i % STAGES);
-        epilogue_store<BN>(g, tmem_base, tmem_full, m0, n0, warp, lane, nkb > 0);
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub)
+            epilogue_store<BN>(g, tmem_base + sub * BN, tmem_full, m0 + sub * BM, n0, warp, lane, nkb > 0);
         tc_fence_before();
     }
     __syncthreads();
@@ -593,16 +619,16 @@ int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_
     return MR_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 int launch_conv(const CUtensorMap &tb, const ConvArgs &a, cudaStream_t st) {
-    using L = SmemLayout<BN, STAGES>;
-    auto kern = conv_fprop_tcgen05_kernel<BN, STAGES>;
+    using L = ConvSmem<BN, STAGES, MT>;
+    auto kern = conv_fprop_tcgen05_kernel<BN, STAGES, MT>;
     static bool attr_set = false;
     if (!attr_set) {
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_fprop smem attr");
         attr_set = true;
     }
-    dim3 grid((unsigned)ceil_div(a.g.M, BM), (unsigned)ceil_div(a.g.N, BN), 1);
+    dim3 grid((unsigned)ceil_div(a.g.M, BM * MT), (unsigned)ceil_div(a.g.N, BN), 1);
     kern<<<grid, 192, L::TOTAL, st>>>(tb, a);
     return check_launch("conv_fprop_tcgen05_kernel");
 }
@@ -698,9 +724,10 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
     int rc = make_map(&tb, Wm, K, Cout, K, BK, BN);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (BN == 256) return launch_conv<256, 4>(tb, a, st);
-    if (BN == 128) return launch_conv<128, 6>(tb, a, st);
-    return launch_conv<64, 8>(tb, a, st);
+    const bool big = P >= 4 * 148 * 128;      /* enough 256-row tiles to fill the chip a few times */
+    if (BN == 256) return big ? launch_conv<256, 3, 2>(tb, a, st) : launch_conv<256, 4, 1>(tb, a, st);
+    if (BN == 128) return big ? launch_conv<128, 4, 2>(tb, a, st) : launch_conv<128, 6, 1>(tb, a, st);
+    return big ? launch_conv<64, 5, 2>(tb, a, st) : launch_conv<64, 8, 1>(tb, a, st);
 }
 
 /* Implicit-GEMM weight gradient: dWm[Cout, kh*kw*C] (fp32, ACCUMULATED atomically: zero it first) from

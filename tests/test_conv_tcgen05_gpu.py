@@ -49,3 +49,17 @@ def test_fprop_bias_relu_bf16_out(cuda):
     y, Ho, Wo = nnops.conv_fprop_tc(x, _wm(w), 3, 3, 1, 1, bias=b, relu=True)
     ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1))
     torch.testing.assert_close(y.float().view(2, Ho, Wo, 128).permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("geo", [(40, 16, 128, 64, 128, 3, 1), (160, 8, 64, 128, 256, 3, 1), (300, 4, 65, 64, 64, 3, 1)],
+                         ids=["bn128", "bn256", "bn64"])
+def test_fprop_two_subtile_path(cuda, geo):
+    """P >= 4*148*128 selects the 256-row CTA (two 128-row accumulators sharing each weight tile)."""
+    from megreader_b200 import nnops
+    N, H, W, C, Cout, k, p = geo
+    torch.manual_seed(3)
+    x = torch.randn(N, H, W, C, device=cuda).bfloat16()
+    w = (torch.randn(Cout, C, k, k, device=cuda) / (C * k * k) ** 0.5).bfloat16()
+    y, Ho, Wo = nnops.conv_fprop_tc(x, _wm(w), k, k, p, p, out_dtype=torch.float32)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=p)
+    torch.testing.assert_close(y.view(N, Ho, Wo, Cout).permute(0, 3, 1, 2), ref, rtol=1e-3, atol=2e-3)
