@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 using namespace mr;
@@ -724,7 +725,10 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
     int rc = make_map(&tb, Wm, K, Cout, K, BK, BN);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool big = P >= 4 * 148 * 128;      /* enough 256-row tiles to fill the chip a few times */
+    /* 256-row CTAs (MT = 2) measured SLOWER than 128-row CTAs on B200 (conv5: 1186 us vs 841 us): kept selectable for
+     * experiments (MR_CONV_MT2=1), off by default. */
+    static const bool mt2 = getenv("MR_CONV_MT2") && getenv("MR_CONV_MT2")[0] == '1';
+    const bool big = mt2 && P >= 4 * 148 * 128;
     if (BN == 256) return big ? launch_conv<256, 3, 2>(tb, a, st) : launch_conv<256, 4, 1>(tb, a, st);
     if (BN == 128) return big ? launch_conv<128, 4, 2>(tb, a, st) : launch_conv<128, 6, 1>(tb, a, st);
     return big ? launch_conv<64, 5, 2>(tb, a, st) : launch_conv<64, 8, 1>(tb, a, st);

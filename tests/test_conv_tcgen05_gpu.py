@@ -53,8 +53,8 @@ def test_fprop_bias_relu_bf16_out(cuda):
 
 @pytest.mark.parametrize("geo", [(40, 16, 128, 64, 128, 3, 1), (160, 8, 64, 128, 256, 3, 1), (300, 4, 65, 64, 64, 3, 1)],
                          ids=["bn128", "bn256", "bn64"])
-def test_fprop_two_subtile_path(cuda, geo):
-    """P >= 4*148*128 selects the 256-row CTA (two 128-row accumulators sharing each weight tile)."""
+def test_fprop_large_p(cuda, geo):
+    """large pixel counts (the 256-row CTA variant is selected for these when MR_CONV_MT2=1)."""
     from megreader_b200 import nnops
     N, H, W, C, Cout, k, p = geo
     torch.manual_seed(3)
