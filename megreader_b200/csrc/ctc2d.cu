@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -550,6 +551,178 @@ __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-per-sample DP kernel (fp32).  Same phases as ctc2d_dp_kernel, but the two sweeps of a sample run inside ONE
+// warp: lane L keeps states [L*NS, L*NS+NS) of the extended target in registers, neighbours come from warp shuffles,
+// and there is no block barrier inside the 2*T sweep steps (the block-wide version spent its time in 64
+// barrier-separated steps of ~85 instructions per warp; profiles/ctc2d_r1a_summary.md).
+// ------------------------------------------------------------------------------------------------
+template <bool FAST, int MODE, int NS, int HT>
+__global__ void __launch_bounds__(128)
+ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict__ tg,
+                     const int64_t *__restrict__ il, const int64_t *__restrict__ tl,
+                     const float *__restrict__ grad_out, int64_t go_stride, float *__restrict__ nll_out,
+                     float *__restrict__ fac_out, float *__restrict__ grad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const float NINF = -INFINITY;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int b0 = blockIdx.x * q.G;
+    const int Gv = min(q.G, q.N - b0);
+    const int rowElems = q.G * q.C;
+    constexpr int SSp = 32 * NS;
+    float *Qall = reinterpret_cast<float *>(smem_raw);          // [T][G*C]
+    float *acc = Qall + q.T * rowElems;                          // [T][G*C]
+    float *Ra = acc + q.T * rowElems;                            // [G][T][NS][32]
+    float *nlls = Ra + (size_t)q.G * q.T * SSp;                  // [G]
+    unsigned char *pres = reinterpret_cast<unsigned char *>(nlls + q.G);   // [T][G*C]
+
+    for (int i = tid; i < q.T * rowElems; i += nth) { acc[i] = 0.f; pres[i] = 0; }
+    if (q.vec > 1) phase_q<float, FAST, 4, HT>(q, lp, Qall, b0, Gv);
+    else phase_q<float, FAST, 1, HT>(q, lp, Qall, b0, Gv);
+    __syncthreads();
+
+    const int g = warp;
+    if (g < Gv) {
+        const int b = b0 + g;
+        const int64_t Tb = il[b], L = tl[b];
+        const int64_t *row = tg + (int64_t)b * q.tg_sn;
+        int cur[NS];
+        bool in[NS], skf[NS], skb[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const int s = lane * NS + k;
+            cur[k] = q.blank; in[k] = skf[k] = skb[k] = false;
+            if (s < q.SS && s < 2 * L + 1) {
+                in[k] = L > 0;
+                if (s & 1) {
+                    const int64_t me = row[(int64_t)(s >> 1) * q.tg_ss];
+                    cur[k] = clampi(me, q.C);
+                    if (s > 1) skf[k] = row[(int64_t)((s - 2) >> 1) * q.tg_ss] != me;
+                    if (s < 2 * L - 1) skb[k] = row[(int64_t)((s + 2) >> 1) * q.tg_ss] != me;
+                }
+            }
+        }
+        const float *Qg = Qall + g * q.C;
+        float *Rag = Ra + (size_t)g * q.T * SSp + lane;
+        // ---------------- forward sweep
+        float R[NS], a[NS];
+        float f0 = NINF, f1 = NINF;
+#pragma unroll 1
+        for (int t = 0; t < q.T; ++t) {
+            if (t == 0) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const int s = lane * NS + k;
+                    R[k] = (s == 0 || (s == 1 && L > 0)) ? 0.f : NINF;
+                }
+            } else {
+                float up1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
+                float up2 = NS >= 2 ? __shfl_up_sync(0xffffffffu, a[NS >= 2 ? NS - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, a[0], 2);
+                if (lane == 0) up1 = up2 = NINF;
+                if (NS == 1 && lane == 1) up2 = NINF;
+                float Rn[NS];
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const float am1 = k >= 1 ? a[k >= 1 ? k - 1 : 0] : up1;
+                    const float am2 = k >= 2 ? a[k >= 2 ? k - 2 : 0] : (k == 1 ? up1 : up2);
+                    Rn[k] = (t < Tb && in[k]) ? lse3<FAST>(a[k], am1, skf[k] ? am2 : NINF) : NINF;
+                }
+#pragma unroll
+                for (int k = 0; k < NS; ++k) R[k] = Rn[k];
+            }
+            const float *Qt = Qg + t * rowElems;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                Rag[(t * NS + k) * 32] = R[k];
+                a[k] = R[k] + Qt[cur[k]];
+                if (t == Tb - 1) {
+                    const int s = lane * NS + k;
+                    if (s == 2 * L) f0 = a[k];
+                    else if (s == 2 * L - 1) f1 = a[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            f0 = fmaxf(f0, __shfl_xor_sync(0xffffffffu, f0, o));
+            f1 = fmaxf(f1, __shfl_xor_sync(0xffffffffu, f1, o));
+        }
+        const float my_nll = -lse2<FAST>(f0, f1);
+        if (lane == 0) {
+            nlls[g] = my_nll;
+            if (MODE != MODE_GRAD) nll_out[b] = my_nll;
+        }
+        // ---------------- backward sweep + per-class collection
+        float bq[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) bq[k] = NINF;
+#pragma unroll 1
+        for (int t = q.T - 1; t >= 0; --t) {
+            float Rb[NS];
+            if (t == Tb - 1) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const int s = lane * NS + k;
+                    Rb[k] = (s == 2 * L || (L > 0 && s == 2 * L - 1)) ? 0.f : NINF;
+                }
+            } else if (t < Tb - 1) {
+                float dn1 = __shfl_down_sync(0xffffffffu, bq[0], 1);
+                float dn2 = NS >= 2 ? __shfl_down_sync(0xffffffffu, bq[NS >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, bq[0], 2);
+                if (lane == 31) dn1 = dn2 = NINF;
+                if (NS == 1 && lane == 30) dn2 = NINF;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const int s = lane * NS + k;
+                    const float bp1 = k + 1 < NS ? bq[k + 1 < NS ? k + 1 : 0] : dn1;
+                    const float bp2 = k + 2 < NS ? bq[k + 2 < NS ? k + 2 : 0] : (k + 1 < NS ? dn1 : dn2);
+                    Rb[k] = in[k] ? lse3<FAST>(bq[k], s < 2 * L ? bp1 : NINF, skb[k] ? bp2 : NINF) : NINF;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) Rb[k] = NINF;
+            }
+            const float *Qt = Qg + t * rowElems;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                bq[k] = Rb[k] + Qt[cur[k]];
+                if (in[k] && t < Tb) {
+                    const float v = Rag[(t * NS + k) * 32] + Rb[k];
+                    if (v != NINF) {
+                        const int o = t * rowElems + g * q.C + cur[k];
+                        pres[o] = 1;
+                        atomicAdd(acc + o, ex<FAST>(v + my_nll));
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int e = tid; e < Gv * q.C; e += nth) {
+        const int gg = e / q.C;
+        const int cc = e - gg * q.C;
+        const int64_t Tb = il[b0 + gg];
+        const float gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + gg) * go_stride] : 1.f;
+        float *fo = (MODE != MODE_GRAD) ? fac_out + (int64_t)(b0 + gg) * q.C + cc : nullptr;
+        const bool dead = (MODE == MODE_FAC_STD) && q.zero_inf && (nlls[gg] == INFINITY);
+        for (int t = 0; t < q.T; ++t) {
+            const int o = t * rowElems + e;
+            float f = 0.f;
+            if (MODE == MODE_FAC_STD) {
+                if (t < Tb && !dead) f = 1.f - acc[o];
+            } else if (pres[o] && t < Tb) f = (1.f - acc[o]) * gs;
+            if (MODE != MODE_GRAD) fo[(int64_t)t * q.N * q.C] = f;
+            else acc[o] = f;
+        }
+    }
+    if (MODE == MODE_GRAD) {
+        __syncthreads();
+        if (q.vec > 1) phase_grad<float, FAST, 4, HT>(q, lp, acc, grad, b0, Gv);
+        else phase_grad<float, FAST, 1, HT>(q, lp, acc, grad, b0, Gv);
+    }
+}
+
 // Training backward: grad[t,h,b,c] = exp(lp) * gfac[t,b,c] * go[b].  Pure streaming.  blockIdx.y = t, thread = one
 // 16-byte vector column of the [N*C] row; the factor is formed once and reused for the H rows.
 template <bool FAST, int VE, int HT>
@@ -680,6 +853,41 @@ int launch_alpha(const real *lp, const int64_t *tg, const int64_t *il, const int
     return check_launch("ctc2d_alpha_kernel");
 }
 
+template <bool FAST, int MODE, int NS>
+int launch_dp_warp_ns(Geo q, const float *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const float *go,
+                      int64_t go_stride, float *nll, float *fac, float *grad, size_t smem, cudaStream_t st) {
+    auto kern = (q.H == 8) ? ctc2d_dp_warp_kernel<FAST, MODE, NS, 8> : ctc2d_dp_warp_kernel<FAST, MODE, NS, 0>;
+    if (smem > 48 * 1024)
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ctc2d_dp_warp attr");
+    kern<<<(unsigned)ceil_div(q.N, q.G), q.G * 32, smem, st>>>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad);
+    return check_launch("ctc2d_dp_warp_kernel");
+}
+
+// returns MR_ERR_UNSUPPORTED when the warp kernel's shared-memory plan does not fit (caller falls back)
+template <bool FAST, int MODE>
+int launch_dp_warp(Geo q, const float *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const float *go,
+                   int64_t go_stride, float *nll, float *fac, float *grad, cudaStream_t st) {
+    const int need_ns = (q.SS + 31) / 32;
+    const int opts[] = {1, 2, 3, 4, 6, 8, 16, 32};
+    int NS = 0;
+    for (int o : opts) if (o >= need_ns) { NS = o; break; }
+    if (!NS) return MR_ERR_UNSUPPORTED;
+    int G = 4;
+    auto need = [&](int g) {
+        return sizeof(float) * ((size_t)2 * q.T * g * q.C + (size_t)g * q.T * 32 * NS + g) + (size_t)q.T * g * q.C + 16;
+    };
+    while (G > 1 && need(G) > (size_t)100 * 1024) --G;
+    const size_t smem = need(G);
+    if (smem > (size_t)smem_limit()) return MR_ERR_UNSUPPORTED;
+    q.G = G;
+    q.vec = pick_vec<float>(lp, q.N, q.C, G);
+    if (MODE == MODE_GRAD && ((uintptr_t)grad % 16) != 0) q.vec = 1;
+#define MR_NS(NSV) case NSV: return launch_dp_warp_ns<FAST, MODE, NSV>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad, smem, st)
+    switch (NS) { MR_NS(1); MR_NS(2); MR_NS(3); MR_NS(4); MR_NS(6); MR_NS(8); MR_NS(16); MR_NS(32); }
+#undef MR_NS
+    return MR_ERR_UNSUPPORTED;
+}
+
 template <typename real, bool FAST, int MODE>
 int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const real *go,
               int64_t go_stride, int64_t T, int64_t H, int64_t N, int64_t C, int64_t S, int64_t tg_sn,
@@ -688,6 +896,12 @@ int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_
     q.zero_inf = zero_inf;
     q.T = (int)T; q.H = (int)H; q.N = (int)N; q.C = (int)C; q.S = (int)S; q.SS = (int)(2 * S + 1);
     q.blank = (int)blank; q.tg_sn = tg_sn; q.tg_ss = tg_ss;
+    if (sizeof(real) == 4 && !getenv("MR_CTC2D_BLOCK_DP")) {
+        q.G = 4; q.vec = 1;
+        const int rc = launch_dp_warp<FAST, MODE>(q, (const float *)lp, tg, il, tl, (const float *)go, go_stride, (float *)nll,
+                                                  (float *)fac, (float *)grad, st);
+        if (rc != MR_ERR_UNSUPPORTED) return rc;
+    }
     int G = 160 / q.SS;  // fewer samples per CTA than the alpha kernel: the sweeps are latency-bound,
     if (G < 1) G = 1;    // more co-resident CTAs keep HBM busy meanwhile
     if (G > 8) G = 8;
