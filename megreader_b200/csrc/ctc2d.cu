@@ -368,9 +368,16 @@ __device__ __forceinline__ void phase_q(const Geo &q, const real *__restrict__ l
     if (nvec <= nth) {  // thread-fixed vector column, stride over t: no per-item division
         const int tpr = nth / nvec;
         const int t0 = tid / nvec, j = tid - t0 * nvec;
-        if (t0 < tpr)
-            for (int t = t0; t < q.T; t += tpr)
+        if (t0 < tpr) {
+            int t = t0;
+            for (; t + tpr < q.T; t += 2 * tpr) {     // two independent columns in flight per thread
                 lse_rows<real, FAST, VE, HT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
+                lse_rows<real, FAST, VE, HT>(cta + (int64_t)(t + tpr) * H * hs + j * VE, hs, H,
+                                             Qall + (t + tpr) * rowElems + j * VE);
+            }
+            for (; t < q.T; t += tpr)
+                lse_rows<real, FAST, VE, HT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
+        }
     } else {
         for (int i = tid; i < q.T * nvec; i += nth) {
             const int t = i / nvec, j = i - t * nvec;
@@ -558,11 +565,13 @@ __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_
 // barrier-separated steps of ~85 instructions per warp; profiles/ctc2d_r1a_summary.md).
 // ------------------------------------------------------------------------------------------------
 template <bool FAST, int MODE, int NS, int HT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict__ tg,
                      const int64_t *__restrict__ il, const int64_t *__restrict__ tl,
                      const float *__restrict__ grad_out, int64_t go_stride, float *__restrict__ nll_out,
                      float *__restrict__ fac_out, float *__restrict__ grad) {
+    // 2*G warps: warp g (< G) runs the forward sweep of sample g, warp G+g its backward sweep, concurrently; the
+    // per-class collection is a fully parallel pass afterwards.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const float NINF = -INFINITY;
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -570,20 +579,23 @@ ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restr
     const int b0 = blockIdx.x * q.G;
     const int Gv = min(q.G, q.N - b0);
     const int rowElems = q.G * q.C;
-    constexpr int SSp = 32 * NS;
+    const int SS = q.SS;
     float *Qall = reinterpret_cast<float *>(smem_raw);          // [T][G*C]
     float *acc = Qall + q.T * rowElems;                          // [T][G*C]
-    float *Ra = acc + q.T * rowElems;                            // [G][T][NS][32]
-    float *nlls = Ra + (size_t)q.G * q.T * SSp;                  // [G]
-    unsigned char *pres = reinterpret_cast<unsigned char *>(nlls + q.G);   // [T][G*C]
+    float *Ra = acc + q.T * rowElems;                            // [G][T][SS]
+    float *Rbs = Ra + (size_t)q.G * q.T * SS;                    // [G][T][SS]
+    float *nlls = Rbs + (size_t)q.G * q.T * SS;                  // [G]
+    int *curs = reinterpret_cast<int *>(nlls + q.G);             // [G][SS]
+    unsigned char *pres = reinterpret_cast<unsigned char *>(curs + q.G * SS);   // [T][G*C]
 
     for (int i = tid; i < q.T * rowElems; i += nth) { acc[i] = 0.f; pres[i] = 0; }
     if (q.vec > 1) phase_q<float, FAST, 4, HT>(q, lp, Qall, b0, Gv);
     else phase_q<float, FAST, 1, HT>(q, lp, Qall, b0, Gv);
     __syncthreads();
 
-    const int g = warp;
-    if (g < Gv) {
+    const bool is_bwd = warp >= q.G;
+    const int g = is_bwd ? warp - q.G : warp;
+    if (g < Gv && warp < 2 * q.G) {
         const int b = b0 + g;
         const int64_t Tb = il[b], L = tl[b];
         const int64_t *row = tg + (int64_t)b * q.tg_sn;
@@ -593,7 +605,7 @@ ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restr
         for (int k = 0; k < NS; ++k) {
             const int s = lane * NS + k;
             cur[k] = q.blank; in[k] = skf[k] = skb[k] = false;
-            if (s < q.SS && s < 2 * L + 1) {
+            if (s < SS && s < 2 * L + 1) {
                 in[k] = L > 0;
                 if (s & 1) {
                     const int64_t me = row[(int64_t)(s >> 1) * q.tg_ss];
@@ -602,98 +614,116 @@ ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restr
                     if (s < 2 * L - 1) skb[k] = row[(int64_t)((s + 2) >> 1) * q.tg_ss] != me;
                 }
             }
+            if (!is_bwd && s < SS) curs[g * SS + s] = cur[k];
         }
         const float *Qg = Qall + g * q.C;
-        float *Rag = Ra + (size_t)g * q.T * SSp + lane;
-        // ---------------- forward sweep
-        float R[NS], a[NS];
-        float f0 = NINF, f1 = NINF;
+        if (!is_bwd) {
+            // ---------------- forward sweep (K1 recurrence on the height-marginal)
+            float *Rag = Ra + (size_t)g * q.T * SS;
+            float R[NS], a[NS];
+            float f0 = NINF, f1 = NINF;
 #pragma unroll 1
-        for (int t = 0; t < q.T; ++t) {
-            if (t == 0) {
+            for (int t = 0; t < q.T; ++t) {
+                if (t == 0) {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        const int s = lane * NS + k;
+                        R[k] = (s == 0 || (s == 1 && L > 0)) ? 0.f : NINF;
+                    }
+                } else {
+                    float up1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
+                    float up2 = NS >= 2 ? __shfl_up_sync(0xffffffffu, a[NS >= 2 ? NS - 2 : 0], 1)
+                                        : __shfl_up_sync(0xffffffffu, a[0], 2);
+                    if (lane == 0) up1 = up2 = NINF;
+                    if (NS == 1 && lane == 1) up2 = NINF;
+                    float Rn[NS];
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        const float am1 = k >= 1 ? a[k >= 1 ? k - 1 : 0] : up1;
+                        const float am2 = k >= 2 ? a[k >= 2 ? k - 2 : 0] : (k == 1 ? up1 : up2);
+                        Rn[k] = (t < Tb && in[k]) ? lse3<FAST>(a[k], am1, skf[k] ? am2 : NINF) : NINF;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) R[k] = Rn[k];
+                }
+                const float *Qt = Qg + t * rowElems;
 #pragma unroll
                 for (int k = 0; k < NS; ++k) {
                     const int s = lane * NS + k;
-                    R[k] = (s == 0 || (s == 1 && L > 0)) ? 0.f : NINF;
-                }
-            } else {
-                float up1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
-                float up2 = NS >= 2 ? __shfl_up_sync(0xffffffffu, a[NS >= 2 ? NS - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, a[0], 2);
-                if (lane == 0) up1 = up2 = NINF;
-                if (NS == 1 && lane == 1) up2 = NINF;
-                float Rn[NS];
-#pragma unroll
-                for (int k = 0; k < NS; ++k) {
-                    const float am1 = k >= 1 ? a[k >= 1 ? k - 1 : 0] : up1;
-                    const float am2 = k >= 2 ? a[k >= 2 ? k - 2 : 0] : (k == 1 ? up1 : up2);
-                    Rn[k] = (t < Tb && in[k]) ? lse3<FAST>(a[k], am1, skf[k] ? am2 : NINF) : NINF;
-                }
-#pragma unroll
-                for (int k = 0; k < NS; ++k) R[k] = Rn[k];
-            }
-            const float *Qt = Qg + t * rowElems;
-#pragma unroll
-            for (int k = 0; k < NS; ++k) {
-                Rag[(t * NS + k) * 32] = R[k];
-                a[k] = R[k] + Qt[cur[k]];
-                if (t == Tb - 1) {
-                    const int s = lane * NS + k;
-                    if (s == 2 * L) f0 = a[k];
-                    else if (s == 2 * L - 1) f1 = a[k];
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            f0 = fmaxf(f0, __shfl_xor_sync(0xffffffffu, f0, o));
-            f1 = fmaxf(f1, __shfl_xor_sync(0xffffffffu, f1, o));
-        }
-        const float my_nll = -lse2<FAST>(f0, f1);
-        if (lane == 0) {
-            nlls[g] = my_nll;
-            if (MODE != MODE_GRAD) nll_out[b] = my_nll;
-        }
-        // ---------------- backward sweep + per-class collection
-        float bq[NS];
-#pragma unroll
-        for (int k = 0; k < NS; ++k) bq[k] = NINF;
-#pragma unroll 1
-        for (int t = q.T - 1; t >= 0; --t) {
-            float Rb[NS];
-            if (t == Tb - 1) {
-#pragma unroll
-                for (int k = 0; k < NS; ++k) {
-                    const int s = lane * NS + k;
-                    Rb[k] = (s == 2 * L || (L > 0 && s == 2 * L - 1)) ? 0.f : NINF;
-                }
-            } else if (t < Tb - 1) {
-                float dn1 = __shfl_down_sync(0xffffffffu, bq[0], 1);
-                float dn2 = NS >= 2 ? __shfl_down_sync(0xffffffffu, bq[NS >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, bq[0], 2);
-                if (lane == 31) dn1 = dn2 = NINF;
-                if (NS == 1 && lane == 30) dn2 = NINF;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) {
-                    const int s = lane * NS + k;
-                    const float bp1 = k + 1 < NS ? bq[k + 1 < NS ? k + 1 : 0] : dn1;
-                    const float bp2 = k + 2 < NS ? bq[k + 2 < NS ? k + 2 : 0] : (k + 1 < NS ? dn1 : dn2);
-                    Rb[k] = in[k] ? lse3<FAST>(bq[k], s < 2 * L ? bp1 : NINF, skb[k] ? bp2 : NINF) : NINF;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < NS; ++k) Rb[k] = NINF;
-            }
-            const float *Qt = Qg + t * rowElems;
-#pragma unroll
-            for (int k = 0; k < NS; ++k) {
-                bq[k] = Rb[k] + Qt[cur[k]];
-                if (in[k] && t < Tb) {
-                    const float v = Rag[(t * NS + k) * 32] + Rb[k];
-                    if (v != NINF) {
-                        const int o = t * rowElems + g * q.C + cur[k];
-                        pres[o] = 1;
-                        atomicAdd(acc + o, ex<FAST>(v + my_nll));
+                    if (s < SS) Rag[t * SS + s] = R[k];
+                    a[k] = R[k] + Qt[cur[k]];
+                    if (t == Tb - 1) {
+                        if (s == 2 * L) f0 = a[k];
+                        else if (s == 2 * L - 1) f1 = a[k];
                     }
                 }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                f0 = fmaxf(f0, __shfl_xor_sync(0xffffffffu, f0, o));
+                f1 = fmaxf(f1, __shfl_xor_sync(0xffffffffu, f1, o));
+            }
+            const float my_nll = -lse2<FAST>(f0, f1);
+            if (lane == 0) {
+                nlls[g] = my_nll;
+                if (MODE != MODE_GRAD) nll_out[b] = my_nll;
+            }
+        } else {
+            // ---------------- backward sweep (K2 recurrence)
+            float *Rbg = Rbs + (size_t)g * q.T * SS;
+            float bq[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) bq[k] = NINF;
+#pragma unroll 1
+            for (int t = q.T - 1; t >= 0; --t) {
+                float Rb[NS];
+                if (t == Tb - 1) {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        const int s = lane * NS + k;
+                        Rb[k] = (s == 2 * L || (L > 0 && s == 2 * L - 1)) ? 0.f : NINF;
+                    }
+                } else if (t < Tb - 1) {
+                    float dn1 = __shfl_down_sync(0xffffffffu, bq[0], 1);
+                    float dn2 = NS >= 2 ? __shfl_down_sync(0xffffffffu, bq[NS >= 2 ? 1 : 0], 1)
+                                        : __shfl_down_sync(0xffffffffu, bq[0], 2);
+                    if (lane == 31) dn1 = dn2 = NINF;
+                    if (NS == 1 && lane == 30) dn2 = NINF;
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) {
+                        const int s = lane * NS + k;
+                        const float bp1 = k + 1 < NS ? bq[k + 1 < NS ? k + 1 : 0] : dn1;
+                        const float bp2 = k + 2 < NS ? bq[k + 2 < NS ? k + 2 : 0] : (k + 1 < NS ? dn1 : dn2);
+                        Rb[k] = in[k] ? lse3<FAST>(bq[k], s < 2 * L ? bp1 : NINF, skb[k] ? bp2 : NINF) : NINF;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) Rb[k] = NINF;
+                }
+                const float *Qt = Qg + t * rowElems;
+#pragma unroll
+                for (int k = 0; k < NS; ++k) {
+                    const int s = lane * NS + k;
+                    if (s < SS) Rbg[t * SS + s] = Rb[k];
+                    bq[k] = Rb[k] + Qt[cur[k]];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- K3's per-class collection, fully parallel: acc[t][g][l'_s] += exp(R + Rb + nll)
+    {
+        const int per_g = q.T * SS;
+        for (int i = tid; i < Gv * per_g; i += nth) {
+            const int gg = i / per_g;
+            const int r = i - gg * per_g;
+            const float v = Ra[i] + Rbs[i];           // Ra / Rbs share the [G][T][SS] layout
+            if (v != NINF) {
+                const int t = r / SS;
+                const int o = t * rowElems + gg * q.C + curs[gg * SS + (r - t * SS)];
+                pres[o] = 1;
+                atomicAdd(acc + o, ex<FAST>(v + nlls[gg]));
             }
         }
     }
@@ -859,7 +889,7 @@ int launch_dp_warp_ns(Geo q, const float *lp, const int64_t *tg, const int64_t *
     auto kern = (q.H == 8) ? ctc2d_dp_warp_kernel<FAST, MODE, NS, 8> : ctc2d_dp_warp_kernel<FAST, MODE, NS, 0>;
     if (smem > 48 * 1024)
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ctc2d_dp_warp attr");
-    kern<<<(unsigned)ceil_div(q.N, q.G), q.G * 32, smem, st>>>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad);
+    kern<<<(unsigned)ceil_div(q.N, q.G), 256, smem, st>>>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad);
     return check_launch("ctc2d_dp_warp_kernel");
 }
 
@@ -874,9 +904,10 @@ int launch_dp_warp(Geo q, const float *lp, const int64_t *tg, const int64_t *il,
     if (!NS) return MR_ERR_UNSUPPORTED;
     int G = 4;
     auto need = [&](int g) {
-        return sizeof(float) * ((size_t)2 * q.T * g * q.C + (size_t)g * q.T * 32 * NS + g) + (size_t)q.T * g * q.C + 16;
+        return sizeof(float) * ((size_t)2 * q.T * g * q.C + (size_t)2 * g * q.T * q.SS + g + (size_t)g * q.SS) +
+               (size_t)q.T * g * q.C + 16;
     };
-    while (G > 1 && need(G) > (size_t)100 * 1024) --G;
+    while (G > 1 && need(G) > (size_t)112 * 1024) --G;
     const size_t smem = need(G);
     if (smem > (size_t)smem_limit()) return MR_ERR_UNSUPPORTED;
     q.G = G;
