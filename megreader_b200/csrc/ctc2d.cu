@@ -33,8 +33,13 @@ template <typename real> struct Lim;
 template <> struct Lim<float> { static __device__ __forceinline__ float ninf() { return -INFINITY; } };
 template <> struct Lim<double> { static __device__ __forceinline__ double ninf() { return -(double)INFINITY; } };
 
-template <bool FAST> __device__ __forceinline__ float ex(float x) { return FAST ? __expf(x) : expf(x); }
-template <bool FAST> __device__ __forceinline__ float lg(float x) { return FAST ? __logf(x) : logf(x); }
+// fast path: one FMUL + one MUFU each (ex2/lg2.approx.ftz).  __expf/__logf without -use_fast_math expand to
+// denormal-safe sequences (FSETP + 2 extra FMUL) that were 24 % of all issued instructions in the DP kernel
+// (profiles/ctc2d_dpwarp_r1_summary.md); flushing results below 1.2e-38 to zero is harmless in a log-sum-exp.
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <bool FAST> __device__ __forceinline__ float ex(float x) { return FAST ? ex2_ftz(x * 1.4426950408889634f) : expf(x); }
+template <bool FAST> __device__ __forceinline__ float lg(float x) { return FAST ? lg2_ftz(x) * 0.6931471805599453f : logf(x); }
 template <bool FAST> __device__ __forceinline__ double ex(double x) { return exp(x); }
 template <bool FAST> __device__ __forceinline__ double lg(double x) { return log(x); }
 
@@ -714,16 +719,22 @@ ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restr
 
     // ---- K3's per-class collection, fully parallel: acc[t][g][l'_s] += exp(R + Rb + nll)
     {
-        const int per_g = q.T * SS;
-        for (int i = tid; i < Gv * per_g; i += nth) {
-            const int gg = i / per_g;
-            const int r = i - gg * per_g;
-            const float v = Ra[i] + Rbs[i];           // Ra / Rbs share the [G][T][SS] layout
-            if (v != NINF) {
-                const int t = r / SS;
-                const int o = t * rowElems + gg * q.C + curs[gg * SS + (r - t * SS)];
-                pres[o] = 1;
-                atomicAdd(acc + o, ex<FAST>(v + nlls[gg]));
+        const int nwarps = nth >> 5;
+        for (int gg = 0; gg < Gv; ++gg) {
+            const float nl = nlls[gg];
+            const int *cg = curs + gg * SS;
+            for (int t = warp; t < q.T; t += nwarps) {
+                const float *ra = Ra + ((size_t)gg * q.T + t) * SS, *rb = Rbs + ((size_t)gg * q.T + t) * SS;
+                float *accr = acc + t * rowElems + gg * q.C;
+                unsigned char *pr = pres + t * rowElems + gg * q.C;
+                for (int sidx = lane; sidx < SS; sidx += 32) {
+                    const float v = ra[sidx] + rb[sidx];       // Ra / Rbs share the [G][T][SS] layout
+                    if (v != NINF) {
+                        const int c = cg[sidx];
+                        pr[c] = 1;
+                        atomicAdd(accr + c, ex<FAST>(v + nl));
+                    }
+                }
             }
         }
     }
