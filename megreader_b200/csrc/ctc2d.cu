@@ -938,7 +938,9 @@ int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_
     q.zero_inf = zero_inf;
     q.T = (int)T; q.H = (int)H; q.N = (int)N; q.C = (int)C; q.S = (int)S; q.SS = (int)(2 * S + 1);
     q.blank = (int)blank; q.tg_sn = tg_sn; q.tg_ss = tg_ss;
-    if (sizeof(real) == 4 && !getenv("MR_CTC2D_BLOCK_DP")) {
+    // The warp-per-sample variant (sweeps in registers, concurrent forward/backward warps) measured SLOWER than the
+    // block variant below on B200 (forward_train 559 us vs 457 us at N=16384): opt-in via MR_CTC2D_WARP_DP=1.
+    if (sizeof(real) == 4 && getenv("MR_CTC2D_WARP_DP")) {
         q.G = 4; q.vec = 1;
         const int rc = launch_dp_warp<FAST, MODE>(q, (const float *)lp, tg, il, tl, (const float *)go, go_stride, (float *)nll,
                                                   (float *)fac, (float *)grad, st);
