@@ -301,9 +301,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 struct ConvArgs {
     const bf16 *x;
     int N, H, W, C, kh, kw, ph, pw, Ho, Wo;
+    int box_w, box_h, tiles_per_row, tiles_per_img;   // TMA-A variant: a 128-pixel tile = box_h rows x box_w columns
     GemmArgs g;        // M = N*Ho*Wo, N = Cout, K = kh*kw*C
 };
 
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -323,9 +328,12 @@ struct ConvSmem {
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
 };
 
-template <int BN, int STAGES, int MT>
+// TMA_A = 1: "same"-padded convolutions whose 128-pixel tiles are whole row segments (W | 128 or 128 | W) fetch the
+// activation tile with ONE 4-D TMA per K block (tap shift = signed coordinate offset, padding = TMA zero fill)
+// instead of 1024 cp.async from the LSU, which capped the gather at one tile per ~256 cycles.
+template <int BN, int STAGES, int MT, int TMA_A>
 __global__ void __launch_bounds__(192, 1)
-conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
+conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX, ConvArgs a) {
     using L = ConvSmem<BN, STAGES, MT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -342,7 +350,8 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1 + 128); mbar_init(empty + s, 1); }
+        if (TMA_A) tma_prefetch_desc(&tmX);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, TMA_A ? 1 : 1 + 128); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
@@ -353,11 +362,25 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (elect_one()) {                                   // weight tiles by TMA
+        if (elect_one()) {                                   // weight tiles (and, with TMA_A, activation tiles) by TMA
+            int tn = 0, th0 = 0, tw0 = 0;
+            if (TMA_A) {
+                const int tile = blockIdx.x;
+                tn = tile / a.tiles_per_img;
+                const int rt = tile - tn * a.tiles_per_img;
+                const int trow = rt / a.tiles_per_row;
+                th0 = trow * a.box_h;
+                tw0 = (rt - trow * a.tiles_per_row) * a.box_w;
+            }
+            int cc = 0, ti = 0, tj = 0;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
                 mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
-                mbar_expect_tx(full + s, L::B_BYTES);
+                mbar_expect_tx(full + s, TMA_A ? L::STAGE_BYTES : L::B_BYTES);
+                if (TMA_A) {
+                    tma_load_4d(&tmX, full + s, smem + s * L::STAGE_BYTES, cc * BK, tw0 + tj - a.pw, th0 + ti - a.ph, tn);
+                    if (++cc == cchunks) { cc = 0; if (++tj == a.kw) { tj = 0; ++ti; } }
+                }
                 tma_load_2d(&tmB, full + s, smem + s * L::STAGE_BYTES + L::A_BYTES, i * BK, n0);
             }
         }
@@ -382,6 +405,9 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, ConvArgs a) {
             }
             __syncwarp();
         }
+    } else if (TMA_A) {
+        epilogue_store<BN>(g, tmem_base, tmem_full, m0, n0, warp, lane, nkb > 0);
+        tc_fence_before();
     } else {
         // ------------------------------------------------------------ activation gather (one thread = MT tile rows)
         const int r = threadIdx.x - 64;
@@ -453,10 +479,6 @@ struct WgradArgs {
     GemmArgs g;                 // M = Cout, N = kh*kw*C, C = dW, atomic = 1
 };
 
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
 
 template <int BN, int RB, int STAGES>
 struct WgradSmem {
@@ -606,12 +628,12 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const GemmArgs &g, int 
 }
 
 // 4-D bf16 NHWC tensor map {C, W, H, N}, box {64, box_w, 1, 1}
-int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_t H, int64_t N, int box_w) {
+int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_t H, int64_t N, int box_w, int box_h = 1) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return MR_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -620,17 +642,17 @@ int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_
     return MR_OK;
 }
 
-template <int BN, int STAGES, int MT>
-int launch_conv(const CUtensorMap &tb, const ConvArgs &a, cudaStream_t st) {
+template <int BN, int STAGES, int MT, int TMA_A>
+int launch_conv(const CUtensorMap &tb, const CUtensorMap &tx, const ConvArgs &a, cudaStream_t st) {
     using L = ConvSmem<BN, STAGES, MT>;
-    auto kern = conv_fprop_tcgen05_kernel<BN, STAGES, MT>;
+    auto kern = conv_fprop_tcgen05_kernel<BN, STAGES, MT, TMA_A>;
     static bool attr_set = false;
     if (!attr_set) {
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_fprop smem attr");
         attr_set = true;
     }
     dim3 grid((unsigned)ceil_div(a.g.M, BM * MT), (unsigned)ceil_div(a.g.N, BN), 1);
-    kern<<<grid, 192, L::TOTAL, st>>>(tb, a);
+    kern<<<grid, 192, L::TOTAL, st>>>(tb, tx, a);
     return check_launch("conv_fprop_tcgen05_kernel");
 }
 
@@ -729,9 +751,26 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
      * experiments (MR_CONV_MT2=1), off by default. */
     static const bool mt2 = getenv("MR_CONV_MT2") && getenv("MR_CONV_MT2")[0] == '1';
     const bool big = mt2 && P >= 4 * 148 * 128;
-    if (BN == 256) return big ? launch_conv<256, 3, 2>(tb, a, st) : launch_conv<256, 4, 1>(tb, a, st);
-    if (BN == 128) return big ? launch_conv<128, 4, 2>(tb, a, st) : launch_conv<128, 6, 1>(tb, a, st);
-    return big ? launch_conv<64, 5, 2>(tb, a, st) : launch_conv<64, 8, 1>(tb, a, st);
+    /* TMA-A variant: "same" geometry and 128-pixel tiles that are whole row segments of one image */
+    static const bool no_tma_a = getenv("MR_CONV_NO_TMA_A") != nullptr;
+    const bool same = (a.Ho == H && a.Wo == W);
+    const bool rows_ok = (W >= 128) ? (W % 128 == 0) : (128 % W == 0 && H % (128 / W) == 0);
+    a.box_w = a.box_h = a.tiles_per_row = a.tiles_per_img = 0;
+    if (!no_tma_a && !big && same && rows_ok) {
+        a.box_w = W >= 128 ? 128 : W;
+        a.box_h = 128 / a.box_w;
+        a.tiles_per_row = W / a.box_w;
+        a.tiles_per_img = (H / a.box_h) * a.tiles_per_row;
+        CUtensorMap tx;
+        rc = make_map_nhwc(&tx, x, C, W, H, N, a.box_w, a.box_h);
+        if (rc) return rc;
+        if (BN == 256) return launch_conv<256, 4, 1, 1>(tb, tx, a, st);
+        if (BN == 128) return launch_conv<128, 6, 1, 1>(tb, tx, a, st);
+        return launch_conv<64, 8, 1, 1>(tb, tx, a, st);
+    }
+    if (BN == 256) return big ? launch_conv<256, 3, 2, 0>(tb, tb, a, st) : launch_conv<256, 4, 1, 0>(tb, tb, a, st);
+    if (BN == 128) return big ? launch_conv<128, 4, 2, 0>(tb, tb, a, st) : launch_conv<128, 6, 1, 0>(tb, tb, a, st);
+    return big ? launch_conv<64, 5, 2, 0>(tb, tb, a, st) : launch_conv<64, 8, 1, 0>(tb, tb, a, st);
 }
 
 /* Implicit-GEMM weight gradient: dWm[Cout, kh*kw*C] (fp32, ACCUMULATED atomically: zero it first) from

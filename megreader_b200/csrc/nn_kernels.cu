@@ -303,6 +303,52 @@ bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restri
     }
 }
 
+// Non-overlapping windows (kernel == stride, no padding: the two big 2x2/2 pools of the CRNN stack): one thread per
+// POOLED output vector reads y / dy / idx once and writes all kh*kw input positions of its window (dy at the arg-max
+// if y > 0, zeros elsewhere) -- no div/mod per input pixel and no 4x re-read of the pooled tensors.
+// Requires H % kh == 0 and W % kw == 0 so that every input pixel belongs to exactly one window.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_relu_pool_bwd_tiled_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y,
+                                const unsigned char *__restrict__ idx, T *__restrict__ dz, double *__restrict__ bias_sums) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = g.C / VN;
+    const int64_t total = (int64_t)g.N * g.Ho * g.Wo * cv;
+    float bsum[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bsum[e] = 0.f;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c0 = (int)(t % cv) * VN;
+        const int64_t p = t / cv;
+        const int wo = (int)(p % g.Wo);
+        const int64_t r = p / g.Wo;
+        const int ho = (int)(r % g.Ho);
+        const int n = (int)(r / g.Ho);
+        float fy[VN], fd[VN];
+        unsigned char ib[VN];
+        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(y) + t), fy);
+        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(dy) + t), fd);
+        load_bytes<VN>(idx + t * VN, ib);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            if (!(fy[e] > 0.f)) fd[e] = 0.f;        // ReLU' through the pooled value
+            bsum[e] += to_f<T>(from_f<T>(fd[e]));
+        }
+        for (int i = 0; i < g.kh; ++i)
+            for (int j = 0; j < g.kw; ++j) {
+                float o[VN];
+#pragma unroll
+                for (int e = 0; e < VN; ++e) o[e] = (ib[e] == i * g.kw + j) ? fd[e] : 0.f;
+                const int64_t q = (((int64_t)n * g.H + ho * g.kh + i) * g.W + wo * g.kw + j) * g.C + c0;
+                __stcs(reinterpret_cast<uint4 *>(dz + q), pack<T>(o));
+            }
+    }
+    if (bias_sums) {
+        __shared__ float red[256][VN + 1];
+        block_channel_sum<VN>(bsum, cv, bias_sums, red);
+    }
+}
+
 // plain bias (+ optional ReLU) on [rows, C], and its backward mask
 template <typename T>
 __global__ void bias_act_kernel(const T *__restrict__ x, const float *__restrict__ bias, int64_t rows, int C, int relu,
@@ -704,7 +750,12 @@ int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *id
     const int vn = dtype == 0 ? 4 : 8;
     const bool fuse = dbias && sums && (256 % (C / vn) == 0);
     if (fuse) MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * C, st), "memset sums");
-    DISPATCH(dtype, (bias_relu_pool_bwd_kernel<T><<<grid1d((int64_t)N * H * W * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, fuse ? sums : nullptr)));
+    const bool tiled = kh == sh && kw == sw && ph == 0 && pw == 0 && H % kh == 0 && W % kw == 0;
+    if (tiled) {
+        DISPATCH(dtype, (bias_relu_pool_bwd_tiled_kernel<T><<<grid1d((int64_t)N * g.Ho * g.Wo * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, fuse ? sums : nullptr)));
+    } else {
+        DISPATCH(dtype, (bias_relu_pool_bwd_kernel<T><<<grid1d((int64_t)N * H * W * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, fuse ? sums : nullptr)));
+    }
     rc = check_launch("bias_relu_pool_bwd_kernel");
     if (rc || !dbias) return rc;
     if (!fuse) return mr_colsum(dz, (int64_t)N * H * W, C, dtype, dbias, 0, sums, stream);
