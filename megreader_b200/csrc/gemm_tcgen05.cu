@@ -120,9 +120,10 @@ struct GemmArgs {
 // Epilogue shared by the GEMM and convolution kernels: warps 2..5, TMEM -> registers -> (bias, ReLU) -> global.
 template <int BN>
 __device__ __forceinline__ void epilogue_store(const GemmArgs &g, uint32_t tmem_base, uint64_t *tmem_full, int m0, int n0,
-                                               int warp, int lane, bool have_acc) {
+                                               int warp, int lane, bool have_acc, int64_t row_override = -2) {
         const int q = warp & 3;                               // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
+        // output row of this thread: m0 + tile row, or an explicit row (-1 = none) for tiles that are not row ranges
+        const int64_t row = row_override == -2 ? (int64_t)(m0 + q * 32 + lane) : (row_override < 0 ? (int64_t)g.M : row_override);
         const int nkb = have_acc ? 1 : 0;
         if (nkb > 0) {
             mbar_wait(tmem_full, 0);
@@ -301,7 +302,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 struct ConvArgs {
     const bf16 *x;
     int N, H, W, C, kh, kw, ph, pw, Ho, Wo;
-    int box_w, box_h, tiles_per_row, tiles_per_img;   // TMA-A variant: a 128-pixel tile = box_h rows x box_w columns
+    // TMA-A variant: the output space [N, Ho, Wo] is tiled by boxes of bw x bh x bn = 128 pixels; the width is cut
+    // into segments of power-of-two widths (e.g. Wo = 65 -> one 64-wide segment + one 1-wide segment).
+    struct Seg { int w0, bw, bh, bn, h_blocks, tile_begin; } seg[4];
+    int nseg;
     GemmArgs g;        // M = N*Ho*Wo, N = Cout, K = kh*kw*C
 };
 
@@ -333,7 +337,9 @@ struct ConvSmem {
 // instead of 1024 cp.async from the LSU, which capped the gather at one tile per ~256 cycles.
 template <int BN, int STAGES, int MT, int TMA_A>
 __global__ void __launch_bounds__(192, 1)
-conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX, ConvArgs a) {
+conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX0,
+                          const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                          const __grid_constant__ CUtensorMap tmX3, ConvArgs a) {
     using L = ConvSmem<BN, STAGES, MT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -350,7 +356,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmB);
-        if (TMA_A) tma_prefetch_desc(&tmX);
+        if (TMA_A) tma_prefetch_desc(&tmX0);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, TMA_A ? 1 : 1 + 128); mbar_init(empty + s, 1); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
@@ -364,13 +370,16 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
     if (warp == 0) {
         if (elect_one()) {                                   // weight tiles (and, with TMA_A, activation tiles) by TMA
             int tn = 0, th0 = 0, tw0 = 0;
+            const CUtensorMap *tmX = &tmX0;
             if (TMA_A) {
-                const int tile = blockIdx.x;
-                tn = tile / a.tiles_per_img;
-                const int rt = tile - tn * a.tiles_per_img;
-                const int trow = rt / a.tiles_per_row;
-                th0 = trow * a.box_h;
-                tw0 = (rt - trow * a.tiles_per_row) * a.box_w;
+                int sel = 0;
+                for (int q = 1; q < a.nseg; ++q) if ((int)blockIdx.x >= a.seg[q].tile_begin) sel = q;
+                const int lt = blockIdx.x - a.seg[sel].tile_begin;
+                const int nb = lt / a.seg[sel].h_blocks;
+                tn = nb * a.seg[sel].bn;
+                th0 = (lt - nb * a.seg[sel].h_blocks) * a.seg[sel].bh;
+                tw0 = a.seg[sel].w0;
+                tmX = sel == 0 ? &tmX0 : (sel == 1 ? &tmX1 : (sel == 2 ? &tmX2 : &tmX3));
             }
             int cc = 0, ti = 0, tj = 0;
             for (int i = 0; i < nkb; ++i) {
@@ -378,7 +387,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
                 mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
                 mbar_expect_tx(full + s, TMA_A ? L::STAGE_BYTES : L::B_BYTES);
                 if (TMA_A) {
-                    tma_load_4d(&tmX, full + s, smem + s * L::STAGE_BYTES, cc * BK, tw0 + tj - a.pw, th0 + ti - a.ph, tn);
+                    tma_load_4d(tmX, full + s, smem + s * L::STAGE_BYTES, cc * BK, tw0 + tj - a.pw, th0 + ti - a.ph, tn);
                     if (++cc == cchunks) { cc = 0; if (++tj == a.kw) { tj = 0; ++ti; } }
                 }
                 tma_load_2d(&tmB, full + s, smem + s * L::STAGE_BYTES + L::A_BYTES, i * BK, n0);
@@ -406,7 +415,16 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
             __syncwarp();
         }
     } else if (TMA_A) {
-        epilogue_store<BN>(g, tmem_base, tmem_full, m0, n0, warp, lane, nkb > 0);
+        int sel = 0;
+        for (int q = 1; q < a.nseg; ++q) if ((int)blockIdx.x >= a.seg[q].tile_begin) sel = q;
+        const int lt = blockIdx.x - a.seg[sel].tile_begin;
+        const int nb = lt / a.seg[sel].h_blocks;
+        const int bw = a.seg[sel].bw, bh = a.seg[sel].bh;
+        const int r = (warp & 3) * 32 + lane;                // tile row = (dn * bh + dh) * bw + dw
+        const int dw = r % bw, dh = (r / bw) % bh, dn = r / (bw * bh);
+        const int pn = nb * a.seg[sel].bn + dn, phh = (lt - nb * a.seg[sel].h_blocks) * bh + dh, pww = a.seg[sel].w0 + dw;
+        const int64_t prow = (pn < a.N && phh < a.Ho && pww < a.Wo) ? ((int64_t)pn * a.Ho + phh) * a.Wo + pww : -1;
+        epilogue_store<BN>(g, tmem_base, tmem_full, 0, n0, warp, lane, nkb > 0, prow);
         tc_fence_before();
     } else {
         // ------------------------------------------------------------ activation gather (one thread = MT tile rows)
@@ -628,12 +646,13 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const GemmArgs &g, int 
 }
 
 // 4-D bf16 NHWC tensor map {C, W, H, N}, box {64, box_w, 1, 1}
-int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_t H, int64_t N, int box_w, int box_h = 1) {
+int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_t H, int64_t N, int box_w, int box_h = 1,
+                  int box_n = 1) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return MR_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -643,7 +662,7 @@ int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_
 }
 
 template <int BN, int STAGES, int MT, int TMA_A>
-int launch_conv(const CUtensorMap &tb, const CUtensorMap &tx, const ConvArgs &a, cudaStream_t st) {
+int launch_conv(const CUtensorMap &tb, const CUtensorMap *tx, const ConvArgs &a, int tiles, cudaStream_t st) {
     using L = ConvSmem<BN, STAGES, MT>;
     auto kern = conv_fprop_tcgen05_kernel<BN, STAGES, MT, TMA_A>;
     static bool attr_set = false;
@@ -651,8 +670,8 @@ int launch_conv(const CUtensorMap &tb, const CUtensorMap &tx, const ConvArgs &a,
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_fprop smem attr");
         attr_set = true;
     }
-    dim3 grid((unsigned)ceil_div(a.g.M, BM * MT), (unsigned)ceil_div(a.g.N, BN), 1);
-    kern<<<grid, 192, L::TOTAL, st>>>(tb, tx, a);
+    dim3 grid(TMA_A ? (unsigned)tiles : (unsigned)ceil_div(a.g.M, BM * MT), (unsigned)ceil_div(a.g.N, BN), 1);
+    kern<<<grid, 192, L::TOTAL, st>>>(tb, tx[0], tx[1], tx[2], tx[3], a);
     return check_launch("conv_fprop_tcgen05_kernel");
 }
 
@@ -751,26 +770,46 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
      * experiments (MR_CONV_MT2=1), off by default. */
     static const bool mt2 = getenv("MR_CONV_MT2") && getenv("MR_CONV_MT2")[0] == '1';
     const bool big = mt2 && P >= 4 * 148 * 128;
-    /* TMA-A variant: "same" geometry and 128-pixel tiles that are whole row segments of one image */
+    /* TMA-A variant: tile the output space with boxes of 128 pixels, width cut into power-of-two segments. */
     static const bool no_tma_a = getenv("MR_CONV_NO_TMA_A") != nullptr;
-    const bool same = (a.Ho == H && a.Wo == W);
-    const bool rows_ok = (W >= 128) ? (W % 128 == 0) : (128 % W == 0 && H % (128 / W) == 0);
-    a.box_w = a.box_h = a.tiles_per_row = a.tiles_per_img = 0;
-    if (!no_tma_a && !big && same && rows_ok) {
-        a.box_w = W >= 128 ? 128 : W;
-        a.box_h = 128 / a.box_w;
-        a.tiles_per_row = W / a.box_w;
-        a.tiles_per_img = (H / a.box_h) * a.tiles_per_row;
-        CUtensorMap tx;
-        rc = make_map_nhwc(&tx, x, C, W, H, N, a.box_w, a.box_h);
-        if (rc) return rc;
-        if (BN == 256) return launch_conv<256, 4, 1, 1>(tb, tx, a, st);
-        if (BN == 128) return launch_conv<128, 6, 1, 1>(tb, tx, a, st);
-        return launch_conv<64, 8, 1, 1>(tb, tx, a, st);
+    a.nseg = 0;
+    CUtensorMap tx[4];
+    int tiles = 0;
+    if (!no_tma_a && !big) {
+        int w0 = 0;
+        bool ok = true;
+        while (w0 < a.Wo) {
+            if (a.nseg == 4) { ok = false; break; }
+            int bw = 128;
+            while (bw > a.Wo - w0) bw >>= 1;
+            int nrep = (a.Wo - w0) / bw;                  /* consecutive segments of this width share geometry */
+            int bh = 1;
+            while (bh * 2 <= a.Ho && bw * bh * 2 <= 128) bh <<= 1;
+            const int bn = 128 / (bw * bh);
+            const int h_blocks = (int)ceil_div(a.Ho, bh), n_blocks = (int)ceil_div(N, bn);
+            for (int rep = 0; rep < nrep && ok; ++rep) {
+                if (a.nseg == 4) { ok = false; break; }
+                ConvArgs::Seg &sg = a.seg[a.nseg];
+                sg.w0 = w0; sg.bw = bw; sg.bh = bh; sg.bn = bn; sg.h_blocks = h_blocks; sg.tile_begin = tiles;
+                rc = make_map_nhwc(&tx[a.nseg], x, C, W, H, N, bw, bh, bn);
+                if (rc) return rc;
+                tiles += h_blocks * n_blocks;
+                ++a.nseg;
+                w0 += bw;
+            }
+        }
+        if (ok && a.nseg > 0) {
+            for (int q = a.nseg; q < 4; ++q) tx[q] = tx[0];
+            if (BN == 256) return launch_conv<256, 4, 1, 1>(tb, tx, a, tiles, st);
+            if (BN == 128) return launch_conv<128, 6, 1, 1>(tb, tx, a, tiles, st);
+            return launch_conv<64, 8, 1, 1>(tb, tx, a, tiles, st);
+        }
+        a.nseg = 0;
     }
-    if (BN == 256) return big ? launch_conv<256, 3, 2, 0>(tb, tb, a, st) : launch_conv<256, 4, 1, 0>(tb, tb, a, st);
-    if (BN == 128) return big ? launch_conv<128, 4, 2, 0>(tb, tb, a, st) : launch_conv<128, 6, 1, 0>(tb, tb, a, st);
-    return big ? launch_conv<64, 5, 2, 0>(tb, tb, a, st) : launch_conv<64, 8, 1, 0>(tb, tb, a, st);
+    for (int q = 0; q < 4; ++q) tx[q] = tb;
+    if (BN == 256) return big ? launch_conv<256, 3, 2, 0>(tb, tx, a, 0, st) : launch_conv<256, 4, 1, 0>(tb, tx, a, 0, st);
+    if (BN == 128) return big ? launch_conv<128, 4, 2, 0>(tb, tx, a, 0, st) : launch_conv<128, 6, 1, 0>(tb, tx, a, 0, st);
+    return big ? launch_conv<64, 5, 2, 0>(tb, tx, a, 0, st) : launch_conv<64, 8, 1, 0>(tb, tx, a, 0, st);
 }
 
 /* Implicit-GEMM weight gradient: dWm[Cout, kh*kw*C] (fp32, ACCUMULATED atomically: zero it first) from
