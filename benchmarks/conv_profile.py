@@ -27,3 +27,15 @@ b.record()
 torch.cuda.synchronize()
 us = a.elapsed_time(b) * 100
 print("conv5 fprop %.1f us  %.1f TFLOP/s" % (us, 2.0 * N * H * W * Cout * k * k * C / us / 1e6))
+# conv1 (low-channel, epilogue-heavy): 512 x 16 x 128 x 64 -> 128
+x1 = torch.randn(512, 16, 128, 64, device=dev).bfloat16()
+w1 = (torch.randn(128, 9 * 64, device=dev) / 24).bfloat16()
+nnops.conv_fprop_tc(x1, w1, 3, 3, 1, 1)
+torch.cuda.synchronize()
+a.record()
+for _ in range(10):
+    nnops.conv_fprop_tc(x1, w1, 3, 3, 1, 1)
+b.record()
+torch.cuda.synchronize()
+us = a.elapsed_time(b) * 100
+print("conv1 fprop %.1f us  %.1f TFLOP/s" % (us, 2.0 * 512 * 16 * 128 * 128 * 9 * 64 / us / 1e6))

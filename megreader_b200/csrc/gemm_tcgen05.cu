@@ -445,7 +445,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
         }
         const uint32_t row_off = (uint32_t)r * 128u;
         const uint32_t sw = (uint32_t)(r & 7);
-        constexpr int D = 3;                                  // cp.async groups in flight per thread
+        constexpr int D = STAGES >= 4 ? 3 : 2;                // cp.async groups in flight per thread
         static_assert(D - 1 < STAGES, "producer lookahead must be smaller than the ring");
         int cc = 0, ti = 0, tj = 0;
         for (int i = 0; i < nkb; ++i) {
@@ -800,6 +800,15 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
         }
         if (ok && a.nseg > 0) {
             for (int q = a.nseg; q < 4; ++q) tx[q] = tx[0];
+            /* shallow rings leave room for 2-3 CTAs per SM, so one CTA's epilogue overlaps another's main loop
+             * (the kernel is not persistent); MR_CONV_SHALLOW=0/1 overrides the default for experiments. */
+            static const char *sh_env = getenv("MR_CONV_SHALLOW");
+            const bool shallow = sh_env ? sh_env[0] == '1' : true;
+            if (shallow) {
+                if (BN == 256) return launch_conv<256, 2, 1, 1>(tb, tx, a, tiles, st);
+                if (BN == 128) return launch_conv<128, 3, 1, 1>(tb, tx, a, tiles, st);
+                return launch_conv<64, 3, 1, 1>(tb, tx, a, tiles, st);
+            }
             if (BN == 256) return launch_conv<256, 4, 1, 1>(tb, tx, a, tiles, st);
             if (BN == 128) return launch_conv<128, 6, 1, 1>(tb, tx, a, tiles, st);
             return launch_conv<64, 8, 1, 1>(tb, tx, a, tiles, st);
