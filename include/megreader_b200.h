@@ -208,6 +208,19 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
 int mr_conv_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int H, int W, int C, int Cout, int kh, int kw,
                           int ph, int pw, int splits, void *stream);
 
+/* Fused LSTM time steps on tcgen05 (recurrent GEMM + cell in one launch, both directions): gate columns are
+ * UNIT-MAJOR (column 4*j + g = gate g in {i,f,g,o} of hidden unit j), H % 64 == 0, bf16.  Every per-direction argument
+ * is a HOST array of 2 device pointers.  fwd: gates[d] [B,4H] holds the x-projection on entry and the activated gates
+ * on exit; bias[d] [4H] = b_ih + b_hh (unit-major); have_h = 0 on the first step.  bwd: dG_next[d] = gate gradients of
+ * the step processed just before (have_rec = 0 on the first backward step); dc[d] [B,H] is updated in place. */
+int mr_lstm_step_fwd_tcgen05(const void *const *h_prev, const void *const *Whh, void *const *gates,
+                             const float *const *bias, const float *const *c_prev, float *const *c_out,
+                             void *const *h_out, int64_t ldh, void *const *h_next, int have_h, int B, int H,
+                             void *stream);
+int mr_lstm_step_bwd_tcgen05(const void *const *dG_next, const void *const *Whh, const void *const *gates,
+                             const float *const *c, const float *const *c_prev, const void *const *dh_out, int64_t ldh,
+                             float *const *dc, void *const *dgates, int have_rec, int B, int H, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

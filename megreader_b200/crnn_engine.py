@@ -214,6 +214,8 @@ def _bilstm_forward_impl(X, params, dtype, training):
     w_emb, b_emb = params[8], params[9]
     H = w_hh[0].size(1)
     dev = X.device
+    if USE_TCGEN05 and dtype == torch.bfloat16 and H % 64 == 0:
+        return _bilstm_forward_fused(X, params, training)
     Wih = [ops.cast(w.detach(), dtype) for w in w_ih]
     Whh = torch.stack([ops.cast(w.detach(), dtype) for w in w_hh])                 # [2, 4H, H]
     X2 = X.view(T * N, I)
@@ -245,8 +247,91 @@ def _bilstm_forward_impl(X, params, dtype, training):
     return E.view(T, N, nOut), saved
 
 
+def _unit_major_perm(H, dev):
+    """perm[4*j + g] = g*H + j : reference gate-major rows (i|f|g|o blocks) -> unit-major rows."""
+    return torch.arange(4 * H, device=dev).view(4, H).t().reshape(-1)
+
+
+def _bilstm_forward_fused(X, params, training):
+    """bf16 path: each time step is ONE tcgen05 launch (recurrent GEMM + cell, both directions), csrc/gemm_tcgen05.cu."""
+    dtype = torch.bfloat16
+    T, N, I = X.shape
+    w_ih, w_hh = [params[0], params[4]], [params[1], params[5]]
+    b_ih, b_hh = [params[2], params[6]], [params[3], params[7]]
+    w_emb, b_emb = params[8], params[9]
+    H = w_hh[0].size(1)
+    dev = X.device
+    perm = _unit_major_perm(H, dev)
+    Wih = [ops.cast(w.detach()[perm].contiguous(), dtype) for w in w_ih]
+    Whh = [ops.cast(w.detach()[perm].contiguous(), dtype) for w in w_hh]
+    bias = [(b_ih[d].detach() + b_hh[d].detach())[perm].contiguous() for d in (0, 1)]
+    X2 = X.view(T * N, I)
+    G = torch.empty((2, T, N, 4 * H), dtype=dtype, device=dev)
+    for d in range(2):
+        ops.gemm(X2, Wih[d], transB=True, out=G[d].view(T * N, 4 * H))               # input projection, all steps
+    Cst = torch.empty((2, T, N, H), dtype=torch.float32, device=dev)
+    Y = torch.empty((T, N, 2 * H), dtype=dtype, device=dev)
+    hbuf = torch.zeros((2, 2, N, H), dtype=dtype, device=dev)                          # [ping-pong][direction]
+    for s in range(T):
+        ts, tps = (s, T - 1 - s), (s - 1, T - s)
+        cur, nxt = s & 1, (s + 1) & 1
+        ops.lstm_step_fwd_tc([hbuf[cur, 0], hbuf[cur, 1]], Whh, [G[d, ts[d]] for d in (0, 1)], bias,
+                             [Cst[d, tps[d]] if s > 0 else None for d in (0, 1)], [Cst[d, ts[d]] for d in (0, 1)],
+                             [Y[ts[d], :, d * H:(d + 1) * H] for d in (0, 1)], 2 * H, [hbuf[nxt, 0], hbuf[nxt, 1]], s > 0)
+    Wemb = ops.cast(w_emb.detach(), dtype)
+    nOut = Wemb.size(0)
+    out_dtype = dtype if nOut % _vn(dtype) == 0 else torch.float32
+    E = ops.gemm(Y.view(T * N, 2 * H), Wemb, transB=True, out_dtype=out_dtype)
+    ops.bias_act(E, b_emb, relu=False, out=E)
+    saved = dict(X=X, G=G, C=Cst, Y=Y, Wih=Wih, Whh=Whh, Wemb=Wemb, H=H, fused=True, perm=perm) if training else None
+    return E.view(T, N, nOut), saved
+
+
+def _bilstm_backward_fused(dE, sv):
+    dtype = torch.bfloat16
+    X, G, Cst, Y, H, perm = sv["X"], sv["G"], sv["C"], sv["Y"], sv["H"], sv["perm"]
+    T, N, I = X.shape
+    dev = X.device
+    inv = torch.argsort(perm)
+    dE2 = ops.cast(dE.reshape(T * N, -1), dtype)
+    Y2 = Y.view(T * N, 2 * H)
+    dWemb = ops.gemm(dE2, Y2, transA=True, out_dtype=torch.float32)
+    dbemb = ops.colsum(dE2)
+    dY3 = ops.gemm(dE2, sv["Wemb"]).view(T, N, 2 * H)
+    dG = torch.empty((2, T, N, 4 * H), dtype=dtype, device=dev)
+    dc = torch.zeros((2, N, H), dtype=torch.float32, device=dev)
+    for s in range(T - 1, -1, -1):
+        ts, tps, tn = (s, T - 1 - s), (s - 1, T - s), (s + 1, T - 2 - s)
+        have_rec = s < T - 1
+        ops.lstm_step_bwd_tc([dG[d, tn[d]] if have_rec else dG[d, ts[d]] for d in (0, 1)], sv["Whh"],
+                             [G[d, ts[d]] for d in (0, 1)], [Cst[d, ts[d]] for d in (0, 1)],
+                             [Cst[d, tps[d]] if s > 0 else None for d in (0, 1)],
+                             [dY3[ts[d], :, d * H:(d + 1) * H] for d in (0, 1)], 2 * H, [dc[0], dc[1]],
+                             [dG[d, ts[d]] for d in (0, 1)], have_rec)
+    X2 = X.view(T * N, I)
+    grads = []
+    dX = torch.empty((T * N, I), dtype=dtype, device=dev)
+    for d in range(2):
+        dG2 = dG[d].view(T * N, 4 * H)
+        dWih = ops.gemm(dG2, X2, transA=True, out_dtype=torch.float32)[inv]
+        if d == 0:
+            A = dG[0, 1:].reshape((T - 1) * N, 4 * H)
+            Bm = Y[:T - 1].view((T - 1) * N, 2 * H)[:, :H]
+        else:
+            A = dG[1, :T - 1].reshape((T - 1) * N, 4 * H)
+            Bm = Y[1:].view((T - 1) * N, 2 * H)[:, H:]
+        dWhh = (ops.gemm(A, Bm, transA=True, out_dtype=torch.float32) if T > 1
+                else torch.zeros(4 * H, H, device=dev))[inv]
+        db = ops.colsum(dG2)[inv]
+        grads += [dWih, dWhh, db, db.clone()]
+        ops.gemm(dG2, sv["Wih"][d], out=dX, beta=0.0 if d == 0 else 1.0)
+    return dX.view(T, N, I), grads + [dWemb, dbemb]
+
+
 def _bilstm_backward_impl(dE, sv, dtype):
     """dE [T, N, nOut] -> (dX [T, N, I], grads for the 10 parameters in _bilstm_params order)."""
+    if sv.get("fused"):
+        return _bilstm_backward_fused(dE, sv)
     X, G, Cst, Y, H = sv["X"], sv["G"], sv["C"], sv["Y"], sv["H"]
     T, N, I = X.shape
     dev = X.device

@@ -600,6 +600,300 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid
     }
 }
 
+// =====================================================================================================
+// Fused LSTM time step (decoders/crnn.py:13,17 nn.LSTM): recurrent GEMM + cell in ONE launch for both directions.
+// Gate columns are stored UNIT-MAJOR (column 4*j + g holds gate g of hidden unit j; g = i,f,g,o) so that the 32
+// accumulator columns a thread pulls from TMEM are 8 complete units.
+//   forward : gates = Gx[t] + h_prev W_hh^T (+ bias);  c, h = cell(gates);  activated gates saved in place.
+//   backward: dh = dY[t] + dG[t_next] W_hh ;  dG[t], dc = cell'(...)        (the GEMM feeds the cell directly)
+// =====================================================================================================
+struct LstmFwdDir {
+    bf16 *gates;              // [B, 4H] unit-major: in = x-projection, out = activated gates
+    const float *bias;        // [4H] unit-major, b_ih + b_hh
+    const float *c_prev;      // [B, H] or NULL
+    float *c_out;             // [B, H]
+    bf16 *h_out;              // row stride ldh (slice of the [T, B, 2H] layer output)
+    bf16 *h_next;             // [B, H] operand of the next step's GEMM
+};
+struct LstmFwdArgs { LstmFwdDir d[2]; int64_t ldh; int B, H, have_h; };
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+lstm_step_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                             LstmFwdArgs a) {
+    constexpr int BN = 256;
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.z;
+    const CUtensorMap *tmA = dir ? &tmA1 : &tmA0;
+    const CUtensorMap *tmB = dir ? &tmB1 : &tmB0;
+    const LstmFwdDir &q = a.d[dir];
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nkb = a.have_h ? a.H / BK : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(tmA);
+        tma_prefetch_desc(tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+                mbar_expect_tx(full + s, L::STAGE_BYTES);
+                tma_load_2d(tmA, full + s, smem + s * L::STAGE_BYTES, i * BK, m0);
+                tma_load_2d(tmB, full + s, smem + s * L::STAGE_BYTES + L::A_BYTES, i * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(full + s, (i / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
+                              (i | k) != 0);
+                umma_commit(empty + s);
+                if (i == nkb - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int qd = warp & 3;
+        const int row = m0 + qd * 32 + lane;
+        if (nkb > 0) { mbar_wait(tmem_full, 0); tc_fence_after(); }
+        const int H = a.H;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 32), r);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0;
+            }
+            const int col0 = n0 + c * 32;              // unit-major gate column
+            if (row < a.B && col0 < 4 * H) {
+                const int j0 = col0 >> 2;               // first hidden unit of this chunk (8 units)
+                bf16 *gp = q.gates + (int64_t)row * 4 * H + col0;
+                float pre[32];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const uint4 pk = *reinterpret_cast<const uint4 *>(gp + v * 8);
+                    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&pk);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h2[e]);
+                        pre[v * 8 + 2 * e] = f.x;
+                        pre[v * 8 + 2 * e + 1] = f.y;
+                    }
+                }
+                float act[32], cn[8], hn[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float gi = pre[4 * u] + __uint_as_float(r[4 * u]) + q.bias[col0 + 4 * u];
+                    const float gf = pre[4 * u + 1] + __uint_as_float(r[4 * u + 1]) + q.bias[col0 + 4 * u + 1];
+                    const float gg = pre[4 * u + 2] + __uint_as_float(r[4 * u + 2]) + q.bias[col0 + 4 * u + 2];
+                    const float go = pre[4 * u + 3] + __uint_as_float(r[4 * u + 3]) + q.bias[col0 + 4 * u + 3];
+                    const float i_ = sigmoidf_(gi), f_ = sigmoidf_(gf), g_ = tanhf(gg), o_ = sigmoidf_(go);
+                    const float cp = q.c_prev ? q.c_prev[(int64_t)row * H + j0 + u] : 0.f;
+                    cn[u] = f_ * cp + i_ * g_;
+                    hn[u] = o_ * tanhf(cn[u]);
+                    act[4 * u] = i_; act[4 * u + 1] = f_; act[4 * u + 2] = g_; act[4 * u + 3] = o_;
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint4 pk;
+                    __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(act[v * 8 + 2 * e], act[v * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4 *>(gp + v * 8) = pk;
+                }
+                float *cp_out = q.c_out + (int64_t)row * H + j0;
+                *reinterpret_cast<float4 *>(cp_out) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                *reinterpret_cast<float4 *>(cp_out + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                uint4 hp;
+                __nv_bfloat162 *hh = reinterpret_cast<__nv_bfloat162 *>(&hp);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(hn[2 * e], hn[2 * e + 1]);
+                *reinterpret_cast<uint4 *>(q.h_out + (int64_t)row * a.ldh + j0) = hp;
+                *reinterpret_cast<uint4 *>(q.h_next + (int64_t)row * H + j0) = hp;
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+struct LstmBwdDir {
+    const bf16 *gates;        // [B, 4H] activated gates of step t (unit-major)
+    const float *c;           // [B, H] cell state of step t
+    const float *c_prev;      // [B, H] or NULL
+    const bf16 *dh_out;       // dY[t] slice, row stride ldh
+    float *dc;                // [B, H] in/out
+    bf16 *dgates;             // [B, 4H] unit-major, out
+};
+struct LstmBwdArgs { LstmBwdDir d[2]; int64_t ldh; int B, H, have_rec; };
+
+template <int STAGES>
+__global__ void __launch_bounds__(192, 1)
+lstm_step_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                             const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                             LstmBwdArgs a) {
+    constexpr int BN = 64;     // 64 hidden units per CTA
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.z;
+    const CUtensorMap *tmA = dir ? &tmA1 : &tmA0;
+    const CUtensorMap *tmB = dir ? &tmB1 : &tmB0;
+    const LstmBwdDir &q = a.d[dir];
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nkb = a.have_rec ? (4 * a.H) / BK : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(tmA);
+        tma_prefetch_desc(tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+                mbar_expect_tx(full + s, L::STAGE_BYTES);
+                tma_load_2d(tmA, full + s, smem + s * L::STAGE_BYTES, i * BK, m0);          // dG_next [B, 4H], K-major
+                tma_load_2d(tmB, full + s, smem + s * L::STAGE_BYTES + L::A_BYTES, n0, i * BK);   // W_hh [4H, H], MN-major
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, 0, 1);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(full + s, (i / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 2048, BK * 128, 1024),
+                              idesc, (i | k) != 0);
+                umma_commit(empty + s);
+                if (i == nkb - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int qd = warp & 3;
+        const int row = m0 + qd * 32 + lane;
+        if (nkb > 0) { mbar_wait(tmem_full, 0); tc_fence_after(); }
+        const int H = a.H;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 32), r);
+            else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0;
+            }
+            const int j0 = n0 + c * 32;                // first of 32 hidden units
+            if (row < a.B && j0 < H) {
+                const bf16 *gp = q.gates + (int64_t)row * 4 * H + 4 * j0;
+                const bf16 *dyp = q.dh_out + (int64_t)row * a.ldh + j0;
+                const float *cp = q.c + (int64_t)row * H + j0;
+                const float *cpp = q.c_prev ? q.c_prev + (int64_t)row * H + j0 : nullptr;
+                float *dcp = q.dc + (int64_t)row * H + j0;
+                bf16 *dgp = q.dgates + (int64_t)row * 4 * H + 4 * j0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {              // 8 units per 16-byte vector of dY / 32 B of c
+                    const uint4 dyk = *reinterpret_cast<const uint4 *>(dyp + v * 8);
+                    const __nv_bfloat162 *dy2 = reinterpret_cast<const __nv_bfloat162 *>(&dyk);
+                    float dyf[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(dy2[e]); dyf[2 * e] = f.x; dyf[2 * e + 1] = f.y; }
+                    float dgf[32];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {          // 2 units per 16-byte vector of gates... 4 gates x 2 units = 8 bf16
+                        const uint4 gk = *reinterpret_cast<const uint4 *>(gp + v * 32 + h * 8);
+                        const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&gk);
+#pragma unroll
+                        for (int w2 = 0; w2 < 2; ++w2) {
+                            const int u = v * 8 + h * 2 + w2;      // unit index inside this 32-unit chunk
+                            const float2 fi = __bfloat1622float2(g2[2 * w2]);       // (i, f)
+                            const float2 fg = __bfloat1622float2(g2[2 * w2 + 1]);   // (g, o)
+                            const float i_ = fi.x, f_ = fi.y, g_ = fg.x, o_ = fg.y;
+                            const float dh = dyf[h * 2 + w2] + __uint_as_float(r[u]);
+                            const float tc = tanhf(cp[u]);
+                            const float dct = dcp[u] + dh * o_ * (1.f - tc * tc);
+                            const float cprev = cpp ? cpp[u] : 0.f;
+                            const int o4 = (h * 2 + w2) * 4;
+                            dgf[o4] = dct * g_ * i_ * (1.f - i_);
+                            dgf[o4 + 1] = dct * cprev * f_ * (1.f - f_);
+                            dgf[o4 + 2] = dct * i_ * (1.f - g_ * g_);
+                            dgf[o4 + 3] = dh * tc * o_ * (1.f - o_);
+                            dcp[u] = dct * f_;
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        uint4 pk;
+                        __nv_bfloat162 *p2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(dgf[h * 8 + 2 * e], dgf[h * 8 + 2 * e + 1]);
+                        *reinterpret_cast<uint4 *>(dgp + v * 32 + h * 8) = pk;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
 // ---------------------------------------------------------------- host: tensor maps through the driver entry point
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -859,6 +1153,67 @@ int mr_conv_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int 
     if (BN == 256) return launch_wgrad<256, 64, 4>(tdz, tx, a, splits, st);
     if (BN == 128) return launch_wgrad<128, 64, 6>(tdz, tx, a, splits, st);
     return launch_wgrad<64, 64, 8>(tdz, tx, a, splits, st);
+}
+
+/* Fused LSTM steps (both directions per launch).  Unit-major gate layout (column 4*j + g).  H % 64 == 0.
+ * h_prev[d]: [B,H] bf16 operand of this step's recurrent GEMM (ignored when have_h == 0, i.e. the first step);
+ * Whh[d]: [4H, H] bf16 unit-major rows.  Per-direction pointer arguments are HOST arrays of 2 device pointers. */
+int mr_lstm_step_fwd_tcgen05(const void *const *h_prev, const void *const *Whh, void *const *gates,
+                             const float *const *bias, const float *const *c_prev, float *const *c_out,
+                             void *const *h_out, int64_t ldh, void *const *h_next, int have_h, int B, int H,
+                             void *stream) {
+    if (B <= 0 || H <= 0 || H % 64) return MR_ERR_UNSUPPORTED;
+    LstmFwdArgs a;
+    a.ldh = ldh; a.B = B; a.H = H; a.have_h = have_h;
+    CUtensorMap ta[2], tb[2];
+    for (int d = 0; d < 2; ++d) {
+        if (!h_prev[d] || !Whh[d] || !gates[d] || !bias[d] || !c_out[d] || !h_out[d] || !h_next[d]) return MR_ERR_NULL_POINTER;
+        int rc = make_map(&ta[d], h_prev[d], H, B, H, BK, BM);
+        if (rc) return rc;
+        rc = make_map(&tb[d], Whh[d], H, 4 * H, H, BK, 256);
+        if (rc) return rc;
+        a.d[d].gates = (bf16 *)gates[d]; a.d[d].bias = bias[d]; a.d[d].c_prev = c_prev[d]; a.d[d].c_out = c_out[d];
+        a.d[d].h_out = (bf16 *)h_out[d]; a.d[d].h_next = (bf16 *)h_next[d];
+    }
+    using L = SmemLayout<256, 4>;
+    auto kern = lstm_step_fwd_tcgen05_kernel<4>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "lstm fwd smem attr");
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(4 * H / 256), 2);
+    kern<<<grid, 192, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
+    return check_launch("lstm_step_fwd_tcgen05_kernel");
+}
+
+/* dG_next[d]: [B,4H] bf16 gate gradients of the step processed before this one (ignored when have_rec == 0). */
+int mr_lstm_step_bwd_tcgen05(const void *const *dG_next, const void *const *Whh, const void *const *gates,
+                             const float *const *c, const float *const *c_prev, const void *const *dh_out, int64_t ldh,
+                             float *const *dc, void *const *dgates, int have_rec, int B, int H, void *stream) {
+    if (B <= 0 || H <= 0 || H % 64) return MR_ERR_UNSUPPORTED;
+    LstmBwdArgs a;
+    a.ldh = ldh; a.B = B; a.H = H; a.have_rec = have_rec;
+    CUtensorMap ta[2], tb[2];
+    for (int d = 0; d < 2; ++d) {
+        if (!dG_next[d] || !Whh[d] || !gates[d] || !c[d] || !dh_out[d] || !dc[d] || !dgates[d]) return MR_ERR_NULL_POINTER;
+        int rc = make_map(&ta[d], dG_next[d], 4 * H, B, 4 * H, BK, BM);
+        if (rc) return rc;
+        rc = make_map(&tb[d], Whh[d], H, 4 * H, H, 64, BK);
+        if (rc) return rc;
+        a.d[d].gates = (const bf16 *)gates[d]; a.d[d].c = c[d]; a.d[d].c_prev = c_prev[d];
+        a.d[d].dh_out = (const bf16 *)dh_out[d]; a.d[d].dc = dc[d]; a.d[d].dgates = (bf16 *)dgates[d];
+    }
+    using L = SmemLayout<64, 6>;
+    auto kern = lstm_step_bwd_tcgen05_kernel<6>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "lstm bwd smem attr");
+        attr_set = true;
+    }
+    dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(H / 64), 2);
+    kern<<<grid, 192, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
+    return check_launch("lstm_step_bwd_tcgen05_kernel");
 }
 
 }  // extern "C"

@@ -225,3 +225,18 @@ def conv_wgrad_tc(dz, x, kh, kw, ph, pw, splits=0):
     _chk(_lib.lib().mr_conv_wgrad_tcgen05(_p(dz), _p(x), _p(dWm), N, H, W, C, Cout, kh, kw, ph, pw, int(splits), _st()),
          "conv_wgrad_tcgen05")
     return dWm
+
+
+def lstm_step_fwd_tc(h_prev, Whh, gates, bias, c_prev, c_out, h_out, ldh, h_next, have_h):
+    """Fused recurrent GEMM + LSTM cell, both directions (lists of 2 tensors each), unit-major gate layout."""
+    B, H4 = gates[0].shape
+    _chk(_lib.lib().mr_lstm_step_fwd_tcgen05(_ptr_array(h_prev), _ptr_array(Whh), _ptr_array(gates), _ptr_array(bias),
+                                             _ptr_array(c_prev), _ptr_array(c_out), _ptr_array(h_out), ldh,
+                                             _ptr_array(h_next), int(have_h), B, H4 // 4, _st()), "lstm_step_fwd_tcgen05")
+
+
+def lstm_step_bwd_tc(dG_next, Whh, gates, c, c_prev, dh_out, ldh, dc, dgates, have_rec):
+    B, H4 = gates[0].shape
+    _chk(_lib.lib().mr_lstm_step_bwd_tcgen05(_ptr_array(dG_next), _ptr_array(Whh), _ptr_array(gates), _ptr_array(c),
+                                             _ptr_array(c_prev), _ptr_array(dh_out), ldh, _ptr_array(dc),
+                                             _ptr_array(dgates), int(have_rec), B, H4 // 4, _st()), "lstm_step_bwd_tcgen05")

@@ -156,6 +156,41 @@ def test_bilstm_layer_vs_torch(cuda, dtype):
         torch.testing.assert_close(got, want, **(tol if dtype == torch.float32 else dict(rtol=5e-2, atol=0.15)))
 
 
+def test_bilstm_fused_tcgen05_path(cuda):
+    """H % 64 == 0 in bf16 mode routes every time step through the fused tcgen05 GEMM + cell kernels."""
+    from megreader_b200 import crnn_engine
+    torch.manual_seed(6)
+    T, N, I, H, O = 6, 150, 64, 64, 40
+    rnn = torch.nn.LSTM(I, H, bidirectional=True).to(cuda)
+    emb = torch.nn.Linear(2 * H, O).to(cuda)
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.rnn, self.embedding = rnn, emb
+    m = M()
+    x = torch.randn(T, N, I, device=cuda)
+    xr = x.clone().requires_grad_(True)
+    rec, _ = rnn(xr)
+    ref = emb(rec.view(T * N, 2 * H)).view(T, N, O)
+    dout = torch.randn_like(ref)
+    ref.backward(dout)
+    ref_grads = [p.grad.clone() for p in crnn_engine._bilstm_params(m)]
+    for p in m.parameters():
+        p.grad = None
+    crnn_engine.set_compute_dtype(torch.bfloat16)
+    try:
+        xe = x.clone().requires_grad_(True)
+        out = crnn_engine.bilstm_forward(m, xe)
+        out.float().backward(dout)
+    finally:
+        crnn_engine.set_compute_dtype(torch.float32)
+    torch.testing.assert_close(out.float(), ref, rtol=5e-2, atol=5e-2)
+    torch.testing.assert_close(xe.grad, xr.grad, rtol=5e-2, atol=5e-2)
+    for got, want in zip([p.grad for p in crnn_engine._bilstm_params(m)], ref_grads):
+        torch.testing.assert_close(got, want, rtol=5e-2, atol=0.02 * float(want.abs().max()) + 0.05)
+
+
 def test_adam_matches_torch(cuda, ops):
     torch.manual_seed(5)
     p = torch.randn(1000, device=cuda)
