@@ -617,14 +617,32 @@ struct LstmFwdDir {
 };
 struct LstmFwdArgs { LstmFwdDir d[2]; int64_t ldh; int B, H, have_h; };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// MUFU.TANH: one instruction, ~2^-11 relative error -- far below bf16 resolution of the stored activations
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Both LSTM step kernels: 64 output columns per CTA, 2 producer/MMA warps + 16 epilogue warps (4 TMEM lane quarters x
+// 4 groups of 16 columns): the cell arithmetic is transcendental-heavy and latency-bound, so it is spread over as many
+// warps and CTAs as the tile shape allows (a 128x256 tile with 4 epilogue warps took ~27 us per step).
+constexpr int kLstmBN = 64;
+constexpr int kLstmThreads = 64 + 16 * 32;
 
 template <int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_step_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                              const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                              LstmFwdArgs a) {
-    constexpr int BN = 256;
+    constexpr int BN = kLstmBN;
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -682,65 +700,69 @@ lstm_step_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
             __syncwarp();
         }
     } else {
-        const int qd = warp & 3;
+        const int qd = warp & 3, grp = (warp - 2) >> 2;       // TMEM lane quarter, 16-column group
         const int row = m0 + qd * 32 + lane;
         if (nkb > 0) { mbar_wait(tmem_full, 0); tc_fence_after(); }
         const int H = a.H;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 32), r);
-            else {
+        uint32_t r[16];
+        if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 16), r);
+        else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0;
+            for (int j = 0; j < 16; ++j) r[j] = 0;
+        }
+        const int col0 = n0 + grp * 16;                       // unit-major gate column: 4 hidden units
+        if (row < a.B && col0 < 4 * H) {
+            const int j0 = col0 >> 2;
+            bf16 *gp = q.gates + (int64_t)row * 4 * H + col0;
+            float pre[16];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                const uint4 pk = *reinterpret_cast<const uint4 *>(gp + v * 8);
+                const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    pre[v * 8 + 2 * e] = f.x;
+                    pre[v * 8 + 2 * e + 1] = f.y;
+                }
             }
-            const int col0 = n0 + c * 32;              // unit-major gate column
-            if (row < a.B && col0 < 4 * H) {
-                const int j0 = col0 >> 2;               // first hidden unit of this chunk (8 units)
-                bf16 *gp = q.gates + (int64_t)row * 4 * H + col0;
-                float pre[32];
+            float bb[16];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const uint4 pk = *reinterpret_cast<const uint4 *>(gp + v * 8);
-                    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&pk);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 f = __bfloat1622float2(h2[e]);
-                        pre[v * 8 + 2 * e] = f.x;
-                        pre[v * 8 + 2 * e + 1] = f.y;
-                    }
-                }
-                float act[32], cn[8], hn[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const float gi = pre[4 * u] + __uint_as_float(r[4 * u]) + q.bias[col0 + 4 * u];
-                    const float gf = pre[4 * u + 1] + __uint_as_float(r[4 * u + 1]) + q.bias[col0 + 4 * u + 1];
-                    const float gg = pre[4 * u + 2] + __uint_as_float(r[4 * u + 2]) + q.bias[col0 + 4 * u + 2];
-                    const float go = pre[4 * u + 3] + __uint_as_float(r[4 * u + 3]) + q.bias[col0 + 4 * u + 3];
-                    const float i_ = sigmoidf_(gi), f_ = sigmoidf_(gf), g_ = tanhf(gg), o_ = sigmoidf_(go);
-                    const float cp = q.c_prev ? q.c_prev[(int64_t)row * H + j0 + u] : 0.f;
-                    cn[u] = f_ * cp + i_ * g_;
-                    hn[u] = o_ * tanhf(cn[u]);
-                    act[4 * u] = i_; act[4 * u + 1] = f_; act[4 * u + 2] = g_; act[4 * u + 3] = o_;
-                }
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    uint4 pk;
-                    __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(act[v * 8 + 2 * e], act[v * 8 + 2 * e + 1]);
-                    *reinterpret_cast<uint4 *>(gp + v * 8) = pk;
-                }
-                float *cp_out = q.c_out + (int64_t)row * H + j0;
-                *reinterpret_cast<float4 *>(cp_out) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                *reinterpret_cast<float4 *>(cp_out + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-                uint4 hp;
-                __nv_bfloat162 *hh = reinterpret_cast<__nv_bfloat162 *>(&hp);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(hn[2 * e], hn[2 * e + 1]);
-                *reinterpret_cast<uint4 *>(q.h_out + (int64_t)row * a.ldh + j0) = hp;
-                *reinterpret_cast<uint4 *>(q.h_next + (int64_t)row * H + j0) = hp;
+            for (int v = 0; v < 4; ++v) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(q.bias + col0) + v);
+                bb[4 * v] = b4.x; bb[4 * v + 1] = b4.y; bb[4 * v + 2] = b4.z; bb[4 * v + 3] = b4.w;
             }
+            float cpv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (q.c_prev) {
+                const float4 c4 = *reinterpret_cast<const float4 *>(q.c_prev + (int64_t)row * H + j0);
+                cpv[0] = c4.x; cpv[1] = c4.y; cpv[2] = c4.z; cpv[3] = c4.w;
+            }
+            float act[16], cn[4], hn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float i_ = sigmoid_fast(pre[4 * u] + __uint_as_float(r[4 * u]) + bb[4 * u]);
+                const float f_ = sigmoid_fast(pre[4 * u + 1] + __uint_as_float(r[4 * u + 1]) + bb[4 * u + 1]);
+                const float g_ = tanh_fast(pre[4 * u + 2] + __uint_as_float(r[4 * u + 2]) + bb[4 * u + 2]);
+                const float o_ = sigmoid_fast(pre[4 * u + 3] + __uint_as_float(r[4 * u + 3]) + bb[4 * u + 3]);
+                cn[u] = f_ * cpv[u] + i_ * g_;
+                hn[u] = o_ * tanh_fast(cn[u]);
+                act[4 * u] = i_; act[4 * u + 1] = f_; act[4 * u + 2] = g_; act[4 * u + 3] = o_;
+            }
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                uint4 pk;
+                __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(act[v * 8 + 2 * e], act[v * 8 + 2 * e + 1]);
+                *reinterpret_cast<uint4 *>(gp + v * 8) = pk;
+            }
+            *reinterpret_cast<float4 *>(q.c_out + (int64_t)row * H + j0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            uint2 hp;
+            __nv_bfloat162 *hh = reinterpret_cast<__nv_bfloat162 *>(&hp);
+            hh[0] = __floats2bfloat162_rn(hn[0], hn[1]);
+            hh[1] = __floats2bfloat162_rn(hn[2], hn[3]);
+            *reinterpret_cast<uint2 *>(q.h_out + (int64_t)row * a.ldh + j0) = hp;
+            *reinterpret_cast<uint2 *>(q.h_next + (int64_t)row * H + j0) = hp;
         }
         tc_fence_before();
     }
@@ -762,11 +784,11 @@ struct LstmBwdDir {
 struct LstmBwdArgs { LstmBwdDir d[2]; int64_t ldh; int B, H, have_rec; };
 
 template <int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_step_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                              const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                              LstmBwdArgs a) {
-    constexpr int BN = 64;     // 64 hidden units per CTA
+    constexpr int BN = kLstmBN;     // 64 hidden units per CTA
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -824,64 +846,72 @@ lstm_step_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __g
             __syncwarp();
         }
     } else {
-        const int qd = warp & 3;
+        const int qd = warp & 3, grp = (warp - 2) >> 2;
         const int row = m0 + qd * 32 + lane;
         if (nkb > 0) { mbar_wait(tmem_full, 0); tc_fence_after(); }
         const int H = a.H;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t r[32];
-            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(c * 32), r);
-            else {
+        uint32_t r[16];
+        if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 16), r);
+        else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0;
-            }
-            const int j0 = n0 + c * 32;                // first of 32 hidden units
-            if (row < a.B && j0 < H) {
-                const bf16 *gp = q.gates + (int64_t)row * 4 * H + 4 * j0;
-                const bf16 *dyp = q.dh_out + (int64_t)row * a.ldh + j0;
-                const float *cp = q.c + (int64_t)row * H + j0;
-                const float *cpp = q.c_prev ? q.c_prev + (int64_t)row * H + j0 : nullptr;
-                float *dcp = q.dc + (int64_t)row * H + j0;
-                bf16 *dgp = q.dgates + (int64_t)row * 4 * H + 4 * j0;
+            for (int j = 0; j < 16; ++j) r[j] = 0;
+        }
+        const int j0 = n0 + grp * 16;                          // first of 16 hidden units
+        if (row < a.B && j0 < H) {
+            const bf16 *gp = q.gates + (int64_t)row * 4 * H + 4 * j0;
+            const bf16 *dyp = q.dh_out + (int64_t)row * a.ldh + j0;
+            const float *cp = q.c + (int64_t)row * H + j0;
+            const float *cpp = q.c_prev ? q.c_prev + (int64_t)row * H + j0 : nullptr;
+            float *dcp = q.dc + (int64_t)row * H + j0;
+            bf16 *dgp = q.dgates + (int64_t)row * 4 * H + 4 * j0;
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {              // 8 units per 16-byte vector of dY / 32 B of c
-                    const uint4 dyk = *reinterpret_cast<const uint4 *>(dyp + v * 8);
-                    const __nv_bfloat162 *dy2 = reinterpret_cast<const __nv_bfloat162 *>(&dyk);
-                    float dyf[8];
+            for (int v = 0; v < 2; ++v) {                      // 8 units per 16-byte vector of dY
+                const uint4 dyk = *reinterpret_cast<const uint4 *>(dyp + v * 8);
+                const __nv_bfloat162 *dy2 = reinterpret_cast<const __nv_bfloat162 *>(&dyk);
+                float dyf[8], cf[8], cpf[8], dcf[8];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(dy2[e]); dyf[2 * e] = f.x; dyf[2 * e + 1] = f.y; }
-                    float dgf[32];
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(dy2[e]); dyf[2 * e] = f.x; dyf[2 * e + 1] = f.y; }
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {          // 2 units per 16-byte vector of gates... 4 gates x 2 units = 8 bf16
-                        const uint4 gk = *reinterpret_cast<const uint4 *>(gp + v * 32 + h * 8);
-                        const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&gk);
+                for (int e = 0; e < 2; ++e) {
+                    const float4 c4 = *reinterpret_cast<const float4 *>(cp + v * 8 + 4 * e);
+                    cf[4 * e] = c4.x; cf[4 * e + 1] = c4.y; cf[4 * e + 2] = c4.z; cf[4 * e + 3] = c4.w;
+                    const float4 d4 = *reinterpret_cast<const float4 *>(dcp + v * 8 + 4 * e);
+                    dcf[4 * e] = d4.x; dcf[4 * e + 1] = d4.y; dcf[4 * e + 2] = d4.z; dcf[4 * e + 3] = d4.w;
+                    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (cpp) p4 = *reinterpret_cast<const float4 *>(cpp + v * 8 + 4 * e);
+                    cpf[4 * e] = p4.x; cpf[4 * e + 1] = p4.y; cpf[4 * e + 2] = p4.z; cpf[4 * e + 3] = p4.w;
+                }
+                float dgf[32];
 #pragma unroll
-                        for (int w2 = 0; w2 < 2; ++w2) {
-                            const int u = v * 8 + h * 2 + w2;      // unit index inside this 32-unit chunk
-                            const float2 fi = __bfloat1622float2(g2[2 * w2]);       // (i, f)
-                            const float2 fg = __bfloat1622float2(g2[2 * w2 + 1]);   // (g, o)
-                            const float i_ = fi.x, f_ = fi.y, g_ = fg.x, o_ = fg.y;
-                            const float dh = dyf[h * 2 + w2] + __uint_as_float(r[u]);
-                            const float tc = tanhf(cp[u]);
-                            const float dct = dcp[u] + dh * o_ * (1.f - tc * tc);
-                            const float cprev = cpp ? cpp[u] : 0.f;
-                            const int o4 = (h * 2 + w2) * 4;
-                            dgf[o4] = dct * g_ * i_ * (1.f - i_);
-                            dgf[o4 + 1] = dct * cprev * f_ * (1.f - f_);
-                            dgf[o4 + 2] = dct * i_ * (1.f - g_ * g_);
-                            dgf[o4 + 3] = dh * tc * o_ * (1.f - o_);
-                            dcp[u] = dct * f_;
-                        }
+                for (int h = 0; h < 4; ++h) {                  // 2 units (8 gate values) per 16-byte vector of gates
+                    const uint4 gk = *reinterpret_cast<const uint4 *>(gp + v * 32 + h * 8);
+                    const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&gk);
+#pragma unroll
+                    for (int w2 = 0; w2 < 2; ++w2) {
+                        const int uu = h * 2 + w2;             // unit inside this group of 8
+                        const float2 fi = __bfloat1622float2(g2[2 * w2]);       // (i, f)
+                        const float2 fg = __bfloat1622float2(g2[2 * w2 + 1]);   // (g, o)
+                        const float i_ = fi.x, f_ = fi.y, g_ = fg.x, o_ = fg.y;
+                        const float dh = dyf[uu] + __uint_as_float(r[v * 8 + uu]);
+                        const float tc = tanh_fast(cf[uu]);
+                        const float dct = dcf[uu] + dh * o_ * (1.f - tc * tc);
+                        dgf[uu * 4] = dct * g_ * i_ * (1.f - i_);
+                        dgf[uu * 4 + 1] = dct * cpf[uu] * f_ * (1.f - f_);
+                        dgf[uu * 4 + 2] = dct * i_ * (1.f - g_ * g_);
+                        dgf[uu * 4 + 3] = dh * tc * o_ * (1.f - o_);
+                        dcf[uu] = dct * f_;
                     }
+                }
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        uint4 pk;
-                        __nv_bfloat162 *p2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+                for (int e = 0; e < 2; ++e)
+                    *reinterpret_cast<float4 *>(dcp + v * 8 + 4 * e) = make_float4(dcf[4 * e], dcf[4 * e + 1], dcf[4 * e + 2], dcf[4 * e + 3]);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(dgf[h * 8 + 2 * e], dgf[h * 8 + 2 * e + 1]);
-                        *reinterpret_cast<uint4 *>(dgp + v * 32 + h * 8) = pk;
-                    }
+                for (int h = 0; h < 4; ++h) {
+                    uint4 pk;
+                    __nv_bfloat162 *p2 = reinterpret_cast<__nv_bfloat162 *>(&pk);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(dgf[h * 8 + 2 * e], dgf[h * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4 *>(dgp + v * 32 + h * 8) = pk;
                 }
             }
         }
@@ -1170,20 +1200,20 @@ int mr_lstm_step_fwd_tcgen05(const void *const *h_prev, const void *const *Whh, 
         if (!h_prev[d] || !Whh[d] || !gates[d] || !bias[d] || !c_out[d] || !h_out[d] || !h_next[d]) return MR_ERR_NULL_POINTER;
         int rc = make_map(&ta[d], h_prev[d], H, B, H, BK, BM);
         if (rc) return rc;
-        rc = make_map(&tb[d], Whh[d], H, 4 * H, H, BK, 256);
+        rc = make_map(&tb[d], Whh[d], H, 4 * H, H, BK, kLstmBN);
         if (rc) return rc;
         a.d[d].gates = (bf16 *)gates[d]; a.d[d].bias = bias[d]; a.d[d].c_prev = c_prev[d]; a.d[d].c_out = c_out[d];
         a.d[d].h_out = (bf16 *)h_out[d]; a.d[d].h_next = (bf16 *)h_next[d];
     }
-    using L = SmemLayout<256, 4>;
+    using L = SmemLayout<kLstmBN, 4>;
     auto kern = lstm_step_fwd_tcgen05_kernel<4>;
     static bool attr_set = false;
     if (!attr_set) {
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "lstm fwd smem attr");
         attr_set = true;
     }
-    dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(4 * H / 256), 2);
-    kern<<<grid, 192, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
+    dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(4 * H / kLstmBN), 2);
+    kern<<<grid, kLstmThreads, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
     return check_launch("lstm_step_fwd_tcgen05_kernel");
 }
 
@@ -1204,15 +1234,15 @@ int mr_lstm_step_bwd_tcgen05(const void *const *dG_next, const void *const *Whh,
         a.d[d].gates = (const bf16 *)gates[d]; a.d[d].c = c[d]; a.d[d].c_prev = c_prev[d];
         a.d[d].dh_out = (const bf16 *)dh_out[d]; a.d[d].dc = dc[d]; a.d[d].dgates = (bf16 *)dgates[d];
     }
-    using L = SmemLayout<64, 6>;
+    using L = SmemLayout<kLstmBN, 6>;
     auto kern = lstm_step_bwd_tcgen05_kernel<6>;
     static bool attr_set = false;
     if (!attr_set) {
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "lstm bwd smem attr");
         attr_set = true;
     }
-    dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(H / 64), 2);
-    kern<<<grid, 192, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
+    dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(H / kLstmBN), 2);
+    kern<<<grid, kLstmThreads, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
     return check_launch("lstm_step_bwd_tcgen05_kernel");
 }
 
