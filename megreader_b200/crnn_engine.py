@@ -20,6 +20,10 @@ _COMPUTE_DTYPE = torch.float32
 # bf16 mode: convolutions with C % 64 == 0 run as tcgen05 implicit GEMMs (csrc/gemm_tcgen05.cu); False routes them
 # through im2col + cuBLAS (kept for A/B comparison in benchmarks)
 USE_TCGEN05 = __import__("os").environ.get("MEGREADER_B200_TCGEN05", "1") != "0"
+# Fused tcgen05 LSTM time steps (recurrent GEMM + cell in one launch).  Correct (tests/test_nn_kernels_gpu.py) but
+# measured 0.7 ms/step SLOWER at batch 512 than cuBLAS strided-batched GEMM + cell kernel (per-launch TMEM/barrier
+# set-up dominates a 4-k-block GEMM), so it is opt-in.
+LSTM_FUSED = __import__("os").environ.get("MEGREADER_B200_LSTM_FUSED", "0") == "1"
 
 
 def set_compute_dtype(dtype):
@@ -214,7 +218,7 @@ def _bilstm_forward_impl(X, params, dtype, training):
     w_emb, b_emb = params[8], params[9]
     H = w_hh[0].size(1)
     dev = X.device
-    if USE_TCGEN05 and dtype == torch.bfloat16 and H % 64 == 0:
+    if LSTM_FUSED and USE_TCGEN05 and dtype == torch.bfloat16 and H % 64 == 0:
         return _bilstm_forward_fused(X, params, training)
     Wih = [ops.cast(w.detach(), dtype) for w in w_ih]
     Whh = torch.stack([ops.cast(w.detach(), dtype) for w in w_hh])                 # [2, 4H, H]

@@ -179,12 +179,15 @@ def test_bilstm_fused_tcgen05_path(cuda):
     for p in m.parameters():
         p.grad = None
     crnn_engine.set_compute_dtype(torch.bfloat16)
+    fused_before = crnn_engine.LSTM_FUSED
+    crnn_engine.LSTM_FUSED = True
     try:
         xe = x.clone().requires_grad_(True)
         out = crnn_engine.bilstm_forward(m, xe)
         out.float().backward(dout)
     finally:
         crnn_engine.set_compute_dtype(torch.float32)
+        crnn_engine.LSTM_FUSED = fused_before
     torch.testing.assert_close(out.float(), ref, rtol=5e-2, atol=5e-2)
     torch.testing.assert_close(xe.grad, xr.grad, rtol=5e-2, atol=5e-2)
     for got, want in zip([p.grad for p in crnn_engine._bilstm_params(m)], ref_grads):
