@@ -348,7 +348,7 @@ def bench_conv_roofline(dev, iters=10):
     sec = a.elapsed_time(b) / iters * 1e-3
     flops = 2.0 * N * H * W * Cout * k * k * C
     pk = peaks()
-    return {"kernel": "conv_fprop_tcgen05_kernel<256,4> (implicit-GEMM 3x3 conv, conv5 shape, bf16 in / fp32 acc)",
+    return {"kernel": "conv_fprop_tcgen05_kernel<256,2,1,1> (implicit-GEMM 3x3 conv via 4-D TMA, conv5 shape, bf16 in / fp32 acc)",
             "bound": "tensor", "achieved": flops / sec / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": flops / sec / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
             "alg_flops_per_launch": flops, "us_per_launch": sec * 1e6}
