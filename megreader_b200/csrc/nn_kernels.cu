@@ -502,7 +502,8 @@ bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const flo
 #pragma unroll
     for (int e = 0; e < VN; ++e) bsum[e] = 0.f;
     int c_cached = -1;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += 2 * stride) {
         const int c0 = (int)(t % cv) * VN;
         if (c0 != c_cached) {
 #pragma unroll
@@ -516,18 +517,52 @@ bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const flo
             }
             c_cached = c0;
         }
+        // two independent vectors in flight per thread (the second shares the channel vector when cv | stride)
+        const int64_t t2 = t + stride;
+        const bool two = t2 < total && ((int)(t2 % cv) * VN == c0);
+        uint4 rd = __ldg(reinterpret_cast<const uint4 *>(dy) + t), rx = __ldg(reinterpret_cast<const uint4 *>(x) + t);
+        uint4 rd2 = rd, rx2 = rx;
+        if (two) { rd2 = __ldg(reinterpret_cast<const uint4 *>(dy) + t2); rx2 = __ldg(reinterpret_cast<const uint4 *>(x) + t2); }
         float fd[VN], fx[VN];
-        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(dy) + t), fd);
-        unpack<T>(__ldg(reinterpret_cast<const uint4 *>(x) + t), fx);
+        unpack<T>(rd, fd);
+        unpack<T>(rx, fx);
 #pragma unroll
         for (int e = 0; e < VN; ++e) fd[e] = A[e] * (fd[e] - k1[e] - (fx[e] + shf[e]) * is[e] * k2[e]);
-        const uint4 packed = pack<T>(fd);
+        uint4 packed = pack<T>(fd);
         reinterpret_cast<uint4 *>(dx)[t] = packed;
         if (bias_sums) {
             float fr[VN];
             unpack<T>(packed, fr);
 #pragma unroll
             for (int e = 0; e < VN; ++e) bsum[e] += fr[e];
+        }
+        if (two) {
+            unpack<T>(rd2, fd);
+            unpack<T>(rx2, fx);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) fd[e] = A[e] * (fd[e] - k1[e] - (fx[e] + shf[e]) * is[e] * k2[e]);
+            packed = pack<T>(fd);
+            reinterpret_cast<uint4 *>(dx)[t2] = packed;
+            if (bias_sums) {
+                float fr[VN];
+                unpack<T>(packed, fr);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) bsum[e] += fr[e];
+            }
+        } else if (t2 < total) {
+            // channel vector differs (cv does not divide the stride): handle it in the plain way
+            const int c2 = (int)(t2 % cv) * VN;
+            float gd[VN], gx[VN];
+            unpack<T>(__ldg(reinterpret_cast<const uint4 *>(dy) + t2), gd);
+            unpack<T>(__ldg(reinterpret_cast<const uint4 *>(x) + t2), gx);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) {
+                const int c = c2 + e;
+                const float isv = invstd[c];
+                gd[e] = gamma[c] * isv * (gd[e] - (float)sums[c] * inv_rows -
+                                          (gx[e] + (bias ? bias[c] : 0.f) - mean[c]) * isv * (float)sums[C + c] * inv_rows);
+            }
+            reinterpret_cast<uint4 *>(dx)[t2] = pack<T>(gd);
         }
     }
     if (bias_sums) {
@@ -547,6 +582,18 @@ __global__ void sums_to_float_kernel(const double *__restrict__ s, int n, float 
 // gates_pre [B, 4H] (T): x-projection + h_{t-1} W_hh^T already summed by the GEMMs; bias_ih + bias_hh added here.
 // Writes the activated gates back in place (saved for backward), c_t [B,H] fp32, h_t [B,H] (T) into `h_out` (row
 // stride ldh, so it lands directly in the [T, B, 2H] output of the bidirectional layer).
+// bf16 mode uses MUFU.TANH (tanh.approx, ~2^-11 relative error, below bf16 resolution); fp32 mode keeps expf/tanhf
+// so that the parity path stays within 1e-4 of the reference.
+template <typename T> struct CellMath;
+template <> struct CellMath<float> {
+    static __device__ __forceinline__ float th(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float sg(float x) { return 1.f / (1.f + expf(-x)); }
+};
+template <> struct CellMath<bf16> {
+    static __device__ __forceinline__ float th(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float sg(float x) { return fmaf(0.5f, th(0.5f * x), 0.5f); }
+};
+
 struct CellFwdDir { void *gates; const float *b_ih, *b_hh, *c_prev; float *c_out; void *h_out, *h_state; };
 struct CellFwdArgs { CellFwdDir d[2]; int64_t ldh; int B, H; };
 
@@ -565,9 +612,9 @@ __global__ void lstm_cell_fwd_kernel(CellFwdArgs a) {
         const float gf = to_f<T>(gp[H + j]) + q.b_ih[H + j] + q.b_hh[H + j];
         const float gg = to_f<T>(gp[2 * H + j]) + q.b_ih[2 * H + j] + q.b_hh[2 * H + j];
         const float go = to_f<T>(gp[3 * H + j]) + q.b_ih[3 * H + j] + q.b_hh[3 * H + j];
-        const float i_ = 1.f / (1.f + expf(-gi)), f_ = 1.f / (1.f + expf(-gf)), g_ = tanhf(gg), o_ = 1.f / (1.f + expf(-go));
+        const float i_ = CellMath<T>::sg(gi), f_ = CellMath<T>::sg(gf), g_ = CellMath<T>::th(gg), o_ = CellMath<T>::sg(go);
         const float c = f_ * (q.c_prev ? q.c_prev[t] : 0.f) + i_ * g_;
-        const float h = o_ * tanhf(c);
+        const float h = o_ * CellMath<T>::th(c);
         gp[j] = from_f<T>(i_); gp[H + j] = from_f<T>(f_); gp[2 * H + j] = from_f<T>(g_); gp[3 * H + j] = from_f<T>(o_);
         q.c_out[t] = c;
         const T hv = from_f<T>(h);
@@ -595,7 +642,7 @@ __global__ void lstm_cell_bwd_kernel(CellBwdArgs a) {
         const T *gp = gates + (int64_t)b * 4 * H;
         const float i_ = to_f<T>(gp[j]), f_ = to_f<T>(gp[H + j]), g_ = to_f<T>(gp[2 * H + j]), o_ = to_f<T>(gp[3 * H + j]);
         const float dh = to_f<T>(dh_out[(int64_t)b * a.ldh + j]) + (dh_rec ? to_f<T>(dh_rec[t]) : 0.f);
-        const float tc = tanhf(q.c[t]);
+        const float tc = CellMath<T>::th(q.c[t]);
         const float dct = q.dc[t] + dh * o_ * (1.f - tc * tc);
         const float cp = q.c_prev ? q.c_prev[t] : 0.f;
         T *dg = dgates + (int64_t)b * 4 * H;
