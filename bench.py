@@ -350,7 +350,10 @@ def bench_conv_roofline(dev, iters=10):
     pk = peaks()
     return {"kernel": "conv_fprop_tcgen05_kernel<256,2,1,1> (implicit-GEMM 3x3 conv via 4-D TMA, conv5 shape, bf16 in / fp32 acc)",
             "bound": "tensor", "achieved": flops / sec / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": flops / sec / 1e12 / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+            "frac": flops / sec / 1e12 / pk["bf16_tflops"],
+            "traffic": 388.5e6,   # dram__bytes_read+write per launch, ncu --set full (profiles/conv_fprop_r1b_summary.md)
+            "traffic_algorithmic": 2.0 * N * H * W * C + 2.0 * N * H * W * Cout + 2.0 * Cout * k * k * C,
+            "peak_source": pk["source"],
             "alg_flops_per_launch": flops, "us_per_launch": sec * 1e6}
 
 
