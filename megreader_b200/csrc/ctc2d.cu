@@ -327,7 +327,7 @@ __device__ __forceinline__ void st_cs(real *p, const VecT<real, VE> &v) {
 }
 
 // LSE over the H rows of one vector column, H processed in register chunks of 8.
-template <typename real, bool FAST, int VE, int HT>
+template <typename real, bool FAST, int VE, int HT, bool LOG2OUT = false>
 __device__ __forceinline__ void lse_rows(const real *base, int64_t hs, int H, real *dst) {
     const real NINF = Lim<real>::ninf();
     real m[VE], sum[VE];
@@ -359,10 +359,13 @@ __device__ __forceinline__ void lse_rows(const real *base, int64_t hs, int H, re
         }
     }
 #pragma unroll
-    for (int k = 0; k < VE; ++k) dst[k] = (m[k] == NINF) ? NINF : m[k] + lg<FAST>(sum[k]);
+    for (int k = 0; k < VE; ++k) {
+        if (LOG2OUT) dst[k] = (m[k] == NINF) ? NINF : (real)(m[k] * (real)1.4426950408889634 + (real)lg2_ftz((float)sum[k]));
+        else dst[k] = (m[k] == NINF) ? NINF : m[k] + lg<FAST>(sum[k]);
+    }
 }
 
-template <typename real, bool FAST, int VE, int HT>
+template <typename real, bool FAST, int VE, int HT, bool LOG2OUT = false>
 __device__ __forceinline__ void phase_q(const Geo &q, const real *__restrict__ lp, real *Qall, int b0, int Gv) {
     const int H = HT > 0 ? HT : q.H;
     const int rowElems = q.G * q.C;
@@ -376,17 +379,17 @@ __device__ __forceinline__ void phase_q(const Geo &q, const real *__restrict__ l
         if (t0 < tpr) {
             int t = t0;
             for (; t + tpr < q.T; t += 2 * tpr) {     // two independent columns in flight per thread
-                lse_rows<real, FAST, VE, HT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
-                lse_rows<real, FAST, VE, HT>(cta + (int64_t)(t + tpr) * H * hs + j * VE, hs, H,
+                lse_rows<real, FAST, VE, HT, LOG2OUT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
+                lse_rows<real, FAST, VE, HT, LOG2OUT>(cta + (int64_t)(t + tpr) * H * hs + j * VE, hs, H,
                                              Qall + (t + tpr) * rowElems + j * VE);
             }
             for (; t < q.T; t += tpr)
-                lse_rows<real, FAST, VE, HT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
+                lse_rows<real, FAST, VE, HT, LOG2OUT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
         }
     } else {
         for (int i = tid; i < q.T * nvec; i += nth) {
             const int t = i / nvec, j = i - t * nvec;
-            lse_rows<real, FAST, VE, HT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
+            lse_rows<real, FAST, VE, HT, LOG2OUT>(cta + (int64_t)t * H * hs + j * VE, hs, H, Qall + t * rowElems + j * VE);
         }
     }
 }
@@ -564,203 +567,227 @@ __global__ void ctc2d_dp_kernel(Geo q, const real *__restrict__ lp, const int64_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-per-sample DP kernel (fp32).  Same phases as ctc2d_dp_kernel, but the two sweeps of a sample run inside ONE
-// warp: lane L keeps states [L*NS, L*NS+NS) of the extended target in registers, neighbours come from warp shuffles,
-// and there is no block barrier inside the 2*T sweep steps (the block-wide version spent its time in 64
-// barrier-separated steps of ~85 instructions per warp; profiles/ctc2d_r1a_summary.md).
+// Warp-per-sample DP kernel (fp32, fast math), third revision.  Same phases as ctc2d_dp_kernel, but:
+//   * the two sweeps of a sample run inside ONE warp, states in registers (lane L holds states [L*NS, L*NS+NS)),
+//     neighbours by warp shuffle, no block barrier inside the 2*T steps (ncu on the block version: barrier stalls
+//     6.6 per issued instruction, issue slots 32 % busy -- profiles/ctc2d_dpblock_r1_summary.md);
+//   * NS is chosen PER SAMPLE from its target length (2L+1 <= 32 -> one state per lane), so short targets do a third
+//     of the work of the padded S = 32 layout;
+//   * everything is in log2 units (Q2 = log2(e) * Q): no FMUL around the MUFUs, and the log-sum-exp of three terms
+//     costs two ex2 + one lg2 (the largest term contributes exactly 1);
+//   * the per-class sums reuse the Q row they correspond to (dead once the backward sweep has passed it) and a bit
+//     mask records "class present", so a sample needs T*C + T*(2S+1) floats of shared memory: 16 warps per SM.
 // ------------------------------------------------------------------------------------------------
-template <bool FAST, int MODE, int NS, int HT>
+__device__ __forceinline__ float lse3_l2(float a, float b, float c) {
+    const float t1 = fmaxf(a, b), t0 = fminf(a, b);
+    const float m = fmaxf(t1, c), x1 = fminf(t1, c);
+    const float ms = (m == -INFINITY) ? 0.f : m;
+    return m + lg2_ftz(1.f + ex2_ftz(x1 - ms) + ex2_ftz(t0 - ms));
+}
+__device__ __forceinline__ float lse2_l2(float a, float b) {
+    const float m = fmaxf(a, b), x = fminf(a, b);
+    const float ms = (m == -INFINITY) ? 0.f : m;
+    return m + lg2_ftz(1.f + ex2_ftz(x - ms));
+}
+
+struct WarpDpCtx {
+    const Geo *q;
+    const int64_t *row;       // targets of this sample
+    int64_t Tb, L;
+    float *Qg;                // Q2 rows of this sample: Qg[t * rowElems + c]; later the per-class sums
+    float *Rag;               // [T][SS]
+    unsigned *maskg;          // [T][MW] class-present bits
+    int rowElems, MW;
+};
+
+template <int NS, int MODE>
+__device__ __forceinline__ float warp_sweeps(const WarpDpCtx &w, int lane) {
+    const Geo &q = *w.q;
+    const float NINF = -INFINITY;
+    const int SS = q.SS;
+    const int64_t Tb = w.Tb, L = w.L;
+    int cur[NS];
+    bool in[NS], skf[NS], skb[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int s = lane * NS + k;
+        cur[k] = q.blank; in[k] = skf[k] = skb[k] = false;
+        if (s < SS && s < 2 * L + 1) {
+            in[k] = L > 0;
+            if (s & 1) {
+                const int64_t me = w.row[(int64_t)(s >> 1) * q.tg_ss];
+                cur[k] = clampi(me, q.C);
+                if (s > 1) skf[k] = w.row[(int64_t)((s - 2) >> 1) * q.tg_ss] != me;
+                if (s < 2 * L - 1) skb[k] = w.row[(int64_t)((s + 2) >> 1) * q.tg_ss] != me;
+            }
+        }
+    }
+    // ---------------- forward sweep
+    float R[NS], a[NS];
+    float f0 = NINF, f1 = NINF;
+#pragma unroll 1
+    for (int t = 0; t < q.T; ++t) {
+        if (t == 0) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int s = lane * NS + k;
+                R[k] = (s == 0 || (s == 1 && L > 0)) ? 0.f : NINF;
+            }
+        } else {
+            float up1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
+            float up2 = NS >= 2 ? __shfl_up_sync(0xffffffffu, a[NS >= 2 ? NS - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, a[0], 2);
+            if (lane == 0) up1 = up2 = NINF;
+            if (NS == 1 && lane == 1) up2 = NINF;
+            float Rn[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const float am1 = k >= 1 ? a[k >= 1 ? k - 1 : 0] : up1;
+                const float am2 = k >= 2 ? a[k >= 2 ? k - 2 : 0] : (k == 1 ? up1 : up2);
+                const float v = lse3_l2(a[k], am1, skf[k] ? am2 : NINF);
+                Rn[k] = (t < Tb && in[k]) ? v : NINF;
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) R[k] = Rn[k];
+        }
+        const float *Qt = w.Qg + t * w.rowElems;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const int s = lane * NS + k;
+            if (s < SS) w.Rag[t * SS + s] = R[k];
+            a[k] = R[k] + Qt[cur[k]];
+            if (t == Tb - 1) {
+                if (s == 2 * L) f0 = a[k];
+                else if (s == 2 * L - 1) f1 = a[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        f0 = fmaxf(f0, __shfl_xor_sync(0xffffffffu, f0, o));
+        f1 = fmaxf(f1, __shfl_xor_sync(0xffffffffu, f1, o));
+    }
+    const float nll2 = -lse2_l2(f0, f1);                    // in log2 units
+    // ---------------- backward sweep fused with the per-class collection (the Q row becomes the sum row)
+    float bq[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) bq[k] = NINF;
+#pragma unroll 1
+    for (int t = q.T - 1; t >= 0; --t) {
+        float Rb[NS];
+        if (t == Tb - 1) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int s = lane * NS + k;
+                Rb[k] = (s == 2 * L || (L > 0 && s == 2 * L - 1)) ? 0.f : NINF;
+            }
+        } else if (t < Tb - 1) {
+            float dn1 = __shfl_down_sync(0xffffffffu, bq[0], 1);
+            float dn2 = NS >= 2 ? __shfl_down_sync(0xffffffffu, bq[NS >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, bq[0], 2);
+            if (lane == 31) dn1 = dn2 = NINF;
+            if (NS == 1 && lane == 30) dn2 = NINF;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int s = lane * NS + k;
+                const float bp1 = k + 1 < NS ? bq[k + 1 < NS ? k + 1 : 0] : dn1;
+                const float bp2 = k + 2 < NS ? bq[k + 2 < NS ? k + 2 : 0] : (k + 1 < NS ? dn1 : dn2);
+                const float v = lse3_l2(bq[k], s < 2 * L ? bp1 : NINF, skb[k] ? bp2 : NINF);
+                Rb[k] = in[k] ? v : NINF;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Rb[k] = NINF;
+        }
+        float *Qt = w.Qg + t * w.rowElems;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) bq[k] = Rb[k] + Qt[cur[k]];
+        __syncwarp();                                        // every lane has read Q2[t] -> the row may be reused
+        for (int cidx = lane; cidx < q.C; cidx += 32) Qt[cidx] = 0.f;
+        for (int mw = lane; mw < w.MW; mw += 32) w.maskg[t * w.MW + mw] = 0u;
+        __syncwarp();
+        if (t < Tb) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int s = lane * NS + k;
+                if (in[k] && s < SS) {
+                    const float v = w.Rag[t * SS + s] + Rb[k];
+                    if (v != NINF) {
+                        atomicOr(w.maskg + t * w.MW + (cur[k] >> 5), 1u << (cur[k] & 31));
+                        atomicAdd(Qt + cur[k], ex2_ftz(v + nll2));
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    return nll2 * 0.6931471805599453f;
+}
+
+template <int MODE, int NSMAX, int HT>
 __global__ void __launch_bounds__(256)
 ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict__ tg,
                      const int64_t *__restrict__ il, const int64_t *__restrict__ tl,
                      const float *__restrict__ grad_out, int64_t go_stride, float *__restrict__ nll_out,
                      float *__restrict__ fac_out, float *__restrict__ grad) {
-    // 2*G warps: warp g (< G) runs the forward sweep of sample g, warp G+g its backward sweep, concurrently; the
-    // per-class collection is a fully parallel pass afterwards.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const float NINF = -INFINITY;
-    const int tid = threadIdx.x, nth = blockDim.x;
+    const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int b0 = blockIdx.x * q.G;
     const int Gv = min(q.G, q.N - b0);
     const int rowElems = q.G * q.C;
     const int SS = q.SS;
-    float *Qall = reinterpret_cast<float *>(smem_raw);          // [T][G*C]
-    float *acc = Qall + q.T * rowElems;                          // [T][G*C]
-    float *Ra = acc + q.T * rowElems;                            // [G][T][SS]
-    float *Rbs = Ra + (size_t)q.G * q.T * SS;                    // [G][T][SS]
-    float *nlls = Rbs + (size_t)q.G * q.T * SS;                  // [G]
-    int *curs = reinterpret_cast<int *>(nlls + q.G);             // [G][SS]
-    unsigned char *pres = reinterpret_cast<unsigned char *>(curs + q.G * SS);   // [T][G*C]
+    const int MW = (q.C + 31) >> 5;
+    float *Qall = reinterpret_cast<float *>(smem_raw);          // [T][G*C]  Q2, then per-class sums, then factors
+    float *Ra = Qall + q.T * rowElems;                           // [G][T][SS]
+    unsigned *mask = reinterpret_cast<unsigned *>(Ra + (size_t)q.G * q.T * SS);   // [G][T][MW]
+    float *nlls = reinterpret_cast<float *>(mask + (size_t)q.G * q.T * MW);       // [G]
 
-    for (int i = tid; i < q.T * rowElems; i += nth) { acc[i] = 0.f; pres[i] = 0; }
-    if (q.vec > 1) phase_q<float, FAST, 4, HT>(q, lp, Qall, b0, Gv);
-    else phase_q<float, FAST, 1, HT>(q, lp, Qall, b0, Gv);
+    if (q.vec > 1) phase_q<float, true, 4, HT, true>(q, lp, Qall, b0, Gv);
+    else phase_q<float, true, 1, HT, true>(q, lp, Qall, b0, Gv);
     __syncthreads();
 
-    const bool is_bwd = warp >= q.G;
-    const int g = is_bwd ? warp - q.G : warp;
-    if (g < Gv && warp < 2 * q.G) {
+    const int g = warp;
+    if (g < Gv) {
         const int b = b0 + g;
-        const int64_t Tb = il[b], L = tl[b];
-        const int64_t *row = tg + (int64_t)b * q.tg_sn;
-        int cur[NS];
-        bool in[NS], skf[NS], skb[NS];
-#pragma unroll
-        for (int k = 0; k < NS; ++k) {
-            const int s = lane * NS + k;
-            cur[k] = q.blank; in[k] = skf[k] = skb[k] = false;
-            if (s < SS && s < 2 * L + 1) {
-                in[k] = L > 0;
-                if (s & 1) {
-                    const int64_t me = row[(int64_t)(s >> 1) * q.tg_ss];
-                    cur[k] = clampi(me, q.C);
-                    if (s > 1) skf[k] = row[(int64_t)((s - 2) >> 1) * q.tg_ss] != me;
-                    if (s < 2 * L - 1) skb[k] = row[(int64_t)((s + 2) >> 1) * q.tg_ss] != me;
-                }
-            }
-            if (!is_bwd && s < SS) curs[g * SS + s] = cur[k];
+        WarpDpCtx w;
+        w.q = &q; w.row = tg + (int64_t)b * q.tg_sn; w.Tb = il[b]; w.L = tl[b];
+        w.Qg = Qall + g * q.C; w.Rag = Ra + (size_t)g * q.T * SS; w.maskg = mask + (size_t)g * q.T * MW;
+        w.rowElems = rowElems; w.MW = MW;
+        int64_t need64 = 2 * w.L + 1;
+        if (need64 > SS) need64 = SS;
+        if (need64 < 1) need64 = 1;
+        const int need = (int)((need64 + 31) >> 5);
+        float nll;
+        if (NSMAX == 1 || need <= 1) nll = warp_sweeps<1, MODE>(w, lane);
+        else if (NSMAX == 2 || need <= 2) nll = warp_sweeps<(NSMAX >= 2 ? 2 : NSMAX), MODE>(w, lane);
+        else if (NSMAX == 3 || need <= 3) nll = warp_sweeps<(NSMAX >= 3 ? 3 : NSMAX), MODE>(w, lane);
+        else if (NSMAX == 4 || need <= 4) nll = warp_sweeps<(NSMAX >= 4 ? 4 : NSMAX), MODE>(w, lane);
+        else if (NSMAX == 8 || need <= 8) nll = warp_sweeps<(NSMAX >= 8 ? 8 : NSMAX), MODE>(w, lane);
+        else if (NSMAX == 16 || need <= 16) nll = warp_sweeps<(NSMAX >= 16 ? 16 : NSMAX), MODE>(w, lane);
+        else nll = warp_sweeps<NSMAX, MODE>(w, lane);
+        if (lane == 0) {
+            nlls[g] = nll;
+            if (MODE != MODE_GRAD) nll_out[b] = nll;
         }
-        const float *Qg = Qall + g * q.C;
-        if (!is_bwd) {
-            // ---------------- forward sweep (K1 recurrence on the height-marginal)
-            float *Rag = Ra + (size_t)g * q.T * SS;
-            float R[NS], a[NS];
-            float f0 = NINF, f1 = NINF;
-#pragma unroll 1
-            for (int t = 0; t < q.T; ++t) {
-                if (t == 0) {
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) {
-                        const int s = lane * NS + k;
-                        R[k] = (s == 0 || (s == 1 && L > 0)) ? 0.f : NINF;
-                    }
-                } else {
-                    float up1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
-                    float up2 = NS >= 2 ? __shfl_up_sync(0xffffffffu, a[NS >= 2 ? NS - 2 : 0], 1)
-                                        : __shfl_up_sync(0xffffffffu, a[0], 2);
-                    if (lane == 0) up1 = up2 = NINF;
-                    if (NS == 1 && lane == 1) up2 = NINF;
-                    float Rn[NS];
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) {
-                        const float am1 = k >= 1 ? a[k >= 1 ? k - 1 : 0] : up1;
-                        const float am2 = k >= 2 ? a[k >= 2 ? k - 2 : 0] : (k == 1 ? up1 : up2);
-                        Rn[k] = (t < Tb && in[k]) ? lse3<FAST>(a[k], am1, skf[k] ? am2 : NINF) : NINF;
-                    }
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) R[k] = Rn[k];
-                }
-                const float *Qt = Qg + t * rowElems;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) {
-                    const int s = lane * NS + k;
-                    if (s < SS) Rag[t * SS + s] = R[k];
-                    a[k] = R[k] + Qt[cur[k]];
-                    if (t == Tb - 1) {
-                        if (s == 2 * L) f0 = a[k];
-                        else if (s == 2 * L - 1) f1 = a[k];
-                    }
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                f0 = fmaxf(f0, __shfl_xor_sync(0xffffffffu, f0, o));
-                f1 = fmaxf(f1, __shfl_xor_sync(0xffffffffu, f1, o));
-            }
-            const float my_nll = -lse2<FAST>(f0, f1);
-            if (lane == 0) {
-                nlls[g] = my_nll;
-                if (MODE != MODE_GRAD) nll_out[b] = my_nll;
-            }
-        } else {
-            // ---------------- backward sweep (K2 recurrence)
-            float *Rbg = Rbs + (size_t)g * q.T * SS;
-            float bq[NS];
-#pragma unroll
-            for (int k = 0; k < NS; ++k) bq[k] = NINF;
-#pragma unroll 1
-            for (int t = q.T - 1; t >= 0; --t) {
-                float Rb[NS];
-                if (t == Tb - 1) {
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) {
-                        const int s = lane * NS + k;
-                        Rb[k] = (s == 2 * L || (L > 0 && s == 2 * L - 1)) ? 0.f : NINF;
-                    }
-                } else if (t < Tb - 1) {
-                    float dn1 = __shfl_down_sync(0xffffffffu, bq[0], 1);
-                    float dn2 = NS >= 2 ? __shfl_down_sync(0xffffffffu, bq[NS >= 2 ? 1 : 0], 1)
-                                        : __shfl_down_sync(0xffffffffu, bq[0], 2);
-                    if (lane == 31) dn1 = dn2 = NINF;
-                    if (NS == 1 && lane == 30) dn2 = NINF;
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) {
-                        const int s = lane * NS + k;
-                        const float bp1 = k + 1 < NS ? bq[k + 1 < NS ? k + 1 : 0] : dn1;
-                        const float bp2 = k + 2 < NS ? bq[k + 2 < NS ? k + 2 : 0] : (k + 1 < NS ? dn1 : dn2);
-                        Rb[k] = in[k] ? lse3<FAST>(bq[k], s < 2 * L ? bp1 : NINF, skb[k] ? bp2 : NINF) : NINF;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < NS; ++k) Rb[k] = NINF;
-                }
-                const float *Qt = Qg + t * rowElems;
-#pragma unroll
-                for (int k = 0; k < NS; ++k) {
-                    const int s = lane * NS + k;
-                    if (s < SS) Rbg[t * SS + s] = Rb[k];
-                    bq[k] = Rb[k] + Qt[cur[k]];
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- K3's per-class collection, fully parallel: acc[t][g][l'_s] += exp(R + Rb + nll)
-    {
-        const int nwarps = nth >> 5;
-        for (int gg = 0; gg < Gv; ++gg) {
-            const float nl = nlls[gg];
-            const int *cg = curs + gg * SS;
-            for (int t = warp; t < q.T; t += nwarps) {
-                const float *ra = Ra + ((size_t)gg * q.T + t) * SS, *rb = Rbs + ((size_t)gg * q.T + t) * SS;
-                float *accr = acc + t * rowElems + gg * q.C;
-                unsigned char *pr = pres + t * rowElems + gg * q.C;
-                for (int sidx = lane; sidx < SS; sidx += 32) {
-                    const float v = ra[sidx] + rb[sidx];       // Ra / Rbs share the [G][T][SS] layout
-                    if (v != NINF) {
-                        const int c = cg[sidx];
-                        pr[c] = 1;
-                        atomicAdd(accr + c, ex<FAST>(v + nl));
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    for (int e = tid; e < Gv * q.C; e += nth) {
-        const int gg = e / q.C;
-        const int cc = e - gg * q.C;
-        const int64_t Tb = il[b0 + gg];
-        const float gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + gg) * go_stride] : 1.f;
-        float *fo = (MODE != MODE_GRAD) ? fac_out + (int64_t)(b0 + gg) * q.C + cc : nullptr;
-        const bool dead = (MODE == MODE_FAC_STD) && q.zero_inf && (nlls[gg] == INFINITY);
+        // ---- factor: (1 - sum) [* go] where the class is present and t < Tb, else 0 (K3 :501-515)
+        const int64_t Tb = w.Tb;
+        const float gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)b * go_stride] : 1.f;
+        const bool dead = (MODE == MODE_FAC_STD) && q.zero_inf && (nll == INFINITY);
         for (int t = 0; t < q.T; ++t) {
-            const int o = t * rowElems + e;
-            float f = 0.f;
-            if (MODE == MODE_FAC_STD) {
-                if (t < Tb && !dead) f = 1.f - acc[o];
-            } else if (pres[o] && t < Tb) f = (1.f - acc[o]) * gs;
-            if (MODE != MODE_GRAD) fo[(int64_t)t * q.N * q.C] = f;
-            else acc[o] = f;
+            float *Qt = w.Qg + t * rowElems;
+            for (int c = lane; c < q.C; c += 32) {
+                float f = 0.f;
+                if (MODE == MODE_FAC_STD) {
+                    if (t < Tb && !dead) f = 1.f - Qt[c];
+                } else if (t < Tb && ((w.maskg[t * MW + (c >> 5)] >> (c & 31)) & 1u)) f = (1.f - Qt[c]) * gs;
+                if (MODE != MODE_GRAD) fac_out[((int64_t)t * q.N + b) * q.C + c] = f;
+                else Qt[c] = f;
+            }
         }
     }
     if (MODE == MODE_GRAD) {
         __syncthreads();
-        if (q.vec > 1) phase_grad<float, FAST, 4, HT>(q, lp, acc, grad, b0, Gv);
-        else phase_grad<float, FAST, 1, HT>(q, lp, acc, grad, b0, Gv);
+        if (q.vec > 1) phase_grad<float, true, 4, HT>(q, lp, Qall, grad, b0, Gv);
+        else phase_grad<float, true, 1, HT>(q, lp, Qall, grad, b0, Gv);
     }
 }
 
@@ -894,10 +921,10 @@ int launch_alpha(const real *lp, const int64_t *tg, const int64_t *il, const int
     return check_launch("ctc2d_alpha_kernel");
 }
 
-template <bool FAST, int MODE, int NS>
+template <int MODE, int NSMAX>
 int launch_dp_warp_ns(Geo q, const float *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const float *go,
                       int64_t go_stride, float *nll, float *fac, float *grad, size_t smem, cudaStream_t st) {
-    auto kern = (q.H == 8) ? ctc2d_dp_warp_kernel<FAST, MODE, NS, 8> : ctc2d_dp_warp_kernel<FAST, MODE, NS, 0>;
+    auto kern = (q.H == 8) ? ctc2d_dp_warp_kernel<MODE, NSMAX, 8> : ctc2d_dp_warp_kernel<MODE, NSMAX, 0>;
     if (smem > 48 * 1024)
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "ctc2d_dp_warp attr");
     kern<<<(unsigned)ceil_div(q.N, q.G), 256, smem, st>>>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad);
@@ -905,27 +932,27 @@ int launch_dp_warp_ns(Geo q, const float *lp, const int64_t *tg, const int64_t *
 }
 
 // returns MR_ERR_UNSUPPORTED when the warp kernel's shared-memory plan does not fit (caller falls back)
-template <bool FAST, int MODE>
+template <int MODE>
 int launch_dp_warp(Geo q, const float *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const float *go,
                    int64_t go_stride, float *nll, float *fac, float *grad, cudaStream_t st) {
     const int need_ns = (q.SS + 31) / 32;
-    const int opts[] = {1, 2, 3, 4, 6, 8, 16, 32};
+    const int opts[] = {1, 2, 3, 4, 8, 16, 32};
     int NS = 0;
     for (int o : opts) if (o >= need_ns) { NS = o; break; }
     if (!NS) return MR_ERR_UNSUPPORTED;
-    int G = 4;
+    int G = 8;                                               // one warp per sample, 8 samples per CTA
     auto need = [&](int g) {
-        return sizeof(float) * ((size_t)2 * q.T * g * q.C + (size_t)2 * g * q.T * q.SS + g + (size_t)g * q.SS) +
-               (size_t)q.T * g * q.C + 16;
+        return sizeof(float) * ((size_t)q.T * g * q.C + (size_t)g * q.T * q.SS + g) +
+               sizeof(unsigned) * (size_t)g * q.T * ((q.C + 31) / 32) + 16;
     };
-    while (G > 1 && need(G) > (size_t)112 * 1024) --G;
+    while (G > 1 && need(G) > (size_t)110 * 1024) --G;
     const size_t smem = need(G);
     if (smem > (size_t)smem_limit()) return MR_ERR_UNSUPPORTED;
     q.G = G;
     q.vec = pick_vec<float>(lp, q.N, q.C, G);
     if (MODE == MODE_GRAD && ((uintptr_t)grad % 16) != 0) q.vec = 1;
-#define MR_NS(NSV) case NSV: return launch_dp_warp_ns<FAST, MODE, NSV>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad, smem, st)
-    switch (NS) { MR_NS(1); MR_NS(2); MR_NS(3); MR_NS(4); MR_NS(6); MR_NS(8); MR_NS(16); MR_NS(32); }
+#define MR_NS(NSV) case NSV: return launch_dp_warp_ns<MODE, NSV>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad, smem, st)
+    switch (NS) { MR_NS(1); MR_NS(2); MR_NS(3); MR_NS(4); MR_NS(8); MR_NS(16); MR_NS(32); }
 #undef MR_NS
     return MR_ERR_UNSUPPORTED;
 }
@@ -938,12 +965,12 @@ int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_
     q.zero_inf = zero_inf;
     q.T = (int)T; q.H = (int)H; q.N = (int)N; q.C = (int)C; q.S = (int)S; q.SS = (int)(2 * S + 1);
     q.blank = (int)blank; q.tg_sn = tg_sn; q.tg_ss = tg_ss;
-    // The warp-per-sample variant (sweeps in registers, concurrent forward/backward warps) measured SLOWER than the
-    // block variant below on B200 (forward_train 559 us vs 457 us at N=16384): opt-in via MR_CTC2D_WARP_DP=1.
-    if (sizeof(real) == 4 && getenv("MR_CTC2D_WARP_DP")) {
-        q.G = 4; q.vec = 1;
-        const int rc = launch_dp_warp<FAST, MODE>(q, (const float *)lp, tg, il, tl, (const float *)go, go_stride, (float *)nll,
-                                                  (float *)fac, (float *)grad, st);
+    // fp32 fast-math requests use the warp-per-sample kernel (MR_CTC2D_BLOCK_DP=1 forces the block variant below);
+    // accurate-math and fp64 requests, and shapes whose plan does not fit, use the block variant.
+    if (sizeof(real) == 4 && FAST && !getenv("MR_CTC2D_BLOCK_DP")) {
+        q.G = 8; q.vec = 1;
+        const int rc = launch_dp_warp<MODE>(q, (const float *)lp, tg, il, tl, (const float *)go, go_stride, (float *)nll,
+                                            (float *)fac, (float *)grad, st);
         if (rc != MR_ERR_UNSUPPORTED) return rc;
     }
     int G = 160 / q.SS;  // fewer samples per CTA than the alpha kernel: the sweeps are latency-bound,
