@@ -701,8 +701,14 @@ __device__ __forceinline__ float warp_sweeps(const WarpDpCtx &w, int lane) {
 #pragma unroll
         for (int k = 0; k < NS; ++k) bq[k] = Rb[k] + Qt[cur[k]];
         __syncwarp();                                        // every lane has read Q2[t] -> the row may be reused
-        for (int cidx = lane; cidx < q.C; cidx += 32) Qt[cidx] = 0.f;
-        for (int mw = lane; mw < w.MW; mw += 32) w.maskg[t * w.MW + mw] = 0u;
+        if (q.C <= 64) {                                     // common case: two predicated stores, no loop
+            if (lane < q.C) Qt[lane] = 0.f;
+            if (lane + 32 < q.C) Qt[lane + 32] = 0.f;
+            if (lane < w.MW) w.maskg[t * w.MW + lane] = 0u;
+        } else {
+            for (int cidx = lane; cidx < q.C; cidx += 32) Qt[cidx] = 0.f;
+            for (int mw = lane; mw < w.MW; mw += 32) w.maskg[t * w.MW + mw] = 0u;
+        }
         __syncwarp();
         if (t < Tb) {
 #pragma unroll
