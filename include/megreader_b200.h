@@ -221,6 +221,15 @@ int mr_lstm_step_bwd_tcgen05(const void *const *dG_next, const void *const *Whh,
                              const float *const *c, const float *const *c_prev, const void *const *dh_out, int64_t ldh,
                              float *const *dc, void *const *dgates, int have_rec, int B, int H, void *stream);
 
+/* Greedy CTC decoding to label indices (structure/representers/ctc_representer.py:22-34, ctc_representer2d.py:27-51):
+ * arg-max class per column (2D: along the arg-max-height path of classify*mask), then collapse repeats / skip
+ * `unknown` / drop blanks.  prob strides (sN,sC,sH,sW) in elements; mask nullable with strides (mN,mH,mW).
+ * out int32 [N,W] blank-padded.  mr_blank_after_first_blank: sequence_recognition_representer.py:23-28. */
+int mr_ctc_greedy_decode(const float *prob, const float *mask, int N, int C, int H, int W, int64_t sN, int64_t sC,
+                         int64_t sH, int64_t sW, int64_t mN, int64_t mH, int64_t mW, int blank, int unknown, int *out,
+                         void *stream);
+int mr_blank_after_first_blank(int *pred, int N, int W, int blank, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -687,6 +687,65 @@ __global__ void cast_kernel(const TI *__restrict__ x, int64_t n, TO *__restrict_
         y[i] = from_f<TO>(to_f<TI>(x[i]));
 }
 
+
+// ---------------------------------------------------------------- greedy CTC decoding
+// structure/representers/ctc_representer.py:22-34 and ctc_representer2d.py:27-51: per column the arg-max class
+// (2D: along the arg-max-height path of classify*mask), then the collapse rule: skip a column whose class equals the
+// previous kept class OR is `unknown` (without updating `previous`); otherwise emit it unless it is blank, and
+// remember it.  Output int32 [N, W], blank-padded.  One CTA per sample: threads = columns, thread 0 runs the scan.
+__global__ void ctc_greedy_decode_kernel(const float *__restrict__ prob, const float *__restrict__ mask, int C, int H,
+                                         int W, int64_t sN, int64_t sC, int64_t sH, int64_t sW, int64_t mN, int64_t mH,
+                                         int64_t mW, int blank, int unknown, int *__restrict__ out) {
+    extern __shared__ int pred[];
+    const int n = blockIdx.x;
+    const float *p = prob + (int64_t)n * sN;
+    const float *m = mask ? mask + (int64_t)n * mN : nullptr;
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+        int hbest = 0;
+        if (H > 1 || m) {                       // arg-max over heights of max over classes of classify*mask
+            float best = -INFINITY;
+            for (int h = 0; h < H; ++h) {
+                const float mv = m ? m[h * mH + w * mW] : 1.f;
+                float cmax = -INFINITY;
+                for (int c = 0; c < C; ++c) cmax = fmaxf(cmax, p[c * sC + h * sH + w * sW] * mv);
+                if (cmax > best) { best = cmax; hbest = h; }
+            }
+        }
+        const float mv = m ? m[hbest * mH + w * mW] : 1.f;
+        float best = -INFINITY;
+        int cbest = 0;
+        for (int c = 0; c < C; ++c) {
+            const float v = p[c * sC + hbest * sH + w * sW] * mv;
+            if (v > best) { best = v; cbest = c; }          // first maximum wins
+        }
+        pred[w] = cbest;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int valid = 0, previous = blank;
+        int *o = out + (int64_t)n * W;
+        for (int w = 0; w < W; ++w) {
+            const int c = pred[w];
+            if (c == previous || c == unknown) continue;
+            if (c != blank) o[valid++] = c;
+            previous = c;
+        }
+        for (int w = valid; w < W; ++w) o[w] = blank;
+    }
+}
+
+// sequence_recognition_representer.py:23-28: everything from the first blank on becomes blank (attention decoder output)
+__global__ void blank_after_first_blank_kernel(int *__restrict__ pred, int N, int W, int blank) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    int *r = pred + (int64_t)n * W;
+    bool seen = false;
+    for (int w = 0; w < W; ++w) {
+        seen = seen || (r[w] == blank);
+        if (seen) r[w] = blank;
+    }
+}
+
 #define DISPATCH(dtype, CALL)                                   \
     do { if ((dtype) == 0) { using T = float; CALL; }           \
          else if ((dtype) == 1) { using T = bf16; CALL; }       \
@@ -978,6 +1037,29 @@ int mr_cast(const void *x, int src_dtype, int64_t n, int dst_dtype, void *y, voi
     else if (src_dtype == 1 && dst_dtype == 1) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16 *)x, n, (bf16 *)y);
     else return MR_ERR_BAD_SHAPE;
     return check_launch("cast_kernel");
+}
+
+/* Greedy CTC decoding to label indices (bit-exact integer output).  prob: class scores with element strides
+ * (sN, sC, sH, sW); mask (nullable, 2D-CTC): strides (mN, mH, mW).  out int32 [N, W]. */
+int mr_ctc_greedy_decode(const float *prob, const float *mask, int N, int C, int H, int W, int64_t sN, int64_t sC,
+                         int64_t sH, int64_t sW, int64_t mN, int64_t mH, int64_t mW, int blank, int unknown, int *out,
+                         void *stream) {
+    if (N < 0 || C <= 0 || H <= 0 || W <= 0) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!prob || !out) return MR_ERR_NULL_POINTER;
+    if ((size_t)W * sizeof(int) > 48 * 1024) return MR_ERR_UNSUPPORTED;
+    const int threads = W < 32 ? 32 : (W > 256 ? 256 : (int)round_up(W, 32));
+    ctc_greedy_decode_kernel<<<N, threads, (size_t)W * sizeof(int), (cudaStream_t)stream>>>(prob, mask, C, H, W, sN, sC, sH, sW,
+                                                                                        mN, mH, mW, blank, unknown, out);
+    return check_launch("ctc_greedy_decode_kernel");
+}
+
+int mr_blank_after_first_blank(int *pred, int N, int W, int blank, void *stream) {
+    if (N < 0 || W <= 0) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!pred) return MR_ERR_NULL_POINTER;
+    blank_after_first_blank_kernel<<<(int)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(pred, N, W, blank);
+    return check_launch("blank_after_first_blank_kernel");
 }
 
 }  // extern "C"
