@@ -1,0 +1,167 @@
+"""Attention recogniser head with the reference's surface (decoders/attention_decoder.py:10-231).
+
+Same modules, parameter names and shapes (state-dict compatible):
+  encode.{0,1,3,4,6,7,9}.{0,1}   conv+BN(+ReLU) stack with pools (2,2),(2,1),(2,1) and a closing (2,3)/(2,1) conv
+  onehot_embedding_{x,y}          identity-initialised position embeddings (max_size / height wide)
+  decoder.{embedding,word_linear,attn.attn,attn.v,rnn,out}   Bahdanau cell: Linear(2H+E -> H), v, GRUCell(2H+E -> H)
+
+What is done differently (same numbers up to fp32 re-association):
+  * the additive-attention energy is Linear([h ; enc_l]) for every position l; the encoder half of that product
+    does not depend on the step, so it is computed ONCE per call ((N,L,E)x(E,H)) and each step only adds the
+    (N,H) hidden half — the reference rebuilds the (N,L,2H+E) concatenation and redoes the full product on each
+    of its 32 steps (attention_decoder.py:152-169);
+  * the eval loop issues all steps without a host round-trip and applies the reference's early exit
+    ("stop once every sample emitted blank", attention_decoder.py:129-130) afterwards on the device: columns
+    after the first all-blank step are blank, which is exactly what the break leaves behind.
+Random draws during training (teacher-forcing coin, step dropout) consume numpy / torch CPU generators in the
+reference's order (attention_decoder.py:106-114), so seeded runs line up.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from megreader_b200.charset import default_charset
+
+
+class Attn(nn.Module):
+    def __init__(self, method, hidden_dims, embed_size):
+        super().__init__()
+        self.method = method
+        self.hidden_dims = hidden_dims
+        self.embed_size = embed_size
+        self.attn = nn.Linear(2 * hidden_dims + embed_size, hidden_dims)
+        self.v = nn.Parameter(torch.empty(hidden_dims).normal_(mean=0, std=1.0 / math.sqrt(hidden_dims)))
+
+    def project_encoder(self, encoder_outputs):
+        """Step-invariant half of the energy: (L,N,H+E) -> (N,L,H), bias included."""
+        w_enc = self.attn.weight[:, self.hidden_dims:]
+        return torch.matmul(encoder_outputs.transpose(0, 1), w_enc.t()) + self.attn.bias
+
+    def forward(self, hidden, encoder_outputs, projected=None):
+        """hidden (N,H) [or (1,N,H)], encoder_outputs (L,N,H+E) -> attention weights (N,1,L)."""
+        if projected is None:
+            projected = self.project_encoder(encoder_outputs)
+        hidden = hidden.reshape(-1, self.hidden_dims)
+        from_hidden = F.linear(hidden, self.attn.weight[:, :self.hidden_dims])        # (N,H)
+        energy = torch.tanh(projected + from_hidden.unsqueeze(1))                        # (N,L,H)
+        return F.softmax(torch.matmul(energy, self.v), dim=1).unsqueeze(1)
+
+    def score(self, hidden, encoder_outputs):
+        """Reference-shaped entry (attention_decoder.py:160-171): hidden (N,L,H), encoder_outputs (N,L,H+E) -> (N,L)."""
+        energy = torch.tanh(self.attn(torch.cat([hidden, encoder_outputs], 2)))
+        return torch.matmul(energy, self.v)
+
+
+class AttentionRNNCell(nn.Module):
+    def __init__(self, hidden_dims, embedded_dims, nr_classes, n_layers=1, dropout_p=0, bidirectional=False):
+        super().__init__()
+        self.hidden_dims = hidden_dims
+        self.embedded_dims = embedded_dims
+        self.nr_classes = nr_classes
+        self.n_layers = n_layers
+        self.dropout_p = dropout_p
+        self.embedding = nn.Embedding(nr_classes, nr_classes)
+        self.embedding.weight.data = torch.eye(nr_classes)
+        self.dropout = nn.Dropout(dropout_p)
+        self.word_linear = nn.Linear(nr_classes, hidden_dims)
+        self.attn = Attn('concat', hidden_dims, embedded_dims)
+        self.rnn = nn.GRUCell(2 * hidden_dims + embedded_dims, hidden_dims)
+        self.out = nn.Linear(hidden_dims, nr_classes)
+
+    def forward(self, word_input, last_hidden, encoder_outputs, train=True, projected=None, encoder_bt=None):
+        """One decoding step: word_input (N,), last_hidden (N,H), encoder_outputs (L,N,H+E)
+        -> (log-probs or probs (N,V), hidden (N,H), attention (N,1,L))."""
+        n = word_input.size(0)
+        word = self.word_linear(self.embedding(word_input.to(last_hidden.device).long()))     # (N,H)
+        weights = self.attn(last_hidden, encoder_outputs, projected)
+        if encoder_bt is None:
+            encoder_bt = encoder_outputs.transpose(0, 1)
+        context = torch.bmm(weights, encoder_bt).squeeze(1)                                    # (N,H+E)
+        hidden = self.rnn(torch.cat([word, context], 1), last_hidden.view(n, -1))
+        logits = self.out(hidden)
+        return (F.log_softmax(logits, dim=1) if train else F.softmax(logits, dim=1)), hidden, weights
+
+
+class AttentionDecoder(nn.Module):
+    def __init__(self, in_channels, charset=None, inner_channels=512, max_size=32, height=1, gt_as_output=None,
+                 step_dropout=0, **kwargs):
+        super().__init__()
+        self.inner_channels = inner_channels
+        self.encode = self._init_encoder(in_channels)
+        self.max_size = max_size
+        self.charset = charset if charset is not None else default_charset()
+        self.height = height
+        self.decoder = AttentionRNNCell(inner_channels, max_size + height, len(self.charset))
+        self.step_dropout = step_dropout
+        self.onehot_embedding_x = nn.Embedding(max_size, max_size)
+        self.onehot_embedding_x.weight.data = torch.eye(max_size)
+        self.onehot_embedding_y = nn.Embedding(height, height)
+        self.onehot_embedding_y.weight.data = torch.eye(height)
+        self.gt_as_output = gt_as_output
+        self.loss_function = nn.NLLLoss(reduction='none')
+
+    def conv_bn_relu(self, input_channels, output_channels, kernel_size=3, stride=1, padding=1):
+        return nn.Sequential(nn.Conv2d(input_channels, output_channels, kernel_size, stride, padding),
+                             nn.BatchNorm2d(output_channels), nn.ReLU(inplace=True))
+
+    def _init_encoder(self, in_channels, stride=(2, 1), padding=(0, 1)):
+        c = self.inner_channels
+        cbr = self.conv_bn_relu
+        return nn.Sequential(cbr(in_channels, c), cbr(c, c), nn.MaxPool2d((2, 2), (2, 2), (0, 0)),
+                             cbr(c, c), cbr(c, c), nn.MaxPool2d(stride, stride, (0, 0)),
+                             cbr(c, c), cbr(c, c), nn.MaxPool2d(stride, stride, (0, 0)),
+                             cbr(c, c, kernel_size=(2, 3), stride=stride, padding=padding))
+
+    def _get_gt_as_output(self):
+        if self.gt_as_output is not None:
+            return self.gt_as_output
+        return np.random.rand() < 0.5
+
+    def _positions(self, batch, device):
+        """(N, height+max_size, height, max_size): one-hot row then column coordinates of every cell."""
+        ys = torch.arange(self.height, device=device).view(-1, 1).expand(self.height, self.max_size)
+        xs = torch.arange(self.max_size, device=device).view(1, -1).expand(self.height, self.max_size)
+        ey = self.onehot_embedding_y(ys).permute(2, 0, 1)
+        ex = self.onehot_embedding_x(xs).permute(2, 0, 1)
+        return torch.cat([ey, ex], 0).unsqueeze(0).expand(batch, -1, -1, -1)
+
+    def forward(self, feature, targets=None, lengths=None, train=False):
+        device = feature.device
+        n = feature.shape[0]
+        grid = torch.cat([self.encode(feature), self._positions(n, device)], dim=1)
+        memory = grid.reshape(n, grid.shape[1], -1).permute(2, 0, 1)            # (L,N,H+E), L = height*max_size
+        memory_bt = memory.transpose(0, 1)
+        projected = self.decoder.attn.project_encoder(memory)
+        blank = self.charset.blank
+        hidden = feature.new_zeros(n, self.inner_channels)
+        word = torch.full((n,), blank, dtype=torch.long, device=device)
+        vocab = len(self.charset)
+
+        if self.training:
+            targets = targets.long()
+            lengths = lengths.to(device)
+            loss = None
+            attention = []
+            for t in range(self.max_size):
+                logp, hidden, weights = self.decoder(word, hidden, memory, True, projected, memory_bt)
+                step = self.loss_function(logp, targets[:, t]) * (t <= lengths).float()
+                loss = step if loss is None else loss + step
+                attention.append(weights)
+                word = targets[:, t] if self._get_gt_as_output() else logp.argmax(dim=1).detach()
+                # step dropout: a random class replaces the fed-back symbol with probability step_dropout
+                swap = (torch.rand(*word.shape) < self.step_dropout).long().to(device)
+                noise = torch.randint(high=vocab, size=word.shape).to(device)
+                word = word.to(device) * (1 - swap) + noise * swap
+            return loss, torch.cat(attention, 1).view(n, -1, self.height, self.max_size)
+
+        steps = []
+        for t in range(self.max_size):
+            prob, hidden, _ = self.decoder(word, hidden, memory, False, projected, memory_bt)
+            word = prob.argmax(dim=1)
+            steps.append(word)
+        pred = torch.stack(steps, 1)                                             # (N, max_size)
+        finished = (pred == blank).all(dim=0).long().cummax(0).values.bool()   # step t or an earlier one was all-blank
+        return pred.masked_fill(finished.unsqueeze(0), blank).to(torch.int32)

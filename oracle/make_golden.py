@@ -108,6 +108,56 @@ def make_crnn():
         fill_state_dict(bb, "bb."); fill_state_dict(dec, "dec.")
 
 
+def make_surfaces():
+    """Recognition-side surfaces around the hot path (SURVEY.md §8 A9/A10 + the 1-D CTC conv head): outputs of the
+    UNMODIFIED reference modules on CPU, fp32, weights from tests.weights.fill_state_dict (name-seeded)."""
+    from tests.weights import fill_state_dict, surface_inputs
+    ref_loader.install()
+    import backbones as rb
+    import decoders as rd
+    x, x2, feat, tg_pad, ln = surface_inputs()
+    tx = torch.from_numpy(x)
+    out = {}
+    with torch.no_grad():
+        m = fill_state_dict(rb.resnet18(pretrained=False), "r18.").eval()
+        for i, f in enumerate(m(tx)):
+            out["r18.%d" % i] = f.numpy()
+        m = fill_state_dict(rb.resnet50dilated_ppm(), "ppm.").eval()
+        out["ppm"] = m(tx).numpy()
+        m = fill_state_dict(rb.Resnet50FPN(resnet_pretrained=False), "fpn50.").eval()
+        out["fpn50"] = m(tx).numpy()
+    # training-mode trunk (batch statistics) with a gradient norm per stage
+    m = fill_state_dict(rb.Resnet18FPN(resnet_pretrained=False), "fpn18.").train()
+    y = m(torch.from_numpy(x2))
+    y.square().mean().backward()
+    out["fpn18.train"] = y.detach().numpy()
+    for k in ("bottom_up.conv1.weight", "bottom_up.layer3.0.downsample.0.weight", "top_down.merge_layer.weight"):
+        out["fpn18.gnorm." + k] = np.float64(dict(m.named_parameters())[k].grad.double().norm().item())
+
+    tf, tt, tl = torch.from_numpy(feat), torch.from_numpy(tg_pad), torch.from_numpy(ln)
+    att = fill_state_dict(rd.AttentionDecoder(256, gt_as_output=True), "attn.").train()
+    loss, amap = att(tf, targets=tt, lengths=tl)
+    loss.sum().backward()
+    out["attn.loss"] = loss.detach().numpy()
+    out["attn.map"] = amap.detach().numpy()
+    for k in ("encode.0.0.weight", "decoder.attn.attn.weight", "decoder.attn.v", "decoder.rnn.weight_hh",
+              "decoder.embedding.weight", "onehot_embedding_x.weight"):
+        out["attn.gnorm." + k] = np.float64(dict(att.named_parameters())[k].grad.double().norm().item())
+    with torch.no_grad():
+        out["attn.eval"] = att.eval()(tf).numpy()
+    ctc = fill_state_dict(rd.CTCDecoder(256), "ctc1d.")
+    with torch.no_grad():                                     # eval first: pristine BN running statistics
+        out["ctc1d.eval"] = ctc.eval()(tf, train=False).numpy()
+    loss, lp = ctc.train()(tf, targets=tt, lengths=tl, train=True)
+    loss.backward()
+    out["ctc1d.loss"] = np.float64(loss.item())
+    out["ctc1d.log_probs"] = lp.detach().numpy()
+    for k in ("encode.0.0.weight", "pred_conv.weight", "pred_conv.bias"):
+        out["ctc1d.gnorm." + k] = np.float64(dict(ctc.named_parameters())[k].grad.double().norm().item())
+    np.savez_compressed(os.path.join(GOLD, "surfaces_ref.npz"), **out)
+    print("surfaces", {k: getattr(v, "shape", v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["ctc2d"]
@@ -115,3 +165,5 @@ if __name__ == "__main__":
         make_ctc2d()
     if "crnn" in which:
         make_crnn()
+    if "surfaces" in which:
+        make_surfaces()

@@ -45,3 +45,16 @@ def crnn_batch(seed, N, W, L_max, T, n_classes=38, S=32):
     for b in range(N):
         labels[b, :lengths[b]] = rng.randint(2, n_classes, size=lengths[b])
     return x, labels, lengths
+
+
+def surface_inputs():
+    """Seeded inputs of tests/golden/surfaces_ref.npz (regenerated on both sides instead of stored)."""
+    rng = np.random.RandomState(11)
+    x = rng.standard_normal((1, 3, 32, 64)).astype(np.float32)
+    x2 = rng.standard_normal((2, 3, 32, 64)).astype(np.float32)
+    feat = (rng.standard_normal((3, 256, 16, 64)) * 0.5).astype(np.float32)
+    lengths = np.array([5, 9, 31], np.int64)
+    targets = rng.randint(2, 38, size=(3, 32)).astype(np.int64)
+    for b in range(3):
+        targets[b, lengths[b]:] = 0
+    return x, x2, feat, targets, lengths
