@@ -221,6 +221,23 @@ int mr_lstm_step_bwd_tcgen05(const void *const *dG_next, const void *const *Whh,
                              const float *const *c, const float *const *c_prev, const void *const *dh_out, int64_t ldh,
                              float *const *dc, void *const *dgates, int have_rec, int B, int H, void *stream);
 
+/* Whole-sequence recurrence of ONE bidirectional LSTM layer in a single persistent launch (csrc/lstm_seq_tcgen05.cu):
+ * replaces the T per-step launches of the cuDNN LSTM the reference calls (decoders/crnn.py:13,17 nn.LSTM;
+ * SURVEY.md section 8 A7).  bf16 operands, unit-major gate columns, H % 64 == 0.
+ *   Whh   : HOST array of 2 device pointers, [4H, H] bf16 unit-major rows (direction 0 = forward in time, 1 = reverse)
+ *   G     : [2, T, B, 4H] bf16 -- x-projection on entry, activated gates (i,f,g,o) on exit
+ *   bias  : HOST array of 2 device pointers, [4H] fp32 unit-major (b_ih + b_hh)
+ *   C     : [2, T, B, H] fp32 cell states, out;   Y : [T, B, 2H] bf16 layer output, out (direction d -> columns d*H..)
+ *   flags : [2*ceil(B/128) + 1] uint32 scratch (zeroed by the call); after completion the last word is 0, or a non-zero
+ *           code if an inter-CTA wait timed out (results then undefined)
+ * bwd:  dY [T, B, 2H] bf16 -> dG [2, T, B, 4H] bf16 gate gradients (the weight/input gradients are plain GEMMs on dG).
+ * MR_ERR_UNSUPPORTED when the CTA grid cannot be co-resident on this device or H exceeds the shared-memory budget
+ * (fwd H <= 512, bwd H <= 256): callers then use the per-step entry points above. */
+int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const *bias, float *C, void *Y,
+                            unsigned *flags, int T, int B, int H, void *stream);
+int mr_lstm_seq_bwd_tcgen05(const void *const *Whh, const void *G, const float *C, const void *dY, void *dG,
+                            unsigned *flags, int T, int B, int H, void *stream);
+
 /* Greedy CTC decoding to label indices (structure/representers/ctc_representer.py:22-34, ctc_representer2d.py:27-51):
  * arg-max class per column (2D: along the arg-max-height path of classify*mask), then collapse repeats / skip
  * `unknown` / drop blanks.  prob strides (sN,sC,sH,sW) in elements; mask nullable with strides (mN,mH,mW).

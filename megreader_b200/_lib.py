@@ -54,6 +54,8 @@ _SIGS = {
     "mr_conv_wgrad_tcgen05": [c_p] * 3 + [c_int] * 10 + [c_p],
     "mr_lstm_step_fwd_tcgen05": [c_p] * 7 + [c_i64, c_p, c_int, c_int, c_int, c_p],
     "mr_lstm_step_bwd_tcgen05": [c_p] * 6 + [c_i64, c_p, c_p, c_int, c_int, c_int, c_p],
+    "mr_lstm_seq_fwd_tcgen05": [c_p] * 6 + [c_int] * 3 + [c_p],
+    "mr_lstm_seq_bwd_tcgen05": [c_p] * 6 + [c_int] * 3 + [c_p],
     "mr_ctc_greedy_decode": [c_p, c_p] + [c_int] * 4 + [c_i64] * 7 + [c_int, c_int, c_p, c_p],
     "mr_blank_after_first_blank": [c_p, c_int, c_int, c_int, c_p],
     "mr_dcn_workspace_bytes": [c_i64] * 6,
@@ -88,6 +90,9 @@ def lib():
             fn.restype = _RESTYPES.get(name, c_int)
         _lib = L
     return _lib
+
+
+MR_ERR_UNSUPPORTED = 5      # include/megreader_b200.h
 
 
 def check(status, what=""):

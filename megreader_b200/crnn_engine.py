@@ -23,7 +23,12 @@ USE_TCGEN05 = __import__("os").environ.get("MEGREADER_B200_TCGEN05", "1") != "0"
 # Fused tcgen05 LSTM time steps (recurrent GEMM + cell in one launch).  Correct (tests/test_nn_kernels_gpu.py) but
 # measured 0.7 ms/step SLOWER at batch 512 than cuBLAS strided-batched GEMM + cell kernel (per-launch TMEM/barrier
 # set-up dominates a 4-k-block GEMM), so it is opt-in.
-LSTM_FUSED = __import__("os").environ.get("MEGREADER_B200_LSTM_FUSED", "0") == "1"
+# BiLSTM recurrence on the bf16 path: "seq" = one persistent tcgen05 launch per layer and pass (csrc/lstm_seq_tcgen05.cu),
+# "step" = one fused tcgen05 launch per time step, "cublas" = strided-batched cuBLAS GEMM + cell kernel per step.
+LSTM_MODE = __import__("os").environ.get("MEGREADER_B200_LSTM", "seq")
+if __import__("os").environ.get("MEGREADER_B200_LSTM_FUSED", "0") == "1":     # older switch
+    LSTM_MODE = "step"
+LAST_LSTM_FLAGS = None      # scratch of the most recent persistent launch; last word != 0 <=> an inter-CTA wait timed out
 
 
 def set_compute_dtype(dtype):
@@ -218,7 +223,7 @@ def _bilstm_forward_impl(X, params, dtype, training):
     w_emb, b_emb = params[8], params[9]
     H = w_hh[0].size(1)
     dev = X.device
-    if LSTM_FUSED and USE_TCGEN05 and dtype == torch.bfloat16 and H % 64 == 0:
+    if LSTM_MODE != "cublas" and USE_TCGEN05 and dtype == torch.bfloat16 and H % 64 == 0:
         return _bilstm_forward_fused(X, params, training)
     Wih = [ops.cast(w.detach(), dtype) for w in w_ih]
     Whh = torch.stack([ops.cast(w.detach(), dtype) for w in w_hh])                 # [2, 4H, H]
@@ -275,8 +280,14 @@ def _bilstm_forward_fused(X, params, training):
         ops.gemm(X2, Wih[d], transB=True, out=G[d].view(T * N, 4 * H))               # input projection, all steps
     Cst = torch.empty((2, T, N, H), dtype=torch.float32, device=dev)
     Y = torch.empty((T, N, 2 * H), dtype=dtype, device=dev)
-    hbuf = torch.zeros((2, 2, N, H), dtype=dtype, device=dev)                          # [ping-pong][direction]
-    for s in range(T):
+    global LAST_LSTM_FLAGS
+    flags = LAST_LSTM_FLAGS = ops.lstm_seq_flags(N, dev).zero_()
+    if LSTM_MODE == "seq" and ops.lstm_seq_fwd_tc(Whh, G, bias, Cst, Y, flags):
+        steps = ()                                                                     # whole sequence done in one launch
+    else:
+        steps = range(T)
+        hbuf = torch.zeros((2, 2, N, H), dtype=dtype, device=dev)                      # [ping-pong][direction]
+    for s in steps:
         ts, tps = (s, T - 1 - s), (s - 1, T - s)
         cur, nxt = s & 1, (s + 1) & 1
         ops.lstm_step_fwd_tc([hbuf[cur, 0], hbuf[cur, 1]], Whh, [G[d, ts[d]] for d in (0, 1)], bias,
@@ -287,7 +298,7 @@ def _bilstm_forward_fused(X, params, training):
     out_dtype = dtype if nOut % _vn(dtype) == 0 else torch.float32
     E = ops.gemm(Y.view(T * N, 2 * H), Wemb, transB=True, out_dtype=out_dtype)
     ops.bias_act(E, b_emb, relu=False, out=E)
-    saved = dict(X=X, G=G, C=Cst, Y=Y, Wih=Wih, Whh=Whh, Wemb=Wemb, H=H, fused=True, perm=perm) if training else None
+    saved = dict(X=X, G=G, C=Cst, Y=Y, Wih=Wih, Whh=Whh, Wemb=Wemb, H=H, fused=True, perm=perm, flags=flags) if training else None
     return E.view(T, N, nOut), saved
 
 
@@ -304,7 +315,11 @@ def _bilstm_backward_fused(dE, sv):
     dY3 = ops.gemm(dE2, sv["Wemb"]).view(T, N, 2 * H)
     dG = torch.empty((2, T, N, 4 * H), dtype=dtype, device=dev)
     dc = torch.zeros((2, N, H), dtype=torch.float32, device=dev)
-    for s in range(T - 1, -1, -1):
+    if LSTM_MODE == "seq" and ops.lstm_seq_bwd_tc(sv["Whh"], G, Cst, dY3, dG, sv["flags"]):
+        steps = ()
+    else:
+        steps = range(T - 1, -1, -1)
+    for s in steps:
         ts, tps, tn = (s, T - 1 - s), (s - 1, T - s), (s + 1, T - 2 - s)
         have_rec = s < T - 1
         ops.lstm_step_bwd_tc([dG[d, tn[d]] if have_rec else dG[d, ts[d]] for d in (0, 1)], sv["Whh"],

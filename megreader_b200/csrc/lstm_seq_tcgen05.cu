@@ -1,0 +1,489 @@
+// Persistent bidirectional-LSTM recurrence for sm_100a (decoders/crnn.py:13,17 nn.LSTM inside BidirectionalLSTM).
+//
+// The recurrence h_t = cell(Gx_t + h_{t-1} W_hh^T) is T dependent steps of a small GEMM ([B,H] x [H,4H]) plus a
+// transcendental-heavy cell.  Launched step by step it is launch- and latency-bound (2 launches x T x 2 layers x
+// fwd/bwd = 520 launches of 5-10 us in the CRNN train step).  Here ONE launch runs the whole sequence of one layer,
+// both directions:
+//   * the CTA grid tiles (batch rows / 128) x (gate columns / 64) x direction and stays resident for all T steps;
+//   * each CTA keeps its W_hh slice in shared memory for the whole sequence (loaded once by TMA);
+//   * per step, the h_{t-1} tile is TMA-loaded from the layer output Y itself (L2-resident), tcgen05.mma accumulates
+//     the recurrent product in TMEM, 16 epilogue warps add the x-projection, apply the cell and write h_t, c_t and
+//     the activated gates; the cell state (fwd) / its gradient (bwd) never leaves registers;
+//   * the CTAs that share batch rows exchange h_t (fwd) / dG_t (bwd) through global memory and a monotonically
+//     increasing arrival counter per (direction, row tile): writers  st -> bar.sync -> __threadfence -> atomicAdd,
+//     readers  ld.acquire spin -> fence.proxy.async -> TMA.  All CTAs must be co-resident: the host refuses grids
+//     larger than the device can hold (MR_ERR_UNSUPPORTED -> callers use the per-step kernels).
+// Gate columns are UNIT-MAJOR (column 4*j + g = gate g of hidden unit j; g = i,f,g,o) as in gemm_tcgen05.cu.
+// Every wait is bounded: on timeout the CTA records an error word (flags[2*row_tiles]) and runs to completion with
+// undefined results instead of hanging the device.
+#include "tcgen05.cuh"
+
+namespace {
+
+constexpr int kBN = 64;                       // gate columns (fwd) / hidden units (bwd) per CTA
+constexpr int kThreads = 64 + 16 * 32;        // producer warp, MMA warp, 16 epilogue warps
+constexpr int kEpiThreads = 16 * 32;
+
+__device__ __forceinline__ uint32_t ld_acquire(const unsigned *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+__device__ __forceinline__ uint64_t now_ns() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+constexpr uint64_t kTimeoutNs = 2000000000ull;     // 2 s: ~10^5 x the longest legitimate wait
+
+// Bounded waits: give up (false) when the error word is already set or after kTimeoutNs, so that a protocol failure
+// drains the grid in bounded time instead of hanging the device.
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t *bar, uint32_t parity, const volatile unsigned *err) {
+    uint64_t t0 = 0;
+    for (uint32_t it = 1;; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return true;
+        if ((it & 63u) == 0) {
+            if (*err) return false;
+            const uint64_t t = now_ns();
+            if (!t0) t0 = t;
+            else if (t - t0 > kTimeoutNs) return false;
+        }
+    }
+}
+__device__ __forceinline__ bool flag_wait_bounded(const unsigned *flag, uint32_t target, const volatile unsigned *err) {
+    uint64_t t0 = 0;
+    for (uint32_t it = 1;; ++it) {
+        if (ld_acquire(flag) >= target) return true;
+        if ((it & 63u) == 0) {
+            if (*err) return false;
+            const uint64_t t = now_ns();
+            if (!t0) t0 = t;
+            else if (t - t0 > kTimeoutNs) return false;
+        }
+    }
+}
+
+struct SeqFwdArgs {
+    bf16 *G;                  // [2, T, B, 4H] unit-major: x-projection on entry, activated gates on exit
+    const float *bias[2];     // [4H] unit-major, b_ih + b_hh
+    float *C;                 // [2, T, B, H] cell states (saved for the backward pass)
+    bf16 *Y;                  // [T, B, 2H] layer output: direction d owns columns [d*H, (d+1)*H)
+    unsigned *flags;          // [2 * row_tiles + 1], zeroed before launch; last word = error
+    int T, B, H;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW0,
+                    const __grid_constant__ CUtensorMap tmW1, SeqFwdArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nkb = a.H / BK;
+    unsigned char *As = smem;                             // nkb x [128 rows x 128 B]   h_{t-1} tile, K-major SW128
+    unsigned char *Ws = smem + nkb * 16384;               // nkb x [ 64 rows x 128 B]   W_hh slice, K-major SW128
+    uint64_t *wfull = (uint64_t *)(Ws + nkb * 8192);
+    uint64_t *afull = wfull + 1;                          // [8]
+    uint64_t *tmem_full = afull + 8;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.z;
+    const CUtensorMap *tmW = dir ? &tmW1 : &tmW0;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * kBN;
+    const int T = a.T, B = a.B, H = a.H;
+    unsigned *flag = a.flags + dir * gridDim.x + blockIdx.x;
+    unsigned *err = a.flags + 2 * gridDim.x;
+    const uint32_t arrivals = gridDim.y;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(tmW);
+        mbar_init(wfull, 1);
+        for (int i = 0; i < 8; ++i) mbar_init(afull + i, 1);
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kBN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(wfull, nkb * 8192);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tmW, wfull, Ws + kb * 8192, kb * BK, n0);
+            for (int s = 1; s < T; ++s) {
+                const int t_prev = dir ? T - s : s - 1;
+                if (!flag_wait_bounded(flag, arrivals * (uint32_t)s, err)) atomicExch(err, 1u);
+                fence_proxy_async_global();
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_expect_tx(afull + kb, 16384);
+                    tma_load_2d(&tmY, afull + kb, As + kb * 16384, dir * H + kb * BK, t_prev * B + m0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, kBN, 0, 0);
+        if (!mbar_wait_bounded(wfull, 0, err)) atomicExch(err, 2u);
+        for (int s = 1; s < T; ++s) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                if (!mbar_wait_bounded(afull + kb, (s - 1) & 1, err)) atomicExch(err, 3u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(As + kb * 16384), b_addr = smem_u32(Ws + kb * 8192);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
+                                  (kb | k) != 0);
+                    if (kb == nkb - 1) umma_commit(tmem_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int qd = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter, group of 16 gate columns = 4 units
+        const int row = m0 + qd * 32 + lane;
+        const int col0 = n0 + grp * 16, j0 = col0 >> 2;
+        const bool live = row < B;
+        float bb[16];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>((dir ? a.bias[1] : a.bias[0]) + col0) + v);
+            bb[4 * v] = b4.x; bb[4 * v + 1] = b4.y; bb[4 * v + 2] = b4.z; bb[4 * v + 3] = b4.w;
+        }
+        float cst[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 16);
+        for (int s = 0; s < T; ++s) {
+            const int t = dir ? T - 1 - s : s;
+            const int64_t grow = ((int64_t)dir * T + t) * B + row;
+            bf16 *gp = a.G + grow * 4 * H + col0;
+            uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (live) {                                          // x-projection: issued before the accumulator wait
+                pk[0] = *reinterpret_cast<const uint4 *>(gp);
+                pk[1] = *reinterpret_cast<const uint4 *>(gp + 8);
+            }
+            uint32_t r[16];
+            if (s > 0) {
+                if (!mbar_wait_bounded(tmem_full, (s - 1) & 1, err)) atomicExch(err, 4u);
+                tc_fence_after();
+                tmem_ld16(taddr, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0;
+            }
+            if (live) {
+                float pre[16];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    const __nv_bfloat162 *h2 = reinterpret_cast<const __nv_bfloat162 *>(&pk[v]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h2[e]);
+                        pre[v * 8 + 2 * e] = f.x;
+                        pre[v * 8 + 2 * e + 1] = f.y;
+                    }
+                }
+                float act[16], hn[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float i_ = sigmoid_fast(pre[4 * u] + __uint_as_float(r[4 * u]) + bb[4 * u]);
+                    const float f_ = sigmoid_fast(pre[4 * u + 1] + __uint_as_float(r[4 * u + 1]) + bb[4 * u + 1]);
+                    const float g_ = tanh_fast(pre[4 * u + 2] + __uint_as_float(r[4 * u + 2]) + bb[4 * u + 2]);
+                    const float o_ = sigmoid_fast(pre[4 * u + 3] + __uint_as_float(r[4 * u + 3]) + bb[4 * u + 3]);
+                    cst[u] = f_ * cst[u] + i_ * g_;
+                    hn[u] = o_ * tanh_fast(cst[u]);
+                    act[4 * u] = i_; act[4 * u + 1] = f_; act[4 * u + 2] = g_; act[4 * u + 3] = o_;
+                }
+                uint2 hp;
+                __nv_bfloat162 *hh = reinterpret_cast<__nv_bfloat162 *>(&hp);
+                hh[0] = __floats2bfloat162_rn(hn[0], hn[1]);
+                hh[1] = __floats2bfloat162_rn(hn[2], hn[3]);
+                *reinterpret_cast<uint2 *>(a.Y + ((int64_t)t * B + row) * 2 * H + dir * H + j0) = hp;   // first: peers wait on it
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    uint4 o4;
+                    __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&o4);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(act[v * 8 + 2 * e], act[v * 8 + 2 * e + 1]);
+                    *reinterpret_cast<uint4 *>(gp + v * 8) = o4;
+                }
+                *reinterpret_cast<float4 *>(a.C + grow * H + j0) = make_float4(cst[0], cst[1], cst[2], cst[3]);
+            }
+            tc_fence_before();
+            epi_bar_sync();                                      // all h_t of this tile stored, accumulator drained
+            if (threadIdx.x == 64) {
+                __threadfence();
+                atomicAdd(flag, 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kBN);
+    }
+}
+
+struct SeqBwdArgs {
+    const bf16 *G;            // [2, T, B, 4H] activated gates (unit-major) from the forward pass
+    const float *C;           // [2, T, B, H]
+    const bf16 *dY;           // [T, B, 2H] gradient of the layer output
+    bf16 *dG;                 // [2, T, B, 4H] gate gradients, out (unit-major)
+    unsigned *flags;
+    int T, B, H;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_constant__ CUtensorMap tmW0,
+                    const __grid_constant__ CUtensorMap tmW1, SeqBwdArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nkb = 4 * a.H / BK;
+    unsigned char *As = smem;                             // STAGES x [128 rows x 128 B]  dG_{next} k-block, K-major SW128
+    unsigned char *Ws = smem + STAGES * 16384;            // nkb x [64 k-rows x 128 B]    W_hh[kb*64.., n0..n0+64), MN-major
+    uint64_t *wfull = (uint64_t *)(Ws + nkb * 8192);
+    uint64_t *full = wfull + 1;
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dir = blockIdx.z;
+    const CUtensorMap *tmW = dir ? &tmW1 : &tmW0;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * kBN;
+    const int T = a.T, B = a.B, H = a.H;
+    unsigned *flag = a.flags + dir * gridDim.x + blockIdx.x;
+    unsigned *err = a.flags + 2 * gridDim.x;
+    const uint32_t arrivals = gridDim.y;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmDG);
+        tma_prefetch_desc(tmW);
+        mbar_init(wfull, 1);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kBN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // processing order u = 0..T-1 is the reverse of the forward order: direction 0 walks t = T-1..0, direction 1 t = 0..T-1
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(wfull, nkb * 8192);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tmW, wfull, Ws + kb * 8192, n0, kb * BK);
+            int it = 0;
+            for (int u = 1; u < T; ++u) {
+                const int t_next = dir ? u - 1 : T - u;          // the time index processed at order u-1
+                if (!flag_wait_bounded(flag, arrivals * (uint32_t)u, err)) atomicExch(err, 1u);
+                fence_proxy_async_global();
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    if (!mbar_wait_bounded(empty + s, ((it / STAGES) & 1) ^ 1, err)) atomicExch(err, 5u);
+                    mbar_expect_tx(full + s, 16384);
+                    tma_load_2d(&tmDG, full + s, As + s * 16384, kb * BK, (dir * T + t_next) * B + m0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, kBN, 0, 1);
+        if (!mbar_wait_bounded(wfull, 0, err)) atomicExch(err, 2u);
+        int it = 0;
+        for (int u = 1; u < T; ++u) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                if (!mbar_wait_bounded(full + s, (it / STAGES) & 1, err)) atomicExch(err, 3u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(As + s * 16384), b_addr = smem_u32(Ws + kb * 8192);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 2048, BK * 128, 1024),
+                                  idesc, (kb | k) != 0);
+                    umma_commit(empty + s);
+                    if (kb == nkb - 1) umma_commit(tmem_full);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int qd = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter, group of 16 hidden units
+        const int row = m0 + qd * 32 + lane;
+        const int j0 = n0 + grp * 16;
+        const bool live = row < B;
+        float dcs[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dcs[j] = 0.f;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 16);
+        for (int u = 0; u < T; ++u) {
+            const int t = dir ? u : T - 1 - u;
+            const int tp = dir ? t + 1 : t - 1;                  // forward-order predecessor (source of c_prev)
+            const bool have_prev = dir ? (t < T - 1) : (t > 0);
+            const int64_t grow = ((int64_t)dir * T + t) * B + row;
+            const bf16 *gp = a.G + grow * 4 * H + 4 * j0;
+            const bf16 *dyp = a.dY + ((int64_t)t * B + row) * 2 * H + dir * H + j0;
+            const float *cp = a.C + grow * H + j0;
+            const float *cpp = a.C + (((int64_t)dir * T + tp) * B + row) * H + j0;
+            bf16 *dgp = a.dG + grow * 4 * H + 4 * j0;
+            uint4 dyk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            if (live) {                                          // issued before the accumulator wait
+                dyk[0] = *reinterpret_cast<const uint4 *>(dyp);
+                dyk[1] = *reinterpret_cast<const uint4 *>(dyp + 8);
+            }
+            uint32_t r[16];
+            if (u > 0) {
+                if (!mbar_wait_bounded(tmem_full, (u - 1) & 1, err)) atomicExch(err, 4u);
+                tc_fence_after();
+                tmem_ld16(taddr, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0;
+            }
+            if (live) {
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {                    // 8 units per pass
+                    const __nv_bfloat162 *dy2 = reinterpret_cast<const __nv_bfloat162 *>(&dyk[v]);
+                    float dyf[8], cf[8], cpf[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(dy2[e]); dyf[2 * e] = f.x; dyf[2 * e + 1] = f.y; }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float4 c4 = *reinterpret_cast<const float4 *>(cp + v * 8 + 4 * e);
+                        cf[4 * e] = c4.x; cf[4 * e + 1] = c4.y; cf[4 * e + 2] = c4.z; cf[4 * e + 3] = c4.w;
+                        float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (have_prev) p4 = *reinterpret_cast<const float4 *>(cpp + v * 8 + 4 * e);
+                        cpf[4 * e] = p4.x; cpf[4 * e + 1] = p4.y; cpf[4 * e + 2] = p4.z; cpf[4 * e + 3] = p4.w;
+                    }
+                    float dgf[32];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {                // 2 units (8 gate values) per 16-byte vector
+                        const uint4 gk = *reinterpret_cast<const uint4 *>(gp + v * 32 + h * 8);
+                        const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&gk);
+#pragma unroll
+                        for (int w2 = 0; w2 < 2; ++w2) {
+                            const int uu = h * 2 + w2;
+                            const float2 fi = __bfloat1622float2(g2[2 * w2]);
+                            const float2 fg = __bfloat1622float2(g2[2 * w2 + 1]);
+                            const float i_ = fi.x, f_ = fi.y, g_ = fg.x, o_ = fg.y;
+                            const float dh = dyf[uu] + __uint_as_float(r[v * 8 + uu]);
+                            const float tc = tanh_fast(cf[uu]);
+                            const float dct = dcs[v * 8 + uu] + dh * o_ * (1.f - tc * tc);
+                            dgf[uu * 4] = dct * g_ * i_ * (1.f - i_);
+                            dgf[uu * 4 + 1] = dct * cpf[uu] * f_ * (1.f - f_);
+                            dgf[uu * 4 + 2] = dct * i_ * (1.f - g_ * g_);
+                            dgf[uu * 4 + 3] = dh * tc * o_ * (1.f - o_);
+                            dcs[v * 8 + uu] = dct * f_;
+                        }
+                    }
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        uint4 o4;
+                        __nv_bfloat162 *p2 = reinterpret_cast<__nv_bfloat162 *>(&o4);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(dgf[h * 8 + 2 * e], dgf[h * 8 + 2 * e + 1]);
+                        *reinterpret_cast<uint4 *>(dgp + v * 32 + h * 8) = o4;
+                    }
+                }
+            }
+            tc_fence_before();
+            epi_bar_sync();
+            if (threadIdx.x == 64) {
+                __threadfence();
+                atomicAdd(flag, 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kBN);
+    }
+}
+
+int resident_ok(const void *kern, int threads, size_t smem, int ctas) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess) return 0;
+    return ctas <= sms * per_sm;
+}
+
+constexpr int kBwdStages = 5;
+
+}  // namespace
+
+extern "C" {
+
+/* Whole-sequence recurrence of one bidirectional LSTM layer, forward.  See include/megreader_b200.h. */
+int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const *bias, float *C, void *Y,
+                            unsigned *flags, int T, int B, int H, void *stream) {
+    if (T <= 0 || B <= 0 || H <= 0 || H % 64 || H > 512) return MR_ERR_UNSUPPORTED;
+    if (!Whh || !Whh[0] || !Whh[1] || !G || !bias || !bias[0] || !bias[1] || !C || !Y || !flags) return MR_ERR_NULL_POINTER;
+    if ((int64_t)2 * T * B >= (int64_t)1 << 31) return MR_ERR_UNSUPPORTED;
+    const int nkb = H / BK, row_tiles = ceil_div(B, BM);
+    const size_t smem = (size_t)nkb * (16384 + 8192) + 16 * 8 + 1024;
+    auto kern = lstm_seq_fwd_kernel;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm seq fwd smem attr");
+        attr_smem = smem;
+    }
+    dim3 grid((unsigned)row_tiles, (unsigned)(4 * H / kBN), 2);
+    if (!resident_ok((const void *)kern, kThreads, smem, (int)(grid.x * grid.y * grid.z))) return MR_ERR_UNSUPPORTED;
+    CUtensorMap ty, tw[2];
+    int rc = make_map(&ty, Y, 2 * H, (int64_t)T * B, 2 * H, BK, BM);
+    if (rc) return rc;
+    for (int d = 0; d < 2; ++d) {
+        rc = make_map(&tw[d], Whh[d], H, 4 * H, H, BK, kBN);
+        if (rc) return rc;
+    }
+    SeqFwdArgs a;
+    a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags;
+    a.T = T; a.B = B; a.H = H;
+    MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ty, tw[0], tw[1], a);
+    return check_launch("lstm_seq_fwd_kernel");
+}
+
+int mr_lstm_seq_bwd_tcgen05(const void *const *Whh, const void *G, const float *C, const void *dY, void *dG,
+                            unsigned *flags, int T, int B, int H, void *stream) {
+    if (T <= 0 || B <= 0 || H <= 0 || H % 64) return MR_ERR_UNSUPPORTED;
+    if (!Whh || !Whh[0] || !Whh[1] || !G || !C || !dY || !dG || !flags) return MR_ERR_NULL_POINTER;
+    if ((int64_t)2 * T * B >= (int64_t)1 << 31) return MR_ERR_UNSUPPORTED;
+    const int nkb = 4 * H / BK, row_tiles = ceil_div(B, BM);
+    const size_t smem = (size_t)kBwdStages * 16384 + (size_t)nkb * 8192 + (2 * kBwdStages + 4) * 8 + 1024;
+    if (smem > 227 * 1024) return MR_ERR_UNSUPPORTED;
+    auto kern = lstm_seq_bwd_kernel<kBwdStages>;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm seq bwd smem attr");
+        attr_smem = smem;
+    }
+    dim3 grid((unsigned)row_tiles, (unsigned)(H / kBN), 2);
+    if (!resident_ok((const void *)kern, kThreads, smem, (int)(grid.x * grid.y * grid.z))) return MR_ERR_UNSUPPORTED;
+    CUtensorMap tdg, tw[2];
+    int rc = make_map(&tdg, dG, 4 * H, (int64_t)2 * T * B, 4 * H, BK, BM);
+    if (rc) return rc;
+    for (int d = 0; d < 2; ++d) {
+        rc = make_map(&tw[d], Whh[d], H, 4 * H, H, kBN, BK);
+        if (rc) return rc;
+    }
+    SeqBwdArgs a;
+    a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags;
+    a.T = T; a.B = B; a.H = H;
+    MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tdg, tw[0], tw[1], a);
+    return check_launch("lstm_seq_bwd_kernel");
+}
+
+}  // extern "C"

@@ -240,3 +240,29 @@ def lstm_step_bwd_tc(dG_next, Whh, gates, c, c_prev, dh_out, ldh, dc, dgates, ha
     _chk(_lib.lib().mr_lstm_step_bwd_tcgen05(_ptr_array(dG_next), _ptr_array(Whh), _ptr_array(gates), _ptr_array(c),
                                              _ptr_array(c_prev), _ptr_array(dh_out), ldh, _ptr_array(dc),
                                              _ptr_array(dgates), int(have_rec), B, H4 // 4, _st()), "lstm_step_bwd_tcgen05")
+
+
+def lstm_seq_flags(B, device):
+    return torch.empty((2 * ((B + 127) // 128) + 1,), dtype=torch.int32, device=device)
+
+
+def lstm_seq_fwd_tc(Whh, G, bias, C, Y, flags):
+    """Persistent whole-sequence recurrence (both directions).  Returns False when the device cannot hold the grid
+    (MR_ERR_UNSUPPORTED): the caller then runs the per-step kernels."""
+    _, T, B, H4 = G.shape
+    rc = _lib.lib().mr_lstm_seq_fwd_tcgen05(_ptr_array(Whh), G.data_ptr(), _ptr_array(bias), C.data_ptr(), Y.data_ptr(),
+                                            flags.data_ptr(), T, B, H4 // 4, _st())
+    if rc == _lib.MR_ERR_UNSUPPORTED:
+        return False
+    _chk(rc, "lstm_seq_fwd_tcgen05")
+    return True
+
+
+def lstm_seq_bwd_tc(Whh, G, C, dY, dG, flags):
+    _, T, B, H4 = G.shape
+    rc = _lib.lib().mr_lstm_seq_bwd_tcgen05(_ptr_array(Whh), G.data_ptr(), C.data_ptr(), dY.data_ptr(), dG.data_ptr(),
+                                            flags.data_ptr(), T, B, H4 // 4, _st())
+    if rc == _lib.MR_ERR_UNSUPPORTED:
+        return False
+    _chk(rc, "lstm_seq_bwd_tcgen05")
+    return True

@@ -156,11 +156,9 @@ def test_bilstm_layer_vs_torch(cuda, dtype):
         torch.testing.assert_close(got, want, **(tol if dtype == torch.float32 else dict(rtol=5e-2, atol=0.15)))
 
 
-def test_bilstm_fused_tcgen05_path(cuda):
-    """H % 64 == 0 in bf16 mode routes every time step through the fused tcgen05 GEMM + cell kernels."""
+def _bilstm_case(cuda, T, N, I, H, O, seed):
     from megreader_b200 import crnn_engine
-    torch.manual_seed(6)
-    T, N, I, H, O = 6, 150, 64, 64, 40
+    torch.manual_seed(seed)
     rnn = torch.nn.LSTM(I, H, bidirectional=True).to(cuda)
     emb = torch.nn.Linear(2 * H, O).to(cuda)
 
@@ -176,22 +174,57 @@ def test_bilstm_fused_tcgen05_path(cuda):
     dout = torch.randn_like(ref)
     ref.backward(dout)
     ref_grads = [p.grad.clone() for p in crnn_engine._bilstm_params(m)]
+    return m, x, dout, ref, xr.grad, ref_grads
+
+
+def _bilstm_run(m, x, dout, mode):
+    from megreader_b200 import crnn_engine
     for p in m.parameters():
         p.grad = None
     crnn_engine.set_compute_dtype(torch.bfloat16)
-    fused_before = crnn_engine.LSTM_FUSED
-    crnn_engine.LSTM_FUSED = True
+    before = crnn_engine.LSTM_MODE
+    crnn_engine.LSTM_MODE = mode
     try:
         xe = x.clone().requires_grad_(True)
         out = crnn_engine.bilstm_forward(m, xe)
         out.float().backward(dout)
+        torch.cuda.synchronize()
     finally:
         crnn_engine.set_compute_dtype(torch.float32)
-        crnn_engine.LSTM_FUSED = fused_before
-    torch.testing.assert_close(out.float(), ref, rtol=5e-2, atol=5e-2)
-    torch.testing.assert_close(xe.grad, xr.grad, rtol=5e-2, atol=5e-2)
-    for got, want in zip([p.grad for p in crnn_engine._bilstm_params(m)], ref_grads):
+        crnn_engine.LSTM_MODE = before
+    return out.float(), xe.grad, [p.grad.clone() for p in crnn_engine._bilstm_params(m)]
+
+
+@pytest.mark.parametrize("mode", ["step", "seq"])
+@pytest.mark.parametrize("shape", [(6, 150, 64, 64, 40), (9, 512, 128, 256, 38), (1, 7, 64, 64, 8)])
+def test_bilstm_fused_tcgen05_paths(cuda, mode, shape):
+    """H % 64 == 0 in bf16 mode: per-step fused tcgen05 kernels ("step") and the persistent whole-sequence kernels
+    ("seq", csrc/lstm_seq_tcgen05.cu) against nn.LSTM + nn.Linear in fp32."""
+    from megreader_b200 import crnn_engine
+    m, x, dout, ref, ref_dx, ref_grads = _bilstm_case(cuda, *shape, seed=6)
+    out, dx, grads = _bilstm_run(m, x, dout, mode)
+    if mode == "seq":
+        assert int(crnn_engine.LAST_LSTM_FLAGS[-1]) == 0, "inter-CTA wait timed out"
+    torch.testing.assert_close(out, ref, rtol=5e-2, atol=5e-2)
+    torch.testing.assert_close(dx, ref_dx, rtol=5e-2, atol=0.02 * float(ref_dx.abs().max()) + 5e-2)
+    for got, want in zip(grads, ref_grads):
         torch.testing.assert_close(got, want, rtol=5e-2, atol=0.02 * float(want.abs().max()) + 0.05)
+
+
+@pytest.mark.parametrize("shape", [(26, 300, 512, 256, 256), (65, 512, 256, 256, 38), (5, 1100, 64, 128, 16)])
+def test_bilstm_persistent_equals_stepwise(cuda, shape):
+    """The persistent kernels run the same arithmetic as the per-step fused kernels (same tiles, same accumulation
+    order), at the CRNN shapes (T = 26 / 65, N = 512, H = 256), with a ragged last row tile and with > 8 row tiles:
+    outputs and every gradient agree to bf16 rounding of the last step."""
+    from megreader_b200 import crnn_engine
+    m, x, dout, _, _, _ = _bilstm_case(cuda, *shape, seed=8)
+    out_a, dx_a, g_a = _bilstm_run(m, x, dout, "step")
+    out_b, dx_b, g_b = _bilstm_run(m, x, dout, "seq")
+    assert int(crnn_engine.LAST_LSTM_FLAGS[-1]) == 0, "inter-CTA wait timed out"
+    torch.testing.assert_close(out_b, out_a, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(dx_b, dx_a, rtol=1e-2, atol=1e-2 * float(dx_a.abs().max()) + 1e-3)
+    for got, want in zip(g_b, g_a):
+        torch.testing.assert_close(got, want, rtol=1e-2, atol=1e-2 * float(want.abs().max()) + 1e-3)
 
 
 def test_adam_matches_torch(cuda, ops):
