@@ -230,13 +230,17 @@ int mr_lstm_step_bwd_tcgen05(const void *const *dG_next, const void *const *Whh,
  *   C     : [2, T, B, H] fp32 cell states, out;   Y : [T, B, 2H] bf16 layer output, out (direction d -> columns d*H..)
  *   flags : [2*ceil(B/128) + 1] uint32 scratch (zeroed by the call); after completion the last word is 0, or a non-zero
  *           code if an inter-CTA wait timed out (results then undefined)
- * bwd:  dY [T, B, 2H] bf16 -> dG [2, T, B, 4H] bf16 gate gradients (the weight/input gradients are plain GEMMs on dG).
+ * bwd:  dY [T, B, 2H] bf16 -> dG [2, T, B, 4H] bf16 gate gradients (the weight/input gradients are plain GEMMs on dG);
+ *       WhhT = the recurrent weights TRANSPOSED, HOST array of 2 device pointers to [H, 4H] bf16 (unit-major columns).
  * MR_ERR_UNSUPPORTED when the CTA grid cannot be co-resident on this device or H exceeds the shared-memory budget
  * (fwd H <= 512, bwd H <= 256): callers then use the per-step entry points above. */
 int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const *bias, float *C, void *Y,
                             unsigned *flags, int T, int B, int H, void *stream);
-int mr_lstm_seq_bwd_tcgen05(const void *const *Whh, const void *G, const float *C, const void *dY, void *dG,
+int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float *C, const void *dY, void *dG,
                             unsigned *flags, int T, int B, int H, void *stream);
+/* Development aid: device buffer [T][8] of int64 clock stamps written by CTA (0,0,0) of the next mr_lstm_seq_* launches
+ * (NULL switches it off); slot meaning in csrc/lstm_seq_tcgen05.cu. */
+int mr_lstm_seq_set_trace(void *buf);
 
 /* Greedy CTC decoding to label indices (structure/representers/ctc_representer.py:22-34, ctc_representer2d.py:27-51):
  * arg-max class per column (2D: along the arg-max-height path of classify*mask), then collapse repeats / skip

@@ -315,7 +315,8 @@ def _bilstm_backward_fused(dE, sv):
     dY3 = ops.gemm(dE2, sv["Wemb"]).view(T, N, 2 * H)
     dG = torch.empty((2, T, N, 4 * H), dtype=dtype, device=dev)
     dc = torch.zeros((2, N, H), dtype=torch.float32, device=dev)
-    if LSTM_MODE == "seq" and ops.lstm_seq_bwd_tc(sv["Whh"], G, Cst, dY3, dG, sv["flags"]):
+    WhhT = [w.t().contiguous() for w in sv["Whh"]]                                   # [H, 4H]: K-major operand of dG W_hh
+    if LSTM_MODE == "seq" and ops.lstm_seq_bwd_tc(WhhT, G, Cst, dY3, dG, sv["flags"]):
         steps = ()
     else:
         steps = range(T - 1, -1, -1)

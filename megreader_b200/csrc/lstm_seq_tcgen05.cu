@@ -32,6 +32,7 @@ __device__ __forceinline__ uint32_t ld_acquire(const unsigned *p) {
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
+#define MR_TRACE(step, slot) do { if (trace) trace[(step) * 8 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ uint64_t now_ns() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 constexpr uint64_t kTimeoutNs = 2000000000ull;     // 2 s: ~10^5 x the longest legitimate wait
 
@@ -75,6 +76,7 @@ struct SeqFwdArgs {
     float *C;                 // [2, T, B, H] cell states (saved for the backward pass)
     bf16 *Y;                  // [T, B, 2H] layer output: direction d owns columns [d*H, (d+1)*H)
     unsigned *flags;          // [2 * row_tiles + 1], zeroed before launch; last word = error
+    long long *trace;         // optional [T][8] clock64 stamps of CTA (0,0,0) (mr_lstm_seq_set_trace), else NULL
     int T, B, H;
 };
 
@@ -99,6 +101,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     unsigned *flag = a.flags + dir * gridDim.x + blockIdx.x;
     unsigned *err = a.flags + 2 * gridDim.x;
     const uint32_t arrivals = gridDim.y;
+    long long *trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? a.trace : nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY);
@@ -121,11 +124,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
             for (int s = 1; s < T; ++s) {
                 const int t_prev = dir ? T - s : s - 1;
                 if (!flag_wait_bounded(flag, arrivals * (uint32_t)s, err)) atomicExch(err, 1u);
+                MR_TRACE(s, 0);
                 fence_proxy_async_global();
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_expect_tx(afull + kb, 16384);
                     tma_load_2d(&tmY, afull + kb, As + kb * 16384, dir * H + kb * BK, t_prev * B + m0);
                 }
+                MR_TRACE(s, 1);
             }
         }
     } else if (warp == 1) {
@@ -141,12 +146,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
                                   (kb | k) != 0);
-                    if (kb == nkb - 1) umma_commit(tmem_full);
+                    if (kb == nkb - 1) { umma_commit(tmem_full); MR_TRACE(s, 2); }
                 }
                 __syncwarp();
             }
         }
     } else {
+        if (threadIdx.x != 64) trace = nullptr;
         const int qd = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter, group of 16 gate columns = 4 units
         const int row = m0 + qd * 32 + lane;
         const int col0 = n0 + grp * 16, j0 = col0 >> 2;
@@ -177,6 +183,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 16; ++j) r[j] = 0;
             }
+            MR_TRACE(s, 3);
+            float act[16];
             if (live) {
                 float pre[16];
 #pragma unroll
@@ -189,7 +197,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
                         pre[v * 8 + 2 * e + 1] = f.y;
                     }
                 }
-                float act[16], hn[4];
+                float hn[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float i_ = sigmoid_fast(pre[4 * u] + __uint_as_float(r[4 * u]) + bb[4 * u]);
@@ -204,7 +212,20 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
                 __nv_bfloat162 *hh = reinterpret_cast<__nv_bfloat162 *>(&hp);
                 hh[0] = __floats2bfloat162_rn(hn[0], hn[1]);
                 hh[1] = __floats2bfloat162_rn(hn[2], hn[3]);
-                *reinterpret_cast<uint2 *>(a.Y + ((int64_t)t * B + row) * 2 * H + dir * H + j0) = hp;   // first: peers wait on it
+                *reinterpret_cast<uint2 *>(a.Y + ((int64_t)t * B + row) * 2 * H + dir * H + j0) = hp;
+            }
+            // h_t is all the peers wait for: post the arrival before the state that only the backward pass reads
+            MR_TRACE(s, 4);
+            tc_fence_before();
+            epi_bar_sync();                                      // every h_t of this tile stored, accumulator drained
+            MR_TRACE(s, 5);
+            if (threadIdx.x == 64) {
+                __threadfence();
+                MR_TRACE(s, 6);
+                atomicAdd(flag, 1u);
+                MR_TRACE(s, 7);
+            }
+            if (live) {
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
                     uint4 o4;
@@ -214,12 +235,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
                     *reinterpret_cast<uint4 *>(gp + v * 8) = o4;
                 }
                 *reinterpret_cast<float4 *>(a.C + grow * H + j0) = make_float4(cst[0], cst[1], cst[2], cst[3]);
-            }
-            tc_fence_before();
-            epi_bar_sync();                                      // all h_t of this tile stored, accumulator drained
-            if (threadIdx.x == 64) {
-                __threadfence();
-                atomicAdd(flag, 1u);
             }
         }
     }
@@ -236,8 +251,23 @@ struct SeqBwdArgs {
     const bf16 *dY;           // [T, B, 2H] gradient of the layer output
     bf16 *dG;                 // [2, T, B, 4H] gate gradients, out (unit-major)
     unsigned *flags;
+    long long *trace;
     int T, B, H;
 };
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Backward recurrence: dh_{t} += dG_{t_next} W_hh needs the FULL gate-gradient row block [128 x 4H] per output tile, so
+// the per-step operand traffic is (H / units-per-CTA) x the dG tile.  32 hidden units per CTA spreads the step over
+// (B/128) x (H/32) x 2 CTAs (64 at the CRNN shape) with a deep TMA ring; everything the cell gradient needs besides the
+// accumulator (dY, c, c_prev, activated gates) is fetched into registers while the operand streams in.
+constexpr int kBwdBN = 32;
+constexpr int kBwdWTile = kBwdBN * 128;       // one k-block of W_hh^T: 32 unit rows x 128 B (K-major, SW128)
 
 template <int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -247,8 +277,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nkb = 4 * a.H / BK;
     unsigned char *As = smem;                             // STAGES x [128 rows x 128 B]  dG_{next} k-block, K-major SW128
-    unsigned char *Ws = smem + STAGES * 16384;            // nkb x [64 k-rows x 128 B]    W_hh[kb*64.., n0..n0+64), MN-major
-    uint64_t *wfull = (uint64_t *)(Ws + nkb * 8192);
+    unsigned char *Ws = smem + STAGES * 16384;            // nkb x [32 rows x 128 B]      W_hh^T[n0.., kb*64..), K-major SW128
+    uint64_t *wfull = (uint64_t *)(Ws + nkb * kBwdWTile);
     uint64_t *full = wfull + 1;
     uint64_t *empty = full + STAGES;
     uint64_t *tmem_full = empty + STAGES;
@@ -257,11 +287,12 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.z;
     const CUtensorMap *tmW = dir ? &tmW1 : &tmW0;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * kBN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * kBwdBN;
     const int T = a.T, B = a.B, H = a.H;
     unsigned *flag = a.flags + dir * gridDim.x + blockIdx.x;
     unsigned *err = a.flags + 2 * gridDim.x;
     const uint32_t arrivals = gridDim.y;
+    long long *trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? a.trace : nullptr;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmDG);
@@ -271,7 +302,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kBN);
+    if (warp == 1) tmem_alloc(tmem_slot, kBwdBN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -280,12 +311,13 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
     // processing order u = 0..T-1 is the reverse of the forward order: direction 0 walks t = T-1..0, direction 1 t = 0..T-1
     if (warp == 0) {
         if (elect_one()) {
-            mbar_expect_tx(wfull, nkb * 8192);
-            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tmW, wfull, Ws + kb * 8192, n0, kb * BK);
+            mbar_expect_tx(wfull, nkb * kBwdWTile);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tmW, wfull, Ws + kb * kBwdWTile, kb * BK, n0);
             int it = 0;
             for (int u = 1; u < T; ++u) {
                 const int t_next = dir ? u - 1 : T - u;          // the time index processed at order u-1
                 if (!flag_wait_bounded(flag, arrivals * (uint32_t)u, err)) atomicExch(err, 1u);
+                MR_TRACE(u, 0);
                 fence_proxy_async_global();
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
@@ -293,10 +325,11 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                     mbar_expect_tx(full + s, 16384);
                     tma_load_2d(&tmDG, full + s, As + s * 16384, kb * BK, (dir * T + t_next) * B + m0);
                 }
+                MR_TRACE(u, 1);
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(BM, kBN, 0, 1);
+        constexpr uint32_t idesc = make_idesc(BM, kBwdBN, 0, 0);
         if (!mbar_wait_bounded(wfull, 0, err)) atomicExch(err, 2u);
         int it = 0;
         for (int u = 1; u < T; ++u) {
@@ -305,108 +338,113 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                 if (!mbar_wait_bounded(full + s, (it / STAGES) & 1, err)) atomicExch(err, 3u);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a_addr = smem_u32(As + s * 16384), b_addr = smem_u32(Ws + kb * 8192);
+                    const uint32_t a_addr = smem_u32(As + s * 16384), b_addr = smem_u32(Ws + kb * kBwdWTile);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 2048, BK * 128, 1024),
-                                  idesc, (kb | k) != 0);
+                        umma_bf16(tmem_base, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
+                                  (kb | k) != 0);
                     umma_commit(empty + s);
-                    if (kb == nkb - 1) umma_commit(tmem_full);
+                    if (kb == nkb - 1) { umma_commit(tmem_full); MR_TRACE(u, 2); }
                 }
                 __syncwarp();
             }
         }
     } else {
-        const int qd = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter, group of 16 hidden units
+        if (threadIdx.x != 64) trace = nullptr;
+        const int qd = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter, group of 8 hidden units
         const int row = m0 + qd * 32 + lane;
-        const int j0 = n0 + grp * 16;
+        const int j0 = n0 + grp * 8;
         const bool live = row < B;
-        float dcs[16];
+        float dcs[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dcs[j] = 0.f;
-        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 16);
+        for (int j = 0; j < 8; ++j) dcs[j] = 0.f;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 8);
         for (int u = 0; u < T; ++u) {
             const int t = dir ? u : T - 1 - u;
             const int tp = dir ? t + 1 : t - 1;                  // forward-order predecessor (source of c_prev)
             const bool have_prev = dir ? (t < T - 1) : (t > 0);
             const int64_t grow = ((int64_t)dir * T + t) * B + row;
-            const bf16 *gp = a.G + grow * 4 * H + 4 * j0;
-            const bf16 *dyp = a.dY + ((int64_t)t * B + row) * 2 * H + dir * H + j0;
-            const float *cp = a.C + grow * H + j0;
-            const float *cpp = a.C + (((int64_t)dir * T + tp) * B + row) * H + j0;
-            bf16 *dgp = a.dG + grow * 4 * H + 4 * j0;
-            uint4 dyk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (live) {                                          // issued before the accumulator wait
-                dyk[0] = *reinterpret_cast<const uint4 *>(dyp);
-                dyk[1] = *reinterpret_cast<const uint4 *>(dyp + 8);
+            // operands that do not depend on the recurrent product: in flight while the dG tile streams through the ring
+            uint4 dyk = make_uint4(0, 0, 0, 0), gk[4];
+            float4 c4[2], p4[2];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gk[e] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) { c4[e] = make_float4(0.f, 0.f, 0.f, 0.f); p4[e] = c4[e]; }
+            if (live) {
+                const bf16 *gp = a.G + grow * 4 * H + 4 * j0;
+                const float *cp = a.C + grow * H + j0;
+                dyk = *reinterpret_cast<const uint4 *>(a.dY + ((int64_t)t * B + row) * 2 * H + dir * H + j0);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) gk[e] = *reinterpret_cast<const uint4 *>(gp + e * 8);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) c4[e] = *reinterpret_cast<const float4 *>(cp + 4 * e);
+                if (have_prev) {
+                    const float *cpp = a.C + (((int64_t)dir * T + tp) * B + row) * H + j0;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) p4[e] = *reinterpret_cast<const float4 *>(cpp + 4 * e);
+                }
             }
-            uint32_t r[16];
+            uint32_t r[8];
             if (u > 0) {
                 if (!mbar_wait_bounded(tmem_full, (u - 1) & 1, err)) atomicExch(err, 4u);
                 tc_fence_after();
-                tmem_ld16(taddr, r);
+                tmem_ld8(taddr, r);
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = 0;
+                for (int j = 0; j < 8; ++j) r[j] = 0;
             }
+            MR_TRACE(u, 3);
             if (live) {
+                const __nv_bfloat162 *dy2 = reinterpret_cast<const __nv_bfloat162 *>(&dyk);
+                float dyf[8];
 #pragma unroll
-                for (int v = 0; v < 2; ++v) {                    // 8 units per pass
-                    const __nv_bfloat162 *dy2 = reinterpret_cast<const __nv_bfloat162 *>(&dyk[v]);
-                    float dyf[8], cf[8], cpf[8];
+                for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(dy2[e]); dyf[2 * e] = f.x; dyf[2 * e + 1] = f.y; }
+                const float cf[8] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w};
+                const float cpf[8] = {p4[0].x, p4[0].y, p4[0].z, p4[0].w, p4[1].x, p4[1].y, p4[1].z, p4[1].w};
+                bf16 *dgp = a.dG + grow * 4 * H + 4 * j0;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(dy2[e]); dyf[2 * e] = f.x; dyf[2 * e + 1] = f.y; }
+                for (int h = 0; h < 4; ++h) {                    // 2 units (8 gate values) per 16-byte vector
+                    const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&gk[h]);
+                    float dgf[8];
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float4 c4 = *reinterpret_cast<const float4 *>(cp + v * 8 + 4 * e);
-                        cf[4 * e] = c4.x; cf[4 * e + 1] = c4.y; cf[4 * e + 2] = c4.z; cf[4 * e + 3] = c4.w;
-                        float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (have_prev) p4 = *reinterpret_cast<const float4 *>(cpp + v * 8 + 4 * e);
-                        cpf[4 * e] = p4.x; cpf[4 * e + 1] = p4.y; cpf[4 * e + 2] = p4.z; cpf[4 * e + 3] = p4.w;
+                    for (int w2 = 0; w2 < 2; ++w2) {
+                        const int uu = h * 2 + w2;
+                        const float2 fi = __bfloat1622float2(g2[2 * w2]);
+                        const float2 fg = __bfloat1622float2(g2[2 * w2 + 1]);
+                        const float i_ = fi.x, f_ = fi.y, g_ = fg.x, o_ = fg.y;
+                        const float dh = dyf[uu] + __uint_as_float(r[uu]);
+                        const float tc = tanh_fast(cf[uu]);
+                        const float dct = dcs[uu] + dh * o_ * (1.f - tc * tc);
+                        dgf[w2 * 4] = dct * g_ * i_ * (1.f - i_);
+                        dgf[w2 * 4 + 1] = dct * cpf[uu] * f_ * (1.f - f_);
+                        dgf[w2 * 4 + 2] = dct * i_ * (1.f - g_ * g_);
+                        dgf[w2 * 4 + 3] = dh * tc * o_ * (1.f - o_);
+                        dcs[uu] = dct * f_;
                     }
-                    float dgf[32];
+                    uint4 o4;
+                    __nv_bfloat162 *p2 = reinterpret_cast<__nv_bfloat162 *>(&o4);
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {                // 2 units (8 gate values) per 16-byte vector
-                        const uint4 gk = *reinterpret_cast<const uint4 *>(gp + v * 32 + h * 8);
-                        const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&gk);
-#pragma unroll
-                        for (int w2 = 0; w2 < 2; ++w2) {
-                            const int uu = h * 2 + w2;
-                            const float2 fi = __bfloat1622float2(g2[2 * w2]);
-                            const float2 fg = __bfloat1622float2(g2[2 * w2 + 1]);
-                            const float i_ = fi.x, f_ = fi.y, g_ = fg.x, o_ = fg.y;
-                            const float dh = dyf[uu] + __uint_as_float(r[v * 8 + uu]);
-                            const float tc = tanh_fast(cf[uu]);
-                            const float dct = dcs[v * 8 + uu] + dh * o_ * (1.f - tc * tc);
-                            dgf[uu * 4] = dct * g_ * i_ * (1.f - i_);
-                            dgf[uu * 4 + 1] = dct * cpf[uu] * f_ * (1.f - f_);
-                            dgf[uu * 4 + 2] = dct * i_ * (1.f - g_ * g_);
-                            dgf[uu * 4 + 3] = dh * tc * o_ * (1.f - o_);
-                            dcs[v * 8 + uu] = dct * f_;
-                        }
-                    }
-#pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        uint4 o4;
-                        __nv_bfloat162 *p2 = reinterpret_cast<__nv_bfloat162 *>(&o4);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(dgf[h * 8 + 2 * e], dgf[h * 8 + 2 * e + 1]);
-                        *reinterpret_cast<uint4 *>(dgp + v * 32 + h * 8) = o4;
-                    }
+                    for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(dgf[2 * e], dgf[2 * e + 1]);
+                    *reinterpret_cast<uint4 *>(dgp + h * 8) = o4;
                 }
             }
+            MR_TRACE(u, 4);
             tc_fence_before();
             epi_bar_sync();
+            MR_TRACE(u, 5);
             if (threadIdx.x == 64) {
                 __threadfence();
+                MR_TRACE(u, 6);
                 atomicAdd(flag, 1u);
+                MR_TRACE(u, 7);
             }
         }
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kBN);
+        tmem_dealloc(tmem_base, kBwdBN);
     }
 }
 
@@ -418,11 +456,17 @@ int resident_ok(const void *kern, int threads, size_t smem, int ctas) {
     return ctas <= sms * per_sm;
 }
 
-constexpr int kBwdStages = 5;
+constexpr int kBwdStages = 9;
+long long *g_trace = nullptr;
 
 }  // namespace
 
 extern "C" {
+
+/* Development aid: clock64 stamps [T][8] of CTA (0,0,0) for the next launches (NULL = off).  Slots: 0 peers' arrival
+ * seen, 1 TMA issued, 2 last MMA committed, 3 accumulator in registers, 4 stores issued, 5 tile barrier passed,
+ * 6 __threadfence done, 7 arrival posted. */
+int mr_lstm_seq_set_trace(void *buf) { g_trace = (long long *)buf; return MR_OK; }
 
 /* Whole-sequence recurrence of one bidirectional LSTM layer, forward.  See include/megreader_b200.h. */
 int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const *bias, float *C, void *Y,
@@ -448,20 +492,20 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
         if (rc) return rc;
     }
     SeqFwdArgs a;
-    a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags;
+    a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags; a.trace = g_trace;
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ty, tw[0], tw[1], a);
     return check_launch("lstm_seq_fwd_kernel");
 }
 
-int mr_lstm_seq_bwd_tcgen05(const void *const *Whh, const void *G, const float *C, const void *dY, void *dG,
+int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float *C, const void *dY, void *dG,
                             unsigned *flags, int T, int B, int H, void *stream) {
     if (T <= 0 || B <= 0 || H <= 0 || H % 64) return MR_ERR_UNSUPPORTED;
-    if (!Whh || !Whh[0] || !Whh[1] || !G || !C || !dY || !dG || !flags) return MR_ERR_NULL_POINTER;
+    if (!WhhT || !WhhT[0] || !WhhT[1] || !G || !C || !dY || !dG || !flags) return MR_ERR_NULL_POINTER;
     if ((int64_t)2 * T * B >= (int64_t)1 << 31) return MR_ERR_UNSUPPORTED;
     const int nkb = 4 * H / BK, row_tiles = ceil_div(B, BM);
-    const size_t smem = (size_t)kBwdStages * 16384 + (size_t)nkb * 8192 + (2 * kBwdStages + 4) * 8 + 1024;
+    const size_t smem = (size_t)kBwdStages * 16384 + (size_t)nkb * kBwdWTile + (2 * kBwdStages + 4) * 8 + 1024;
     if (smem > 227 * 1024) return MR_ERR_UNSUPPORTED;
     auto kern = lstm_seq_bwd_kernel<kBwdStages>;
     static size_t attr_smem = 0;
@@ -469,17 +513,17 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *Whh, const void *G, const float *
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm seq bwd smem attr");
         attr_smem = smem;
     }
-    dim3 grid((unsigned)row_tiles, (unsigned)(H / kBN), 2);
+    dim3 grid((unsigned)row_tiles, (unsigned)(H / kBwdBN), 2);
     if (!resident_ok((const void *)kern, kThreads, smem, (int)(grid.x * grid.y * grid.z))) return MR_ERR_UNSUPPORTED;
     CUtensorMap tdg, tw[2];
     int rc = make_map(&tdg, dG, 4 * H, (int64_t)2 * T * B, 4 * H, BK, BM);
     if (rc) return rc;
     for (int d = 0; d < 2; ++d) {
-        rc = make_map(&tw[d], Whh[d], H, 4 * H, H, kBN, BK);
+        rc = make_map(&tw[d], WhhT[d], 4 * H, H, 4 * H, BK, kBwdBN);      // W_hh^T [H, 4H]: K (= gate index) contiguous
         if (rc) return rc;
     }
     SeqBwdArgs a;
-    a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags;
+    a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags; a.trace = g_trace;
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tdg, tw[0], tw[1], a);

@@ -258,9 +258,10 @@ def lstm_seq_fwd_tc(Whh, G, bias, C, Y, flags):
     return True
 
 
-def lstm_seq_bwd_tc(Whh, G, C, dY, dG, flags):
+def lstm_seq_bwd_tc(WhhT, G, C, dY, dG, flags):
+    """WhhT: the two recurrent weight matrices transposed, [H, 4H] bf16 (unit-major gate columns)."""
     _, T, B, H4 = G.shape
-    rc = _lib.lib().mr_lstm_seq_bwd_tcgen05(_ptr_array(Whh), G.data_ptr(), C.data_ptr(), dY.data_ptr(), dG.data_ptr(),
+    rc = _lib.lib().mr_lstm_seq_bwd_tcgen05(_ptr_array(WhhT), G.data_ptr(), C.data_ptr(), dY.data_ptr(), dG.data_ptr(),
                                             flags.data_ptr(), T, B, H4 // 4, _st())
     if rc == _lib.MR_ERR_UNSUPPORTED:
         return False

@@ -149,7 +149,7 @@ def test_bilstm_layer_vs_torch(cuda, dtype):
         out.float().backward(dout)
     finally:
         crnn_engine.set_compute_dtype(torch.float32)
-    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=5e-2, atol=5e-2)
+    tol = dict(rtol=1e-3, atol=3e-4) if dtype == torch.float32 else dict(rtol=5e-2, atol=5e-2)
     torch.testing.assert_close(out.float(), ref, **tol)
     torch.testing.assert_close(xe.grad, xr.grad, **tol)
     for got, want in zip([p.grad for p in crnn_engine._bilstm_params(m)], ref_grads):

@@ -74,7 +74,7 @@ def test_deformable_resnet50_zero_offsets_closed_form():
     sd = {k: v for k, v in net.state_dict().items() if "conv2_offset" not in k}
     for k in list(sd):
         # offset 0 / mask sigmoid(0) = 1/2 in every unit of layers 2-4 (resnet.py:222-226,161-165)
-        if k.endswith("conv2.weight") and not k.startswith("layer1"):
+        if k.endswith("conv2.weight") and k.startswith(("layer2", "layer3", "layer4")):
             sd[k] = sd[k] * 0.5
     plain.load_state_dict(sd)
     net, plain = net.cuda().eval(), plain.cuda().eval()
