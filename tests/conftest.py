@@ -18,3 +18,15 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _fp32_references_are_fp32():
+    """The torch fp32 references (cuDNN LSTM / conv, matmul) must not silently run in TF32: cudnn.allow_tf32 defaults to
+    True, which moves the *reference* by ~1e-3 and made fp32 parity depend on test order."""
+    import torch
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
