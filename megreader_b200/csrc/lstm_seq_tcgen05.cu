@@ -17,6 +17,7 @@
 // Every wait is bounded: on timeout the CTA records an error word (flags[2*row_tiles]) and runs to completion with
 // undefined results instead of hanging the device.
 #include "tcgen05.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -77,6 +78,7 @@ struct SeqFwdArgs {
     bf16 *Y;                  // [T, B, 2H] layer output: direction d owns columns [d*H, (d+1)*H)
     unsigned *flags;          // [2 * row_tiles + 1], zeroed before launch; last word = error
     long long *trace;         // optional [T][8] clock64 stamps of CTA (0,0,0) (mr_lstm_seq_set_trace), else NULL
+    int exp;                  // development: MR_LSTM_SEQ_EXP bit mask (1 no operand loads, 2 no state stores, 4 no peer wait, 8 no GEMM)
     int T, B, H;
 };
 
@@ -123,9 +125,10 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tmW, wfull, Ws + kb * 8192, kb * BK, n0);
             for (int s = 1; s < T; ++s) {
                 const int t_prev = dir ? T - s : s - 1;
-                if (!flag_wait_bounded(flag, arrivals * (uint32_t)s, err)) atomicExch(err, 1u);
+                if (!(a.exp & 4) && !flag_wait_bounded(flag, arrivals * (uint32_t)s, err)) atomicExch(err, 1u);
                 MR_TRACE(s, 0);
                 fence_proxy_async_global();
+                if (a.exp & 8) continue;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_expect_tx(afull + kb, 16384);
                     tma_load_2d(&tmY, afull + kb, As + kb * 16384, dir * H + kb * BK, t_prev * B + m0);
@@ -136,7 +139,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc(BM, kBN, 0, 0);
         if (!mbar_wait_bounded(wfull, 0, err)) atomicExch(err, 2u);
-        for (int s = 1; s < T; ++s) {
+        for (int s = 1; s < T && !(a.exp & 8); ++s) {
             for (int kb = 0; kb < nkb; ++kb) {
                 if (!mbar_wait_bounded(afull + kb, (s - 1) & 1, err)) atomicExch(err, 3u);
                 tc_fence_after();
@@ -170,12 +173,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
             const int64_t grow = ((int64_t)dir * T + t) * B + row;
             bf16 *gp = a.G + grow * 4 * H + col0;
             uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (live) {                                          // x-projection: issued before the accumulator wait
+            if (live && !(a.exp & 1)) {                          // x-projection: issued before the accumulator wait
                 pk[0] = *reinterpret_cast<const uint4 *>(gp);
                 pk[1] = *reinterpret_cast<const uint4 *>(gp + 8);
             }
             uint32_t r[16];
-            if (s > 0) {
+            if (s > 0 && !(a.exp & 8)) {
                 if (!mbar_wait_bounded(tmem_full, (s - 1) & 1, err)) atomicExch(err, 4u);
                 tc_fence_after();
                 tmem_ld16(taddr, r);
@@ -225,7 +228,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
                 atomicAdd(flag, 1u);
                 MR_TRACE(s, 7);
             }
-            if (live) {
+            if (live && !(a.exp & 2)) {
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
                     uint4 o4;
@@ -252,6 +255,7 @@ struct SeqBwdArgs {
     bf16 *dG;                 // [2, T, B, 4H] gate gradients, out (unit-major)
     unsigned *flags;
     long long *trace;
+    int exp;
     int T, B, H;
 };
 
@@ -262,27 +266,50 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// 16-byte chunk `c` of row `r` in a [rows x 128 B] tile written by TMA with the 128-byte swizzle (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
 // Backward recurrence: dh_{t} += dG_{t_next} W_hh needs the FULL gate-gradient row block [128 x 4H] per output tile, so
-// the per-step operand traffic is (H / units-per-CTA) x the dG tile.  32 hidden units per CTA spreads the step over
-// (B/128) x (H/32) x 2 CTAs (64 at the CRNN shape) with a deep TMA ring; everything the cell gradient needs besides the
-// accumulator (dY, c, c_prev, activated gates) is fetched into registers while the operand streams in.
+// the per-step operand traffic is (H / units-per-CTA) x the dG tile.  32 hidden units per CTA spread the step over
+// (B/128) x (H/32) x 2 CTAs (64 at the CRNN shape).  A thread owns one batch row (TMEM lane), so direct global access
+// would touch 32 different rows per warp instruction (measured: 4.4 us of an 11 us step for the operand loads alone).
+// Instead the per-step operands -- activated gates [128 x 128] bf16 and cell state [128 x 32] fp32 -- are TMA-loaded as
+// swizzled tiles one step ahead and read conflict-free from shared memory; the gate gradients are written back into the
+// gates tile and leave through one TMA store.  c_prev of this step is the c tile of the next one: one new tile per step.
 constexpr int kBwdBN = 32;
 constexpr int kBwdWTile = kBwdBN * 128;       // one k-block of W_hh^T: 32 unit rows x 128 B (K-major, SW128)
 
 template <int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_constant__ CUtensorMap tmW0,
-                    const __grid_constant__ CUtensorMap tmW1, SeqBwdArgs a) {
+                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmG3,
+                    const __grid_constant__ CUtensorMap tmDG3, const __grid_constant__ CUtensorMap tmC3, SeqBwdArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nkb = 4 * a.H / BK;
     unsigned char *As = smem;                             // STAGES x [128 rows x 128 B]  dG_{next} k-block, K-major SW128
-    unsigned char *Ws = smem + STAGES * 16384;            // nkb x [32 rows x 128 B]      W_hh^T[n0.., kb*64..), K-major SW128
+    unsigned char *Gs = smem + STAGES * 16384;            // 2 x [128 x 128 B]            gates of this step -> dG of this step
+    unsigned char *Cs = Gs + 32768;                       // 2 x [128 x 128 B]            cell-state tiles (fp32, 32 units)
+    unsigned char *Ws = Cs + 32768;                       // nkb x [32 rows x 128 B]      W_hh^T[n0.., kb*64..), K-major SW128
     uint64_t *wfull = (uint64_t *)(Ws + nkb * kBwdWTile);
     uint64_t *full = wfull + 1;
     uint64_t *empty = full + STAGES;
     uint64_t *tmem_full = empty + STAGES;
-    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    uint64_t *gfull = tmem_full + 1;
+    uint64_t *cfull = gfull + 1;                          // [2]
+    uint32_t *tmem_slot = (uint32_t *)(cfull + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.z;
@@ -297,9 +324,15 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmDG);
         tma_prefetch_desc(tmW);
+        tma_prefetch_desc(&tmG3);
+        tma_prefetch_desc(&tmDG3);
+        tma_prefetch_desc(&tmC3);
         mbar_init(wfull, 1);
         for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(tmem_full, 1);
+        mbar_init(gfull, 1);
+        mbar_init(cfull, 1);
+        mbar_init(cfull + 1, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kBwdBN);
@@ -319,6 +352,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                 if (!flag_wait_bounded(flag, arrivals * (uint32_t)u, err)) atomicExch(err, 1u);
                 MR_TRACE(u, 0);
                 fence_proxy_async_global();
+                if (a.exp & 8) continue;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     if (!mbar_wait_bounded(empty + s, ((it / STAGES) & 1) ^ 1, err)) atomicExch(err, 5u);
@@ -332,7 +366,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
         constexpr uint32_t idesc = make_idesc(BM, kBwdBN, 0, 0);
         if (!mbar_wait_bounded(wfull, 0, err)) atomicExch(err, 2u);
         int it = 0;
-        for (int u = 1; u < T; ++u) {
+        for (int u = 1; u < T && !(a.exp & 8); ++u) {
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 if (!mbar_wait_bounded(full + s, (it / STAGES) & 1, err)) atomicExch(err, 3u);
@@ -350,43 +384,56 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
             }
         }
     } else {
-        if (threadIdx.x != 64) trace = nullptr;
+        const bool leader = threadIdx.x == 64;
+        if (!leader) trace = nullptr;
         const int qd = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter, group of 8 hidden units
-        const int row = m0 + qd * 32 + lane;
+        const int rl = qd * 32 + lane, row = m0 + rl;
         const int j0 = n0 + grp * 8;
         const bool live = row < B;
+        // this thread's slices of the staged tiles: gates/dG 4 chunks in box (grp >> 1), cell state 2 chunks
+        unsigned char *gtile = Gs + (grp >> 1) * 16384;
+        const int gch = (grp & 1) * 4, cch = grp * 2;
         float dcs[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) dcs[j] = 0.f;
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 8);
+        auto time_of = [&](int u) { return dir ? u : T - 1 - u; };
+        auto load_gates = [&](int u) {
+            const int z = dir * T + time_of(u);
+            mbar_expect_tx(gfull, 32768);
+            tma_load_3d(&tmG3, gfull, Gs, 4 * n0, m0, z);
+            tma_load_3d(&tmG3, gfull, Gs + 16384, 4 * n0 + 64, m0, z);
+        };
+        auto load_cell = [&](int u) {
+            mbar_expect_tx(cfull + (u & 1), 16384);
+            tma_load_3d(&tmC3, cfull + (u & 1), Cs + (u & 1) * 16384, n0, m0, dir * T + time_of(u));
+        };
+        if (leader) {
+            load_gates(0);
+            load_cell(0);
+            if (T > 1) load_cell(1);
+        }
         for (int u = 0; u < T; ++u) {
-            const int t = dir ? u : T - 1 - u;
-            const int tp = dir ? t + 1 : t - 1;                  // forward-order predecessor (source of c_prev)
-            const bool have_prev = dir ? (t < T - 1) : (t > 0);
-            const int64_t grow = ((int64_t)dir * T + t) * B + row;
-            // operands that do not depend on the recurrent product: in flight while the dG tile streams through the ring
-            uint4 dyk = make_uint4(0, 0, 0, 0), gk[4];
+            const int t = time_of(u);
+            const bool have_prev = u < T - 1;                    // forward-order predecessor = the step processed next
+            uint4 dyk = make_uint4(0, 0, 0, 0);
+            if (live && !(a.exp & 1))
+                dyk = *reinterpret_cast<const uint4 *>(a.dY + ((int64_t)t * B + row) * 2 * H + dir * H + j0);
+            if (!mbar_wait_bounded(gfull, u & 1, err)) atomicExch(err, 6u);
+            if (!mbar_wait_bounded(cfull + (u & 1), (u >> 1) & 1, err)) atomicExch(err, 7u);
+            if (have_prev && !mbar_wait_bounded(cfull + ((u + 1) & 1), ((u + 1) >> 1) & 1, err)) atomicExch(err, 8u);
+            uint4 gk[4];
             float4 c4[2], p4[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) gk[e] = make_uint4(0, 0, 0, 0);
+            for (int e = 0; e < 4; ++e) gk[e] = *reinterpret_cast<const uint4 *>(gtile + swz(rl, gch + e));
 #pragma unroll
-            for (int e = 0; e < 2; ++e) { c4[e] = make_float4(0.f, 0.f, 0.f, 0.f); p4[e] = c4[e]; }
-            if (live) {
-                const bf16 *gp = a.G + grow * 4 * H + 4 * j0;
-                const float *cp = a.C + grow * H + j0;
-                dyk = *reinterpret_cast<const uint4 *>(a.dY + ((int64_t)t * B + row) * 2 * H + dir * H + j0);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) gk[e] = *reinterpret_cast<const uint4 *>(gp + e * 8);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) c4[e] = *reinterpret_cast<const float4 *>(cp + 4 * e);
-                if (have_prev) {
-                    const float *cpp = a.C + (((int64_t)dir * T + tp) * B + row) * H + j0;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) p4[e] = *reinterpret_cast<const float4 *>(cpp + 4 * e);
-                }
+            for (int e = 0; e < 2; ++e) {
+                c4[e] = *reinterpret_cast<const float4 *>(Cs + (u & 1) * 16384 + swz(rl, cch + e));
+                p4[e] = have_prev ? *reinterpret_cast<const float4 *>(Cs + ((u + 1) & 1) * 16384 + swz(rl, cch + e))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             uint32_t r[8];
-            if (u > 0) {
+            if (u > 0 && !(a.exp & 8)) {
                 if (!mbar_wait_bounded(tmem_full, (u - 1) & 1, err)) atomicExch(err, 4u);
                 tc_fence_after();
                 tmem_ld8(taddr, r);
@@ -395,16 +442,15 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                 for (int j = 0; j < 8; ++j) r[j] = 0;
             }
             MR_TRACE(u, 3);
-            if (live) {
+            {
                 const __nv_bfloat162 *dy2 = reinterpret_cast<const __nv_bfloat162 *>(&dyk);
                 float dyf[8];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(dy2[e]); dyf[2 * e] = f.x; dyf[2 * e + 1] = f.y; }
                 const float cf[8] = {c4[0].x, c4[0].y, c4[0].z, c4[0].w, c4[1].x, c4[1].y, c4[1].z, c4[1].w};
                 const float cpf[8] = {p4[0].x, p4[0].y, p4[0].z, p4[0].w, p4[1].x, p4[1].y, p4[1].z, p4[1].w};
-                bf16 *dgp = a.dG + grow * 4 * H + 4 * j0;
 #pragma unroll
-                for (int h = 0; h < 4; ++h) {                    // 2 units (8 gate values) per 16-byte vector
+                for (int h = 0; h < 4; ++h) {                    // 2 units (8 gate values) per 16-byte chunk
                     const __nv_bfloat162 *g2 = reinterpret_cast<const __nv_bfloat162 *>(&gk[h]);
                     float dgf[8];
 #pragma unroll
@@ -426,18 +472,28 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                     __nv_bfloat162 *p2 = reinterpret_cast<__nv_bfloat162 *>(&o4);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) p2[e] = __floats2bfloat162_rn(dgf[2 * e], dgf[2 * e + 1]);
-                    *reinterpret_cast<uint4 *>(dgp + h * 8) = o4;
+                    *reinterpret_cast<uint4 *>(gtile + swz(rl, gch + h)) = o4;       // rows >= B are clipped by the TMA store
                 }
             }
+            fence_proxy_async();                                 // generic-proxy tile writes -> visible to the TMA store
             MR_TRACE(u, 4);
             tc_fence_before();
             epi_bar_sync();
             MR_TRACE(u, 5);
-            if (threadIdx.x == 64) {
+            if (leader) {
+                const int z = dir * T + t;
+                if (!(a.exp & 2)) {
+                    tma_store_3d(&tmDG3, Gs, 4 * n0, m0, z);
+                    tma_store_3d(&tmDG3, Gs + 16384, 4 * n0 + 64, m0, z);
+                }
+                tma_store_commit_wait();                         // gate gradients written (and the tile is free again)
+                fence_proxy_async_global();
                 __threadfence();
                 MR_TRACE(u, 6);
                 atomicAdd(flag, 1u);
                 MR_TRACE(u, 7);
+                if (u + 1 < T) load_gates(u + 1);
+                if (u + 2 < T) load_cell(u + 2);                 // into the buffer that held c_t of this step
             }
         }
     }
@@ -448,6 +504,21 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
     }
 }
 
+// 3-D tiled map over a row-major [outer, mid, inner] tensor, box {box_inner, box_mid, 1}, 128-byte swizzle
+int make_map_3d(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esize, int64_t inner, int64_t mid, int64_t outer,
+                int box_inner, int box_mid) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return MR_ERR_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)mid, (cuuint64_t)outer};
+    cuuint64_t strides[2] = {(cuuint64_t)inner * esize, (cuuint64_t)mid * inner * esize};
+    cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_mid, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(3d)"); return MR_ERR_CUDA; }
+    return MR_OK;
+}
+
 int resident_ok(const void *kern, int threads, size_t smem, int ctas) {
     int dev = 0, sms = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -456,8 +527,9 @@ int resident_ok(const void *kern, int threads, size_t smem, int ctas) {
     return ctas <= sms * per_sm;
 }
 
-constexpr int kBwdStages = 9;
+constexpr int kBwdStages = 5;
 long long *g_trace = nullptr;
+int exp_mask() { const char *e = getenv("MR_LSTM_SEQ_EXP"); return e ? atoi(e) : 0; }
 
 }  // namespace
 
@@ -492,7 +564,7 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
         if (rc) return rc;
     }
     SeqFwdArgs a;
-    a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags; a.trace = g_trace;
+    a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags; a.trace = g_trace; a.exp = exp_mask();
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ty, tw[0], tw[1], a);
@@ -505,7 +577,7 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float 
     if (!WhhT || !WhhT[0] || !WhhT[1] || !G || !C || !dY || !dG || !flags) return MR_ERR_NULL_POINTER;
     if ((int64_t)2 * T * B >= (int64_t)1 << 31) return MR_ERR_UNSUPPORTED;
     const int nkb = 4 * H / BK, row_tiles = ceil_div(B, BM);
-    const size_t smem = (size_t)kBwdStages * 16384 + (size_t)nkb * kBwdWTile + (2 * kBwdStages + 4) * 8 + 1024;
+    const size_t smem = (size_t)kBwdStages * 16384 + 65536 + (size_t)nkb * kBwdWTile + (2 * kBwdStages + 8) * 8 + 1024;
     if (smem > 227 * 1024) return MR_ERR_UNSUPPORTED;
     auto kern = lstm_seq_bwd_kernel<kBwdStages>;
     static size_t attr_smem = 0;
@@ -522,11 +594,18 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float 
         rc = make_map(&tw[d], WhhT[d], 4 * H, H, 4 * H, BK, kBwdBN);      // W_hh^T [H, 4H]: K (= gate index) contiguous
         if (rc) return rc;
     }
+    CUtensorMap tg3, tdg3, tc3;
+    rc = make_map_3d(&tg3, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4 * H, B, (int64_t)2 * T, BK, BM);
+    if (rc) return rc;
+    rc = make_map_3d(&tdg3, dG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4 * H, B, (int64_t)2 * T, BK, BM);
+    if (rc) return rc;
+    rc = make_map_3d(&tc3, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, H, B, (int64_t)2 * T, kBwdBN, BM);
+    if (rc) return rc;
     SeqBwdArgs a;
-    a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags; a.trace = g_trace;
+    a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags; a.trace = g_trace; a.exp = exp_mask();
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
-    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tdg, tw[0], tw[1], a);
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tdg, tw[0], tw[1], tg3, tdg3, tc3, a);
     return check_launch("lstm_seq_bwd_kernel");
 }
 
