@@ -29,7 +29,7 @@ def timed(fn, reps=20, warm=3):
 def trace(fn, T, dev, name):
     """median clock deltas between the stamps of CTA (0,0,0), see mr_lstm_seq_set_trace"""
     from megreader_b200 import _lib
-    buf = torch.zeros(T, 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(T, 32, dtype=torch.int64, device=dev)
     _lib.lib().mr_lstm_seq_set_trace(buf.data_ptr())
     fn()
     torch.cuda.synchronize()
@@ -45,6 +45,11 @@ def trace(fn, T, dev, name):
     d["period"] = t[steps, 7] - prev_post
     print(json.dumps({"bench": "lstm_seq_trace", "kernel": name, "unit": "SM clocks (median over steps)",
                       **{k: float(v.median()) for k, v in d.items()}}), flush=True)
+    if name == "bwd":      # operand stream detail: k-block arrival (MMA warp) and issue (producer) times after "seen"
+        arr = [float((t[steps, 8 + k] - t[steps, 0]).median()) for k in range(16)]
+        iss = [float((t[steps, 24 + k] - t[steps, 0]).median()) for k in range(8)]
+        print(json.dumps({"bench": "lstm_seq_trace_stream", "kblock_arrival_after_seen": arr,
+                          "kblock_4_to_11_issue_after_seen": iss}), flush=True)
 
 
 def kernels(N, H, dev):

@@ -238,7 +238,7 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
                             unsigned *flags, int T, int B, int H, void *stream);
 int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float *C, const void *dY, void *dG,
                             unsigned *flags, int T, int B, int H, void *stream);
-/* Development aid: device buffer [T][8] of int64 clock stamps written by CTA (0,0,0) of the next mr_lstm_seq_* launches
+/* Development aid: device buffer [T][32] of int64 clock stamps written by CTA (0,0,0) of the next mr_lstm_seq_* launches
  * (NULL switches it off); slot meaning in csrc/lstm_seq_tcgen05.cu. */
 int mr_lstm_seq_set_trace(void *buf);
 

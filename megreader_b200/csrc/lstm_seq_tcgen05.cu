@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t ld_acquire(const unsigned *p) {
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
 
-#define MR_TRACE(step, slot) do { if (trace) trace[(step) * 8 + (slot)] = clock64(); } while (0)
+#define MR_TRACE(step, slot) do { if (trace) trace[(step) * 32 + (slot)] = clock64(); } while (0)
 __device__ __forceinline__ uint64_t now_ns() { uint64_t t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 constexpr uint64_t kTimeoutNs = 2000000000ull;     // 2 s: ~10^5 x the longest legitimate wait
 
@@ -357,6 +357,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                     const int s = it % STAGES;
                     if (!mbar_wait_bounded(empty + s, ((it / STAGES) & 1) ^ 1, err)) atomicExch(err, 5u);
                     mbar_expect_tx(full + s, 16384);
+                    if (kb >= 4 && kb < 12) MR_TRACE(u, 20 + kb);
                     tma_load_2d(&tmDG, full + s, As + s * 16384, kb * BK, (dir * T + t_next) * B + m0);
                 }
                 MR_TRACE(u, 1);
@@ -372,6 +373,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                 if (!mbar_wait_bounded(full + s, (it / STAGES) & 1, err)) atomicExch(err, 3u);
                 tc_fence_after();
                 if (elect_one()) {
+                    if (kb < 16) MR_TRACE(u, 8 + kb);
                     const uint32_t a_addr = smem_u32(As + s * 16384), b_addr = smem_u32(Ws + kb * kBwdWTile);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
@@ -535,7 +537,7 @@ int exp_mask() { const char *e = getenv("MR_LSTM_SEQ_EXP"); return e ? atoi(e) :
 
 extern "C" {
 
-/* Development aid: clock64 stamps [T][8] of CTA (0,0,0) for the next launches (NULL = off).  Slots: 0 peers' arrival
+/* Development aid: clock64 stamps [T][32] of CTA (0,0,0) for the next launches (NULL = off).  Slots: 0 peers' arrival
  * seen, 1 TMA issued, 2 last MMA committed, 3 accumulator in registers, 4 stores issued, 5 tile barrier passed,
  * 6 __threadfence done, 7 arrival posted. */
 int mr_lstm_seq_set_trace(void *buf) { g_trace = (long long *)buf; return MR_OK; }
