@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <math.h>
+#include <algorithm>
 #include <string.h>
 
 namespace {
@@ -74,6 +75,71 @@ __device__ __forceinline__ void block_channel_sum(const float *acc, int cv, doub
             atomicAdd(sums + cvec * VN + e, (double)t);
         }
     }
+}
+
+// Same reduction without atomics: every block stores its per-channel sums as one row of a [gridDim.x, C] fp32 scratch;
+// partials_finalize_kernel adds the rows in double.  (fp64 atomics from thousands of blocks onto C addresses serialise
+// at ~40 ns each: measured 150-200 us per launch for C = 512 and a 4736-block grid, more than the streaming itself.)
+template <int VN>
+__device__ __forceinline__ void block_channel_partial(const float *acc, int cv, float *part_row, float (*red)[VN + 1]) {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) red[threadIdx.x][e] = acc[e];
+    __syncthreads();
+    if ((int)threadIdx.x < cv) {
+        const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int cvec = (int)(gtid % cv);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+            float t = 0.f;
+            for (int k = threadIdx.x; k < (int)blockDim.x; k += cv) t += red[k][e];
+            part_row[cvec * VN + e] = t;
+        }
+    }
+}
+
+// out[c] = sum_b part[b, c] (double).  Block = 32 columns x 32 row lanes: each lane walks rows lane, lane+32, ... with
+// four loads in flight (a one-thread-per-column loop over ~1000 rows is a 50 us latency chain), then a shared-memory
+// reduction over the lanes.
+__global__ void __launch_bounds__(1024)
+partials_finalize_kernel(const float *__restrict__ part, int nb, int ncols, double *__restrict__ out) {
+    __shared__ double red[32][33];
+    const int cx = threadIdx.x, ry = threadIdx.y;
+    const int c = blockIdx.x * 32 + cx;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (c < ncols) {
+        int b = ry;
+        for (; b + 96 < nb; b += 128) {
+            const float v0 = part[(int64_t)b * ncols + c], v1 = part[(int64_t)(b + 32) * ncols + c];
+            const float v2 = part[(int64_t)(b + 64) * ncols + c], v3 = part[(int64_t)(b + 96) * ncols + c];
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        }
+        for (; b < nb; b += 32) a0 += part[(int64_t)b * ncols + c];
+    }
+    red[ry][cx] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (ry == 0 && c < ncols) {
+        double t = 0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) t += red[k][cx];
+        out[c] = t;
+    }
+}
+
+constexpr int kMaxPartialBlocks = 148 * 8;
+constexpr int kMaxPartialCols = 2048;
+// Library-owned scratch for the block partial sums (stream-ordered use on one stream at a time).  Allocated on first
+// use, which must not happen inside a CUDA-graph capture: callers run one eager step before capturing (as they must
+// for cuBLAS anyway).  NULL when the allocation is impossible -> the fp64-atomic path is used instead.
+float *partials_scratch() {
+    static float *buf = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        if (cudaMalloc(&p, sizeof(float) * (size_t)kMaxPartialBlocks * kMaxPartialCols) == cudaSuccess) buf = (float *)p;
+        else { cudaGetLastError(); tried = false; }      // e.g. called under capture: retry on the next eager call
+    }
+    return buf;
 }
 
 inline int grid1d(int64_t work, int block, int per_sm = 16) {
@@ -250,7 +316,8 @@ __global__ void bias_relu_pool_fwd_kernel(PoolGeo g, const T *__restrict__ x, co
 template <typename T>
 __global__ void __launch_bounds__(256)
 bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y,
-                          const unsigned char *__restrict__ idx, T *__restrict__ dz, double *__restrict__ bias_sums) {
+                          const unsigned char *__restrict__ idx, T *__restrict__ dz, double *__restrict__ bias_sums,
+                          float *__restrict__ part) {
     constexpr int VN = 16 / sizeof(T);
     const int cv = g.C / VN;
     const int64_t total = (int64_t)g.N * g.H * g.W * cv;
@@ -290,16 +357,17 @@ bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restri
         }
         const uint4 packed = pack<T>(acc);
         reinterpret_cast<uint4 *>(dz)[t] = packed;
-        if (bias_sums) {                 // sum what was actually stored (the rounded values), like a separate pass would
+        if (bias_sums || part) {         // sum what was actually stored (the rounded values), like a separate pass would
             float fr[VN];
             unpack<T>(packed, fr);
 #pragma unroll
             for (int e = 0; e < VN; ++e) bsum[e] += fr[e];
         }
     }
-    if (bias_sums) {                     // only launched with blockDim % cv == 0: the channel vector is thread-invariant
+    if (bias_sums || part) {             // only launched with blockDim % cv == 0: the channel vector is thread-invariant
         __shared__ float red[256][VN + 1];
-        block_channel_sum<VN>(bsum, cv, bias_sums, red);
+        if (part) block_channel_partial<VN>(bsum, cv, part + (int64_t)blockIdx.x * g.C, red);
+        else block_channel_sum<VN>(bsum, cv, bias_sums, red);
     }
 }
 
@@ -310,7 +378,8 @@ bias_relu_pool_bwd_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restri
 template <typename T>
 __global__ void __launch_bounds__(256)
 bias_relu_pool_bwd_tiled_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y,
-                                const unsigned char *__restrict__ idx, T *__restrict__ dz, double *__restrict__ bias_sums) {
+                                const unsigned char *__restrict__ idx, T *__restrict__ dz, double *__restrict__ bias_sums,
+                                float *__restrict__ part) {
     constexpr int VN = 16 / sizeof(T);
     const int cv = g.C / VN;
     const int64_t total = (int64_t)g.N * g.Ho * g.Wo * cv;
@@ -343,10 +412,202 @@ bias_relu_pool_bwd_tiled_kernel(PoolGeo g, const T *__restrict__ dy, const T *__
                 __stcs(reinterpret_cast<uint4 *>(dz + q), pack<T>(o));
             }
     }
-    if (bias_sums) {
+    if (bias_sums || part) {
         __shared__ float red[256][VN + 1];
-        block_channel_sum<VN>(bsum, cv, bias_sums, red);
+        if (part) block_channel_partial<VN>(bsum, cv, part + (int64_t)blockIdx.x * g.C, red);
+        else block_channel_sum<VN>(bsum, cv, bias_sums, red);
     }
+}
+
+// ---- row-organised 2x2-window variants (every pool of the CRNN stack: backbones/crnn.py:18-35) -------------------------
+// One block walks output rows (n, ho); threads walk (wo, channel-vector) items with the channel vector fixed per thread
+// (256 % cv == 0, cv a power of two), so there is no 64-bit div/mod per element, the bias vector sits in registers and
+// all window loads of an item are issued before the first compare.
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256)
+pool_fwd_rows_kernel(PoolGeo g, const T *__restrict__ x, const float *__restrict__ bias, T *__restrict__ y,
+                     unsigned char *__restrict__ idx, int cv_shift) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = 1 << cv_shift;
+    const int cvec = threadIdx.x & (cv - 1), wl = threadIdx.x >> cv_shift, WL = 256 >> cv_shift;
+    float bb[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bb[e] = bias[cvec * VN + e];
+    const uint4 *px = reinterpret_cast<const uint4 *>(x) + cvec;
+    const int nrows = g.N * g.Ho;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = row / g.Ho, ho = row - n * g.Ho;
+        const int h0 = ho * g.sh - g.ph;
+        for (int wo = wl; wo < g.Wo; wo += WL) {
+            const int w0 = wo * g.sw - g.pw;
+            uint4 v[KH * KW];
+            bool ok[KH * KW];
+#pragma unroll
+            for (int i = 0; i < KH; ++i)
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    const int h = h0 + i, w = w0 + j;
+                    ok[i * KW + j] = h >= 0 && h < g.H && w >= 0 && w < g.W;
+                    v[i * KW + j] = make_uint4(0, 0, 0, 0);
+                    if (ok[i * KW + j]) v[i * KW + j] = __ldg(px + ((int64_t)(n * g.H + h) * g.W + w) * cv);
+                }
+            float best[VN];
+            int bi[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) { best[e] = -INFINITY; bi[e] = 0; }
+#pragma unroll
+            for (int k = 0; k < KH * KW; ++k) {
+                if (!ok[k]) continue;
+                float f[VN];
+                unpack<T>(v[k], f);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    const float a = to_f<T>(from_f<T>(fmaxf(f[e] + bb[e], 0.f)));
+                    if (a > best[e]) { best[e] = a; bi[e] = k; }
+                }
+            }
+            const int64_t t = ((int64_t)row * g.Wo + wo) * cv + cvec;
+            reinterpret_cast<uint4 *>(y)[t] = pack<T>(best);
+            unsigned char ib[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) ib[e] = (unsigned char)bi[e];
+            store_bytes<VN>(idx + t * VN, ib);
+        }
+    }
+}
+
+// backward, one block per INPUT row (n, h): every input pixel gathers from the <= KH*KW windows that contain it
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256)
+pool_bwd_rows_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y, const unsigned char *__restrict__ idx,
+                     T *__restrict__ dz, float *__restrict__ part, int cv_shift) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = 1 << cv_shift;
+    const int cvec = threadIdx.x & (cv - 1), wl = threadIdx.x >> cv_shift, WL = 256 >> cv_shift;
+    float bsum[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bsum[e] = 0.f;
+    const int nrows = g.N * g.H;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = row / g.H, h = row - n * g.H;
+        int hos[KH];                                             // pooled row reached through window offset i, or -1
+#pragma unroll
+        for (int i = 0; i < KH; ++i) {
+            const int hn = h + g.ph - i;
+            hos[i] = (hn >= 0 && hn % g.sh == 0 && hn / g.sh < g.Ho) ? hn / g.sh : -1;
+        }
+        for (int w = wl; w < g.W; w += WL) {
+            uint4 vy[KH * KW], vd[KH * KW];
+            unsigned char ib[KH * KW][VN];
+            bool ok[KH * KW];
+#pragma unroll
+            for (int i = 0; i < KH; ++i)
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                    const int k = i * KW + j;
+                    const int wn = w + g.pw - j;
+                    const int wo = wn / g.sw;
+                    ok[k] = hos[i] >= 0 && wn >= 0 && wn % g.sw == 0 && wo < g.Wo;
+                    if (ok[k]) {
+                        const int64_t q = ((int64_t)(n * g.Ho + hos[i]) * g.Wo + wo) * cv + cvec;
+                        vy[k] = __ldg(reinterpret_cast<const uint4 *>(y) + q);
+                        vd[k] = __ldg(reinterpret_cast<const uint4 *>(dy) + q);
+                        load_bytes<VN>(idx + q * VN, ib[k]);
+                    }
+                }
+            float acc[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+#pragma unroll
+            for (int k = 0; k < KH * KW; ++k) {
+                if (!ok[k]) continue;
+                float fy[VN], fd[VN];
+                unpack<T>(vy[k], fy);
+                unpack<T>(vd[k], fd);
+#pragma unroll
+                for (int e = 0; e < VN; ++e)
+                    if (ib[k][e] == k && fy[e] > 0.f) acc[e] += fd[e];
+            }
+            const uint4 packed = pack<T>(acc);
+            __stcs(reinterpret_cast<uint4 *>(dz) + ((int64_t)row * g.W + w) * cv + cvec, packed);
+            if (part) {
+                float fr[VN];
+                unpack<T>(packed, fr);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) bsum[e] += fr[e];
+            }
+        }
+    }
+    if (part) {
+        __shared__ float red[256][VN + 1];
+        block_channel_partial<VN>(bsum, cv, part + (int64_t)blockIdx.x * g.C, red);
+    }
+}
+
+// backward for non-overlapping windows, one block per POOLED row (n, ho): read once, write the KH*KW input positions
+template <typename T, int KH, int KW>
+__global__ void __launch_bounds__(256)
+pool_bwd_tiled_rows_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y,
+                           const unsigned char *__restrict__ idx, T *__restrict__ dz, float *__restrict__ part, int cv_shift) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = 1 << cv_shift;
+    const int cvec = threadIdx.x & (cv - 1), wl = threadIdx.x >> cv_shift, WL = 256 >> cv_shift;
+    float bsum[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bsum[e] = 0.f;
+    const int nrows = g.N * g.Ho;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = row / g.Ho, ho = row - n * g.Ho;
+        for (int wo = wl; wo < g.Wo; wo += 2 * WL) {             // two pooled vectors in flight
+            const int wo2 = wo + WL;
+            const bool two = wo2 < g.Wo;
+            const int64_t t = ((int64_t)row * g.Wo + wo) * cv + cvec, t2 = ((int64_t)row * g.Wo + wo2) * cv + cvec;
+            uint4 ry[2], rd[2];
+            unsigned char ib[2][VN];
+            ry[0] = __ldg(reinterpret_cast<const uint4 *>(y) + t);
+            rd[0] = __ldg(reinterpret_cast<const uint4 *>(dy) + t);
+            load_bytes<VN>(idx + t * VN, ib[0]);
+            if (two) {
+                ry[1] = __ldg(reinterpret_cast<const uint4 *>(y) + t2);
+                rd[1] = __ldg(reinterpret_cast<const uint4 *>(dy) + t2);
+                load_bytes<VN>(idx + t2 * VN, ib[1]);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                float fy[VN], fd[VN];
+                unpack<T>(ry[u], fy);
+                unpack<T>(rd[u], fd);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    if (!(fy[e] > 0.f)) fd[e] = 0.f;            // ReLU' through the pooled value
+                    bsum[e] += to_f<T>(from_f<T>(fd[e]));
+                }
+                const int wcur = u ? wo2 : wo;
+#pragma unroll
+                for (int i = 0; i < KH; ++i)
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) {
+                        float o[VN];
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) o[e] = (ib[u][e] == i * KW + j) ? fd[e] : 0.f;
+                        const int64_t q = ((int64_t)(n * g.H + ho * KH + i) * g.W + wcur * KW + j) * cv + cvec;
+                        __stcs(reinterpret_cast<uint4 *>(dz) + q, pack<T>(o));
+                    }
+            }
+        }
+    }
+    if (part) {
+        __shared__ float red[256][VN + 1];
+        block_channel_partial<VN>(bsum, cv, part + (int64_t)blockIdx.x * g.C, red);
+    }
+}
+
+inline int pow2_shift(int v) {      // log2(v) if v is a power of two, else -1
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int sft = 0;
+    while ((1 << sft) < v) ++sft;
+    return sft;
 }
 
 // plain bias (+ optional ReLU) on [rows, C], and its backward mask
@@ -388,7 +649,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 col_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, const float *__restrict__ bias,
                   const float *__restrict__ mean, const float *__restrict__ invstd, int64_t rows, int C,
-                  int64_t rows_per_cta, double *__restrict__ sums) {
+                  int64_t rows_per_cta, double *__restrict__ sums, float *__restrict__ part) {
     constexpr int VN = 16 / sizeof(T);
     const int cv = C / VN;
     const int lane_c = threadIdx.x & 31, lane_r = threadIdx.x >> 5;   // 32 x 8
@@ -406,20 +667,33 @@ col_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, const float 
             mm[e] = (MODE == 1) ? mean[v * VN + e] : 0.f;
             is[e] = (MODE == 1) ? invstd[v * VN + e] : 0.f;
         }
-        for (int64_t r = r0 + lane_r; r < r1; r += 8) {
-            float fa[VN];
-            unpack<T>(__ldg(reinterpret_cast<const uint4 *>(a + r * C) + v), fa);
-            if (MODE == 0) {
+        constexpr int U = 4;             // rows in flight per thread
+        for (int64_t r = r0 + lane_r; r < r1; r += 8 * U) {
+            uint4 ra[U], rb[U];
 #pragma unroll
-                for (int e = 0; e < VN; ++e) { const float x = fa[e] + bb[e]; s0[e] += x; s1[e] += x * x; }
-            } else if (MODE == 1) {
-                float fb[VN];
-                unpack<T>(__ldg(reinterpret_cast<const uint4 *>(b + r * C) + v), fb);
+            for (int k = 0; k < U; ++k) {
+                const int64_t rr = r + 8 * k;
+                const bool ok = rr < r1;
+                ra[k] = ok ? __ldg(reinterpret_cast<const uint4 *>(a + rr * C) + v) : make_uint4(0, 0, 0, 0);
+                if (MODE == 1) rb[k] = ok ? __ldg(reinterpret_cast<const uint4 *>(b + rr * C) + v) : make_uint4(0, 0, 0, 0);
+            }
 #pragma unroll
-                for (int e = 0; e < VN; ++e) { s0[e] += fa[e]; s1[e] += fa[e] * ((fb[e] + bb[e] - mm[e]) * is[e]); }
-            } else {
+            for (int k = 0; k < U; ++k) {
+                if (r + 8 * k >= r1) break;
+                float fa[VN];
+                unpack<T>(ra[k], fa);
+                if (MODE == 0) {
 #pragma unroll
-                for (int e = 0; e < VN; ++e) s0[e] += fa[e];
+                    for (int e = 0; e < VN; ++e) { const float x = fa[e] + bb[e]; s0[e] += x; s1[e] += x * x; }
+                } else if (MODE == 1) {
+                    float fb[VN];
+                    unpack<T>(rb[k], fb);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) { s0[e] += fa[e]; s1[e] += fa[e] * ((fb[e] + bb[e] - mm[e]) * is[e]); }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) s0[e] += fa[e];
+                }
             }
         }
     }
@@ -433,8 +707,13 @@ col_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, const float 
             float t0 = 0.f, t1 = 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) { t0 += red[0][k][lane_c][e]; t1 += red[1][k][lane_c][e]; }
-            atomicAdd(sums + v * VN + e, (double)t0);
-            if (MODE != 2) atomicAdd(sums + C + v * VN + e, (double)t1);
+            if (part) {                  // one row of [gridDim.y, 2C] per row block, added up by partials_finalize_kernel
+                part[(int64_t)blockIdx.y * 2 * C + v * VN + e] = t0;
+                part[(int64_t)blockIdx.y * 2 * C + C + v * VN + e] = (MODE != 2) ? t1 : 0.f;
+            } else {
+                atomicAdd(sums + v * VN + e, (double)t0);
+                if (MODE != 2) atomicAdd(sums + C + v * VN + e, (double)t1);
+            }
         }
     }
 }
@@ -569,6 +848,114 @@ bn_bwd_apply_kernel(const T *__restrict__ dy, const T *__restrict__ x, const flo
         __shared__ float red[256][VN + 1];
         block_channel_sum<VN>(bsum, cv, bias_sums, red);
     }
+}
+
+// Row-tiled variants of the two BatchNorm streaming kernels for 256 % (C / VN) == 0: a thread keeps ONE channel vector
+// (coefficients live in registers, no per-element index arithmetic), a block owns a contiguous range of rows and keeps
+// U rows per thread in flight.  Grid = one resident wave.
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_rows_kernel(const T *__restrict__ dy, const T *__restrict__ x, const float *__restrict__ bias,
+                         const float *__restrict__ mean, const float *__restrict__ invstd, const float *__restrict__ gamma,
+                         const double *__restrict__ sums, int64_t rows, int C, int64_t rows_per_cta, T *__restrict__ dx,
+                         float *__restrict__ part) {
+    constexpr int VN = 16 / sizeof(T);
+    constexpr int U = 4;
+    const int cv = C / VN;
+    const int cvec = threadIdx.x % cv, rl = threadIdx.x / cv, RL = 256 / cv;
+    const float inv_rows = 1.f / (float)rows;
+    float A[VN], k1[VN], t1[VN], shf[VN], bsum[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+        const int c = cvec * VN + e;
+        const float is = invstd[c];
+        A[e] = gamma[c] * is;
+        k1[e] = (float)sums[c] * inv_rows;
+        t1[e] = is * ((float)sums[C + c] * inv_rows);
+        shf[e] = (bias ? bias[c] : 0.f) - mean[c];
+        bsum[e] = 0.f;
+    }
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    const uint4 *pd = reinterpret_cast<const uint4 *>(dy) + cvec;
+    const uint4 *px = reinterpret_cast<const uint4 *>(x) + cvec;
+    uint4 *po = reinterpret_cast<uint4 *>(dx) + cvec;
+    for (int64_t r = r0 + rl; r < r1; r += (int64_t)U * RL) {
+        uint4 rd[U], rx[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t rr = r + (int64_t)k * RL;
+            if (rr < r1) { rd[k] = __ldg(pd + rr * cv); rx[k] = __ldg(px + rr * cv); }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t rr = r + (int64_t)k * RL;
+            if (rr >= r1) break;
+            float fd[VN], fx[VN];
+            unpack<T>(rd[k], fd);
+            unpack<T>(rx[k], fx);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) fd[e] = A[e] * (fd[e] - k1[e] - (fx[e] + shf[e]) * t1[e]);
+            const uint4 packed = pack<T>(fd);
+            __stcs(po + rr * cv, packed);
+            if (part) {
+                float fr[VN];
+                unpack<T>(packed, fr);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) bsum[e] += fr[e];
+            }
+        }
+    }
+    if (part) {
+        __shared__ float red[256][VN + 1];
+        block_channel_partial<VN>(bsum, cv, part + (int64_t)blockIdx.x * C, red);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+bn_apply_rows_kernel(const T *__restrict__ x, const float *__restrict__ bias, const float *__restrict__ mean,
+                     const float *__restrict__ invstd, const float *__restrict__ gamma, const float *__restrict__ beta,
+                     int64_t rows, int C, int64_t rows_per_cta, T *__restrict__ y) {
+    constexpr int VN = 16 / sizeof(T);
+    constexpr int U = 4;
+    const int cv = C / VN;
+    const int cvec = threadIdx.x % cv, rl = threadIdx.x / cv, RL = 256 / cv;
+    float sc[VN], sh[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+        const int c = cvec * VN + e;
+        sc[e] = invstd[c] * gamma[c];
+        sh[e] = ((bias ? bias[c] : 0.f) - mean[c]) * sc[e] + beta[c];
+    }
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    const uint4 *px = reinterpret_cast<const uint4 *>(x) + cvec;
+    uint4 *po = reinterpret_cast<uint4 *>(y) + cvec;
+    for (int64_t r = r0 + rl; r < r1; r += (int64_t)U * RL) {
+        uint4 rx[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t rr = r + (int64_t)k * RL;
+            if (rr < r1) rx[k] = __ldg(px + rr * cv);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t rr = r + (int64_t)k * RL;
+            if (rr >= r1) break;
+            float f[VN];
+            unpack<T>(rx[k], f);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) f[e] = f[e] * sc[e] + sh[e];
+            po[rr * cv] = pack<T>(f);
+        }
+    }
+}
+
+// rows per block for a one-wave grid of `per_sm` blocks per SM, rounded to the row step of the row-tiled kernels
+inline int64_t rows_per_block(int64_t rows, int row_step, int per_sm, int *grid) {
+    int64_t rpc = ceil_div(rows, (int64_t)148 * per_sm);
+    rpc = ceil_div(rpc, (int64_t)row_step) * row_step;
+    *grid = (int)ceil_div(rows, rpc);
+    return rpc;
 }
 
 __global__ void sums_to_float_kernel(const double *__restrict__ s, int n, float scale, float *__restrict__ out, int accumulate) {
@@ -839,6 +1226,12 @@ int mr_bias_relu_pool_fwd(const void *x, const float *bias, int N, int H, int W,
     if (!vec_ok(dtype, C)) return MR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int vn = dtype == 0 ? 4 : 8;
+    const int sft = pow2_shift(C / vn);
+    if (kh == 2 && kw == 2 && sft >= 0 && sft <= 8 && (int64_t)N * H * W < ((int64_t)1 << 31)) {
+        const int nblocks = (int)std::min<int64_t>((int64_t)N * g.Ho, 148 * 16);
+        DISPATCH(dtype, (pool_fwd_rows_kernel<T, 2, 2><<<nblocks, 256, 0, st>>>(g, (const T *)x, bias, (T *)y, idx, sft)));
+        return check_launch("pool_fwd_rows_kernel");
+    }
     DISPATCH(dtype, (bias_relu_pool_fwd_kernel<T><<<grid1d((int64_t)N * g.Ho * g.Wo * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)x, bias, (T *)y, idx)));
     return check_launch("bias_relu_pool_fwd_kernel");
 }
@@ -855,12 +1248,31 @@ int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *id
     cudaStream_t st = (cudaStream_t)stream;
     const int vn = dtype == 0 ? 4 : 8;
     const bool fuse = dbias && sums && (256 % (C / vn) == 0);
-    if (fuse) MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * C, st), "memset sums");
+    float *part = (fuse && C <= kMaxPartialCols) ? partials_scratch() : nullptr;
+    if (fuse && !part) MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * C, st), "memset sums");
     const bool tiled = kh == sh && kw == sw && ph == 0 && pw == 0 && H % kh == 0 && W % kw == 0;
-    if (tiled) {
-        DISPATCH(dtype, (bias_relu_pool_bwd_tiled_kernel<T><<<grid1d((int64_t)N * g.Ho * g.Wo * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, fuse ? sums : nullptr)));
+    const int per_sm = part ? 8 : 32;                /* the partial-sum scratch has one row per block */
+    int nblocks;
+    const int sft = pow2_shift(C / vn);
+    if (kh == 2 && kw == 2 && sft >= 0 && sft <= 8 && (part || !dbias) && (int64_t)N * H * W < ((int64_t)1 << 31)) {
+        if (tiled) {
+            nblocks = (int)std::min<int64_t>((int64_t)N * g.Ho, kMaxPartialBlocks);
+            DISPATCH(dtype, (pool_bwd_tiled_rows_kernel<T, 2, 2><<<nblocks, 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, part, sft)));
+        } else {
+            nblocks = (int)std::min<int64_t>((int64_t)N * H, kMaxPartialBlocks);
+            DISPATCH(dtype, (pool_bwd_rows_kernel<T, 2, 2><<<nblocks, 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, part, sft)));
+        }
+    } else if (tiled) {
+        nblocks = grid1d((int64_t)N * g.Ho * g.Wo * (C / vn), 256, per_sm);
+        DISPATCH(dtype, (bias_relu_pool_bwd_tiled_kernel<T><<<nblocks, 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, (fuse && !part) ? sums : nullptr, part)));
     } else {
-        DISPATCH(dtype, (bias_relu_pool_bwd_kernel<T><<<grid1d((int64_t)N * H * W * (C / vn), 256, 32), 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, fuse ? sums : nullptr)));
+        nblocks = grid1d((int64_t)N * H * W * (C / vn), 256, per_sm);
+        DISPATCH(dtype, (bias_relu_pool_bwd_kernel<T><<<nblocks, 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, (fuse && !part) ? sums : nullptr, part)));
+    }
+    if (part) {
+        rc = check_launch("bias_relu_pool_bwd_kernel");
+        if (rc) return rc;
+        partials_finalize_kernel<<<(int)ceil_div(C, 32), dim3(32, 32), 0, st>>>(part, nblocks, C, sums);
     }
     rc = check_launch("bias_relu_pool_bwd_kernel");
     if (rc || !dbias) return rc;
@@ -894,11 +1306,18 @@ static int launch_reduce(int mode, int dtype, const void *a, const void *b, cons
     int64_t rpc = ceil_div(rows, gy);
     if (rpc < 64) rpc = 64;
     gy = ceil_div(rows, rpc);
-    MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st), "memset sums");
+    float *part = (gy <= kMaxPartialBlocks && 2 * C <= kMaxPartialCols) ? partials_scratch() : nullptr;
+    if (!part) MR_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st), "memset sums");
     dim3 grid(gx, (unsigned)gy);
-#define RL(MODEV) DISPATCH(dtype, (col_reduce_kernel<T, MODEV><<<grid, 256, 0, st>>>((const T *)a, (const T *)b, bias, mean, invstd, rows, C, rpc, sums)))
+#define RL(MODEV) DISPATCH(dtype, (col_reduce_kernel<T, MODEV><<<grid, 256, 0, st>>>((const T *)a, (const T *)b, bias, mean, invstd, rows, C, rpc, sums, part)))
     if (mode == 0) RL(0); else if (mode == 1) RL(1); else RL(2);
 #undef RL
+    if (part) {
+        int rc = check_launch("col_reduce_kernel");
+        if (rc) return rc;
+        partials_finalize_kernel<<<(int)ceil_div(2 * C, 32), dim3(32, 32), 0, st>>>(part, (int)gy, 2 * C, sums);
+        return check_launch("partials_finalize_kernel");
+    }
     return check_launch("col_reduce_kernel");
 }
 
@@ -916,7 +1335,13 @@ int mr_bn_train_fwd(const void *x, const float *bias, const float *gamma, const 
     rc = check_launch("bn_finalize_kernel");
     if (rc) return rc;
     const int vn = dtype == 0 ? 4 : 8;
-    DISPATCH(dtype, (bn_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, (T *)y)));
+    if (256 % (C / vn) == 0) {
+        int grid;
+        const int64_t rpc = rows_per_block(rows, 4 * (256 / (C / vn)), 2, &grid);
+        DISPATCH(dtype, (bn_apply_rows_kernel<T><<<grid, 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, rpc, (T *)y)));
+    } else {
+        DISPATCH(dtype, (bn_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, (T *)y)));
+    }
     return check_launch("bn_apply_kernel");
 }
 
@@ -929,7 +1354,13 @@ int mr_bn_apply(const void *x, const float *bias, const float *mean, const float
     if (!vec_ok(dtype, C)) return MR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int vn = dtype == 0 ? 4 : 8;
-    DISPATCH(dtype, (bn_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, (T *)y)));
+    if (256 % (C / vn) == 0) {
+        int grid;
+        const int64_t rpc = rows_per_block(rows, 4 * (256 / (C / vn)), 2, &grid);
+        DISPATCH(dtype, (bn_apply_rows_kernel<T><<<grid, 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, rpc, (T *)y)));
+    } else {
+        DISPATCH(dtype, (bn_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)x, bias, mean, invstd, gamma, beta, rows, C, (T *)y)));
+    }
     return check_launch("bn_apply_kernel");
 }
 
@@ -948,7 +1379,20 @@ int mr_bn_train_bwd(const void *dy, const void *x, const float *bias, const floa
     if (rc) return rc;
     const int vn = dtype == 0 ? 4 : 8;
     /* `sums` holds 2*C doubles of statistics + C more for the fused conv-bias gradient (sum of dx). */
-    const bool fuse = dbias && (256 % (C / vn) == 0);
+    const int cv = C / vn;
+    const bool fuse = dbias && vec_ok(dtype, C) && (256 % cv == 0);
+    if (vec_ok(dtype, C) && 256 % cv == 0) {
+        int grid;
+        const int64_t rpc = rows_per_block(rows, 4 * (256 / cv), 2, &grid);
+        float *part = (fuse && C <= kMaxPartialCols) ? partials_scratch() : nullptr;
+        DISPATCH(dtype, (bn_bwd_apply_rows_kernel<T><<<grid, 256, 0, st>>>((const T *)dy, (const T *)x, bias, mean, invstd, gamma, sums, rows, C, rpc, (T *)dx, part)));
+        rc = check_launch("bn_bwd_apply_rows_kernel");
+        if (rc || !dbias) return rc;
+        if (!part) return mr_colsum(dx, rows, C, dtype, dbias, 0, sums, stream);
+        partials_finalize_kernel<<<(int)ceil_div(C, 32), dim3(32, 32), 0, st>>>(part, grid, C, sums + 2 * C);
+        sums_to_float_kernel<<<(int)ceil_div(C, 128), 128, 0, st>>>(sums + 2 * C, C, 1.f, dbias, 0);
+        return check_launch("sums_to_float_kernel");
+    }
     if (fuse) MR_CUDA_TRY(cudaMemsetAsync(sums + 2 * C, 0, sizeof(double) * C, st), "memset sums");
     DISPATCH(dtype, (bn_bwd_apply_kernel<T><<<grid1d(rows * (C / vn), 256, 32), 256, 0, st>>>((const T *)dy, (const T *)x, bias, mean, invstd, gamma, sums, rows, C, (T *)dx, fuse ? sums + 2 * C : nullptr)));
     rc = check_launch("bn_bwd_apply_kernel");
