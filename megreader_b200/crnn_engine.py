@@ -256,9 +256,17 @@ def _bilstm_forward_impl(X, params, dtype, training):
     return E.view(T, N, nOut), saved
 
 
+_PERM_CACHE = {}
+
+
 def _unit_major_perm(H, dev):
-    """perm[4*j + g] = g*H + j : reference gate-major rows (i|f|g|o blocks) -> unit-major rows."""
-    return torch.arange(4 * H, device=dev).view(4, H).t().reshape(-1)
+    """perm[4*j + g] = g*H + j : reference gate-major rows (i|f|g|o blocks) -> unit-major rows; inv undoes it."""
+    key = (H, str(dev))
+    if key not in _PERM_CACHE:
+        perm = torch.arange(4 * H, device=dev).view(4, H).t().reshape(-1)
+        inv = torch.arange(4 * H, device=dev).view(H, 4).t().reshape(-1)
+        _PERM_CACHE[key] = (perm, inv)
+    return _PERM_CACHE[key]
 
 
 def _bilstm_forward_fused(X, params, training):
@@ -270,7 +278,7 @@ def _bilstm_forward_fused(X, params, training):
     w_emb, b_emb = params[8], params[9]
     H = w_hh[0].size(1)
     dev = X.device
-    perm = _unit_major_perm(H, dev)
+    perm, _ = _unit_major_perm(H, dev)
     Wih = [ops.cast(w.detach()[perm].contiguous(), dtype) for w in w_ih]
     Whh = [ops.cast(w.detach()[perm].contiguous(), dtype) for w in w_hh]
     bias = [(b_ih[d].detach() + b_hh[d].detach())[perm].contiguous() for d in (0, 1)]
@@ -307,7 +315,7 @@ def _bilstm_backward_fused(dE, sv):
     X, G, Cst, Y, H, perm = sv["X"], sv["G"], sv["C"], sv["Y"], sv["H"], sv["perm"]
     T, N, I = X.shape
     dev = X.device
-    inv = torch.argsort(perm)
+    _, inv = _unit_major_perm(H, dev)
     dE2 = ops.cast(dE.reshape(T * N, -1), dtype)
     Y2 = Y.view(T * N, 2 * H)
     dWemb = ops.gemm(dE2, Y2, transA=True, out_dtype=torch.float32)
