@@ -87,6 +87,19 @@ int mr_ctc2d_backward_apply_f32(const float *grad_out, int64_t grad_out_stride, 
                                 const float *gfac, int64_t T, int64_t H, int64_t N, int64_t C, int fast_math,
                                 float *grad, void *stream);
 
+/* Fused epilogue of the 2D-CTC head (decoders/ctc_decoder2d.py:37-45): from the two conv branches' raw outputs
+ *   mask_logits [N,1,H,W] (before nn.Softmax(dim=2), :21) and cls_logits [N,C,H,W] (before softmax(dim=1), :41)
+ * straight to log_probs [W,H,N,C] = log(max(softmax_H(mask) * softmax_C(cls), tiny)).permute(3,2,0,1)   (fp32).
+ * Backward: either the explicit gradient grad_log_probs [W,H,N,C], or (grad_log_probs = NULL) the 2D-CTC training
+ * factor gfac [W,N,C] + grad_out [N] of mr_ctc2d_forward_train_f32, so that d(log_probs) never exists in HBM.
+ * Outputs grad_cls_logits [N,C,H,W], grad_mask_logits [N,1,H,W].  MR_ERR_UNSUPPORTED for charsets too large for the
+ * shared-memory tile (C > ~750 forward). */
+int mr_ctc2d_head_fwd_f32(const float *mask_logits, const float *cls_logits, int N, int C, int H, int W, float tiny,
+                          float *log_probs, void *stream);
+int mr_ctc2d_head_bwd_f32(const float *mask_logits, const float *cls_logits, const float *grad_log_probs, const float *gfac,
+                          const float *grad_out, int64_t grad_out_stride, int N, int C, int H, int W, float tiny,
+                          float *grad_cls_logits, float *grad_mask_logits, void *stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 1D CTC head of the CRNN decoder (replaces the `log_softmax -> nn.CTCLoss(zero_infinity=True)` call,
  * decoders/crnn.py:47-48,95-99; arithmetic restated in decoders/ctc_loss.py:65-122).  fp32.

@@ -158,6 +158,64 @@ def make_surfaces():
     print("surfaces", {k: getattr(v, "shape", v) for k, v in out.items()})
 
 
+def make_head():
+    """2D-CTC head epilogue (decoders/ctc_decoder2d.py:37-45): run the UNMODIFIED reference module on CPU with its
+    `ctc_loss` replaced by a fixed linear functional of `pred`, capture the two conv branches' raw outputs with
+    forward hooks, and record pred plus the gradients that reach those raw outputs."""
+    import types
+    from tests.weights import fill_state_dict
+    ref_loader.install()
+    ops_stub = types.ModuleType("ops")
+    ops_stub.ctc_loss_2d = None
+    saved = sys.modules.get("ops")
+    sys.modules["ops"] = ops_stub
+    try:
+        import decoders as rd
+        dec = fill_state_dict(rd.CTCDecoder2D(16, inner_channels=8), "d2.").train()
+    finally:
+        if saved is not None:
+            sys.modules["ops"] = saved
+        else:
+            del sys.modules["ops"]
+    rng = np.random.RandomState(21)
+    feat = torch.from_numpy((rng.standard_normal((5, 16, 8, 32)) * 3.0).astype(np.float32))
+    weight = torch.from_numpy(rng.standard_normal((32, 8, 5, 38)).astype(np.float32))
+    lengths = torch.tensor([3, 1, 4, 2, 5])
+    captured = {}
+
+    def grab(name):
+        def hook(module, inputs, output):
+            output.retain_grad()
+            captured[name] = output
+        return hook
+    dec.pred_mask[2].register_forward_hook(grab("mask_logits"))
+    dec.pred_classify[2].register_forward_hook(grab("cls_logits"))
+    dec.ctc_loss = lambda pred, *a: (pred * weight).sum(dim=(0, 1, 3))
+    out = {}
+    # case "a": `saved_tiny` as fill_state_dict left it (a large value: the clamp and its zero gradient hit ~half the
+    # entries); "b": the real tiny = finfo(float32).tiny, ordinary logits; "c": real tiny, 1x1 convs scaled x25 so that
+    # part of mask*classify underflows below tiny
+    real_tiny = float(torch.finfo(torch.float32).tiny)
+    for tag, tiny, gain in (("a", None, 1.0), ("b", real_tiny, 1.0), ("c", real_tiny, 25.0)):
+        with torch.no_grad():
+            if tiny is not None:
+                dec.saved_tiny.fill_(tiny)
+            dec.pred_mask[2].weight.mul_(gain)
+            dec.pred_classify[2].weight.mul_(gain)
+        dec.zero_grad()
+        loss, pred = dec(feat, targets=torch.zeros(5, 32), lengths=lengths, train=True)
+        loss.sum().backward()
+        dlp = (weight / lengths.float().view(1, 1, -1, 1)).contiguous()      # the upstream gradient that reached pred
+        out.update({tag + ".tiny": np.float32(dec.saved_tiny.item()),
+                    tag + ".mask_logits": captured["mask_logits"].detach().numpy(),
+                    tag + ".cls_logits": captured["cls_logits"].detach().numpy(), tag + ".pred": pred.detach().numpy(),
+                    tag + ".grad_pred": dlp.numpy(), tag + ".grad_mask_logits": captured["mask_logits"].grad.numpy(),
+                    tag + ".grad_cls_logits": captured["cls_logits"].grad.numpy()})
+        print("head", tag, tuple(pred.shape), "tiny", dec.saved_tiny.item(), "clamped fraction",
+              float((pred <= float(np.log(dec.saved_tiny.item())) + 1e-6).float().mean()))
+    np.savez_compressed(os.path.join(GOLD, "ctc2d_head_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["ctc2d"]
@@ -167,3 +225,5 @@ if __name__ == "__main__":
         make_crnn()
     if "surfaces" in which:
         make_surfaces()
+    if "head" in which:
+        make_head()
