@@ -21,32 +21,112 @@
 namespace {
 using namespace mr;
 
-constexpr int kTW = 32;          // columns per block
+constexpr int kTW = 32;          // columns per block (tile row stride kTW + 1 = 33 floats)
 constexpr int kThreads = 256;
 
 struct HeadGeo { int N, C, H, W, NT; };
 
-// log-softmax of the mask logits over H at (n, w) for height h; also returns softmax value
-__device__ __forceinline__ float mask_logsoftmax(const float *__restrict__ m, int n, int h, int w, int H, int W) {
-    const float *col = m + (int64_t)n * H * W + w;
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+// mask tile mt[nl][k][w] <- mask_logits[n0+nl, 0, k, w0+w]: all heights of the block's samples / columns (the softmax over
+// H needs every height); loaded with the logits tile so that no thread waits on a chain of dependent global loads.
+__device__ __forceinline__ void load_mask_tile(const HeadGeo &g, const float *__restrict__ m, int n0, int w0, float *mt) {
+    const int w = threadIdx.x & 31, r0 = threadIdx.x >> 5;
+    const int rows = g.NT * g.H;
+    constexpr int RS = kThreads / 32, B = 8;
+    for (int rb = r0; rb < rows; rb += RS * B) {
+        float v[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int r = rb + j * RS;
+            const int nl = r / g.H, k = r - nl * g.H;
+            const int n = n0 + nl;
+            v[j] = 0.f;
+            if (r < rows && n < g.N && w0 + w < g.W) v[j] = __ldg(m + ((int64_t)n * g.H + k) * g.W + w0 + w);
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int r = rb + j * RS;
+            if (r < rows) mt[r * (kTW + 1) + w] = v[j];
+        }
+    }
+}
+// log-probability (natural log) of height h under softmax_H of the mask column held in mt
+__device__ __forceinline__ float mask_logsoftmax(const float *mt, int nl, int h, int w, int H) {
+    const float *col = mt + (nl * H) * (kTW + 1) + w;
     float mx = -INFINITY;
-    for (int k = 0; k < H; ++k) mx = fmaxf(mx, __ldg(col + (int64_t)k * W));
+    for (int k = 0; k < H; ++k) mx = fmaxf(mx, col[k * (kTW + 1)]);
     float s = 0.f;
-    for (int k = 0; k < H; ++k) s += expf(__ldg(col + (int64_t)k * W) - mx);
-    return __ldg(col + (int64_t)h * W) - mx - logf(s);
+    for (int k = 0; k < H; ++k) s += ex2f((col[k * (kTW + 1)] - mx) * kLog2e);
+    return col[h * (kTW + 1)] - mx - lg2f(s) * kLn2;
+}
+
+// max and sum of 2^(v*log2e - max) over one tile column (stride kTW+1), four independent chains
+__device__ __forceinline__ void column_max_sum(const float *col, int C, float &mx, float &s) {
+    constexpr int ST = 33;
+    float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+        m0 = fmaxf(m0, col[c * ST]); m1 = fmaxf(m1, col[(c + 1) * ST]);
+        m2 = fmaxf(m2, col[(c + 2) * ST]); m3 = fmaxf(m3, col[(c + 3) * ST]);
+    }
+    for (; c < C; ++c) m0 = fmaxf(m0, col[c * ST]);
+    mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    const float off = mx * kLog2e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    c = 0;
+    for (; c + 4 <= C; c += 4) {
+        s0 += ex2f(fmaf(col[c * ST], kLog2e, -off)); s1 += ex2f(fmaf(col[(c + 1) * ST], kLog2e, -off));
+        s2 += ex2f(fmaf(col[(c + 2) * ST], kLog2e, -off)); s3 += ex2f(fmaf(col[(c + 3) * ST], kLog2e, -off));
+    }
+    for (; c < C; ++c) s0 += ex2f(fmaf(col[c * ST], kLog2e, -off));
+    s = (s0 + s1) + (s2 + s3);
 }
 
 // tile[nl][c][w] <-> z[n0+nl, c, h, w0+w]  (rows of 32 floats along W)
 __device__ __forceinline__ void load_nchw_tile(const HeadGeo &g, const float *__restrict__ z, int n0, int h, int w0,
                                                float *tile) {
+    // batches of 8 independent loads per thread before the first shared-memory store: a load -> store loop body makes
+    // every iteration wait for its own load (38 serialised memory latencies per block; measured 28-46 us per block)
     const int w = threadIdx.x & 31, r0 = threadIdx.x >> 5;
     const int rows = g.NT * g.C;
-    for (int r = r0; r < rows; r += kThreads / 32) {
-        const int nl = r / g.C, c = r - nl * g.C;
-        const int n = n0 + nl;
-        float v = 0.f;
-        if (n < g.N && w0 + w < g.W) v = __ldg(z + (((int64_t)n * g.C + c) * g.H + h) * g.W + w0 + w);
-        tile[r * (kTW + 1) + w] = v;
+    constexpr int RS = kThreads / 32, B = 20;           // 8 samples x 38 classes = 304 rows = 2 batches per thread
+    for (int rb = r0; rb < rows; rb += RS * B) {
+        float v[B];
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int r = rb + j * RS;
+            const int nl = r / g.C, c = r - nl * g.C;
+            const int n = n0 + nl;
+            v[j] = 0.f;
+            if (r < rows && n < g.N && w0 + w < g.W) v[j] = __ldg(z + (((int64_t)n * g.C + c) * g.H + h) * g.W + w0 + w);
+        }
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int r = rb + j * RS;
+            if (r < rows) tile[r * (kTW + 1) + w] = v[j];
+        }
+    }
+}
+
+// tile[e][w] <- src_w[e] for the 32 columns of the block, src_w = base + w * col_stride (NT*C contiguous floats each)
+__device__ __forceinline__ void load_thnc_tile(const float *__restrict__ base, int64_t col_stride, int ncols, int per_col,
+                                               int nvalid, float *tile) {
+    constexpr int B = 16;
+    for (int e0 = threadIdx.x; e0 < per_col; e0 += kThreads) {
+        for (int wb = 0; wb < ncols; wb += B) {
+            float v[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                v[j] = 0.f;
+                if (wb + j < ncols && e0 < nvalid) v[j] = __ldg(base + (int64_t)(wb + j) * col_stride + e0);
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j)
+                if (wb + j < kTW) tile[e0 * (kTW + 1) + wb + j] = v[j];
+        }
     }
 }
 
@@ -65,9 +145,11 @@ __device__ __forceinline__ void store_nchw_tile(const HeadGeo &g, float *__restr
 __global__ void __launch_bounds__(kThreads)
 ctc2d_head_fwd_kernel(HeadGeo g, const float *__restrict__ mask_logits, const float *__restrict__ cls_logits,
                       float log_tiny, float *__restrict__ lp) {
-    extern __shared__ float tile[];                      // [NT*C][33]
+    extern __shared__ float tile[];                      // [NT*C][33] logits, then [NT*H][33] mask logits
+    float *mt = tile + g.NT * g.C * (kTW + 1);
     const int w0 = blockIdx.x * kTW, h = blockIdx.y, n0 = blockIdx.z * g.NT;
     load_nchw_tile(g, cls_logits, n0, h, w0, tile);
+    load_mask_tile(g, mask_logits, n0, w0, mt);
     __syncthreads();
     // one thread per (sample, column): class log-softmax + mask log-softmax, clamp at log(tiny)
     for (int item = threadIdx.x; item < g.NT * kTW; item += kThreads) {
@@ -75,11 +157,11 @@ ctc2d_head_fwd_kernel(HeadGeo g, const float *__restrict__ mask_logits, const fl
         const int n = n0 + nl;
         if (n >= g.N || w0 + w >= g.W) continue;
         float *col = tile + (nl * g.C) * (kTW + 1) + w;
-        float mx = -INFINITY;
-        for (int c = 0; c < g.C; ++c) mx = fmaxf(mx, col[c * (kTW + 1)]);
-        float s = 0.f;
-        for (int c = 0; c < g.C; ++c) s += expf(col[c * (kTW + 1)] - mx);
-        const float shift = mask_logsoftmax(mask_logits, n, h, w0 + w, g.H, g.W) - mx - logf(s);
+        float mx, sum;
+        column_max_sum(col, g.C, mx, sum);
+        // log(mask * classify) = z - max - ln(sum) + log mask ; one exponential per element in total
+        const float shift = mask_logsoftmax(mt, nl, h, w, g.H) - mx - lg2f(sum) * kLn2;
+#pragma unroll 4
         for (int c = 0; c < g.C; ++c) col[c * (kTW + 1)] = fmaxf(col[c * (kTW + 1)] + shift, log_tiny);
     }
     __syncthreads();
@@ -98,45 +180,58 @@ template <bool FACTORED>
 __global__ void __launch_bounds__(kThreads)
 ctc2d_head_bwd_kernel(HeadGeo g, const float *__restrict__ mask_logits, const float *__restrict__ cls_logits,
                       const float *__restrict__ dlp, const float *__restrict__ gfac, const float *__restrict__ go,
-                      int64_t go_stride, float log_tiny, float *__restrict__ dcls, float *__restrict__ gsum) {
+                      int64_t go_stride, float tiny, float *__restrict__ dcls, float *__restrict__ gsum) {
     extern __shared__ float smem[];
     const int per_col = g.NT * g.C;
     float *zt = smem;                                    // [NT*C][33] logits -> d logits
     float *gt = smem + per_col * (kTW + 1);              // [NT*C][33] upstream gradient (or factor)
+    float *mt = gt + per_col * (kTW + 1);                // [NT*H][33] mask logits
     const int w0 = blockIdx.x * kTW, h = blockIdx.y, n0 = blockIdx.z * g.NT;
     load_nchw_tile(g, cls_logits, n0, h, w0, zt);
+    load_mask_tile(g, mask_logits, n0, w0, mt);
     const int nvalid = min(g.NT, g.N - n0) * g.C;
-    for (int w = 0; w < kTW && w0 + w < g.W; ++w) {
-        // explicit gradient is [T,H,N,C]; the factor is [T,N,C] (shared by all heights)
-        const float *src = FACTORED ? gfac + ((int64_t)(w0 + w) * g.N + n0) * g.C
-                                    : dlp + (((int64_t)(w0 + w) * g.H + h) * g.N + n0) * g.C;
-        for (int e = threadIdx.x; e < per_col; e += kThreads) gt[e * (kTW + 1) + w] = e < nvalid ? __ldg(src + e) : 0.f;
-    }
+    // explicit gradient is [T,H,N,C]; the factor is [T,N,C] (shared by all heights)
+    if (FACTORED) load_thnc_tile(gfac + ((int64_t)w0 * g.N + n0) * g.C, (int64_t)g.N * g.C, min(kTW, g.W - w0), per_col, nvalid, gt);
+    else load_thnc_tile(dlp + (((int64_t)w0 * g.H + h) * g.N + n0) * g.C, (int64_t)g.H * g.N * g.C, min(kTW, g.W - w0), per_col, nvalid, gt);
     __syncthreads();
     for (int item = threadIdx.x; item < g.NT * kTW; item += kThreads) {
         const int nl = item >> 5, w = item & 31;
         const int n = n0 + nl;
         if (n >= g.N || w0 + w >= g.W) continue;
         float *zc = zt + (nl * g.C) * (kTW + 1) + w;
-        const float *gc = gt + (nl * g.C) * (kTW + 1) + w;
-        float mx = -INFINITY;
-        for (int c = 0; c < g.C; ++c) mx = fmaxf(mx, zc[c * (kTW + 1)]);
-        float s = 0.f;
-        for (int c = 0; c < g.C; ++c) s += expf(zc[c * (kTW + 1)] - mx);
-        const float lse = mx + logf(s);
-        const float lm = mask_logsoftmax(mask_logits, n, h, w0 + w, g.H, g.W);
+        float *gc = gt + (nl * g.C) * (kTW + 1) + w;
+        float mx, sum;
+        column_max_sum(zc, g.C, mx, sum);
+        const float inv = 1.f / sum, off = mx * kLog2e;
+        const float maskp = ex2f(mask_logsoftmax(mt, nl, h, w, g.H) * kLog2e);
         const float gout = FACTORED ? __ldg(go + (int64_t)n * go_stride) : 1.f;
-        float tot = 0.f;
-        for (int c = 0; c < g.C; ++c) {
-            const float lc = zc[c * (kTW + 1)] - lse;
-            const float l = lm + lc;
-            float gv = 0.f;
-            if (l > log_tiny) gv = FACTORED ? expf(l) * gc[c * (kTW + 1)] * gout : gc[c * (kTW + 1)];   // max(.,tiny): no gradient when clamped
-            tot += gv;
-            zc[c * (kTW + 1)] = lc;                       // keep log-softmax, combine below
-            const_cast<float *>(gc)[c * (kTW + 1)] = gv;
+        // probability domain: p = classify prob, q = mask * p (what the reference clamps at tiny); max(q, tiny) passes no
+        // gradient where q <= tiny.  With the CTC factor the upstream gradient is exp(log_probs) * gfac * go = q * gfac * go.
+        float t0 = 0.f, t1 = 0.f;
+        int c = 0;
+        for (; c + 2 <= g.C; c += 2) {
+            const float p0 = ex2f(fmaf(zc[c * (kTW + 1)], kLog2e, -off)) * inv;
+            const float p1 = ex2f(fmaf(zc[(c + 1) * (kTW + 1)], kLog2e, -off)) * inv;
+            const float q0 = p0 * maskp, q1 = p1 * maskp;
+            const float u0 = gc[c * (kTW + 1)], u1 = gc[(c + 1) * (kTW + 1)];
+            const float g0 = q0 > tiny ? (FACTORED ? q0 * u0 * gout : u0) : 0.f;
+            const float g1 = q1 > tiny ? (FACTORED ? q1 * u1 * gout : u1) : 0.f;
+            t0 += g0; t1 += g1;
+            zc[c * (kTW + 1)] = p0; zc[(c + 1) * (kTW + 1)] = p1;
+            gc[c * (kTW + 1)] = g0; gc[(c + 1) * (kTW + 1)] = g1;
         }
-        for (int c = 0; c < g.C; ++c) zc[c * (kTW + 1)] = gc[c * (kTW + 1)] - expf(zc[c * (kTW + 1)]) * tot;
+        for (; c < g.C; ++c) {
+            const float p0 = ex2f(fmaf(zc[c * (kTW + 1)], kLog2e, -off)) * inv;
+            const float q0 = p0 * maskp;
+            const float u0 = gc[c * (kTW + 1)];
+            const float g0 = q0 > tiny ? (FACTORED ? q0 * u0 * gout : u0) : 0.f;
+            t0 += g0;
+            zc[c * (kTW + 1)] = p0;
+            gc[c * (kTW + 1)] = g0;
+        }
+        const float tot = t0 + t1;
+#pragma unroll 4
+        for (int k = 0; k < g.C; ++k) zc[k * (kTW + 1)] = gc[k * (kTW + 1)] - zc[k * (kTW + 1)] * tot;
         gsum[((int64_t)n * g.H + h) * g.W + w0 + w] = tot;
     }
     __syncthreads();
@@ -153,16 +248,17 @@ __global__ void ctc2d_head_mask_bwd_kernel(int N, int H, int W, const float *__r
     float mx = -INFINITY, tot = 0.f;
     for (int k = 0; k < H; ++k) { mx = fmaxf(mx, m[(int64_t)k * W]); tot += gp[(int64_t)k * W]; }
     float s = 0.f;
-    for (int k = 0; k < H; ++k) s += expf(m[(int64_t)k * W] - mx);
+    for (int k = 0; k < H; ++k) s += ex2f((m[(int64_t)k * W] - mx) * kLog2e);
     const float inv = 1.f / s;
-    for (int k = 0; k < H; ++k) gp[(int64_t)k * W] -= expf(m[(int64_t)k * W] - mx) * inv * tot;
+    for (int k = 0; k < H; ++k) gp[(int64_t)k * W] -= ex2f((m[(int64_t)k * W] - mx) * kLog2e) * inv * tot;
 }
 
-int pick_nt(int C, int tiles, size_t *smem) {
-    // samples per block: as many as fit 48 KB per tile (two tiles in the backward), at most 8
+int pick_nt(int C, int H, int tiles, size_t *smem) {
+    // samples per block: as many as keep the logits tiles within 96 KB (so that >= 2 blocks share an SM), at most 8
+    auto bytes = [&](int nt) { return (size_t)nt * ((size_t)C * tiles + H) * (kTW + 1) * sizeof(float); };
     int nt = 8;
-    while (nt > 1 && (size_t)nt * C * (kTW + 1) * sizeof(float) * tiles > 96 * 1024) nt >>= 1;
-    *smem = (size_t)nt * C * (kTW + 1) * sizeof(float) * tiles;
+    while (nt > 1 && bytes(nt) > 96 * 1024) nt >>= 1;
+    *smem = bytes(nt);
     return *smem <= 200 * 1024 ? nt : 0;
 }
 
@@ -177,7 +273,7 @@ int mr_ctc2d_head_fwd_f32(const float *mask_logits, const float *cls_logits, int
     if (!mask_logits || !cls_logits || !log_probs) return MR_ERR_NULL_POINTER;
     HeadGeo g{N, C, H, W, 0};
     size_t smem;
-    g.NT = pick_nt(C, 1, &smem);
+    g.NT = pick_nt(C, H, 1, &smem);
     if (!g.NT || H > 65535 || ceil_div(N, g.NT) > 65535) return MR_ERR_UNSUPPORTED;
     static size_t attr = 0;
     if (smem > attr) {
@@ -200,7 +296,7 @@ int mr_ctc2d_head_bwd_f32(const float *mask_logits, const float *cls_logits, con
     if (factored && (!gfac || !grad_out)) return MR_ERR_NULL_POINTER;
     HeadGeo g{N, C, H, W, 0};
     size_t smem;
-    g.NT = pick_nt(C, 2, &smem);
+    g.NT = pick_nt(C, H, 2, &smem);
     if (!g.NT || H > 65535 || ceil_div(N, g.NT) > 65535) return MR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     static size_t attr[2] = {0, 0};
@@ -212,10 +308,10 @@ int mr_ctc2d_head_bwd_f32(const float *mask_logits, const float *cls_logits, con
     dim3 grid((unsigned)ceil_div(W, kTW), (unsigned)H, (unsigned)ceil_div(N, g.NT));
     if (factored)
         ctc2d_head_bwd_kernel<true><<<grid, kThreads, smem, st>>>(g, mask_logits, cls_logits, nullptr, gfac, grad_out, grad_out_stride,
-                                                                   logf(tiny), grad_cls_logits, grad_mask_logits);
+                                                                   tiny, grad_cls_logits, grad_mask_logits);
     else
         ctc2d_head_bwd_kernel<false><<<grid, kThreads, smem, st>>>(g, mask_logits, cls_logits, grad_log_probs, nullptr, nullptr, 0,
-                                                                    logf(tiny), grad_cls_logits, grad_mask_logits);
+                                                                    tiny, grad_cls_logits, grad_mask_logits);
     int rc = check_launch("ctc2d_head_bwd_kernel");
     if (rc) return rc;
     const int64_t cols = (int64_t)N * W;
