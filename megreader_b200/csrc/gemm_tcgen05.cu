@@ -213,7 +213,7 @@ struct ConvArgs {
     // TMA-A variant: the output space [N, Ho, Wo] is tiled by boxes of bw x bh x bn = 128 pixels; the width is cut
     // into segments of power-of-two widths (e.g. Wo = 65 -> one 64-wide segment + one 1-wide segment).
     struct Seg { int w0, bw, bh, bn, h_blocks, tile_begin; } seg[4];
-    int nseg;
+    int nseg, ntiles;
     GemmArgs g;        // M = N*Ho*Wo, N = Cout, K = kh*kw*C
 };
 
@@ -277,17 +277,26 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
 
     if (warp == 0) {
         if (elect_one()) {                                   // weight tiles (and, with TMA_A, activation tiles) by TMA
-            int tn = 0, th0 = 0, tw0 = 0;
-            const CUtensorMap *tmX = &tmX0;
-            if (TMA_A) {
-                int sel = 0;
-                for (int q = 1; q < a.nseg; ++q) if ((int)blockIdx.x >= a.seg[q].tile_begin) sel = q;
-                const int lt = blockIdx.x - a.seg[sel].tile_begin;
-                const int nb = lt / a.seg[sel].h_blocks;
-                tn = nb * a.seg[sel].bn;
-                th0 = (lt - nb * a.seg[sel].h_blocks) * a.seg[sel].bh;
-                tw0 = a.seg[sel].w0;
-                tmX = sel == 0 ? &tmX0 : (sel == 1 ? &tmX1 : (sel == 2 ? &tmX2 : &tmX3));
+            // TMA_A: this CTA owns MT consecutive tiles of the segment enumeration (tile id = blockIdx.x * MT + sub); a
+            // tile id past the end (odd tile count) loads an all-out-of-bounds box (zero fill) and stores nothing
+            int tn[MT], th0[MT], tw0[MT];
+            const CUtensorMap *tmX[MT];
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub) {
+                tn[sub] = th0[sub] = tw0[sub] = 0;
+                tmX[sub] = &tmX0;
+                if (TMA_A) {
+                    const int tile = (int)blockIdx.x * MT + sub;
+                    if (tile >= a.ntiles) { tn[sub] = a.N; continue; }
+                    int sel = 0;
+                    for (int q = 1; q < a.nseg; ++q) if (tile >= a.seg[q].tile_begin) sel = q;
+                    const int lt = tile - a.seg[sel].tile_begin;
+                    const int nb = lt / a.seg[sel].h_blocks;
+                    tn[sub] = nb * a.seg[sel].bn;
+                    th0[sub] = (lt - nb * a.seg[sel].h_blocks) * a.seg[sel].bh;
+                    tw0[sub] = a.seg[sel].w0;
+                    tmX[sub] = sel == 0 ? &tmX0 : (sel == 1 ? &tmX1 : (sel == 2 ? &tmX2 : &tmX3));
+                }
             }
             int cc = 0, ti = 0, tj = 0;
             for (int i = 0; i < nkb; ++i) {
@@ -295,7 +304,10 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
                 mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
                 mbar_expect_tx(full + s, TMA_A ? L::STAGE_BYTES : L::B_BYTES);
                 if (TMA_A) {
-                    tma_load_4d(tmX, full + s, smem + s * L::STAGE_BYTES, cc * BK, tw0 + tj - a.pw, th0 + ti - a.ph, tn);
+#pragma unroll
+                    for (int sub = 0; sub < MT; ++sub)
+                        tma_load_4d(tmX[sub], full + s, smem + s * L::STAGE_BYTES + sub * (BM * BK * 2), cc * BK,
+                                    tw0[sub] + tj - a.pw, th0[sub] + ti - a.ph, tn[sub]);
                     if (++cc == cchunks) { cc = 0; if (++tj == a.kw) { tj = 0; ++ti; } }
                 }
                 tma_load_2d(&tmB, full + s, smem + s * L::STAGE_BYTES + L::A_BYTES, i * BK, n0);
@@ -323,16 +335,23 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
             __syncwarp();
         }
     } else if (TMA_A) {
-        int sel = 0;
-        for (int q = 1; q < a.nseg; ++q) if ((int)blockIdx.x >= a.seg[q].tile_begin) sel = q;
-        const int lt = blockIdx.x - a.seg[sel].tile_begin;
-        const int nb = lt / a.seg[sel].h_blocks;
-        const int bw = a.seg[sel].bw, bh = a.seg[sel].bh;
-        const int r = (warp & 3) * 32 + lane;                // tile row = (dn * bh + dh) * bw + dw
-        const int dw = r % bw, dh = (r / bw) % bh, dn = r / (bw * bh);
-        const int pn = nb * a.seg[sel].bn + dn, phh = (lt - nb * a.seg[sel].h_blocks) * bh + dh, pww = a.seg[sel].w0 + dw;
-        const int64_t prow = (pn < a.N && phh < a.Ho && pww < a.Wo) ? ((int64_t)pn * a.Ho + phh) * a.Wo + pww : -1;
-        epilogue_store<BN>(g, tmem_base, tmem_full, 0, n0, warp, lane, nkb > 0, prow);
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {
+            const int tile = (int)blockIdx.x * MT + sub;
+            int64_t prow = -1;
+            if (tile < a.ntiles) {
+                int sel = 0;
+                for (int q = 1; q < a.nseg; ++q) if (tile >= a.seg[q].tile_begin) sel = q;
+                const int lt = tile - a.seg[sel].tile_begin;
+                const int nb = lt / a.seg[sel].h_blocks;
+                const int bw = a.seg[sel].bw, bh = a.seg[sel].bh;
+                const int r = (warp & 3) * 32 + lane;        // tile row = (dn * bh + dh) * bw + dw
+                const int dw = r % bw, dh = (r / bw) % bh, dn = r / (bw * bh);
+                const int pn = nb * a.seg[sel].bn + dn, phh = (lt - nb * a.seg[sel].h_blocks) * bh + dh, pww = a.seg[sel].w0 + dw;
+                if (pn < a.N && phh < a.Ho && pww < a.Wo) prow = ((int64_t)pn * a.Ho + phh) * a.Wo + pww;
+            }
+            epilogue_store<BN>(g, tmem_base + sub * BN, tmem_full, 0, n0, warp, lane, nkb > 0, prow);
+        }
         tc_fence_before();
     } else {
         // ------------------------------------------------------------ activation gather (one thread = MT tile rows)
@@ -857,7 +876,7 @@ int launch_conv(const CUtensorMap &tb, const CUtensorMap *tx, const ConvArgs &a,
         MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_fprop smem attr");
         attr_set = true;
     }
-    dim3 grid(TMA_A ? (unsigned)tiles : (unsigned)ceil_div(a.g.M, BM * MT), (unsigned)ceil_div(a.g.N, BN), 1);
+    dim3 grid(TMA_A ? (unsigned)ceil_div(tiles, MT) : (unsigned)ceil_div(a.g.M, BM * MT), (unsigned)ceil_div(a.g.N, BN), 1);
     kern<<<grid, 192, L::TOTAL, st>>>(tb, tx[0], tx[1], tx[2], tx[3], a);
     return check_launch("conv_fprop_tcgen05_kernel");
 }
@@ -955,11 +974,11 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
     cudaStream_t st = (cudaStream_t)stream;
     /* 256-row CTAs (MT = 2) measured SLOWER than 128-row CTAs on B200 (conv5: 1186 us vs 841 us): kept selectable for
      * experiments (MR_CONV_MT2=1), off by default. */
-    static const bool mt2 = getenv("MR_CONV_MT2") && getenv("MR_CONV_MT2")[0] == '1';
+    static const bool mt2 = getenv("MR_CONV_GATHER_MT2") && getenv("MR_CONV_GATHER_MT2")[0] == '1';
     const bool big = mt2 && P >= 4 * 148 * 128;
     /* TMA-A variant: tile the output space with boxes of 128 pixels, width cut into power-of-two segments. */
     static const bool no_tma_a = getenv("MR_CONV_NO_TMA_A") != nullptr;
-    a.nseg = 0;
+    a.nseg = 0; a.ntiles = 0;
     CUtensorMap tx[4];
     int tiles = 0;
     if (!no_tma_a && !big) {
@@ -991,10 +1010,17 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
              * (the kernel is not persistent); MR_CONV_SHALLOW=0/1 overrides the default for experiments. */
             static const char *sh_env = getenv("MR_CONV_SHALLOW");
             const bool shallow = sh_env ? sh_env[0] == '1' : true;
+            a.ntiles = tiles;
+            /* narrow outputs (Cout <= 128): a CTA can take TWO pixel tiles per weight tile (two TMEM accumulators,
+             * 2 x BN <= 256 columns: still two CTAs per SM), which cuts the operand bytes per FLOP by a third.  Measured
+             * NEUTRAL on the CRNN step (9.262 vs 9.266 ms): these layers are not operand-bound.  Parity-tested, selectable
+             * with MR_CONV_MT2=1, off by default. */
+            const char *mt2_env = getenv("MR_CONV_MT2");
+            const bool pair = mt2_env && mt2_env[0] == '1' && BN <= 128 && tiles >= 4 * 148;
             if (shallow) {
                 if (BN == 256) return launch_conv<256, 2, 1, 1>(tb, tx, a, tiles, st);
-                if (BN == 128) return launch_conv<128, 3, 1, 1>(tb, tx, a, tiles, st);
-                return launch_conv<64, 3, 1, 1>(tb, tx, a, tiles, st);
+                if (BN == 128) return pair ? launch_conv<128, 2, 2, 1>(tb, tx, a, tiles, st) : launch_conv<128, 3, 1, 1>(tb, tx, a, tiles, st);
+                return pair ? launch_conv<64, 2, 2, 1>(tb, tx, a, tiles, st) : launch_conv<64, 3, 1, 1>(tb, tx, a, tiles, st);
             }
             if (BN == 256) return launch_conv<256, 4, 1, 1>(tb, tx, a, tiles, st);
             if (BN == 128) return launch_conv<128, 6, 1, 1>(tb, tx, a, tiles, st);

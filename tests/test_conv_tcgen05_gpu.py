@@ -51,15 +51,19 @@ def test_fprop_bias_relu_bf16_out(cuda):
     torch.testing.assert_close(y.float().view(2, Ho, Wo, 128).permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
 
 
-@pytest.mark.parametrize("geo", [(40, 16, 128, 64, 128, 3, 1), (160, 8, 64, 128, 256, 3, 1), (300, 4, 65, 64, 64, 3, 1)],
-                         ids=["bn128", "bn256", "bn64"])
-def test_fprop_large_p(cuda, geo):
-    """large pixel counts (the 256-row CTA variant is selected for these when MR_CONV_MT2=1)."""
+@pytest.mark.parametrize("geo", [(40, 16, 128, 64, 128, 3, 1), (160, 8, 64, 128, 256, 3, 1), (300, 4, 65, 64, 64, 3, 1),
+                                 (593, 1, 128, 64, 128, 3, 1)],
+                         ids=["bn128", "bn256", "bn64", "odd_tiles"])
+def test_fprop_large_p(cuda, geo, monkeypatch):
+    """large pixel counts, once with the default one-tile CTAs and once with the two-tiles-per-CTA variant (MR_CONV_MT2=1):
+    pairs that straddle a width-segment boundary in "bn64", an unpaired last tile in "odd_tiles"."""
     from megreader_b200 import nnops
     N, H, W, C, Cout, k, p = geo
     torch.manual_seed(3)
     x = torch.randn(N, H, W, C, device=cuda).bfloat16()
     w = (torch.randn(Cout, C, k, k, device=cuda) / (C * k * k) ** 0.5).bfloat16()
-    y, Ho, Wo = nnops.conv_fprop_tc(x, _wm(w), k, k, p, p, out_dtype=torch.float32)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=p)
-    torch.testing.assert_close(y.view(N, Ho, Wo, Cout).permute(0, 3, 1, 2), ref, rtol=1e-3, atol=2e-3)
+    for mt2 in ("0", "1"):
+        monkeypatch.setenv("MR_CONV_MT2", mt2)
+        y, Ho, Wo = nnops.conv_fprop_tc(x, _wm(w), k, k, p, p, out_dtype=torch.float32)
+        torch.testing.assert_close(y.view(N, Ho, Wo, Cout).permute(0, 3, 1, 2), ref, rtol=1e-3, atol=2e-3)
