@@ -70,17 +70,6 @@ def kernels(N, H, dev):
         G.copy_(G0)
         ops.lstm_seq_fwd_tc(Whh, G, bias, C, Y, flags)
         ms_b = timed(lambda: ops.lstm_seq_bwd_tc(WhhT, G, C, dY, dG, flags))
-        if T == 65 and os.environ.get("MR_LSTM_MICRO_EXP"):
-            # development masks (csrc/lstm_seq_tcgen05.cu): 1 no operand loads, 2 no state stores, 4 no peer wait, 8 no GEMM
-            for mask in (0, 1, 2, 3, 8):
-                os.environ["MR_LSTM_SEQ_EXP"] = str(mask)
-                f = timed(lambda: ops.lstm_seq_fwd_tc(Whh, G, bias, C, Y, flags), reps=10)
-                b = timed(lambda: ops.lstm_seq_bwd_tc(WhhT, G, C, dY, dG, flags), reps=10)
-                print(json.dumps({"bench": "lstm_seq_exp", "mask": mask, "fwd_us_per_step": 1e3 * f / T,
-                                  "bwd_us_per_step": 1e3 * b / T}), flush=True)
-            os.environ["MR_LSTM_SEQ_EXP"] = "0"
-            G.copy_(G0)
-            ops.lstm_seq_fwd_tc(Whh, G, bias, C, Y, flags)
         if T == 65:
             trace(lambda: ops.lstm_seq_fwd_tc(Whh, G, bias, C, Y, flags), T, dev, "fwd")
             trace(lambda: ops.lstm_seq_bwd_tc(WhhT, G, C, dY, dG, flags), T, dev, "bwd")

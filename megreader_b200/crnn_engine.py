@@ -28,6 +28,18 @@ USE_TCGEN05 = __import__("os").environ.get("MEGREADER_B200_TCGEN05", "1") != "0"
 LSTM_MODE = __import__("os").environ.get("MEGREADER_B200_LSTM", "seq")
 if __import__("os").environ.get("MEGREADER_B200_LSTM_FUSED", "0") == "1":     # older switch
     LSTM_MODE = "step"
+# conv weight gradients on a side stream, overlapped with the rest of the backward chain (MEGREADER_B200_WGRAD_STREAM=0: off)
+WGRAD_SIDE_STREAM = __import__("os").environ.get("MEGREADER_B200_WGRAD_STREAM", "1") == "1"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = str(dev)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 LAST_LSTM_FLAGS = None      # scratch of the most recent persistent launch; last word != 0 <=> an inter-CTA wait timed out
 
 
@@ -151,6 +163,12 @@ class _BackboneFn(torch.autograd.Function):
         dtype = ctx.dtype
         dy = ops.cast(dfeat.permute(0, 2, 3, 1).contiguous(), dtype).view(N * Hf * Wf, Cf)
         grads = []
+        # The weight gradients are off the critical path (dz_L -> dgrad_L -> pool/BN backward_{L-1} -> ...): they run on a
+        # side stream and fill the SMs that the HBM-bound elementwise kernels and the tail waves of the dgrad kernels
+        # leave idle.  Joined before the gradients are handed back (also inside CUDA-graph capture: fork/join by events).
+        main = torch.cuda.current_stream(dfeat.device)
+        side = _side_stream(dfeat.device) if WGRAD_SIDE_STREAM else None
+        deferred = []                                   # (slot in grads, dWm, Cin, C, kh, kw) finished after the join
         for li in range(len(ctx.layers) - 1, -1, -1):
             conv, bn, pool = ctx.layers[li]
             rec = ctx.saved[li]
@@ -165,13 +183,24 @@ class _BackboneFn(torch.autograd.Function):
                 k, s, p = rec["pool"]
                 dz, dbias = ops.bias_relu_pool_bwd(dy, rec["y"], rec["idx"], Nn, Ho, Wo, Cout, k, s, p)
                 dgamma = dbeta = None
+            dW = None
             if rec["x"] is not None:
                 dz4 = dz.view(Nn, Ho, Wo, Cout)
-                dWm = ops.conv_wgrad_tc(dz4, rec["x"], kh, kw, ph, pw)                     # [Cout, K] fp32
+                if side is not None:
+                    dWm = torch.zeros((Cout, kh * kw * C), dtype=torch.float32, device=dz.device)
+                    side.wait_stream(main)
+                    dz.record_stream(side)
+                    rec["x"].record_stream(side)
+                    with torch.cuda.stream(side):
+                        ops.conv_wgrad_tc(dz4, rec["x"], kh, kw, ph, pw, out=dWm)
+                    deferred.append((dWm, rec["Cin"], C, kh, kw))
+                else:
+                    dWm = ops.conv_wgrad_tc(dz4, rec["x"], kh, kw, ph, pw)                 # [Cout, K] fp32
+                    dW = _weight_grad(dWm, rec["Cin"], C, kh, kw)
             else:
                 dWm = ops.gemm(dz, rec["col"], transA=True, out_dtype=torch.float32)      # [Cout, Kp]
-            dW = _weight_grad(dWm, rec["Cin"], C, kh, kw)
-            layer_grads = [dW, dbias] + ([dgamma, dbeta] if bn is not None else [])
+                dW = _weight_grad(dWm, rec["Cin"], C, kh, kw)
+            layer_grads = [dW if dW is not None else deferred[-1]] + [dbias] + ([dgamma, dbeta] if bn is not None else [])
             grads = layer_grads + grads
             if li > 0:
                 if rec["x"] is not None and Cout % 64 == 0:
@@ -183,6 +212,9 @@ class _BackboneFn(torch.autograd.Function):
                     dcol = ops.gemm(dz, rec["Wm"])                                           # [P, Kp]
                     dy = ops.col2im(dcol, Nn, H, W, C, kh, kw, ph, pw).view(Nn * H * W, C)
             rec.clear()
+        if deferred:
+            main.wait_stream(side)
+            grads = [_weight_grad(*g) if isinstance(g, tuple) else g for g in grads]
         return (None, None, None, None) + tuple(grads)
 
 

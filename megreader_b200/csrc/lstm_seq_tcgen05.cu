@@ -78,7 +78,6 @@ struct SeqFwdArgs {
     bf16 *Y;                  // [T, B, 2H] layer output: direction d owns columns [d*H, (d+1)*H)
     unsigned *flags;          // [2 * row_tiles + 1], zeroed before launch; last word = error
     long long *trace;         // optional [T][8] clock64 stamps of CTA (0,0,0) (mr_lstm_seq_set_trace), else NULL
-    int exp;                  // development: MR_LSTM_SEQ_EXP bit mask (1 no operand loads, 2 no state stores, 4 no peer wait, 8 no GEMM)
     int T, B, H;
 };
 
@@ -125,10 +124,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
             for (int kb = 0; kb < nkb; ++kb) tma_load_2d(tmW, wfull, Ws + kb * 8192, kb * BK, n0);
             for (int s = 1; s < T; ++s) {
                 const int t_prev = dir ? T - s : s - 1;
-                if (!(a.exp & 4) && !flag_wait_bounded(flag, arrivals * (uint32_t)s, err)) atomicExch(err, 1u);
+                if (!flag_wait_bounded(flag, arrivals * (uint32_t)s, err)) atomicExch(err, 1u);
                 MR_TRACE(s, 0);
                 fence_proxy_async_global();
-                if (a.exp & 8) continue;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_expect_tx(afull + kb, 16384);
                     tma_load_2d(&tmY, afull + kb, As + kb * 16384, dir * H + kb * BK, t_prev * B + m0);
@@ -139,7 +137,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     } else if (warp == 1) {
         constexpr uint32_t idesc = make_idesc(BM, kBN, 0, 0);
         if (!mbar_wait_bounded(wfull, 0, err)) atomicExch(err, 2u);
-        for (int s = 1; s < T && !(a.exp & 8); ++s) {
+        for (int s = 1; s < T; ++s) {
             for (int kb = 0; kb < nkb; ++kb) {
                 if (!mbar_wait_bounded(afull + kb, (s - 1) & 1, err)) atomicExch(err, 3u);
                 tc_fence_after();
@@ -173,12 +171,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
             const int64_t grow = ((int64_t)dir * T + t) * B + row;
             bf16 *gp = a.G + grow * 4 * H + col0;
             uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (live && !(a.exp & 1)) {                          // x-projection: issued before the accumulator wait
+            if (live) {                                          // x-projection: issued before the accumulator wait
                 pk[0] = *reinterpret_cast<const uint4 *>(gp);
                 pk[1] = *reinterpret_cast<const uint4 *>(gp + 8);
             }
             uint32_t r[16];
-            if (s > 0 && !(a.exp & 8)) {
+            if (s > 0) {
                 if (!mbar_wait_bounded(tmem_full, (s - 1) & 1, err)) atomicExch(err, 4u);
                 tc_fence_after();
                 tmem_ld16(taddr, r);
@@ -228,7 +226,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
                 atomicAdd(flag, 1u);
                 MR_TRACE(s, 7);
             }
-            if (live && !(a.exp & 2)) {
+            if (live) {
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
                     uint4 o4;
@@ -255,7 +253,6 @@ struct SeqBwdArgs {
     bf16 *dG;                 // [2, T, B, 4H] gate gradients, out (unit-major)
     unsigned *flags;
     long long *trace;
-    int exp;
     int T, B, H;
 };
 
@@ -352,7 +349,6 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                 if (!flag_wait_bounded(flag, arrivals * (uint32_t)u, err)) atomicExch(err, 1u);
                 MR_TRACE(u, 0);
                 fence_proxy_async_global();
-                if (a.exp & 8) continue;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     if (!mbar_wait_bounded(empty + s, ((it / STAGES) & 1) ^ 1, err)) atomicExch(err, 5u);
@@ -367,7 +363,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
         constexpr uint32_t idesc = make_idesc(BM, kBwdBN, 0, 0);
         if (!mbar_wait_bounded(wfull, 0, err)) atomicExch(err, 2u);
         int it = 0;
-        for (int u = 1; u < T && !(a.exp & 8); ++u) {
+        for (int u = 1; u < T; ++u) {
             for (int kb = 0; kb < nkb; ++kb, ++it) {
                 const int s = it % STAGES;
                 if (!mbar_wait_bounded(full + s, (it / STAGES) & 1, err)) atomicExch(err, 3u);
@@ -419,7 +415,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
             const int t = time_of(u);
             const bool have_prev = u < T - 1;                    // forward-order predecessor = the step processed next
             uint4 dyk = make_uint4(0, 0, 0, 0);
-            if (live && !(a.exp & 1))
+            if (live)
                 dyk = *reinterpret_cast<const uint4 *>(a.dY + ((int64_t)t * B + row) * 2 * H + dir * H + j0);
             if (!mbar_wait_bounded(gfull, u & 1, err)) atomicExch(err, 6u);
             if (!mbar_wait_bounded(cfull + (u & 1), (u >> 1) & 1, err)) atomicExch(err, 7u);
@@ -435,7 +431,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             uint32_t r[8];
-            if (u > 0 && !(a.exp & 8)) {
+            if (u > 0) {
                 if (!mbar_wait_bounded(tmem_full, (u - 1) & 1, err)) atomicExch(err, 4u);
                 tc_fence_after();
                 tmem_ld8(taddr, r);
@@ -484,10 +480,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
             MR_TRACE(u, 5);
             if (leader) {
                 const int z = dir * T + t;
-                if (!(a.exp & 2)) {
-                    tma_store_3d(&tmDG3, Gs, 4 * n0, m0, z);
-                    tma_store_3d(&tmDG3, Gs + 16384, 4 * n0 + 64, m0, z);
-                }
+                tma_store_3d(&tmDG3, Gs, 4 * n0, m0, z);
+                tma_store_3d(&tmDG3, Gs + 16384, 4 * n0 + 64, m0, z);
                 tma_store_commit_wait();                         // gate gradients written (and the tile is free again)
                 fence_proxy_async_global();
                 __threadfence();
@@ -531,7 +525,6 @@ int resident_ok(const void *kern, int threads, size_t smem, int ctas) {
 
 constexpr int kBwdStages = 5;
 long long *g_trace = nullptr;
-int exp_mask() { const char *e = getenv("MR_LSTM_SEQ_EXP"); return e ? atoi(e) : 0; }
 
 }  // namespace
 
@@ -566,7 +559,7 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
         if (rc) return rc;
     }
     SeqFwdArgs a;
-    a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags; a.trace = g_trace; a.exp = exp_mask();
+    a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags; a.trace = g_trace;
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ty, tw[0], tw[1], a);
@@ -604,7 +597,7 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float 
     rc = make_map_3d(&tc3, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, H, B, (int64_t)2 * T, kBwdBN, BM);
     if (rc) return rc;
     SeqBwdArgs a;
-    a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags; a.trace = g_trace; a.exp = exp_mask();
+    a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags; a.trace = g_trace;
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
     kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tdg, tw[0], tw[1], tg3, tdg3, tc3, a);

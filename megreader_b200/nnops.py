@@ -213,12 +213,13 @@ def conv_fprop_tc(x, Wm, kh, kw, ph, pw, out_dtype=torch.bfloat16, bias=None, re
     return y, Ho, Wo
 
 
-def conv_wgrad_tc(dz, x, kh, kw, ph, pw, splits=0):
-    """dWm [Cout, kh*kw*C] fp32 from dz [N,Ho,Wo,Cout] and x [N,H,W,C] (NHWC bf16)."""
+def conv_wgrad_tc(dz, x, kh, kw, ph, pw, splits=0, out=None):
+    """dWm [Cout, kh*kw*C] fp32 from dz [N,Ho,Wo,Cout] and x [N,H,W,C] (NHWC bf16).  `out`: a ZEROED [Cout, K] fp32
+    buffer to accumulate into (lets the caller allocate it on another stream than the one the kernel runs on)."""
     N, H, W, C = x.shape
     Cout = dz.size(-1)
     K = kh * kw * C
-    dWm = torch.zeros((Cout, K), dtype=torch.float32, device=x.device)
+    dWm = out if out is not None else torch.zeros((Cout, K), dtype=torch.float32, device=x.device)
     if splits <= 0:
         tiles = ((Cout + 127) // 128) * ((K + 255) // 256)
         splits = max(1, -(-288 // tiles))
