@@ -267,6 +267,10 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "final_loss": final_loss, "clocks": clocks,
     }
+    if crnn_engine.LAST_LSTM_FLAGS is not None:            # error word of the persistent LSTM kernels (0 = no wait timed out)
+        out["lstm_seq_err"] = int(crnn_engine.LAST_LSTM_FLAGS[-1])
+        if out["lstm_seq_err"]:
+            raise SystemExit("persistent LSTM kernel reported an inter-CTA wait time-out: results invalid")
     if rank == 0:
         out["ctc2d"], ctc_roof = bench_ctc2d(dev)
         out["roofline"] = bench_conv_roofline(dev)
@@ -274,7 +278,9 @@ def run_ours(args):
         out["cpu_baseline"] = cpu_arm(steps=3, warmup=1, sample_n=16)
         out["stages"] = {"conv": "megreader_b200 tcgen05 implicit-GEMM kernels (fprop, dgrad, wgrad); conv0 (Cin=3): im2col kernel + cuBLAS",
                          "bias+ReLU+MaxPool, BatchNorm": "megreader_b200 CUDA (fused NHWC kernels)",
-                         "BiLSTM+Linear": "megreader_b200 cell kernels + cuBLAS GEMMs",
+                         "BiLSTM+Linear": "recurrence: megreader_b200 persistent tcgen05 kernels (one launch per layer and pass, mode '%s'); "
+                                          "input projections / Linear / weight-gradient GEMMs: cuBLAS" % crnn_engine.LSTM_MODE,
+                         "conv weight gradients": "side stream, overlapped with the backward chain" if crnn_engine.WGRAD_SIDE_STREAM else "main stream",
                          "log_softmax+CTC": "megreader_b200 CUDA", "Adam": "library (torch fused, capturable)",
                          "allreduce": "NCCL all-reduce of one flat bucket" if world > 1 else "n/a",
                          "launch": "step captured in CUDA graph(s); the NCCL all-reduce runs between two graphs when N > 1"}
@@ -320,7 +326,31 @@ def bench_ctc2d(dev, N=16384, iters=10):
            "alg_bytes_per_sample_fwd_bwd": 3 * lp_b + 2 * idx_b + 12,
            "fwd_bwd_GBps": N * (3 * lp_b + 2 * idx_b + 12) / (tf + tb) / 1e9,
            "frac_of_hbm_peak": N * (3 * lp_b + 2 * idx_b + 12) / (tf + tb) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"]}
-    roof = {"kernel": "ctc2d_dp_kernel<float,fast,FAC> (2D-CTC training forward: Q, alpha/beta sweeps, factors)",
+    # head epilogue in front of the loss (decoders/ctc_decoder2d.py:37-45): logits -> log_probs, and the fused backward
+    try:
+        from megreader_b200 import ctc2d_head
+        m = torch.randn(N, 1, H, T, device=dev)
+        z = torch.randn(N, C, H, T, device=dev)
+        _, gf = fwd()
+        for _ in range(2):
+            ctc2d_head.head_forward(m, z); ctc2d_head.head_backward(m, z, gfac=gf, grad_out=go)
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        for _ in range(iters):
+            ctc2d_head.head_forward(m, z)
+        b.record()
+        for _ in range(iters):
+            ctc2d_head.head_backward(m, z, gfac=gf, grad_out=go)
+        c.record()
+        torch.cuda.synchronize()
+        hf, hb = a.elapsed_time(b) / iters * 1e-3, b.elapsed_time(c) / iters * 1e-3
+        ctc["head_epilogue"] = {"fwd_us": hf * 1e6, "bwd_factored_us": hb * 1e6,
+                                "fwd_GBps": N * (2 * lp_b + H * T * 4) / hf / 1e9,
+                                "bwd_GBps": N * (2 * lp_b + T * C * 4) / hb / 1e9}
+        del m, z
+    except Exception as e:                                   # never let the extra arm take the headline down
+        ctc["head_epilogue"] = {"error": str(e)[:200]}
+    roof = {"kernel": "ctc2d_dp_warp_kernel<FAC> (2D-CTC training forward: Q, alpha/beta sweeps, factors)",
             "bound": "hbm", "achieved": N * fwd_bytes / tf / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": N * fwd_bytes / tf / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
             "alg_bytes_per_launch": N * fwd_bytes,
