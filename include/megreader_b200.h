@@ -255,6 +255,16 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float 
  * (NULL switches it off); slot meaning in csrc/lstm_seq_tcgen05.cu. */
 int mr_lstm_seq_set_trace(void *buf);
 
+/* Weight layout packs of the training engine (one launch instead of permute / pad / flip / gather / cast chains).
+ * mr_conv_weight_pack: nn.Conv2d weight [Cout,Cin,kh,kw] fp32 (backbones/crnn.py:37-44) -> GEMM operand in `dtype`:
+ *   mode 0: forward matrix [Cout, Kp], column (i*kw + j)*Cp + c, zero padded (Cp >= Cin, Kp >= kh*kw*Cp);
+ *   mode 1: input-gradient matrix [Cin, kh*kw*Cout], taps flipped and (Cout,Cin) transposed.
+ * mr_gate_rows_permute: nn.LSTM weight / bias rows [4H, cols] fp32 between the reference's gate-major order (i|f|g|o
+ *   blocks) and the unit-major order of the tcgen05 LSTM kernels; `b` (nullable) is added (b_ih + b_hh). */
+int mr_conv_weight_pack(const float *w, int Cout, int Cin, int kh, int kw, int Cp, int Kp, int mode, int dtype, void *out,
+                        void *stream);
+int mr_gate_rows_permute(const float *a, const float *b, int H, int cols, int inverse, int dtype, void *out, void *stream);
+
 /* Greedy CTC decoding to label indices (structure/representers/ctc_representer.py:22-34, ctc_representer2d.py:27-51):
  * arg-max class per column (2D: along the arg-max-height path of classify*mask), then collapse repeats / skip
  * `unknown` / drop blanks.  prob strides (sN,sC,sH,sW) in elements; mask nullable with strides (mN,mH,mW).

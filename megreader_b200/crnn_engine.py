@@ -87,9 +87,12 @@ def _pair(v):
 
 
 def _weight_matrix(w, Cp, Kp, dtype):
-    """conv weight [Cout, Cin, kh, kw] fp32 -> GEMM operand [Cout, Kp] in `dtype`, column = (i*kw + j)*Cp + c."""
+    """conv weight [Cout, Cin, kh, kw] fp32 -> GEMM operand [Cout, Kp] in `dtype`, column = (i*kw + j)*Cp + c (one launch)."""
+    w = w.detach()
+    if w.dtype == torch.float32 and w.is_contiguous():
+        return ops.conv_weight_pack(w, Cp, Kp, dtype, 0)
     Cout, Cin, kh, kw = w.shape
-    m = w.detach().permute(0, 2, 3, 1)
+    m = w.permute(0, 2, 3, 1)
     if Cp != Cin:
         m = F.pad(m, (0, Cp - Cin))
     m = m.reshape(Cout, kh * kw * Cp)
@@ -205,8 +208,11 @@ class _BackboneFn(torch.autograd.Function):
             if li > 0:
                 if rec["x"] is not None and Cout % 64 == 0:
                     # input gradient = convolution of dz with the flipped, transposed weights, padding k-1-p
-                    Wd = ops.cast(conv.weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(C, kh * kw * Cout)
-                                  .contiguous(), dtype)
+                    wsrc = conv.weight.detach()
+                    if wsrc.dtype == torch.float32 and wsrc.is_contiguous() and wsrc.size(1) == C:
+                        Wd = ops.conv_weight_pack(wsrc, C, kh * kw * C, dtype, 1)          # flipped + transposed, one launch
+                    else:
+                        Wd = ops.cast(wsrc.flip(2, 3).permute(1, 2, 3, 0).reshape(C, kh * kw * Cout).contiguous(), dtype)
                     dy, _, _ = ops.conv_fprop_tc(dz4, Wd, kh, kw, kh - 1 - ph, kw - 1 - pw)
                 else:
                     dcol = ops.gemm(dz, rec["Wm"])                                           # [P, Kp]
@@ -311,9 +317,15 @@ def _bilstm_forward_fused(X, params, training):
     H = w_hh[0].size(1)
     dev = X.device
     perm, _ = _unit_major_perm(H, dev)
-    Wih = [ops.cast(w.detach()[perm].contiguous(), dtype) for w in w_ih]
-    Whh = [ops.cast(w.detach()[perm].contiguous(), dtype) for w in w_hh]
-    bias = [(b_ih[d].detach() + b_hh[d].detach())[perm].contiguous() for d in (0, 1)]
+    def _rows(w, b=None, out_dtype=dtype):
+        w = w.detach()
+        if w.dtype == torch.float32 and w.is_contiguous() and (b is None or b.is_contiguous()):
+            return ops.gate_rows_permute(w, H, out_dtype, b=b)                          # permute (+ add) + cast, one launch
+        v = w if b is None else w + b.detach()
+        return ops.cast(v[perm].contiguous(), out_dtype)
+    Wih = [_rows(w) for w in w_ih]
+    Whh = [_rows(w) for w in w_hh]
+    bias = [_rows(b_ih[d], b_hh[d], torch.float32) for d in (0, 1)]
     X2 = X.view(T * N, I)
     G = torch.empty((2, T, N, 4 * H), dtype=dtype, device=dev)
     for d in range(2):

@@ -963,6 +963,48 @@ __global__ void sums_to_float_kernel(const double *__restrict__ s, int n, float 
     if (i < n) out[i] = (accumulate ? out[i] : 0.f) + scale * (float)s[i];
 }
 
+// ---------------------------------------------------------------- weight layout packs (one launch each instead of the
+// permute / pad / flip / gather / contiguous / cast chains of the host code; the tensors are small and L2-resident)
+// mode 0: conv weight [Cout,Cin,kh,kw] fp32 -> forward GEMM operand [Cout, Kp], column (i*kw + j)*Cp + c (zero padded)
+// mode 1: -> input-gradient operand [Cin, kh*kw*Cout], column ((kh-1-i)*kw + (kw-1-j))*Cout + co  (flipped, transposed)
+template <typename T>
+__global__ void conv_weight_pack_kernel(const float *__restrict__ w, int Cout, int Cin, int kh, int kw, int Cp, int Kp,
+                                        int mode, T *__restrict__ out) {
+    const int64_t total = mode == 0 ? (int64_t)Cout * Kp : (int64_t)Cin * kh * kw * Cout;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (mode == 0) {
+            const int co = (int)(t / Kp), col = (int)(t - (int64_t)co * Kp);
+            if (col < kh * kw * Cp) {
+                const int tap = col / Cp, c = col - tap * Cp;
+                if (c < Cin) v = w[((int64_t)co * Cin + c) * kh * kw + tap];
+            }
+        } else {
+            const int row = kh * kw * Cout;
+            const int c = (int)(t / row), col = (int)(t - (int64_t)c * row);
+            const int tapf = col / Cout, co = col - tapf * Cout;
+            const int tap = kh * kw - 1 - tapf;                  // (kh-1-i')*kw + (kw-1-j')
+            v = w[((int64_t)co * Cin + c) * kh * kw + tap];
+        }
+        out[t] = from_f<T>(v);
+    }
+}
+
+// LSTM gate rows between the reference's gate-major order (row g*H + j) and the unit-major order of the tcgen05 kernels
+// (row 4*j + g): out[r, :] = a[src(r), :] (+ b[src(r), :]);  inverse = 0: unit-major <- gate-major, 1: the way back.
+template <typename T>
+__global__ void gate_rows_permute_kernel(const float *__restrict__ a, const float *__restrict__ b, int H, int cols, int inverse,
+                                         T *__restrict__ out) {
+    const int64_t total = (int64_t)4 * H * cols;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / cols), k = (int)(t - (int64_t)r * cols);
+        const int src = inverse ? ((r % H) * 4 + r / H) : ((r & 3) * H + (r >> 2));
+        float v = a[(int64_t)src * cols + k];
+        if (b) v += b[(int64_t)src * cols + k];
+        out[t] = from_f<T>(v);
+    }
+}
+
 // ---------------------------------------------------------------- LSTM cell (gate order i, f, g, o like ATen)
 // One launch handles up to two directions (blockIdx.y): the forward and the reverse direction of a bidirectional
 // layer advance in lock-step, so their cell updates share a launch.
@@ -1504,6 +1546,28 @@ int mr_blank_after_first_blank(int *pred, int N, int W, int blank, void *stream)
     if (!pred) return MR_ERR_NULL_POINTER;
     blank_after_first_blank_kernel<<<(int)ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(pred, N, W, blank);
     return check_launch("blank_after_first_blank_kernel");
+}
+
+/* Conv weight [Cout,Cin,kh,kw] fp32 -> GEMM operand in `dtype` (0 fp32, 1 bf16): mode 0 forward matrix [Cout, Kp]
+ * (column (i*kw+j)*Cp + c, zero padded), mode 1 input-gradient matrix [Cin, kh*kw*Cout] (taps flipped, transposed). */
+int mr_conv_weight_pack(const float *w, int Cout, int Cin, int kh, int kw, int Cp, int Kp, int mode, int dtype, void *out,
+                        void *stream) {
+    if (Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0 || Cp < Cin || Kp < kh * kw * Cp || (mode != 0 && mode != 1)) return MR_ERR_BAD_SHAPE;
+    if (!w || !out) return MR_ERR_NULL_POINTER;
+    const int64_t total = mode == 0 ? (int64_t)Cout * Kp : (int64_t)Cin * kh * kw * Cout;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH(dtype, (conv_weight_pack_kernel<T><<<grid1d(total, 256, 8), 256, 0, st>>>(w, Cout, Cin, kh, kw, Cp, Kp, mode, (T *)out)));
+    return check_launch("conv_weight_pack_kernel");
+}
+
+/* LSTM gate rows: out[r,:] = a[src(r),:] (+ b[src(r),:]) for a [4H, cols] fp32; inverse = 0 gate-major -> unit-major
+ * (row 4j+g <- row gH+j), inverse = 1 the way back; out in `dtype`. */
+int mr_gate_rows_permute(const float *a, const float *b, int H, int cols, int inverse, int dtype, void *out, void *stream) {
+    if (H <= 0 || cols <= 0) return MR_ERR_BAD_SHAPE;
+    if (!a || !out) return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH(dtype, (gate_rows_permute_kernel<T><<<grid1d((int64_t)4 * H * cols, 256, 8), 256, 0, st>>>(a, b, H, cols, inverse, (T *)out)));
+    return check_launch("gate_rows_permute_kernel");
 }
 
 }  // extern "C"

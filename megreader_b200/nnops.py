@@ -268,3 +268,25 @@ def lstm_seq_bwd_tc(WhhT, G, C, dY, dG, flags):
         return False
     _chk(rc, "lstm_seq_bwd_tcgen05")
     return True
+
+
+def conv_weight_pack(w, Cp, Kp, dtype, mode):
+    """nn.Conv2d weight (fp32) -> GEMM operand: mode 0 [Cout, Kp] forward matrix, mode 1 [Cin, kh*kw*Cout] dgrad matrix."""
+    w = w.detach()
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    Cout, Cin, kh, kw = w.shape
+    out = torch.empty((Cout, Kp) if mode == 0 else (Cin, kh * kw * Cout), dtype=dtype, device=w.device)
+    _chk(_lib.lib().mr_conv_weight_pack(w.data_ptr(), Cout, Cin, kh, kw, Cp, Kp, mode, code(dtype), out.data_ptr(), _st()),
+         "conv_weight_pack")
+    return out
+
+
+def gate_rows_permute(a, H, dtype, b=None, inverse=False):
+    """[4H, cols] (or [4H]) fp32 rows: gate-major <-> unit-major (see mr_gate_rows_permute); optional b is added."""
+    a = a.detach()
+    assert a.dtype == torch.float32 and a.is_contiguous() and a.size(0) == 4 * H
+    cols = a.numel() // (4 * H)
+    out = torch.empty(a.shape, dtype=dtype, device=a.device)
+    _chk(_lib.lib().mr_gate_rows_permute(a.data_ptr(), b.detach().data_ptr() if b is not None else None, H, cols,
+                                         int(inverse), code(dtype), out.data_ptr(), _st()), "gate_rows_permute")
+    return out

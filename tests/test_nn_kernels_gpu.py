@@ -266,3 +266,25 @@ def test_crnn_bf16_mode_close_to_fp32_golden(cuda):
     assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < 3e-2
     gn = dec.rnn[1].embedding.weight.grad.double().norm().item()
     assert abs(gn - float(g["gnorm.rnn.1.embedding.weight"])) / float(g["gnorm.rnn.1.embedding.weight"]) < 0.1
+
+
+def test_weight_pack_kernels(cuda, ops):
+    """one-launch weight layout packs == the permute / pad / flip / gather / cast chains they replace (bit-exact)."""
+    torch.manual_seed(9)
+    for (Cout, Cin, kh, kw, Cp) in [(64, 3, 3, 3, 8), (128, 64, 3, 3, 64), (512, 512, 2, 2, 512)]:
+        w = torch.randn(Cout, Cin, kh, kw, device=cuda)
+        K = kh * kw * Cp
+        Kp = -(-K // 8) * 8 + 8
+        ref = torch.nn.functional.pad(w.permute(0, 2, 3, 1), (0, Cp - Cin)).reshape(Cout, K)
+        ref = torch.nn.functional.pad(ref, (0, Kp - K)).bfloat16()
+        assert torch.equal(ops.conv_weight_pack(w, Cp, Kp, torch.bfloat16, 0), ref)
+        if Cp == Cin:
+            refd = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, kh * kw * Cout).contiguous()
+            assert torch.equal(ops.conv_weight_pack(w, Cp, K, torch.float32, 1), refd)
+    H = 64
+    perm = torch.arange(4 * H, device=cuda).view(4, H).t().reshape(-1)
+    a, b = torch.randn(4 * H, 96, device=cuda), torch.randn(4 * H, 96, device=cuda)
+    assert torch.equal(ops.gate_rows_permute(a, H, torch.bfloat16), a[perm].bfloat16())
+    assert torch.equal(ops.gate_rows_permute(a[:, 0].contiguous(), H, torch.float32, b=b[:, 0].contiguous()), (a[:, 0] + b[:, 0])[perm])
+    um = ops.gate_rows_permute(a, H, torch.float32)
+    assert torch.equal(ops.gate_rows_permute(um, H, torch.float32, inverse=True), a)
