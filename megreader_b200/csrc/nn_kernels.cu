@@ -544,6 +544,73 @@ pool_bwd_rows_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ 
     }
 }
 
+// backward for windows that tile the height exactly (kh == sh == 2, no vertical padding, H even) but may overlap along
+// the width (the (2,1)-stride pools of the CRNN stack): one block per POOLED row (n, ho); a thread owns input column w
+// for BOTH input rows 2*ho and 2*ho+1, so each contributing window (y, dy, arg-max) is loaded once instead of twice.
+template <typename T, int KW>
+__global__ void __launch_bounds__(256)
+pool_bwd_hpair_rows_kernel(PoolGeo g, const T *__restrict__ dy, const T *__restrict__ y, const unsigned char *__restrict__ idx,
+                           T *__restrict__ dz, float *__restrict__ part, int cv_shift) {
+    constexpr int VN = 16 / sizeof(T);
+    const int cv = 1 << cv_shift;
+    const int cvec = threadIdx.x & (cv - 1), wl = threadIdx.x >> cv_shift, WL = 256 >> cv_shift;
+    float bsum[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) bsum[e] = 0.f;
+    const int nrows = g.N * g.Ho;
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int n = row / g.Ho, ho = row - n * g.Ho;
+        for (int w = wl; w < g.W; w += WL) {
+            uint4 vy[KW], vd[KW];
+            unsigned char ib[KW][VN];
+            bool ok[KW];
+#pragma unroll
+            for (int j = 0; j < KW; ++j) {
+                const int wn = w + g.pw - j;
+                const int wo = wn / g.sw;
+                ok[j] = wn >= 0 && wn % g.sw == 0 && wo < g.Wo;
+                if (ok[j]) {
+                    const int64_t q = ((int64_t)row * g.Wo + wo) * cv + cvec;
+                    vy[j] = __ldg(reinterpret_cast<const uint4 *>(y) + q);
+                    vd[j] = __ldg(reinterpret_cast<const uint4 *>(dy) + q);
+                    load_bytes<VN>(idx + q * VN, ib[j]);
+                }
+            }
+            float acc0[VN], acc1[VN];
+#pragma unroll
+            for (int e = 0; e < VN; ++e) acc0[e] = acc1[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) {
+                if (!ok[j]) continue;
+                float fy[VN], fd[VN];
+                unpack<T>(vy[j], fy);
+                unpack<T>(vd[j], fd);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) {
+                    const float gsel = fy[e] > 0.f ? fd[e] : 0.f;
+                    if (ib[j][e] == j) acc0[e] += gsel;              // arg-max in the upper row of the window (i = 0)
+                    if (ib[j][e] == KW + j) acc1[e] += gsel;         // ... in the lower row (i = 1)
+                }
+            }
+            const uint4 p0 = pack<T>(acc0), p1 = pack<T>(acc1);
+            uint4 *o = reinterpret_cast<uint4 *>(dz) + ((int64_t)(n * g.H + 2 * ho) * g.W + w) * cv + cvec;
+            __stcs(o, p0);
+            __stcs(o + (int64_t)g.W * cv, p1);
+            if (part) {
+                float f0[VN], f1[VN];
+                unpack<T>(p0, f0);
+                unpack<T>(p1, f1);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) bsum[e] += f0[e] + f1[e];
+            }
+        }
+    }
+    if (part) {
+        __shared__ float red[256][VN + 1];
+        block_channel_partial<VN>(bsum, cv, part + (int64_t)blockIdx.x * g.C, red);
+    }
+}
+
 // backward for non-overlapping windows, one block per POOLED row (n, ho): read once, write the KH*KW input positions
 template <typename T, int KH, int KW>
 __global__ void __launch_bounds__(256)
@@ -1300,6 +1367,9 @@ int mr_bias_relu_pool_bwd(const void *dy, const void *y, const unsigned char *id
         if (tiled) {
             nblocks = (int)std::min<int64_t>((int64_t)N * g.Ho, kMaxPartialBlocks);
             DISPATCH(dtype, (pool_bwd_tiled_rows_kernel<T, 2, 2><<<nblocks, 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, part, sft)));
+        } else if (sh == 2 && ph == 0 && H % 2 == 0 && g.Ho * 2 == H) {
+            nblocks = (int)std::min<int64_t>((int64_t)N * g.Ho, kMaxPartialBlocks);
+            DISPATCH(dtype, (pool_bwd_hpair_rows_kernel<T, 2><<<nblocks, 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, part, sft)));
         } else {
             nblocks = (int)std::min<int64_t>((int64_t)N * H, kMaxPartialBlocks);
             DISPATCH(dtype, (pool_bwd_rows_kernel<T, 2, 2><<<nblocks, 256, 0, st>>>(g, (const T *)dy, (const T *)y, idx, (T *)dz, part, sft)));
