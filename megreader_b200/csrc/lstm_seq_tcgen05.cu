@@ -71,6 +71,28 @@ __device__ __forceinline__ bool flag_wait_bounded(const unsigned *flag, uint32_t
     }
 }
 
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait_read() {      // until the stores have READ their smem source
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// 16-byte chunk `c` of row `r` in a [rows x 128 B] tile written by TMA with the 128-byte swizzle (tile base 1024-aligned)
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// byte offset `a` inside a 1024-aligned tile written / read by TMA with the 128-byte swizzle (any row pitch)
+__device__ __forceinline__ uint32_t swz_addr(uint32_t a) { return a ^ ((a >> 3) & 0x70u); }
+
 struct SeqFwdArgs {
     bf16 *G;                  // [2, T, B, 4H] unit-major: x-projection on entry, activated gates on exit
     const float *bias[2];     // [4H] unit-major, b_ih + b_hh
@@ -83,16 +105,20 @@ struct SeqFwdArgs {
 
 __global__ void __launch_bounds__(kThreads, 1)
 lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmW0,
-                    const __grid_constant__ CUtensorMap tmW1, SeqFwdArgs a) {
+                    const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmG3,
+                    const __grid_constant__ CUtensorMap tmC3, SeqFwdArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int nkb = a.H / BK;
     unsigned char *As = smem;                             // nkb x [128 rows x 128 B]   h_{t-1} tile, K-major SW128
     unsigned char *Ws = smem + nkb * 16384;               // nkb x [ 64 rows x 128 B]   W_hh slice, K-major SW128
-    uint64_t *wfull = (uint64_t *)(Ws + nkb * 8192);
+    unsigned char *Gt = Ws + nkb * 8192;                  // 2 x [128 rows x 128 B]     gates tile: x-projection in, activations out
+    unsigned char *Ct = Gt + 32768;                       // [128 rows x 64 B]          cell-state tile (16 units fp32), out
+    uint64_t *wfull = (uint64_t *)(Ct + 8192);
     uint64_t *afull = wfull + 1;                          // [8]
     uint64_t *tmem_full = afull + 8;
-    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    uint64_t *gfull = tmem_full + 1;                      // [2]
+    uint32_t *tmem_slot = (uint32_t *)(gfull + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.z;
@@ -107,9 +133,13 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmY);
         tma_prefetch_desc(tmW);
+        tma_prefetch_desc(&tmG3);
+        tma_prefetch_desc(&tmC3);
         mbar_init(wfull, 1);
         for (int i = 0; i < 8; ++i) mbar_init(afull + i, 1);
         mbar_init(tmem_full, 1);
+        mbar_init(gfull, 1);
+        mbar_init(gfull + 1, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, kBN);
@@ -166,15 +196,27 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
         }
         float cst[4] = {0.f, 0.f, 0.f, 0.f};
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 16);
+        // The gates tile [128 rows x 64 columns] of every step comes and goes by TMA (row-per-thread global accesses
+        // cost 32 wavefronts per warp instruction, measured ~1 us per step): loaded two steps ahead into a double
+        // buffer, activated in place, stored together with the cell-state tile by the leader thread.
+        const bool leader = threadIdx.x == 64;
+        const int rl = qd * 32 + lane;
+        auto time_of = [&](int s) { return dir ? T - 1 - s : s; };
+        auto load_gates = [&](int s) {
+            mbar_expect_tx(gfull + (s & 1), 16384);
+            tma_load_3d(&tmG3, gfull + (s & 1), Gt + (s & 1) * 16384, n0, m0, dir * T + time_of(s));
+        };
+        if (leader) {
+            load_gates(0);
+            if (T > 1) load_gates(1);
+        }
         for (int s = 0; s < T; ++s) {
-            const int t = dir ? T - 1 - s : s;
-            const int64_t grow = ((int64_t)dir * T + t) * B + row;
-            bf16 *gp = a.G + grow * 4 * H + col0;
-            uint4 pk[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            if (live) {                                          // x-projection: issued before the accumulator wait
-                pk[0] = *reinterpret_cast<const uint4 *>(gp);
-                pk[1] = *reinterpret_cast<const uint4 *>(gp + 8);
-            }
+            const int t = time_of(s);
+            unsigned char *gt = Gt + (s & 1) * 16384;
+            if (!mbar_wait_bounded(gfull + (s & 1), (s >> 1) & 1, err)) atomicExch(err, 6u);
+            uint4 pk[2];
+            pk[0] = *reinterpret_cast<const uint4 *>(gt + swz(rl, 2 * grp));
+            pk[1] = *reinterpret_cast<const uint4 *>(gt + swz(rl, 2 * grp + 1));
             uint32_t r[16];
             if (s > 0) {
                 if (!mbar_wait_bounded(tmem_full, (s - 1) & 1, err)) atomicExch(err, 4u);
@@ -186,6 +228,8 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
             }
             MR_TRACE(s, 3);
             float act[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) act[j] = 0.f;
             if (live) {
                 float pre[16];
 #pragma unroll
@@ -226,16 +270,24 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_consta
                 atomicAdd(flag, 1u);
                 MR_TRACE(s, 7);
             }
-            if (live) {
+            // activated gates back into the tile, cell state into its tile (rows >= B are clipped by the TMA store)
 #pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    uint4 o4;
-                    __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&o4);
+            for (int v = 0; v < 2; ++v) {
+                uint4 o4;
+                __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&o4);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(act[v * 8 + 2 * e], act[v * 8 + 2 * e + 1]);
-                    *reinterpret_cast<uint4 *>(gp + v * 8) = o4;
-                }
-                *reinterpret_cast<float4 *>(a.C + grow * H + j0) = make_float4(cst[0], cst[1], cst[2], cst[3]);
+                for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(act[v * 8 + 2 * e], act[v * 8 + 2 * e + 1]);
+                *reinterpret_cast<uint4 *>(gt + swz(rl, 2 * grp + v)) = o4;
+            }
+            *reinterpret_cast<float4 *>(Ct + rl * 64 + grp * 16) = make_float4(cst[0], cst[1], cst[2], cst[3]);     // plain rows
+            fence_proxy_async();                                 // generic-proxy tile writes -> visible to the TMA stores
+            epi_bar_sync();
+            if (leader) {
+                const int z = dir * T + t;
+                tma_store_3d(&tmG3, gt, n0, m0, z);
+                tma_store_3d(&tmC3, Ct, n0 >> 2, m0, z);
+                tma_store_commit_wait_read();                    // both tiles may be overwritten again
+                if (s + 2 < T) load_gates(s + 2);
             }
         }
     }
@@ -262,21 +314,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_wait() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-// 16-byte chunk `c` of row `r` in a [rows x 128 B] tile written by TMA with the 128-byte swizzle (tile base 1024-aligned)
-__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 // Backward recurrence: dh_{t} += dG_{t_next} W_hh needs the FULL gate-gradient row block [128 x 4H] per output tile, so
 // the per-step operand traffic is (H / units-per-CTA) x the dG tile.  32 hidden units per CTA spread the step over
@@ -502,7 +539,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmDG, const __grid_const
 
 // 3-D tiled map over a row-major [outer, mid, inner] tensor, box {box_inner, box_mid, 1}, 128-byte swizzle
 int make_map_3d(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int esize, int64_t inner, int64_t mid, int64_t outer,
-                int box_inner, int box_mid) {
+                int box_inner, int box_mid, bool swizzle = true) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return MR_ERR_CUDA; }
     cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)mid, (cuuint64_t)outer};
@@ -510,7 +547,8 @@ int make_map_3d(CUtensorMap *m, const void *base, CUtensorMapDataType dt, int es
     cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_mid, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(3d)"); return MR_ERR_CUDA; }
     return MR_OK;
 }
@@ -542,7 +580,7 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
     if (!Whh || !Whh[0] || !Whh[1] || !G || !bias || !bias[0] || !bias[1] || !C || !Y || !flags) return MR_ERR_NULL_POINTER;
     if ((int64_t)2 * T * B >= (int64_t)1 << 31) return MR_ERR_UNSUPPORTED;
     const int nkb = H / BK, row_tiles = ceil_div(B, BM);
-    const size_t smem = (size_t)nkb * (16384 + 8192) + 16 * 8 + 1024;
+    const size_t smem = (size_t)nkb * (16384 + 8192) + 32768 + 8192 + 16 * 8 + 1024;
     auto kern = lstm_seq_fwd_kernel;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -558,11 +596,16 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
         rc = make_map(&tw[d], Whh[d], H, 4 * H, H, BK, kBN);
         if (rc) return rc;
     }
+    CUtensorMap tg3, tc3;
+    rc = make_map_3d(&tg3, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 4 * H, B, (int64_t)2 * T, BK, BM);
+    if (rc) return rc;
+    rc = make_map_3d(&tc3, C, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, H, B, (int64_t)2 * T, kBN / 4, BM, false);   // 64-byte rows: no swizzle
+    if (rc) return rc;
     SeqFwdArgs a;
     a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags; a.trace = g_trace;
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
-    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ty, tw[0], tw[1], a);
+    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ty, tw[0], tw[1], tg3, tc3, a);
     return check_launch("lstm_seq_fwd_kernel");
 }
 
