@@ -1,7 +1,8 @@
 // NHWC building blocks of the CRNN training engine (sm_100a): layout conversion, im2col / col2im, fused
 // bias+ReLU+max-pool (forward and backward), training-mode BatchNorm (stats / apply / backward), column sums,
-// LSTM cell (forward / backward), fused Adam.  All HBM-bound streaming kernels: 16-byte vector accesses along the
-// channel dimension, fp32 accumulation, no atomics on the data path except the per-channel partial sums.
+// LSTM cell (forward / backward), fused Adam, weight layout packs, greedy CTC decoders.  All HBM-bound streaming
+// kernels: 16-byte vector accesses along the channel dimension, fp32 accumulation; per-channel sums leave each block
+// as one row of an fp32 partial buffer and are added in double by a small second kernel (no atomics on the hot path).
 //
 // Why these exist: with the ATen/cuDNN composition of the reference's modules (backbones/crnn.py:46-55,
 // decoders/crnn.py:8-24) the tensor-core convolutions are ~12 % of a B200 training step; NCHW max-pool forward /
