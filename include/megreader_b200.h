@@ -255,6 +255,21 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float 
  * (NULL switches it off); slot meaning in csrc/lstm_seq_tcgen05.cu. */
 int mr_lstm_seq_set_trace(void *buf);
 
+/* Deformable position-sensitive RoI pooling (assets/ops/dcn/src/deform_pool_cuda.cpp:29-81 ->
+ * deform_pool_cuda_kernel.cu:52-263; python surface functions/deform_pool.py:7-69).  fp32.
+ *   data [batch, channels, H, W]; rois [num_rois, 5] = (image index, x1, y1, x2, y2); trans [num_rois, channels_trans,
+ *   part, part] (ignored when no_trans); out / top_count [num_rois, output_dim, pooled, pooled] (top_count = number of
+ *   in-range samples per bin, float, consumed by the backward).  backward ACCUMULATES into in_grad / trans_grad. */
+int mr_deform_psroi_pool_forward_f32(const float *data, const float *rois, const float *trans, int batch, int channels,
+                                     int height, int width, int num_rois, int channels_trans, int no_trans,
+                                     float spatial_scale, int output_dim, int group_size, int pooled_size, int part_size,
+                                     int sample_per_part, float trans_std, float *out, float *top_count, void *stream);
+int mr_deform_psroi_pool_backward_f32(const float *out_grad, const float *data, const float *rois, const float *trans,
+                                      const float *top_count, int batch, int channels, int height, int width, int num_rois,
+                                      int channels_trans, int no_trans, float spatial_scale, int output_dim, int group_size,
+                                      int pooled_size, int part_size, int sample_per_part, float trans_std, float *in_grad,
+                                      float *trans_grad, void *stream);
+
 /* Weight layout packs of the training engine (one launch instead of permute / pad / flip / gather / cast chains).
  * mr_conv_weight_pack: nn.Conv2d weight [Cout,Cin,kh,kw] fp32 (backbones/crnn.py:37-44) -> GEMM operand in `dtype`:
  *   mode 0: forward matrix [Cout, Kp], column (i*kw + j)*Cp + c, zero padded (Cp >= Cin, Kp >= kh*kw*Cp);

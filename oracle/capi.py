@@ -162,3 +162,44 @@ def dcn_backward(inp, weight, bias, offset, mask, grad_output, stride=1, padding
        ptr(gi), ptr(gw), ptr(gb) if gb is not None else None, ptr(goff), I64(goff[0].size),
        ptr(gmsk) if gmsk is not None else None, I64(gmsk[0].size if gmsk is not None else 0))
     return gi, gw, gb, goff, gmsk
+
+
+# ------------------------------------------------------------------ deformable PS-RoI pooling (oracle/deform_pool_oracle.c)
+def deform_psroi_forward(data, rois, trans, no_trans, spatial_scale, output_dim, group_size, pooled, part_size,
+                         sample_per_part, trans_std):
+    x = np.ascontiguousarray(data)
+    dt = x.dtype
+    B, C, H, W = x.shape
+    r = np.ascontiguousarray(rois, dtype=dt)
+    n = r.shape[0]
+    t = None if no_trans else np.ascontiguousarray(trans, dtype=dt)
+    ct = 2 if no_trans else t.shape[1]
+    out = np.zeros((n, output_dim, pooled, pooled), dt)
+    cnt = np.zeros_like(out)
+    real = ctypes.c_double if dt == np.float64 else ctypes.c_float
+    fn = getattr(lib(), "deform_psroi_forward_" + _suf(dt))
+    fn(ptr(x), ptr(r), ptr(t) if t is not None else None, I32(C), I32(H), I32(W), I32(n), I32(ct), I32(int(no_trans)),
+       real(spatial_scale), I32(output_dim), I32(group_size), I32(pooled), I32(part_size), I32(sample_per_part),
+       real(trans_std), ptr(out), ptr(cnt))
+    return out, cnt
+
+
+def deform_psroi_backward(out_grad, data, rois, trans, top_count, no_trans, spatial_scale, output_dim, group_size, pooled,
+                          part_size, sample_per_part, trans_std):
+    x = np.ascontiguousarray(data)
+    dt = x.dtype
+    B, C, H, W = x.shape
+    r = np.ascontiguousarray(rois, dtype=dt)
+    n = r.shape[0]
+    t = None if no_trans else np.ascontiguousarray(trans, dtype=dt)
+    ct = 2 if no_trans else t.shape[1]
+    go = np.ascontiguousarray(out_grad, dtype=dt)
+    tc = np.ascontiguousarray(top_count, dtype=dt)
+    gin = np.zeros_like(x)
+    gtr = None if no_trans else np.zeros_like(t)
+    real = ctypes.c_double if dt == np.float64 else ctypes.c_float
+    fn = getattr(lib(), "deform_psroi_backward_" + _suf(dt))
+    fn(ptr(go), ptr(x), ptr(r), ptr(t) if t is not None else None, ptr(tc), I32(C), I32(H), I32(W), I32(n), I32(ct),
+       I32(int(no_trans)), real(spatial_scale), I32(output_dim), I32(group_size), I32(pooled), I32(part_size),
+       I32(sample_per_part), real(trans_std), ptr(gin), ptr(gtr) if gtr is not None else None)
+    return gin, gtr

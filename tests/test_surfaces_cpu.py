@@ -72,6 +72,13 @@ def test_state_dict_keys_equal_reference():
     for mod in mine.modules():
         if hasattr(mod, "conv2_offset"):
             assert float(mod.conv2_offset.weight.abs().max()) == 0.0 and float(mod.conv2_offset.bias.abs().max()) == 0.0
+    # deformable RoI pooling packs: same fully-connected stacks
+    import assets.ops.dcn.modules.deform_pool as rpool
+    from megreader_b200 import deform_pool as mpool
+    for cls in ("DeformRoIPoolingPack", "ModulatedDeformRoIPoolingPack"):
+        r = getattr(rpool, cls)(0.5, 3, 8, False, trans_std=0.1, deform_fc_channels=32)
+        m = getattr(mpool, cls)(0.5, 3, 8, False, trans_std=0.1, deform_fc_channels=32)
+        assert _keys(r) == _keys(m)
     # dilation surgery moved the same convs (resnet_dilated.py:37-49)
     rp, mp = rb.resnet50dilated_ppm(), mb.resnet50dilated_ppm()
     geo = lambda net: [(n, c.stride, c.dilation, c.padding) for n, c in net.named_modules() if isinstance(c, torch.nn.Conv2d)]
