@@ -1,0 +1,76 @@
+"""CPU: host-side behaviour of the reference-named surfaces that needs no GPU: constructor signatures / state-dict keys,
+the clamp constant of CTCDecoder2D following its `saved_tiny` buffer, and the loud refusal of CPU tensors."""
+import pytest
+import torch
+
+
+_TOP = ("ops", "decoders", "backbones", "assets", "config", "concern")
+
+
+@pytest.fixture(scope="module")
+def api():
+    """The reference-named top-level packages resolved to megreader_b200/refapi for this module only: whatever another test
+    module imported under the same names (the reference itself, through oracle/ref_loader.py) is put back afterwards."""
+    import os
+    import sys
+    import megreader_b200
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in _TOP}
+    for k in saved:
+        del sys.modules[k]
+    old_path = list(sys.path)
+    refapi_dir = os.path.join(os.path.dirname(megreader_b200.__file__), "refapi")
+    sys.path.insert(0, refapi_dir)
+    try:
+        import backbones
+        import decoders
+        import assets.ops.dcn  # noqa: F401
+        assert "refapi" in decoders.__file__ and "refapi" in backbones.__file__
+        yield backbones, decoders
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in _TOP]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path[:] = old_path
+
+
+def test_ctc_decoder2d_tiny_follows_the_buffer(api):
+    _, decoders = api
+    dec = decoders.CTCDecoder2D(16, inner_channels=8)
+    assert sorted(dec.state_dict()) == ["pred_classify.1.bias", "pred_classify.1.weight", "pred_classify.2.bias",
+                                        "pred_classify.2.weight", "pred_mask.1.bias", "pred_mask.1.weight",
+                                        "pred_mask.2.bias", "pred_mask.2.weight", "saved_tiny"]
+    assert dec._tiny() == float(torch.finfo(torch.float32).tiny)
+    dec.saved_tiny.fill_(0.25)                                   # in-place change (what load_state_dict does)
+    assert dec._tiny() == 0.25
+    sd = dec.state_dict()
+    sd["saved_tiny"] = torch.tensor(0.5)
+    dec.load_state_dict(sd)
+    assert dec._tiny() == 0.5
+    dec = dec.double().float()                                   # buffer object replaced by _apply
+    assert dec._tiny() == 0.5
+
+
+def test_training_surfaces_refuse_cpu(api):
+    backbones, decoders = api
+    dec2d = decoders.CTCDecoder2D(16, inner_channels=8).train()
+    with pytest.raises(NotImplementedError):
+        dec2d(torch.zeros(1, 16, 4, 8), targets=torch.zeros(1, 32), lengths=torch.ones(1), train=True)
+    with pytest.raises(NotImplementedError):
+        backbones.crnn_backbone()(torch.zeros(1, 3, 32, 32))
+    ctc = decoders.CTCDecoder(16, inner_channels=8).train()
+    with pytest.raises(NotImplementedError):
+        ctc(torch.zeros(1, 16, 16, 64), targets=torch.zeros(1, 32, dtype=torch.long), lengths=torch.ones(1, dtype=torch.long),
+            train=True)
+
+
+def test_public_names_match_the_reference_inits(api):
+    backbones, decoders = api
+    for name in ("Resnet18FPN", "Resnet34FPN", "Resnet50FPN", "Resnet101FPN", "Resnet152FPN", "resnet18", "resnet34",
+                 "resnet50", "resnet101", "deformable_resnet50", "crnn_backbone", "resnet50dilated_ppm"):
+        assert callable(getattr(backbones, name)), name           # backbones/__init__.py:1-4
+    for name in ("AttentionDecoder", "CTCDecoder2D", "CTCDecoder", "CRNNDecoder", "CTCLoss2D", "CTC2DLoss"):
+        assert callable(getattr(decoders, name)), name
+    import assets.ops.dcn as dcn
+    assert sorted(dcn.__all__) == sorted(['DeformConv', 'DeformConvPack', 'ModulatedDeformConv', 'ModulatedDeformConvPack',
+                                          'DeformRoIPooling', 'DeformRoIPoolingPack', 'ModulatedDeformRoIPoolingPack',
+                                          'deform_conv', 'modulated_deform_conv', 'deform_roi_pooling'])
