@@ -270,6 +270,17 @@ int mr_deform_psroi_pool_backward_f32(const float *out_grad, const float *data, 
                                       int pooled_size, int part_size, int sample_per_part, float trans_std, float *in_grad,
                                       float *trans_grad, void *stream);
 
+/* Recognition input step on the GPU (data/processes/resize_image.py:29-57 modes "resize" / "pad",
+ * normalize_image.py:10-17, make_recognition_label.py:13-32): a ragged batch of decoded HWC 3-channel images (uint8 or fp32)
+ * -> cv2.resize-equivalent bilinear resize to [dst_h, valid_w[n]] at the left of a zero [dst_h, dst_w] canvas, minus
+ * mean3 (float64, host pointer), / 255, CHW fp32 [N,3,dst_h,dst_w]; and label byte strings -> class indices through a
+ * 256-entry table, blank-padded to max_size, with lengths = min(len, max_size).  Array arguments live on the device. */
+int mr_resize_normalize_f32(const void *src, int src_is_u8, const int64_t *offsets, const int *heights, const int *widths,
+                            const int *valid_w, int N, int dst_h, int dst_w, const double *mean3_host, float *out,
+                            void *stream);
+int mr_pack_labels(const unsigned char *text, const int64_t *offsets, int N, const int *lut, int max_size, int *labels,
+                   int *lengths, void *stream);
+
 /* Weight layout packs of the training engine (one launch instead of permute / pad / flip / gather / cast chains).
  * mr_conv_weight_pack: nn.Conv2d weight [Cout,Cin,kh,kw] fp32 (backbones/crnn.py:37-44) -> GEMM operand in `dtype`:
  *   mode 0: forward matrix [Cout, Kp], column (i*kw + j)*Cp + c, zero padded (Cp >= Cin, Kp >= kh*kw*Cp);

@@ -61,6 +61,8 @@ _SIGS = {
     "mr_ctc2d_head_bwd_f32": [c_p] * 5 + [c_i64] + [c_int] * 4 + [c_f32, c_p, c_p, c_p],
     "mr_deform_psroi_pool_forward_f32": [c_p] * 3 + [c_int] * 7 + [c_f32] + [c_int] * 5 + [c_f32, c_p, c_p, c_p],
     "mr_deform_psroi_pool_backward_f32": [c_p] * 5 + [c_int] * 7 + [c_f32] + [c_int] * 5 + [c_f32, c_p, c_p, c_p],
+    "mr_resize_normalize_f32": [c_p, c_int, c_p, c_p, c_p, c_p, c_int, c_int, c_int, c_p, c_p, c_p],
+    "mr_pack_labels": [c_p, c_p, c_int, c_p, c_int, c_p, c_p, c_p],
     "mr_conv_weight_pack": [c_p] + [c_int] * 8 + [c_p, c_p],
     "mr_gate_rows_permute": [c_p, c_p] + [c_int] * 4 + [c_p, c_p],
     "mr_ctc_greedy_decode": [c_p, c_p] + [c_int] * 4 + [c_i64] * 7 + [c_int, c_int, c_p, c_p],

@@ -216,6 +216,37 @@ def make_head():
     np.savez_compressed(os.path.join(GOLD, "ctc2d_head_ref.npz"), **out)
 
 
+def make_input():
+    """Recognition input step (crnn.yaml processes): run the UNMODIFIED reference ResizeImage (modes resize and pad),
+    NormalizeImage and MakeRecognitionLabel on CPU (cv2 4.x from this image) and record their outputs."""
+    ref_loader.install()
+    from data.processes.resize_image import ResizeImage
+    from data.processes.normalize_image import NormalizeImage
+    from data.processes.make_recognition_label import MakeRecognitionLabel
+    from tests.input_cases import MODES, input_cases
+    images, texts = input_cases()
+    out = {}
+    for mode, size in MODES.items():
+        rz = ResizeImage(mode=mode, image_size=list(size))
+        nm = NormalizeImage()
+        batch = []
+        for im in images:
+            d = {"image": im.astype("float32")}                     # data/lmdb_dataset.py:87
+            d = nm.process(rz.process(d))
+            batch.append(d["image"].numpy())
+        out["image." + mode] = np.stack(batch)
+    mk = MakeRecognitionLabel()
+    labels, lengths = [], []
+    for t in texts:
+        d = mk.process({"gt": t})
+        labels.append(np.asarray(d["label"], np.int32))
+        lengths.append(int(d["length"]))
+    out["labels"] = np.stack(labels)
+    out["lengths"] = np.asarray(lengths, np.int32)
+    np.savez_compressed(os.path.join(GOLD, "input_ref.npz"), **out)
+    print("input", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ["ctc2d"]
@@ -227,3 +258,5 @@ if __name__ == "__main__":
         make_surfaces()
     if "head" in which:
         make_head()
+    if "input" in which:
+        make_input()
