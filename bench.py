@@ -284,7 +284,7 @@ def run_ours(args):
                          "log_softmax+CTC": "megreader_b200 CUDA", "Adam": "library (torch fused, capturable)",
                          "allreduce": "NCCL all-reduce of one flat bucket" if world > 1 else "n/a",
                          "launch": "step captured in CUDA graph(s); the NCCL all-reduce runs between two graphs when N > 1"}
-        print(json.dumps(out), flush=True)
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -456,10 +456,37 @@ def run_reference(args):
                                   "%d-line bounded sample of the 512-line batch" % n, "batch_per_gpu": BATCH_PER_GPU},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit_json(out)
+
+
+class _QuietStdout:
+    """The contract is ONE JSON line on stdout: libraries that write to file descriptor 1 on their own (NCCL prints its
+    version banner there at communicator init) are sent to stderr; `emit` writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self._real, (line + "\n").encode())
+
+
+_OUT = None
+
+
+def emit_json(obj):
+    line = json.dumps(obj)
+    if _OUT is not None:
+        _OUT.emit(line)
+    else:
+        print(line, flush=True)
 
 
 def main():
+    global _OUT
+    _OUT = _QuietStdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
