@@ -108,12 +108,16 @@ def _weight_grad(dWm, Cin, Cp, kh, kw):
 
 class _BackboneFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, module, training, dtype, *params):
+    def forward(ctx, x, module, bn_batch_stats, save, dtype, *params):
+        # bn_batch_stats = module.training: BatchNorm normalises with batch statistics and updates its running buffers
+        #                  (also under torch.no_grad(), exactly like nn.BatchNorm2d);
+        # save           = torch.is_grad_enabled(): keep what the backward needs (also in eval() mode: frozen-BN fine-tuning).
         layers = _conv_layers(module)
         vn = _vn(dtype)
         N, Cin, H, W = x.shape
         Cp = -(-Cin // vn) * vn
         a = ops.nchw_to_nhwc(x.contiguous().float(), Cp, dtype)
+        ctx.in_nhwc, ctx.in_channels, ctx.in_dtype = tuple(a.shape), Cin, x.dtype
         saved = []
         for (conv, bn, pool) in layers:
             kh, kw = conv.kernel_size
@@ -132,18 +136,20 @@ class _BackboneFn(torch.autograd.Function):
                 col, Ho, Wo = ops.im2col(a, kh, kw, ph, pw, Kp)
                 z = ops.gemm(col, Wm, transB=True)                  # [P, Cout] raw conv output (no bias yet)
             Cout = Wm.size(0)
-            rec = {"col": col if training else None, "x": a if (training and implicit) else None, "Wm": Wm,
+            rec = {"col": col if save else None, "x": a if (save and implicit) else None, "Wm": Wm,
                    "in_shape": tuple(a.shape), "k": (kh, kw), "p": (ph, pw), "Cin": conv.in_channels, "out_hw": (Ho, Wo)}
             if bn is not None:
-                if training:
-                    mom = bn.momentum if bn.momentum is not None else 0.1
+                if bn_batch_stats:
+                    # momentum=None is PyTorch's cumulative moving average: factor 1 / num_batches_tracked (after the increment)
+                    mom = bn.momentum if bn.momentum is not None else 1.0 / (float(bn.num_batches_tracked.item()) + 1.0)
                     y, mean, invstd = ops.bn_train_fwd(z, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                                        mom, bn.eps)
                     bn.num_batches_tracked += 1
-                    rec.update(z=z, mean=mean, invstd=invstd, kind="bn")
+                    rec.update(z=z if save else None, mean=mean, invstd=invstd, kind="bn")
                 else:
                     invstd = torch.rsqrt(bn.running_var + bn.eps)
                     y = ops.bn_apply(z, conv.bias, bn.running_mean, invstd, bn.weight, bn.bias)
+                    rec.update(z=z if save else None, mean=bn.running_mean.detach().clone(), invstd=invstd, kind="bn_eval")
                 a = y.view(N, Ho, Wo, Cout)
             else:
                 assert pool is not None, "CRNN: every ReLU block is followed by a MaxPool (backbones/crnn.py:18-35)"
@@ -162,6 +168,9 @@ class _BackboneFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dfeat):
+        if ctx.saved is None or not ctx.saved[-1]:
+            raise RuntimeError("megreader_b200 CRNN backbone: the saved activations were freed by the first backward() "
+                               "(retain_graph is not supported by this engine)")
         N, Hf, Wf, Cf = ctx.feat_shape
         dtype = ctx.dtype
         dy = ops.cast(dfeat.permute(0, 2, 3, 1).contiguous(), dtype).view(N * Hf * Wf, Cf)
@@ -182,6 +191,15 @@ class _BackboneFn(torch.autograd.Function):
             ph, pw = rec["p"]
             if rec["kind"] == "bn":
                 dz, dgamma, dbeta, dbias = ops.bn_train_bwd(dy, rec["z"], conv.bias, rec["mean"], rec["invstd"], bn.weight)
+            elif rec["kind"] == "bn_eval":
+                # eval-mode BatchNorm is a per-channel affine map y = (z + b - mean) * invstd * gamma + beta (rare path:
+                # frozen-BN fine-tuning / saliency; plain tensor arithmetic, fp32)
+                dyf, zf = dy.float(), rec["z"].float()
+                xhat = (zf + conv.bias.detach() - rec["mean"]) * rec["invstd"]
+                dgamma, dbeta = (dyf * xhat).sum(0), dyf.sum(0)
+                dzf = dyf * (bn.weight.detach() * rec["invstd"])
+                dbias = dzf.sum(0)
+                dz = ops.cast(dzf.contiguous(), dtype)
             else:
                 k, s, p = rec["pool"]
                 dz, dbias = ops.bias_relu_pool_bwd(dy, rec["y"], rec["idx"], Nn, Ho, Wo, Cout, k, s, p)
@@ -205,7 +223,7 @@ class _BackboneFn(torch.autograd.Function):
                 dW = _weight_grad(dWm, rec["Cin"], C, kh, kw)
             layer_grads = [dW if dW is not None else deferred[-1]] + [dbias] + ([dgamma, dbeta] if bn is not None else [])
             grads = layer_grads + grads
-            if li > 0:
+            if li > 0 or ctx.needs_input_grad[0]:
                 if rec["x"] is not None and Cout % 64 == 0:
                     # input gradient = convolution of dz with the flipped, transposed weights, padding k-1-p
                     wsrc = conv.weight.detach()
@@ -218,10 +236,14 @@ class _BackboneFn(torch.autograd.Function):
                     dcol = ops.gemm(dz, rec["Wm"])                                           # [P, Kp]
                     dy = ops.col2im(dcol, Nn, H, W, C, kh, kw, ph, pw).view(Nn * H * W, C)
             rec.clear()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            Nn, H0, W0, C0 = ctx.in_nhwc
+            dx = ops.nhwc_to_nchw(dy.view(Nn, H0, W0, C0), ctx.in_channels).to(ctx.in_dtype)
         if deferred:
             main.wait_stream(side)
             grads = [_weight_grad(*g) if isinstance(g, tuple) else g for g in grads]
-        return (None, None, None, None) + tuple(grads)
+        return (dx, None, None, None, None) + tuple(grads)
 
 
 def _backbone_params(module):
@@ -236,7 +258,7 @@ def _backbone_params(module):
 def backbone_forward(module, x):
     """backbones/crnn.py:57-59."""
     _require_cuda(x, "crnn_backbone")
-    return _BackboneFn.apply(x, module, module.training and torch.is_grad_enabled(), compute_dtype(),
+    return _BackboneFn.apply(x, module, module.training, torch.is_grad_enabled(), compute_dtype(),
                              *_backbone_params(module))
 
 

@@ -1,5 +1,7 @@
 #include "common.cuh"
+#include <map>
 #include <mutex>
+#include <utility>
 #include <string>
 
 namespace mr {
@@ -9,6 +11,30 @@ static std::string g_err;
 void set_cuda_error(cudaError_t e, const char *where) {
     std::lock_guard<std::mutex> lk(g_err_mu);
     g_err = std::string(where) + ": " + cudaGetErrorName(e) + ": " + cudaGetErrorString(e);
+}
+static std::mutex g_attr_mu;
+static std::map<std::pair<const void *, int>, size_t> g_attr;
+int ensure_dyn_smem(const void *func, size_t bytes, const char *where) {
+    int dev = 0;
+    MR_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    size_t &have = g_attr[std::make_pair(func, dev)];
+    if (bytes > have) {
+        MR_CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), where);
+        have = bytes;
+    }
+    return MR_OK;
+}
+int sm_count() {
+    static std::atomic<int> cache[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+    int v = cache[dev].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
 }
 static std::mutex g_blas_mu;
 static cublasHandle_t g_blas[16] = {nullptr};

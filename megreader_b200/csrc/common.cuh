@@ -27,6 +27,11 @@ int blas_handle(cublasHandle_t *h, cudaStream_t st);
 #define MR_BLAS_TRY(expr, where)                                                                        \
     do { if ((expr) != CUBLAS_STATUS_SUCCESS) { ::mr::set_cuda_error(cudaErrorUnknown, where); return MR_ERR_CUDA; } } while (0)
 
+// Per-DEVICE caches (a process may drive several GPUs): opt a kernel into `bytes` of dynamic shared memory once per
+// (kernel, device) -- cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute -- and the SM count.
+int ensure_dyn_smem(const void *func, size_t bytes, const char *where);
+int sm_count();
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

@@ -275,11 +275,7 @@ int mr_ctc2d_head_fwd_f32(const float *mask_logits, const float *cls_logits, int
     size_t smem;
     g.NT = pick_nt(C, H, 1, &smem);
     if (!g.NT || H > 65535 || ceil_div(N, g.NT) > 65535) return MR_ERR_UNSUPPORTED;
-    static size_t attr = 0;
-    if (smem > attr) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(ctc2d_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "head fwd smem");
-        attr = smem;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)ctc2d_head_fwd_kernel, smem, "head fwd smem"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)ceil_div(W, kTW), (unsigned)H, (unsigned)ceil_div(N, g.NT));
     ctc2d_head_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
     return check_launch("ctc2d_head_fwd_kernel");
@@ -299,11 +295,10 @@ int mr_ctc2d_head_bwd_f32(const float *mask_logits, const float *cls_logits, con
     g.NT = pick_nt(C, H, 2, &smem);
     if (!g.NT || H > 65535 || ceil_div(N, g.NT) > 65535) return MR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    static size_t attr[2] = {0, 0};
-    if (smem > attr[factored]) {
-        if (factored) MR_CUDA_TRY(cudaFuncSetAttribute(ctc2d_head_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "head bwd smem");
-        else MR_CUDA_TRY(cudaFuncSetAttribute(ctc2d_head_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "head bwd smem");
-        attr[factored] = smem;
+    {
+        int rc_attr = factored ? ensure_dyn_smem((const void *)ctc2d_head_bwd_kernel<true>, smem, "head bwd smem")
+                               : ensure_dyn_smem((const void *)ctc2d_head_bwd_kernel<false>, smem, "head bwd smem");
+        if (rc_attr) return rc_attr;
     }
     dim3 grid((unsigned)ceil_div(W, kTW), (unsigned)H, (unsigned)ceil_div(N, g.NT));
     if (factored)

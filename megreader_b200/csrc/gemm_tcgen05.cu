@@ -841,11 +841,7 @@ template <int BN, int STAGES, int A_MN, int B_MN>
 int launch(const CUtensorMap &ta, const CUtensorMap &tb, const GemmArgs &g, int splits, cudaStream_t st) {
     using L = SmemLayout<BN, STAGES>;
     auto kern = gemm_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "gemm_tcgen05 smem attr");
-        attr_set = true;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)kern, L::TOTAL, "gemm_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)ceil_div(g.M, BM), (unsigned)ceil_div(g.N, BN), (unsigned)splits);
     kern<<<grid, 192, L::TOTAL, st>>>(ta, tb, g);
     return check_launch("gemm_tcgen05_kernel");
@@ -871,11 +867,7 @@ template <int BN, int STAGES, int MT, int TMA_A>
 int launch_conv(const CUtensorMap &tb, const CUtensorMap *tx, const ConvArgs &a, int tiles, cudaStream_t st) {
     using L = ConvSmem<BN, STAGES, MT>;
     auto kern = conv_fprop_tcgen05_kernel<BN, STAGES, MT, TMA_A>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_fprop smem attr");
-        attr_set = true;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)kern, L::TOTAL, "conv_fprop smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid(TMA_A ? (unsigned)ceil_div(tiles, MT) : (unsigned)ceil_div(a.g.M, BM * MT), (unsigned)ceil_div(a.g.N, BN), 1);
     kern<<<grid, 192, L::TOTAL, st>>>(tb, tx[0], tx[1], tx[2], tx[3], a);
     return check_launch("conv_fprop_tcgen05_kernel");
@@ -885,11 +877,7 @@ template <int BN, int RB, int STAGES>
 int launch_wgrad(const CUtensorMap &tdz, const CUtensorMap &tx, const WgradArgs &a, int splits, cudaStream_t st) {
     using L = WgradSmem<BN, RB, STAGES>;
     auto kern = conv_wgrad_tcgen05_kernel<BN, RB, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "conv_wgrad smem attr");
-        attr_set = true;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)kern, L::TOTAL, "conv_wgrad smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)ceil_div(a.g.M, BM), (unsigned)ceil_div(a.g.N, BN), (unsigned)splits);
     kern<<<grid, 192, L::TOTAL, st>>>(tdz, tx, a);
     return check_launch("conv_wgrad_tcgen05_kernel");
@@ -1096,11 +1084,7 @@ int mr_lstm_step_fwd_tcgen05(const void *const *h_prev, const void *const *Whh, 
     }
     using L = SmemLayout<kLstmBN, 4>;
     auto kern = lstm_step_fwd_tcgen05_kernel<4>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "lstm fwd smem attr");
-        attr_set = true;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)kern, L::TOTAL, "lstm fwd smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(4 * H / kLstmBN), 2);
     kern<<<grid, kLstmThreads, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
     return check_launch("lstm_step_fwd_tcgen05_kernel");
@@ -1125,11 +1109,7 @@ int mr_lstm_step_bwd_tcgen05(const void *const *dG_next, const void *const *Whh,
     }
     using L = SmemLayout<kLstmBN, 6>;
     auto kern = lstm_step_bwd_tcgen05_kernel<6>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL), "lstm bwd smem attr");
-        attr_set = true;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)kern, L::TOTAL, "lstm bwd smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)ceil_div(B, BM), (unsigned)(H / kLstmBN), 2);
     kern<<<grid, kLstmThreads, L::TOTAL, (cudaStream_t)stream>>>(ta[0], ta[1], tb[0], tb[1], a);
     return check_launch("lstm_step_bwd_tcgen05_kernel");

@@ -564,6 +564,29 @@ int resident_ok(const void *kern, int threads, size_t smem, int ctas) {
 constexpr int kBwdStages = 5;
 long long *g_trace = nullptr;
 
+// A timed-out inter-CTA wait leaves garbage in the outputs and a non-zero error word.  Callers that never read the word
+// (a training loop inside a CUDA graph) must still notice: if the word is set, the head of the output is overwritten with
+// NaN, which reaches the loss (forward) or every weight gradient (backward) -- no host synchronisation needed.
+__global__ void lstm_seq_poison_kernel(const unsigned *err, bf16 *out, int64_t n) {
+    if (*err == 0u) return;
+    const bf16 nan = __float2bfloat16(__int_as_float(0x7fc00000));
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = nan;
+}
+
+// The persistent kernels spin on flags written by other CTAs of the same grid, so the WHOLE grid must be co-resident.
+// A cooperative launch makes that a guarantee of the runtime (the grid is gang-scheduled, or the launch fails) instead
+// of an occupancy estimate that concurrent work -- NCCL, the weight-gradient side stream -- could invalidate.
+template <typename... Args>
+cudaError_t launch_cooperative(void (*kern)(Args...), dim3 grid, int threads, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads, 1, 1); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 }  // namespace
 
 extern "C" {
@@ -582,11 +605,7 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
     const int nkb = H / BK, row_tiles = ceil_div(B, BM);
     const size_t smem = (size_t)nkb * (16384 + 8192) + 32768 + 8192 + 16 * 8 + 1024;
     auto kern = lstm_seq_fwd_kernel;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm seq fwd smem attr");
-        attr_smem = smem;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)kern, smem, "lstm seq fwd smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)row_tiles, (unsigned)(4 * H / kBN), 2);
     if (!resident_ok((const void *)kern, kThreads, smem, (int)(grid.x * grid.y * grid.z))) return MR_ERR_UNSUPPORTED;
     CUtensorMap ty, tw[2];
@@ -605,8 +624,11 @@ int mr_lstm_seq_fwd_tcgen05(const void *const *Whh, void *G, const float *const 
     a.G = (bf16 *)G; a.bias[0] = bias[0]; a.bias[1] = bias[1]; a.C = C; a.Y = (bf16 *)Y; a.flags = flags; a.trace = g_trace;
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
-    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ty, tw[0], tw[1], tg3, tc3, a);
-    return check_launch("lstm_seq_fwd_kernel");
+    MR_CUDA_TRY(launch_cooperative(kern, grid, kThreads, smem, (cudaStream_t)stream, ty, tw[0], tw[1], tg3, tc3, a), "lstm_seq_fwd_kernel");
+    rc = check_launch("lstm_seq_fwd_kernel");
+    if (rc) return rc;
+    lstm_seq_poison_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(flags + 2 * row_tiles, (bf16 *)Y, (int64_t)T * B * 2 * H);
+    return check_launch("lstm_seq_poison_kernel");
 }
 
 int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float *C, const void *dY, void *dG,
@@ -618,11 +640,7 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float 
     const size_t smem = (size_t)kBwdStages * 16384 + 65536 + (size_t)nkb * kBwdWTile + (2 * kBwdStages + 8) * 8 + 1024;
     if (smem > 227 * 1024) return MR_ERR_UNSUPPORTED;
     auto kern = lstm_seq_bwd_kernel<kBwdStages>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        MR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm seq bwd smem attr");
-        attr_smem = smem;
-    }
+    { int rc_attr = ensure_dyn_smem((const void *)kern, smem, "lstm seq bwd smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)row_tiles, (unsigned)(H / kBwdBN), 2);
     if (!resident_ok((const void *)kern, kThreads, smem, (int)(grid.x * grid.y * grid.z))) return MR_ERR_UNSUPPORTED;
     CUtensorMap tdg, tw[2];
@@ -643,8 +661,11 @@ int mr_lstm_seq_bwd_tcgen05(const void *const *WhhT, const void *G, const float 
     a.G = (const bf16 *)G; a.C = C; a.dY = (const bf16 *)dY; a.dG = (bf16 *)dG; a.flags = flags; a.trace = g_trace;
     a.T = T; a.B = B; a.H = H;
     MR_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (2 * row_tiles + 1), (cudaStream_t)stream), "lstm seq flags");
-    kern<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tdg, tw[0], tw[1], tg3, tdg3, tc3, a);
-    return check_launch("lstm_seq_bwd_kernel");
+    MR_CUDA_TRY(launch_cooperative(kern, grid, kThreads, smem, (cudaStream_t)stream, tdg, tw[0], tw[1], tg3, tdg3, tc3, a), "lstm_seq_bwd_kernel");
+    rc = check_launch("lstm_seq_bwd_kernel");
+    if (rc) return rc;
+    lstm_seq_poison_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(flags + 2 * row_tiles, (bf16 *)dG, (int64_t)2 * T * B * 4 * H);
+    return check_launch("lstm_seq_poison_kernel");
 }
 
 }  // extern "C"

@@ -132,20 +132,20 @@ constexpr int kMaxPartialCols = 2048;
 // use, which must not happen inside a CUDA-graph capture: callers run one eager step before capturing (as they must
 // for cuBLAS anyway).  NULL when the allocation is impossible -> the fp64-atomic path is used instead.
 float *partials_scratch() {
-    static float *buf = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static float *buf[16] = {nullptr};                    // one scratch per DEVICE (a process may drive several GPUs)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (!buf[dev]) {
         void *p = nullptr;
-        if (cudaMalloc(&p, sizeof(float) * (size_t)kMaxPartialBlocks * kMaxPartialCols) == cudaSuccess) buf = (float *)p;
-        else { cudaGetLastError(); tried = false; }      // e.g. called under capture: retry on the next eager call
+        if (cudaMalloc(&p, sizeof(float) * (size_t)kMaxPartialBlocks * kMaxPartialCols) == cudaSuccess) buf[dev] = (float *)p;
+        else cudaGetLastError();                          // e.g. called under capture: retry on the next eager call
     }
-    return buf;
+    return buf[dev];
 }
 
 inline int grid1d(int64_t work, int block, int per_sm = 16) {
     int64_t b = ceil_div(work, block);
-    const int64_t cap = (int64_t)148 * per_sm;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 

@@ -111,3 +111,42 @@ def test_ctc_decoder2d_surface(cuda, api):
     dec.eval()
     classify, mask = dec(feat)
     assert tuple(classify.shape) == (3, 38, 4, 10) and tuple(mask.shape) == (3, 1, 4, 10)
+
+
+def test_backbone_bn_modes_and_input_gradient(cuda, api):
+    """BatchNorm's batch-statistics switch follows module.training (also under no_grad), saving for backward
+    follows grad mode (also in eval()), and the input gradient is returned when the images require grad.  Reference:
+    the same layers as plain torch modules (oracle/crnn_port.py) on the GPU in fp32."""
+    from oracle import crnn_port
+    backbones, _ = api
+    bb = fill_state_dict(backbones.crnn_backbone(), "bb.").to(cuda)
+    ref = fill_state_dict(crnn_port.CRNNBackbonePort(), "bb.").to(cuda)
+    torch.manual_seed(3)
+    x = torch.randn(3, 3, 32, 48, device=cuda)
+    # 1) train() under no_grad: batch statistics + running-stat update
+    bb.train(); ref.train()
+    with torch.no_grad():
+        y, yr = bb(x), ref(x)
+    torch.testing.assert_close(y, yr, rtol=1e-4, atol=1e-4)
+    for k, v in ref.state_dict().items():
+        if "running" in k:
+            torch.testing.assert_close(bb.state_dict()[k], v, rtol=1e-4, atol=1e-5, msg=k)
+    # 2) eval() with grad: running statistics, full backward incl. the input gradient
+    bb.eval(); ref.eval()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y, yr = bb(xa), ref(xb)
+    torch.testing.assert_close(y, yr, rtol=1e-4, atol=1e-4)
+    go = torch.randn_like(yr)
+    y.backward(go); yr.backward(go)
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-3, atol=1e-4 * float(xb.grad.abs().max()))
+    for (n, p), (_, q) in zip(bb.named_parameters(), ref.named_parameters()):
+        torch.testing.assert_close(p.grad, q.grad, rtol=2e-3, atol=2e-4 * max(1e-6, float(q.grad.abs().max())), msg=n)
+    # 3) train() with an input that requires grad; a second backward raises instead of crashing
+    bb.train(); ref.train()
+    bb.zero_grad(); ref.zero_grad()
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y, yr = bb(xa), ref(xb)
+    y.backward(go, retain_graph=True); yr.backward(go)
+    torch.testing.assert_close(xa.grad, xb.grad, rtol=1e-3, atol=1e-4 * float(xb.grad.abs().max()))
+    with pytest.raises(RuntimeError, match="retain_graph"):
+        y.backward(go)
