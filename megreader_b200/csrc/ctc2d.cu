@@ -366,9 +366,9 @@ __device__ __forceinline__ void lse_rows(const real *base, int64_t hs, int H, re
 }
 
 template <typename real, bool FAST, int VE, int HT, bool LOG2OUT = false>
-__device__ __forceinline__ void phase_q(const Geo &q, const real *__restrict__ lp, real *Qall, int b0, int Gv) {
+__device__ __forceinline__ void phase_q(const Geo &q, const real *__restrict__ lp, real *Qall, int b0, int Gv, int pitch = 0) {
     const int H = HT > 0 ? HT : q.H;
-    const int rowElems = q.G * q.C;
+    const int rowElems = pitch > 0 ? pitch : q.G * q.C;
     const int nvec = (Gv * q.C + VE - 1) / VE;  // VE > 1 only when Gv*C % VE == 0 for every CTA
     const int64_t hs = (int64_t)q.N * q.C;
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -425,9 +425,9 @@ __device__ __forceinline__ void grad_rows(const real *src, real *dst, int64_t hs
 
 template <typename real, bool FAST, int VE, int HT>
 __device__ __forceinline__ void phase_grad(const Geo &q, const real *__restrict__ lp, const real *Fs,
-                                           real *__restrict__ grad, int b0, int Gv) {
+                                           real *__restrict__ grad, int b0, int Gv, int pitch = 0) {
     const int H = HT > 0 ? HT : q.H;
-    const int rowElems = q.G * q.C;
+    const int rowElems = pitch > 0 ? pitch : q.G * q.C;
     const int nvec = (Gv * q.C + VE - 1) / VE;
     const int64_t hs = (int64_t)q.N * q.C;
     const int tid = threadIdx.x, nth = blockDim.x;
@@ -797,6 +797,412 @@ ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Warp-per-sample DP kernel, FOURTH revision (round 2; fp32 fast math; modes GRAD and FAC; S <= 32, C <= 64).
+// ncu on v3: ~12 k warp-instructions per sample at IPC 1.6 with 16 warps per SM -- every phase ran as one dependent
+// instruction chain.  What changed (profiles/ctc2d_dp4_r2_summary.md has the per-phase instruction counts):
+//   * the forward and the backward sweep of a sample run INTERLEAVED in the same warp: two independent dependency chains
+//     per iteration, and T+1 instead of 2T chain steps.  The forward chain covers columns 0..m, the backward chain
+//     Tb-1..m (m = Tb/2); they meet at column m, where  -nll = LSE_s(R[m,s] + Rb[m,s] + Q[m,l'_s])  (every path crosses
+//     exactly one state of column m), so K3's terms  E[t,s] = exp(R + Rb + nll)  can be formed right there and, in the
+//     second half of both chains (forward continues to Tb-1 against the stored Rb rows, backward continues to 0 against
+//     the stored R rows), as soon as a step is computed;
+//   * only Tb-1 rows of 32*NS floats are stored per sample, and NS is the sample's own ceil((2L+1)/32): the rows live in a
+//     pool of G slots per CTA (a sample with long targets takes 2-3 slots; if the CTA's samples need more than G, the
+//     warps go in rounds).  Shared memory per CTA drops from 107 KB to 72 KB -> 3 CTAs (24 sample-warps) per SM;
+//   * the Q operand of the NEXT step and the stored row it will need are loaded one iteration ahead;
+//   * K3's per-class collection is TRANSPOSED: the sweeps only overwrite the consumed row with E[t,s] (one store per
+//     state and step, +2^-60 where the state is finite so that "class present" <=> sum > 0); afterwards lane = COLUMN t
+//     adds up the blank states and each label state of its column into the (dead) Q row -- ~100 instructions per sample
+//     for all 32 columns instead of ~50 per column (16-way same-address atomics on the blank, a CAS loop per label);
+//   * phase Q for H = 8 is a straight-line max / fma / ex2 / add sequence (log2 domain); the factor pass has no divisions.
+// ------------------------------------------------------------------------------------------------
+struct Dp4Ctx {
+    const Geo *q;
+    const int64_t *row;       // targets of this sample
+    int Tb, L;
+    float *Qg;                // Q2 rows of this sample: Qg[t * pitch + c]; later the per-class sums / factors
+    float *Rst;               // [T][32*NS + 1] stored sweep rows of this sample, then E[t][s]
+    int pitch;
+};
+
+// LSE over 8 heights of one 4-wide vector column, result in log2 units.
+__device__ __forceinline__ void lse_rows8_l2(const float *base, int64_t hs, float *dst) {
+    float4 x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = __ldg(reinterpret_cast<const float4 *>(base + u * hs));
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = k == 0 ? x[u].x : (k == 1 ? x[u].y : (k == 2 ? x[u].z : x[u].w));
+        const float m = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+        const float m2 = m * 1.4426950408889634f;
+        const float neg = (m == -INFINITY) ? 0.f : -m2;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+            s0 += ex2_ftz(fmaf(v[u], 1.4426950408889634f, neg));
+            s1 += ex2_ftz(fmaf(v[u + 1], 1.4426950408889634f, neg));
+        }
+        out[k] = m2 + lg2_ftz(s0 + s1);                       // m = -inf: -inf + lg2(0) = -inf
+    }
+    *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+__device__ __forceinline__ void phase_q8_l2(const Geo &q, const float *__restrict__ lp, float *Qall, int b0, int Gv, int pitch) {
+    const int nvec = (Gv * q.C) >> 2;                        // callers guarantee (Gv*C) % 4 == 0 on this path
+    const int64_t hs = (int64_t)q.N * q.C;
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const float *cta = lp + (int64_t)b0 * q.C;
+    if (nvec <= nth) {
+        const int tpr = nth / nvec;
+        const int t0 = tid / nvec, j = tid - t0 * nvec;
+        if (t0 < tpr) {
+            const float *src = cta + (int64_t)t0 * 8 * hs + j * 4;
+            float *dst = Qall + t0 * pitch + j * 4;
+            const int64_t sstep = (int64_t)tpr * 8 * hs;
+            for (int t = t0; t < q.T; t += tpr, src += sstep, dst += tpr * pitch) lse_rows8_l2(src, hs, dst);
+        }
+    } else {
+        for (int i = tid; i < q.T * nvec; i += nth) {
+            const int t = i / nvec, j = i - t * nvec;
+            lse_rows8_l2(cta + (int64_t)t * 8 * hs + j * 4, hs, Qall + t * pitch + j * 4);
+        }
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ float warp_sweeps4(const Dp4Ctx &w, int lane) {
+    const Geo &q = *w.q;
+    const float NINF = -INFINITY;
+    const int SS = q.SS;
+    const int Tb = w.Tb, L = w.L;
+    constexpr int P = 32 * NS + 1;                            // odd row pitch: the transposed pass reads columns
+    int cur[NS];
+    bool in[NS], skf[NS], skb[NS], succ1[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int s = lane * NS + k;
+        cur[k] = q.blank; in[k] = skf[k] = skb[k] = false;
+        succ1[k] = s < 2 * L;
+        if (s < SS && s < 2 * L + 1) {
+            in[k] = L > 0;
+            if (s & 1) {
+                const int64_t me = w.row[(int64_t)(s >> 1) * q.tg_ss];
+                cur[k] = clampi(me, q.C);
+                if (s > 1) skf[k] = w.row[(int64_t)((s - 2) >> 1) * q.tg_ss] != me;
+                if (s < 2 * L - 1) skb[k] = w.row[(int64_t)((s + 2) >> 1) * q.tg_ss] != me;
+            }
+        }
+    }
+    if (Tb < 1) return INFINITY;
+    const int m = Tb >> 1;
+    const float *Qg = w.Qg;
+    const int re = w.pitch;
+    float *Rl = w.Rst + lane * NS;                            // this lane's states inside a stored row
+
+    float af[NS], bq[NS], Rf[NS], Rb[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) af[k] = bq[k] = Rf[k] = Rb[k] = NINF;
+
+    // one forward step: R[t] from A[t-1] (held in af), then A[t] = R[t] + Q[t]
+    auto fwd_step = [&](int t, const float *qv) {
+        if (t == 0) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int s = lane * NS + k;
+                Rf[k] = (s == 0 || (s == 1 && L > 0)) ? 0.f : NINF;
+            }
+        } else {
+            float up1 = __shfl_up_sync(0xffffffffu, af[NS - 1], 1);
+            float up2 = NS >= 2 ? __shfl_up_sync(0xffffffffu, af[NS >= 2 ? NS - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, af[0], 2);
+            if (lane == 0) up1 = up2 = NINF;
+            if (NS == 1 && lane == 1) up2 = NINF;
+            float Rn[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const float am1 = k >= 1 ? af[k >= 1 ? k - 1 : 0] : up1;
+                const float am2 = k >= 2 ? af[k >= 2 ? k - 2 : 0] : (k == 1 ? up1 : up2);
+                const float v = lse3_l2(af[k], am1, skf[k] ? am2 : NINF);
+                Rn[k] = in[k] ? v : NINF;
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Rf[k] = Rn[k];
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) af[k] = Rf[k] + qv[k];
+    };
+    // one backward step: Rb[t] from B[t+1] (held in bq), then B[t] = Rb[t] + Q[t]
+    auto bwd_step = [&](int t, const float *qv) {
+        if (t == Tb - 1) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const int s = lane * NS + k;
+                Rb[k] = (s == 2 * L || (L > 0 && s == 2 * L - 1)) ? 0.f : NINF;
+            }
+        } else {
+            float dn1 = __shfl_down_sync(0xffffffffu, bq[0], 1);
+            float dn2 = NS >= 2 ? __shfl_down_sync(0xffffffffu, bq[NS >= 2 ? 1 : 0], 1) : __shfl_down_sync(0xffffffffu, bq[0], 2);
+            if (lane == 31) dn1 = dn2 = NINF;
+            if (NS == 1 && lane == 30) dn2 = NINF;
+            float Rn[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) {
+                const float bp1 = k + 1 < NS ? bq[k + 1 < NS ? k + 1 : 0] : dn1;
+                const float bp2 = k + 2 < NS ? bq[k + 2 < NS ? k + 2 : 0] : (k + 1 < NS ? dn1 : dn2);
+                const float v = lse3_l2(bq[k], succ1[k] ? bp1 : NINF, skb[k] ? bp2 : NINF);
+                Rn[k] = in[k] ? v : NINF;
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Rb[k] = Rn[k];
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) bq[k] = Rb[k] + qv[k];
+    };
+    auto load_q = [&](int t, float *qv) {
+        const float *Qt = Qg + t * re;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) qv[k] = Qt[cur[k]];
+    };
+    // K3's term of column t for this lane's states: E = exp2(R + Rb + nll2) (+ 2^-60: "this state is finite"), else 0
+    auto emit = [&](int t, const float *v, float nll2) {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const int s = lane * NS + k;
+            const bool ok = in[k] && s < SS && v[k] != NINF;
+            Rl[t * P + k] = ok ? ex2_ftz(v[k] + nll2) + 0x1p-60f : 0.f;
+        }
+    };
+
+    // ---------------- phase 1: forward columns 0..m, backward columns Tb-1..m (stored: forward 0..m-1, backward m+1..Tb-1)
+    float qf[NS], qb[NS];
+    load_q(0, qf);
+    load_q(Tb - 1, qb);
+    const int nb1 = Tb - m;                                   // backward steps of phase 1 (Tb-1 .. m)
+#pragma unroll 1
+    for (int i = 0; i <= m; ++i) {
+        float qfn[NS], qbn[NS];
+        load_q(min(i + 1, Tb - 1), qfn);
+        load_q(max(Tb - 2 - i, 0), qbn);
+        fwd_step(i, qf);
+        if (i < m) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) Rl[i * P + k] = Rf[k];
+        }
+        if (i < nb1) {
+            const int tb = Tb - 1 - i;
+            bwd_step(tb, qb);
+            if (tb > m) {
+#pragma unroll
+                for (int k = 0; k < NS; ++k) Rl[tb * P + k] = Rb[k];
+            }
+#pragma unroll
+            for (int k = 0; k < NS; ++k) qb[k] = qbn[k];
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) qf[k] = qfn[k];
+    }
+    // ---------------- meeting column m: -nll2 = LSE2_s( R[m,s] + Rb[m,s] + Q2[m, l'_s] ) = LSE2_s( af[s] + Rb[s] )
+    float nll2;
+    {
+        float mx = NINF;
+        float tv[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const int s = lane * NS + k;
+            tv[k] = (s < SS) ? af[k] + Rb[k] : NINF;
+            mx = fmaxf(mx, tv[k]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (mx == NINF) nll2 = INFINITY;
+        else {
+            float sm = 0.f;
+#pragma unroll
+            for (int k = 0; k < NS; ++k) sm += ex2_ftz(tv[k] - mx);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            nll2 = -(mx + lg2_ftz(sm));
+        }
+        float v[NS];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) v[k] = Rf[k] + Rb[k];
+        emit(m, v, nll2);
+    }
+    // ---------------- phase 2: forward m+1..Tb-1 against the stored Rb rows, backward m-1..0 against the stored R rows
+    const int nf2 = Tb - 1 - m, nb2 = m;
+    const int n2 = nf2 > nb2 ? nf2 : nb2;
+    float sf[NS], sb[NS];                                     // stored rows for the current iteration
+    {
+        const int tf = min(m + 1, Tb - 1), tb = max(m - 1, 0);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { sf[k] = Rl[tf * P + k]; sb[k] = Rl[tb * P + k]; }
+    }
+#pragma unroll 1
+    for (int j = 0; j < n2; ++j) {
+        const int tf = m + 1 + j, tb = m - 1 - j;
+        float qfn[NS], qbn[NS], sfn[NS], sbn[NS];
+        {
+            const int tfn = min(tf + 1, Tb - 1), tbn = max(tb - 1, 0);
+            load_q(tfn, qfn);
+            load_q(tbn, qbn);
+#pragma unroll
+            for (int k = 0; k < NS; ++k) { sfn[k] = Rl[tfn * P + k]; sbn[k] = Rl[tbn * P + k]; }
+        }
+        if (j < nf2) {
+            fwd_step(tf, qf);
+            float v[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) v[k] = Rf[k] + sf[k];
+            emit(tf, v, nll2);
+        }
+        if (j < nb2) {
+            bwd_step(tb, qb);
+            float v[NS];
+#pragma unroll
+            for (int k = 0; k < NS; ++k) v[k] = sb[k] + Rb[k];
+            emit(tb, v, nll2);
+        }
+#pragma unroll
+        for (int k = 0; k < NS; ++k) { qf[k] = qfn[k]; qb[k] = qbn[k]; sf[k] = sfn[k]; sb[k] = sbn[k]; }
+    }
+    __syncwarp();                                             // E rows complete; every lane is done with the Q rows
+    // ---------------- transposed collection: lane = column t.  sums[t][class] (in the dead Q row) = sum of E over the
+    // states of that class; the first label of a class stores, later ones add (firstbits from the caller).
+    return nll2 * 0.6931471805599453f;
+}
+
+// lane = column: per-class sums of E[t][s] into the Q row of column t.  cls[j] = class of label j, firstbits bit j = label j
+// is the first label of its class.
+template <int NS>
+__device__ __forceinline__ void collect_transposed(const Dp4Ctx &w, int lane, const int *cls, unsigned firstbits) {
+    constexpr int P = 32 * NS + 1;
+    const int L = w.L;
+    const int blank = w.q->blank;
+    for (int t0 = 0; t0 < w.Tb; t0 += 32) {
+        const int t = t0 + lane;
+        if (t < w.Tb) {
+            const float *Et = w.Rst + t * P;
+            float *Qt = w.Qg + t * w.pitch;
+            float a0 = 0.f, a1 = 0.f;
+            int s = 0;
+            for (; s + 2 <= 2 * L; s += 4) { a0 += Et[s]; a1 += Et[s + 2]; }
+            if (s <= 2 * L) a0 += Et[s];
+            Qt[blank] = a0 + a1;
+            for (int j = 0; j < L; ++j) {
+                const float e = Et[2 * j + 1];
+                float *dst = Qt + cls[j];
+                *dst = ((firstbits >> j) & 1u) ? e : *dst + e;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int MODE, int HT>
+__global__ void __launch_bounds__(256, 3)
+ctc2d_dp4_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict__ tg,
+                 const int64_t *__restrict__ il, const int64_t *__restrict__ tl,
+                 const float *__restrict__ grad_out, int64_t go_stride, float *__restrict__ nll_out,
+                 float *__restrict__ fac_out, float *__restrict__ grad, int pitch) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int b0 = blockIdx.x * q.G;
+    const int Gv = min(q.G, q.N - b0);
+    float *Qall = reinterpret_cast<float *>(smem_raw);           // [T][pitch]  Q2, then per-class sums, then factors
+    float *pool = Qall + q.T * pitch;                             // [G slots][T][33]
+    int *meta = reinterpret_cast<int *>(pool + (size_t)q.G * q.T * 33);   // [G] slot, round, ns, Tb, L; [1] rounds
+    unsigned *tmask = reinterpret_cast<unsigned *>(meta + 5 * q.G + 1);   // [G][2] classes that occur in the extended target
+    int *cls = reinterpret_cast<int *>(tmask + 2 * q.G);          // [G][32] class of label j
+
+    if (tid == 0) {                                              // slot / round plan of this CTA's samples
+        int used = 0, round = 0;
+        for (int g = 0; g < q.G; ++g) {
+            int ns = 1, Tb = 0, L = 0;
+            if (g < Gv) {
+                int64_t L64 = tl[b0 + g], T64 = il[b0 + g];
+                if (L64 < 0) L64 = 0;
+                if (L64 > q.S) L64 = q.S;
+                if (T64 < 0) T64 = 0;
+                if (T64 > q.T) T64 = q.T;
+                L = (int)L64; Tb = (int)T64;
+                ns = (2 * L + 1 + 31) >> 5;
+            }
+            if (used + ns > q.G) { ++round; used = 0; }
+            meta[g] = used; meta[q.G + g] = round; meta[2 * q.G + g] = ns; meta[3 * q.G + g] = Tb; meta[4 * q.G + g] = L;
+            used += ns;
+        }
+        meta[5 * q.G] = round + 1;
+    }
+    if (HT == 8 && q.vec > 1) phase_q8_l2(q, lp, Qall, b0, Gv, pitch);
+    else if (q.vec > 1) phase_q<float, true, 4, HT, true>(q, lp, Qall, b0, Gv, pitch);
+    else phase_q<float, true, 1, HT, true>(q, lp, Qall, b0, Gv, pitch);
+    __syncthreads();
+
+    const int rounds = meta[5 * q.G];
+    const int g = warp;
+    for (int r = 0; r < rounds; ++r) {
+        if (g < Gv && meta[q.G + g] == r) {
+            const int b = b0 + g;
+            Dp4Ctx w;
+            w.q = &q; w.row = tg + (int64_t)b * q.tg_sn; w.Tb = meta[3 * q.G + g]; w.L = meta[4 * q.G + g];
+            w.Qg = Qall + g * q.C; w.Rst = pool + (size_t)meta[g] * q.T * 33; w.pitch = pitch;
+            const int ns = meta[2 * q.G + g];
+            // labels of this sample (lane j = label j; S <= 32), the classes that occur, and "first label of its class"
+            const int myc = lane < w.L ? clampi(w.row[(int64_t)lane * q.tg_ss], q.C) : -1 - lane;
+            unsigned lo = (lane == 0) ? (q.blank < 32 ? 1u << q.blank : 0u) : 0u;
+            unsigned hi = (lane == 0) ? (q.blank >= 32 ? 1u << (q.blank - 32) : 0u) : 0u;
+            if (myc >= 0) { if (myc < 32) lo |= 1u << myc; else hi |= 1u << (myc - 32); }
+            lo = __reduce_or_sync(0xffffffffu, lo);
+            hi = __reduce_or_sync(0xffffffffu, hi);
+            const unsigned same = __match_any_sync(0xffffffffu, myc);
+            const unsigned firstbits = __ballot_sync(0xffffffffu, myc >= 0 && (__ffs(same) - 1) == lane);
+            cls[g * 32 + lane] = myc >= 0 ? myc : 0;
+            if (lane == 0) { tmask[2 * g] = lo; tmask[2 * g + 1] = hi; }
+            __syncwarp();
+            float nll;
+            if (ns <= 1) { nll = warp_sweeps4<1>(w, lane); collect_transposed<1>(w, lane, cls + g * 32, firstbits); }
+            else if (ns == 2) { nll = warp_sweeps4<2>(w, lane); collect_transposed<2>(w, lane, cls + g * 32, firstbits); }
+            else { nll = warp_sweeps4<3>(w, lane); collect_transposed<3>(w, lane, cls + g * 32, firstbits); }
+            if (MODE != MODE_GRAD && lane == 0) nll_out[b] = nll;
+        }
+        if (rounds > 1) __syncthreads();
+    }
+    __syncthreads();
+    // ---- factor: (1 - sum) [* go] where the class is present and t < Tb, else 0 (K3 :501-515).  Thread = fixed column
+    // e of the [Gv*C] row (its sample / class bits are loop invariants), loop over t: no divisions in the loop.
+    for (int e = tid; e < Gv * q.C; e += blockDim.x) {
+        const int gg = e / q.C, c = e - gg * q.C;
+        const bool listed = (c < 32 ? (tmask[2 * gg] >> c) : (tmask[2 * gg + 1] >> (c - 32))) & 1u;
+        const int Tb = listed ? meta[3 * q.G + gg] : 0;
+        const float gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + gg) * go_stride] : 1.f;
+        float *col = Qall + e;
+        float *out = (MODE != MODE_GRAD) ? fac_out + (int64_t)b0 * q.C + e : nullptr;
+        const int64_t ostep = (int64_t)q.N * q.C;
+        for (int t = 0; t < q.T; ++t) {
+            float f = 0.f;
+            if (t < Tb) {
+                const float sum = col[t * pitch];
+                if (sum > 0.f) {
+                    f = 1.f - sum;
+                    if (f == 0.f) f = 0x1p-30f;     // exact cancellation must not read as "class absent" (grad == 0 pattern)
+                    f *= gs;
+                }
+            }
+            if (MODE != MODE_GRAD) out[t * ostep] = f;
+            else col[t * pitch] = f;
+        }
+    }
+    if (MODE == MODE_GRAD) {
+        __syncthreads();
+        if (q.vec > 1) phase_grad<float, true, 4, HT>(q, lp, Qall, grad, b0, Gv, pitch);
+        else phase_grad<float, true, 1, HT>(q, lp, Qall, grad, b0, Gv, pitch);
+    }
+}
+
 // Training backward: grad[t,h,b,c] = exp(lp) * gfac[t,b,c] * go[b].  Pure streaming.  blockIdx.y = t, thread = one
 // 16-byte vector column of the [N*C] row; the factor is formed once and reused for the H rows.
 template <bool FAST, int VE, int HT>
@@ -912,7 +1318,10 @@ int launch_alpha(const real *lp, const int64_t *tg, const int64_t *il, const int
         G = Gs;
         smem = sizeof(real) * (size_t)kStages * H * G * C + sizeof(real) * ((size_t)G * C + (size_t)G * q.SS + 2 * G);
     } else {
-        smem = small;
+        // large alphabets: shrink the CTA's sample group until the un-staged plan fits
+        auto small_need = [&](int g) { return sizeof(real) * ((size_t)g * C + (size_t)g * q.SS + 2 * g); };
+        while (G > 1 && small_need(G) > (size_t)smem_limit()) --G;
+        smem = small_need(G);
         if (smem > (size_t)smem_limit()) return MR_ERR_UNSUPPORTED;
     }
     q.G = G;
@@ -963,6 +1372,33 @@ int launch_dp_warp(Geo q, const float *lp, const int64_t *tg, const int64_t *il,
     return MR_ERR_UNSUPPORTED;
 }
 
+// Fourth-revision warp DP kernel (ctc2d_dp4_kernel): fp32 fast math, modes GRAD / FAC, S <= 32, C <= 64.
+// Returns MR_ERR_UNSUPPORTED otherwise (callers fall back to the v3 / block kernels).
+template <int MODE>
+int launch_dp4(Geo q, const float *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const float *go,
+               int64_t go_stride, float *nll, float *fac, float *grad, cudaStream_t st) {
+    if (MODE == MODE_FAC_STD || q.S > 32 || q.C > 64) return MR_ERR_UNSUPPORTED;
+    // row pitch of the Q / sums rows: = 4 (mod 8) floats, so that the transposed pass (lane = column t, same class) hits
+    // 8 different banks, and a multiple of 4 whenever the rows are accessed as float4
+    auto pitch_of = [&](int g) { int p = g * q.C; while (p % 8 != 4) ++p; return p; };
+    auto need = [&](int g) {
+        return sizeof(float) * ((size_t)q.T * pitch_of(g) + (size_t)g * q.T * 33) + sizeof(int) * (size_t)(7 * g + 1 + 32 * g) + 16;
+    };
+    int G = 8;
+    while (G > 1 && need(G) > (size_t)75 * 1024) --G;
+    const size_t smem = need(G);
+    if (smem > (size_t)smem_limit()) return MR_ERR_UNSUPPORTED;
+    q.G = G;
+    q.vec = pick_vec<float>(lp, q.N, q.C, G);
+    if (MODE == MODE_GRAD && ((uintptr_t)grad % 16) != 0) q.vec = 1;
+    const int pitch = pitch_of(G);
+    if (pitch % 4) q.vec = 1;
+    auto kern = (q.H == 8) ? ctc2d_dp4_kernel<MODE, 8> : ctc2d_dp4_kernel<MODE, 0>;
+    { int rc_attr = ensure_dyn_smem((const void *)kern, smem, "ctc2d_dp4 attr"); if (rc_attr) return rc_attr; }
+    kern<<<(unsigned)ceil_div(q.N, q.G), 256, smem, st>>>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad, pitch);
+    return check_launch("ctc2d_dp4_kernel");
+}
+
 template <typename real, bool FAST, int MODE>
 int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_t *tl, const real *go,
               int64_t go_stride, int64_t T, int64_t H, int64_t N, int64_t C, int64_t S, int64_t tg_sn,
@@ -973,6 +1409,12 @@ int launch_dp(const real *lp, const int64_t *tg, const int64_t *il, const int64_
     q.blank = (int)blank; q.tg_sn = tg_sn; q.tg_ss = tg_ss;
     // fp32 fast-math requests use the warp-per-sample kernel (MR_CTC2D_BLOCK_DP=1 forces the block variant below);
     // accurate-math and fp64 requests, and shapes whose plan does not fit, use the block variant.
+    if (sizeof(real) == 4 && FAST && MODE != MODE_FAC_STD && !getenv("MR_CTC2D_BLOCK_DP") && !getenv("MR_CTC2D_DP_V3")) {
+        q.G = 8; q.vec = 1;
+        const int rc = launch_dp4<MODE>(q, (const float *)lp, tg, il, tl, (const float *)go, go_stride, (float *)nll,
+                                        (float *)fac, (float *)grad, st);
+        if (rc != MR_ERR_UNSUPPORTED) return rc;
+    }
     if (sizeof(real) == 4 && FAST && !getenv("MR_CTC2D_BLOCK_DP")) {
         q.G = 8; q.vec = 1;
         const int rc = launch_dp_warp<MODE>(q, (const float *)lp, tg, il, tl, (const float *)go, go_stride, (float *)nll,

@@ -18,6 +18,11 @@ OUT = os.path.join(HERE, "_ref")
 SHIM = os.path.join(HERE, "ref_shim")
 REF = os.environ.get("MEGREADER_REFERENCE", "/root/reference")
 
+# The reference launches its 2D-CTC kernels with 1024 threads per block (ctc2d_cuda_kernel.cu:16 CUDA_NUM_THREADS); the
+# fp64 instantiations need more than 64 registers per thread when compiled for sm_100 and then fail to launch ("too many
+# resources requested").  Capping the register count is a compiler flag, not a source change.
+EXTRA_NVCC = {"ref_ctc2d": ["--maxrregcount=64"]}
+
 OPS = {
     # name: sources relative to the reference root
     "ref_ctc2d": ["ops/ctc_2d/csrc/ctc2d.cpp", "ops/ctc_2d/csrc/cuda/ctc2d_cuda.cu",
@@ -52,7 +57,7 @@ def build(verbose=False):
                            extra_cflags=["-O2", "-DWITH_CUDA", "-include", compat, "-w"],
                            extra_cuda_cflags=["-O2", "-DWITH_CUDA", "-include", compat, "-w", "-DCUDA_HAS_FP16=1",
                                               "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__",
-                                              "-D__CUDA_NO_HALF2_OPERATORS__"],
+                                              "-D__CUDA_NO_HALF2_OPERATORS__"] + EXTRA_NVCC.get(name, []),
                            is_python_module=False)
         os.replace(os.path.join(bdir, name + ".so"), dst)
         built[name] = dst
