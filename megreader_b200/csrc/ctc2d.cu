@@ -817,17 +817,26 @@ ctc2d_dp_warp_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restr
 //     for all 32 columns instead of ~50 per column (16-way same-address atomics on the blank, a CAS loop per label);
 //   * phase Q for H = 8 is a straight-line max / fma / ex2 / add sequence (log2 domain); the factor pass has no divisions.
 // ------------------------------------------------------------------------------------------------
+// log2-domain LSE of three terms with a short dependency chain: max3 -> sub -> ex2 -> add -> lg2 -> add.  The floor on the
+// maximum keeps (-inf) - (-inf) from producing NaN: all terms -inf -> 0 + 0 + 0 -> lg2(0) = -inf.
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+    const float m = fmaxf(fmaxf(a, b), fmaxf(c, -1e30f));
+    return m + lg2_ftz(ex2_ftz(a - m) + ex2_ftz(b - m) + ex2_ftz(c - m));
+}
+
 struct Dp4Ctx {
     const Geo *q;
     const int64_t *row;       // targets of this sample
     int Tb, L;
     float *Qg;                // Q2 rows of this sample: Qg[t * pitch + c]; later the per-class sums / factors
     float *Rst;               // [T][32*NS + 1] stored sweep rows of this sample, then E[t][s]
+    const int *raw;           // [32] the sample's targets (shared memory copy, saturated to int)
     int pitch;
 };
 
 // LSE over 8 heights of one 4-wide vector column, result in log2 units.
-__device__ __forceinline__ void lse_rows8_l2(const float *base, int64_t hs, float *dst) {
+template <typename HS>      // HS = int when 8 * N * C fits 31 bits (one IMAD.WIDE per row address), else int64_t
+__device__ __forceinline__ void lse_rows8_l2(const float *base, HS hs, float *dst) {
     float4 x[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) x[u] = __ldg(reinterpret_cast<const float4 *>(base + u * hs));
@@ -851,26 +860,31 @@ __device__ __forceinline__ void lse_rows8_l2(const float *base, int64_t hs, floa
     *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
-__device__ __forceinline__ void phase_q8_l2(const Geo &q, const float *__restrict__ lp, float *Qall, int b0, int Gv, int pitch) {
+template <typename HS>
+__device__ __forceinline__ void phase_q8_l2_impl(const Geo &q, const float *__restrict__ lp, float *Qall, int b0, int Gv, int pitch) {
     const int nvec = (Gv * q.C) >> 2;                        // callers guarantee (Gv*C) % 4 == 0 on this path
-    const int64_t hs = (int64_t)q.N * q.C;
+    const HS hs = (HS)((int64_t)q.N * q.C);
     const int tid = threadIdx.x, nth = blockDim.x;
     const float *cta = lp + (int64_t)b0 * q.C;
     if (nvec <= nth) {
         const int tpr = nth / nvec;
         const int t0 = tid / nvec, j = tid - t0 * nvec;
         if (t0 < tpr) {
-            const float *src = cta + (int64_t)t0 * 8 * hs + j * 4;
+            const float *src = cta + (int64_t)t0 * 8 * (int64_t)hs + j * 4;
             float *dst = Qall + t0 * pitch + j * 4;
-            const int64_t sstep = (int64_t)tpr * 8 * hs;
-            for (int t = t0; t < q.T; t += tpr, src += sstep, dst += tpr * pitch) lse_rows8_l2(src, hs, dst);
+            const int64_t sstep = (int64_t)tpr * 8 * (int64_t)hs;
+            for (int t = t0; t < q.T; t += tpr, src += sstep, dst += tpr * pitch) lse_rows8_l2<HS>(src, hs, dst);
         }
     } else {
         for (int i = tid; i < q.T * nvec; i += nth) {
             const int t = i / nvec, j = i - t * nvec;
-            lse_rows8_l2(cta + (int64_t)t * 8 * hs + j * 4, hs, Qall + t * pitch + j * 4);
+            lse_rows8_l2<HS>(cta + (int64_t)t * 8 * (int64_t)hs + j * 4, hs, Qall + t * pitch + j * 4);
         }
     }
+}
+__device__ __forceinline__ void phase_q8_l2(const Geo &q, const float *__restrict__ lp, float *Qall, int b0, int Gv, int pitch) {
+    if ((int64_t)q.N * q.C < (1 << 27)) phase_q8_l2_impl<int>(q, lp, Qall, b0, Gv, pitch);
+    else phase_q8_l2_impl<int64_t>(q, lp, Qall, b0, Gv, pitch);
 }
 
 template <int NS>
@@ -890,10 +904,11 @@ __device__ __forceinline__ float warp_sweeps4(const Dp4Ctx &w, int lane) {
         if (s < SS && s < 2 * L + 1) {
             in[k] = L > 0;
             if (s & 1) {
-                const int64_t me = w.row[(int64_t)(s >> 1) * q.tg_ss];
-                cur[k] = clampi(me, q.C);
-                if (s > 1) skf[k] = w.row[(int64_t)((s - 2) >> 1) * q.tg_ss] != me;
-                if (s < 2 * L - 1) skb[k] = w.row[(int64_t)((s + 2) >> 1) * q.tg_ss] != me;
+                // w.raw[j] = target j as stored (low 32 bits of the int64; the repeat tests of K1/K2 compare labels)
+                const int me = w.raw[s >> 1];
+                cur[k] = me < 0 ? 0 : (me >= q.C ? q.C - 1 : me);
+                if (s > 1) skf[k] = w.raw[(s - 2) >> 1] != me;
+                if (s < 2 * L - 1) skb[k] = w.raw[(s + 2) >> 1] != me;
             }
         }
     }
@@ -925,7 +940,7 @@ __device__ __forceinline__ float warp_sweeps4(const Dp4Ctx &w, int lane) {
             for (int k = 0; k < NS; ++k) {
                 const float am1 = k >= 1 ? af[k >= 1 ? k - 1 : 0] : up1;
                 const float am2 = k >= 2 ? af[k >= 2 ? k - 2 : 0] : (k == 1 ? up1 : up2);
-                const float v = lse3_l2(af[k], am1, skf[k] ? am2 : NINF);
+                const float v = lse3_fast(af[k], am1, skf[k] ? am2 : NINF);
                 Rn[k] = in[k] ? v : NINF;
             }
 #pragma unroll
@@ -952,7 +967,7 @@ __device__ __forceinline__ float warp_sweeps4(const Dp4Ctx &w, int lane) {
             for (int k = 0; k < NS; ++k) {
                 const float bp1 = k + 1 < NS ? bq[k + 1 < NS ? k + 1 : 0] : dn1;
                 const float bp2 = k + 2 < NS ? bq[k + 2 < NS ? k + 2 : 0] : (k + 1 < NS ? dn1 : dn2);
-                const float v = lse3_l2(bq[k], succ1[k] ? bp1 : NINF, skb[k] ? bp2 : NINF);
+                const float v = lse3_fast(bq[k], succ1[k] ? bp1 : NINF, skb[k] ? bp2 : NINF);
                 Rn[k] = in[k] ? v : NINF;
             }
 #pragma unroll
@@ -1117,6 +1132,12 @@ ctc2d_dp4_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict_
     int *meta = reinterpret_cast<int *>(pool + (size_t)q.G * q.T * 33);   // [G] slot, round, ns, Tb, L; [1] rounds
     unsigned *tmask = reinterpret_cast<unsigned *>(meta + 5 * q.G + 1);   // [G][2] classes that occur in the extended target
     int *cls = reinterpret_cast<int *>(tmask + 2 * q.G);          // [G][32] class of label j
+    int *raw = cls + 32 * q.G;                                    // [G][32] targets as stored
+    for (int i = tid; i < Gv * 32; i += blockDim.x) {            // (S <= 32 on this path)
+        const int gg = i >> 5, j = i & 31;
+        int64_t v = j < q.S ? tg[(int64_t)(b0 + gg) * q.tg_sn + (int64_t)j * q.tg_ss] : 0;
+        raw[i] = v < -2147483647 ? -2147483647 : (v > 2147483647 ? 2147483647 : (int)v);
+    }
 
     if (tid == 0) {                                              // slot / round plan of this CTA's samples
         int used = 0, round = 0;
@@ -1149,10 +1170,11 @@ ctc2d_dp4_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict_
             const int b = b0 + g;
             Dp4Ctx w;
             w.q = &q; w.row = tg + (int64_t)b * q.tg_sn; w.Tb = meta[3 * q.G + g]; w.L = meta[4 * q.G + g];
-            w.Qg = Qall + g * q.C; w.Rst = pool + (size_t)meta[g] * q.T * 33; w.pitch = pitch;
+            w.Qg = Qall + g * q.C; w.Rst = pool + (size_t)meta[g] * q.T * 33; w.pitch = pitch; w.raw = raw + g * 32;
             const int ns = meta[2 * q.G + g];
             // labels of this sample (lane j = label j; S <= 32), the classes that occur, and "first label of its class"
-            const int myc = lane < w.L ? clampi(w.row[(int64_t)lane * q.tg_ss], q.C) : -1 - lane;
+            const int rawc = w.raw[lane];
+            const int myc = lane < w.L ? (rawc < 0 ? 0 : (rawc >= q.C ? q.C - 1 : rawc)) : -1 - lane;
             unsigned lo = (lane == 0) ? (q.blank < 32 ? 1u << q.blank : 0u) : 0u;
             unsigned hi = (lane == 0) ? (q.blank >= 32 ? 1u << (q.blank - 32) : 0u) : 0u;
             if (myc >= 0) { if (myc < 32) lo |= 1u << myc; else hi |= 1u << (myc - 32); }
@@ -1172,28 +1194,57 @@ ctc2d_dp4_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict_
         if (rounds > 1) __syncthreads();
     }
     __syncthreads();
-    // ---- factor: (1 - sum) [* go] where the class is present and t < Tb, else 0 (K3 :501-515).  Thread = fixed column
-    // e of the [Gv*C] row (its sample / class bits are loop invariants), loop over t: no divisions in the loop.
-    for (int e = tid; e < Gv * q.C; e += blockDim.x) {
-        const int gg = e / q.C, c = e - gg * q.C;
-        const bool listed = (c < 32 ? (tmask[2 * gg] >> c) : (tmask[2 * gg + 1] >> (c - 32))) & 1u;
-        const int Tb = listed ? meta[3 * q.G + gg] : 0;
-        const float gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + gg) * go_stride] : 1.f;
-        float *col = Qall + e;
-        float *out = (MODE != MODE_GRAD) ? fac_out + (int64_t)b0 * q.C + e : nullptr;
-        const int64_t ostep = (int64_t)q.N * q.C;
-        for (int t = 0; t < q.T; ++t) {
-            float f = 0.f;
-            if (t < Tb) {
-                const float sum = col[t * pitch];
-                if (sum > 0.f) {
-                    f = 1.f - sum;
-                    if (f == 0.f) f = 0x1p-30f;     // exact cancellation must not read as "class absent" (grad == 0 pattern)
-                    f *= gs;
-                }
+    // ---- factor: (1 - sum) [* go] where the class is present and t < Tb, else 0 (K3 :501-515).  Thread = fixed vector
+    // column of the [Gv*C] row (sample / class bits / lengths are loop invariants), loop over t: no divisions in the loop.
+    auto factor_of = [](float sum, float gs) {
+        float f = 0.f;
+        if (sum > 0.f) {
+            f = 1.f - sum;
+            if (f == 0.f) f = 0x1p-30f;             // exact cancellation must not read as "class absent" (grad == 0 pattern)
+            f *= gs;
+        }
+        return f;
+    };
+    const int64_t ostep = (int64_t)q.N * q.C;
+    if (q.vec > 1) {
+        for (int e4 = tid; e4 < (Gv * q.C) >> 2; e4 += blockDim.x) {
+            int tbs[4];
+            float gsv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int e = e4 * 4 + k;
+                const int gg = e / q.C, c = e - gg * q.C;
+                const bool listed = (c < 32 ? (tmask[2 * gg] >> c) : (tmask[2 * gg + 1] >> (c - 32))) & 1u;
+                tbs[k] = listed ? meta[3 * q.G + gg] : 0;
+                gsv[k] = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + gg) * go_stride] : 1.f;
             }
-            if (MODE != MODE_GRAD) out[t * ostep] = f;
-            else col[t * pitch] = f;
+            float *col = Qall + e4 * 4;
+            float *out = (MODE != MODE_GRAD) ? fac_out + (int64_t)b0 * q.C + e4 * 4 : nullptr;
+#pragma unroll 4
+            for (int t = 0; t < q.T; ++t) {
+                const float4 sv = *reinterpret_cast<const float4 *>(col + t * pitch);
+                float4 f;
+                f.x = t < tbs[0] ? factor_of(sv.x, gsv[0]) : 0.f;
+                f.y = t < tbs[1] ? factor_of(sv.y, gsv[1]) : 0.f;
+                f.z = t < tbs[2] ? factor_of(sv.z, gsv[2]) : 0.f;
+                f.w = t < tbs[3] ? factor_of(sv.w, gsv[3]) : 0.f;
+                if (MODE != MODE_GRAD) *reinterpret_cast<float4 *>(out + t * ostep) = f;
+                else *reinterpret_cast<float4 *>(col + t * pitch) = f;
+            }
+        }
+    } else {
+        for (int e = tid; e < Gv * q.C; e += blockDim.x) {
+            const int gg = e / q.C, c = e - gg * q.C;
+            const bool listed = (c < 32 ? (tmask[2 * gg] >> c) : (tmask[2 * gg + 1] >> (c - 32))) & 1u;
+            const int Tb = listed ? meta[3 * q.G + gg] : 0;
+            const float gs = (MODE == MODE_GRAD) ? grad_out[(int64_t)(b0 + gg) * go_stride] : 1.f;
+            float *col = Qall + e;
+            float *out = (MODE != MODE_GRAD) ? fac_out + (int64_t)b0 * q.C + e : nullptr;
+            for (int t = 0; t < q.T; ++t) {
+                const float f = t < Tb ? factor_of(col[t * pitch], gs) : 0.f;
+                if (MODE != MODE_GRAD) out[t * ostep] = f;
+                else col[t * pitch] = f;
+            }
         }
     }
     if (MODE == MODE_GRAD) {
@@ -1382,7 +1433,7 @@ int launch_dp4(Geo q, const float *lp, const int64_t *tg, const int64_t *il, con
     // 8 different banks, and a multiple of 4 whenever the rows are accessed as float4
     auto pitch_of = [&](int g) { int p = g * q.C; while (p % 8 != 4) ++p; return p; };
     auto need = [&](int g) {
-        return sizeof(float) * ((size_t)q.T * pitch_of(g) + (size_t)g * q.T * 33) + sizeof(int) * (size_t)(7 * g + 1 + 32 * g) + 16;
+        return sizeof(float) * ((size_t)q.T * pitch_of(g) + (size_t)g * q.T * 33) + sizeof(int) * (size_t)(7 * g + 1 + 64 * g) + 16;
     };
     int G = 8;
     while (G > 1 && need(G) > (size_t)75 * 1024) --G;
@@ -1393,6 +1444,7 @@ int launch_dp4(Geo q, const float *lp, const int64_t *tg, const int64_t *il, con
     if (MODE == MODE_GRAD && ((uintptr_t)grad % 16) != 0) q.vec = 1;
     const int pitch = pitch_of(G);
     if (pitch % 4) q.vec = 1;
+    if (MODE != MODE_GRAD && ((uintptr_t)fac % 16) != 0) q.vec = 1;
     auto kern = (q.H == 8) ? ctc2d_dp4_kernel<MODE, 8> : ctc2d_dp4_kernel<MODE, 0>;
     { int rc_attr = ensure_dyn_smem((const void *)kern, smem, "ctc2d_dp4 attr"); if (rc_attr) return rc_attr; }
     kern<<<(unsigned)ceil_div(q.N, q.G), 256, smem, st>>>(q, lp, tg, il, tl, go, go_stride, nll, fac, grad, pitch);
