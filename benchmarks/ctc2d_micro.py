@@ -44,6 +44,24 @@ def timeit(fn, flush, iters=20, warm=3):
     return ts[len(ts) // 2], ts[0]
 
 
+def timeit_graph(fn, iters=20):
+    """device time of one call without the host launch gap: `iters` calls captured in a CUDA graph, replayed once"""
+    fn(); fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e3 / iters
+
+
 def main():
     dev = torch.device("cuda:0")
     Ns = [int(a) for a in sys.argv[1:]] or [32, 256, 2048, 16384]
@@ -65,6 +83,7 @@ def main():
             for name, (fn, bytes_per_sample) in kernels.items():
                 med, best = timeit(fn, flush)
                 print(json.dumps({"N": N, "kernel": name, "fast_math": fast, "us_median": round(med, 2),
+                                  "us_graph": round(timeit_graph(fn), 2) if N <= 2048 else None,
                                   "us_min": round(best, 2), "alg_bytes_per_sample": bytes_per_sample,
                                   "GBps_median": round(N * bytes_per_sample / med / 1e3, 1)}), flush=True)
         del lp, la, gfac

@@ -824,6 +824,11 @@ __device__ __forceinline__ float lse3_fast(float a, float b, float c) {
     return m + lg2_ftz(ex2_ftz(a - m) + ex2_ftz(b - m) + ex2_ftz(c - m));
 }
 
+#ifndef MR_DP4_PREFETCH
+#define MR_DP4_PREFETCH 1
+#endif
+constexpr bool kDp4Prefetch = MR_DP4_PREFETCH != 0;
+
 struct Dp4Ctx {
     const Geo *q;
     const int64_t *row;       // targets of this sample
@@ -835,11 +840,8 @@ struct Dp4Ctx {
 };
 
 // LSE over 8 heights of one 4-wide vector column, result in log2 units.
-template <typename HS>      // HS = int when 8 * N * C fits 31 bits (one IMAD.WIDE per row address), else int64_t
-__device__ __forceinline__ void lse_rows8_l2(const float *base, HS hs, float *dst) {
-    float4 x[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = __ldg(reinterpret_cast<const float4 *>(base + u * hs));
+// LSE over 8 heights of one 4-wide vector column (already in registers), result in log2 units.
+__device__ __forceinline__ void lse8_l2(const float4 *x, float *dst) {
     float out[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -859,8 +861,19 @@ __device__ __forceinline__ void lse_rows8_l2(const float *base, HS hs, float *ds
     }
     *reinterpret_cast<float4 *>(dst) = make_float4(out[0], out[1], out[2], out[3]);
 }
-
+template <typename HS>      // HS = int when 8 * N * C fits 31 bits (one IMAD.WIDE per row address), else int64_t
+__device__ __forceinline__ void load_rows8(const float *base, HS hs, float4 *x) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = __ldg(reinterpret_cast<const float4 *>(base + u * hs));
+}
 template <typename HS>
+__device__ __forceinline__ void lse_rows8_l2(const float *base, HS hs, float *dst) {
+    float4 x[8];
+    load_rows8<HS>(base, hs, x);
+    lse8_l2(x, dst);
+}
+
+template <typename HS, bool PREFETCH>
 __device__ __forceinline__ void phase_q8_l2_impl(const Geo &q, const float *__restrict__ lp, float *Qall, int b0, int Gv, int pitch) {
     const int nvec = (Gv * q.C) >> 2;                        // callers guarantee (Gv*C) % 4 == 0 on this path
     const HS hs = (HS)((int64_t)q.N * q.C);
@@ -873,7 +886,22 @@ __device__ __forceinline__ void phase_q8_l2_impl(const Geo &q, const float *__re
             const float *src = cta + (int64_t)t0 * 8 * (int64_t)hs + j * 4;
             float *dst = Qall + t0 * pitch + j * 4;
             const int64_t sstep = (int64_t)tpr * 8 * (int64_t)hs;
-            for (int t = t0; t < q.T; t += tpr, src += sstep, dst += tpr * pitch) lse_rows8_l2<HS>(src, hs, dst);
+            if (PREFETCH) {
+                // the loads of the NEXT column are in flight while this one is reduced (32 more registers)
+                float4 xa[8], xb[8];
+                load_rows8<HS>(src, hs, xa);
+                int t = t0;
+                for (; t + tpr < q.T; t += 2 * tpr) {
+                    load_rows8<HS>(src + sstep, hs, xb);
+                    lse8_l2(xa, dst);
+                    if (t + 2 * tpr < q.T) load_rows8<HS>(src + 2 * sstep, hs, xa);
+                    lse8_l2(xb, dst + tpr * pitch);
+                    src += 2 * sstep; dst += 2 * tpr * pitch;
+                }
+                if (t < q.T) lse8_l2(xa, dst);
+            } else {
+                for (int t = t0; t < q.T; t += tpr, src += sstep, dst += tpr * pitch) lse_rows8_l2<HS>(src, hs, dst);
+            }
         }
     } else {
         for (int i = tid; i < q.T * nvec; i += nth) {
@@ -883,8 +911,8 @@ __device__ __forceinline__ void phase_q8_l2_impl(const Geo &q, const float *__re
     }
 }
 __device__ __forceinline__ void phase_q8_l2(const Geo &q, const float *__restrict__ lp, float *Qall, int b0, int Gv, int pitch) {
-    if ((int64_t)q.N * q.C < (1 << 27)) phase_q8_l2_impl<int>(q, lp, Qall, b0, Gv, pitch);
-    else phase_q8_l2_impl<int64_t>(q, lp, Qall, b0, Gv, pitch);
+    if ((int64_t)q.N * q.C < (1 << 27)) phase_q8_l2_impl<int, kDp4Prefetch>(q, lp, Qall, b0, Gv, pitch);
+    else phase_q8_l2_impl<int64_t, false>(q, lp, Qall, b0, Gv, pitch);
 }
 
 template <int NS>
@@ -1128,8 +1156,9 @@ ctc2d_dp4_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict_
     const int b0 = blockIdx.x * q.G;
     const int Gv = min(q.G, q.N - b0);
     float *Qall = reinterpret_cast<float *>(smem_raw);           // [T][pitch]  Q2, then per-class sums, then factors
-    float *pool = Qall + q.T * pitch;                             // [G slots][T][33]
-    int *meta = reinterpret_cast<int *>(pool + (size_t)q.G * q.T * 33);   // [G] slot, round, ns, Tb, L; [1] rounds
+    float *pool = Qall + q.T * pitch;                             // [max(G,3) slots][T][33]
+    const int nslots = q.G > 3 ? q.G : 3;                         // a single sample may need 3 slots (S = 32: 65 states)
+    int *meta = reinterpret_cast<int *>(pool + (size_t)nslots * q.T * 33);   // [G] slot, round, ns, Tb, L; [1] rounds
     unsigned *tmask = reinterpret_cast<unsigned *>(meta + 5 * q.G + 1);   // [G][2] classes that occur in the extended target
     int *cls = reinterpret_cast<int *>(tmask + 2 * q.G);          // [G][32] class of label j
     int *raw = cls + 32 * q.G;                                    // [G][32] targets as stored
@@ -1152,7 +1181,7 @@ ctc2d_dp4_kernel(Geo q, const float *__restrict__ lp, const int64_t *__restrict_
                 L = (int)L64; Tb = (int)T64;
                 ns = (2 * L + 1 + 31) >> 5;
             }
-            if (used + ns > q.G) { ++round; used = 0; }
+            if (used + ns > nslots) { ++round; used = 0; }
             meta[g] = used; meta[q.G + g] = round; meta[2 * q.G + g] = ns; meta[3 * q.G + g] = Tb; meta[4 * q.G + g] = L;
             used += ns;
         }
@@ -1433,9 +1462,13 @@ int launch_dp4(Geo q, const float *lp, const int64_t *tg, const int64_t *il, con
     // 8 different banks, and a multiple of 4 whenever the rows are accessed as float4
     auto pitch_of = [&](int g) { int p = g * q.C; while (p % 8 != 4) ++p; return p; };
     auto need = [&](int g) {
-        return sizeof(float) * ((size_t)q.T * pitch_of(g) + (size_t)g * q.T * 33) + sizeof(int) * (size_t)(7 * g + 1 + 64 * g) + 16;
+        return sizeof(float) * ((size_t)q.T * pitch_of(g) + (size_t)(g > 3 ? g : 3) * q.T * 33) + sizeof(int) * (size_t)(7 * g + 1 + 64 * g) + 16;
     };
     int G = 8;
+    // small batches: fewer samples per CTA so that the grid still covers the SMs; the N = 32 launch of a
+    // cfg-3 rank is 16 CTAs of 2 samples instead of 4 CTAs of 8, and its phase Q is 4x shorter
+    const int64_t want_ctas = (int64_t)sm_count();
+    while (G > 2 && ceil_div(q.N, G) < want_ctas) G -= 2;
     while (G > 1 && need(G) > (size_t)75 * 1024) --G;
     const size_t smem = need(G);
     if (smem > (size_t)smem_limit()) return MR_ERR_UNSUPPORTED;
