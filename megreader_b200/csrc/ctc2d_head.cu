@@ -17,6 +17,8 @@
 // 2*C*H*W*4 + T*C*4 with gfac.
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <algorithm>
 
 namespace {
 using namespace mr;
@@ -253,6 +255,290 @@ __global__ void ctc2d_head_mask_bwd_kernel(int N, int H, int W, const float *__r
     for (int k = 0; k < H; ++k) gp[(int64_t)k * W] -= ex2f((m[(int64_t)k * W] - mx) * kLog2e) * inv * tot;
 }
 
+// =====================================================================================================
+// Round-2 kernels: one WARP per slab (sample n, height h, 32 columns), lane = column.
+//
+// ncu / timing of the block-tile kernels above (profiles/ctc2d_head_micro_r1.jsonl): 31 % (forward) and 17 % (backward)
+// of the HBM roofline -- three barrier-separated phases per block, ~1000 instructions per thread around 4-byte accesses.
+// Here a lane keeps ITS column's C class logits in registers: every global read of the NCHW side is a coalesced 128-byte
+// row straight into registers (C + 2H independent loads in flight per lane, no staging), the softmax over C and the
+// log-softmax of the mask column are register arithmetic, and only the (T,H,N,C) side -- whose contiguous direction is
+// the class -- goes through a per-warp shared-memory transpose (odd pitch: conflict-free both ways).  No block barrier,
+// no phases: the SM overlaps the loads of some warps with the arithmetic / stores of others.  CR = register rows (C <= CR);
+// larger alphabets use the block-tile kernels above, and beyond their shared-memory tile the class-tiled kernels below.
+// =====================================================================================================
+
+__device__ __forceinline__ float mask_logsoftmax_col(const float *__restrict__ mcol, int H, int W, int h, bool valid) {
+    // mcol = mask_logits + n*H*W + w ; two passes over the H rows (L1/L2 hits the second time): no register array
+    if (!valid) return 0.f;
+    float mx = -INFINITY;
+    const float *p = mcol;
+    for (int k = 0; k < H; ++k, p += W) mx = fmaxf(mx, __ldg(p));
+    const float off = mx * kLog2e;
+    float s = 0.f, mine = 0.f;
+    p = mcol;
+    for (int k = 0; k < H; ++k, p += W) {
+        const float v = __ldg(p);
+        s += ex2f(fmaf(v, kLog2e, -off));
+        if (k == h) mine = v;
+    }
+    return mine - mx - lg2f(s) * kLn2;
+}
+
+template <int CR, int kWarpsPerBlock>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, CR <= 40 ? 3 : 2)
+ctc2d_head_fwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, const float *__restrict__ cls_logits,
+                           float log_tiny, float *__restrict__ lp) {
+    constexpr int PITCH = CR + 1;                         // odd: lanes over columns write, lanes over classes read
+    __shared__ float sm_all[kWarpsPerBlock][32 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *sm = sm_all[warp];
+    const int wtiles = (g.W + 31) >> 5;
+    const int64_t nslabs = (int64_t)g.N * g.H * wtiles;
+    const int64_t HW = (int64_t)g.H * g.W;
+    for (int64_t slab = (int64_t)blockIdx.x * kWarpsPerBlock + warp; slab < nslabs; slab += (int64_t)gridDim.x * kWarpsPerBlock) {
+        // slab order: sample fastest -- the warps of a block (and neighbouring blocks) write the (T,H,N,C) rows of consecutive
+        // samples at the same time, so the 152-byte per-sample pieces of a row merge into full sectors in L2
+        const int n = (int)(slab % g.N);
+        const int64_t hw = slab / g.N;
+        const int wt = (int)(hw % wtiles);
+        const int h = (int)(hw / wtiles);
+        const int w0 = wt << 5, w = w0 + lane;
+        const bool valid = w < g.W;
+        const float *zp = cls_logits + ((int64_t)n * g.C * g.H + h) * g.W + w;      // + c * H * W
+        float zr[CR];
+        {
+            const float *p = zp;
+#pragma unroll
+            for (int c = 0; c < CR; ++c, p += HW) zr[c] = (valid && c < g.C) ? __ldg(p) : -INFINITY;
+        }
+        const float mlog = mask_logsoftmax_col(mask_logits + (int64_t)n * HW + w, g.H, g.W, h, valid);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CR; ++c) mx = fmaxf(mx, zr[c]);
+        const float off = mx * kLog2e;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CR; c += 2) {
+            s0 += ex2f(fmaf(zr[c], kLog2e, -off));
+            if (c + 1 < CR) s1 += ex2f(fmaf(zr[c + 1], kLog2e, -off));
+        }
+        // log(mask * classify) = z - max - ln(sum) + log mask ; one exponential per element in total
+        const float shift = mlog - mx - lg2f(s0 + s1) * kLn2;
+#pragma unroll
+        for (int c = 0; c < CR; ++c)
+            if (c < g.C) sm[lane * PITCH + c] = fmaxf(zr[c] + shift, log_tiny);
+        __syncwarp();
+        // (T,H,N,C): column w0+wl of this slab = C contiguous floats at (((w0+wl)*H + h)*N + n)*C
+        const int ncol = min(32, g.W - w0);
+        float *dst = lp + (((int64_t)w0 * g.H + h) * g.N + n) * g.C + lane;
+        const int64_t cstep = (int64_t)g.H * g.N * g.C;
+        const bool c0ok = lane < g.C, c1ok = lane + 32 < g.C;              // C <= CR <= 64: two class passes
+        const float *src = sm + lane;
+#pragma unroll 4
+        for (int wl = 0; wl < ncol; ++wl, dst += cstep, src += PITCH) {
+            if (c0ok) dst[0] = src[0];
+            if (c1ok) dst[32] = src[32];
+        }
+        __syncwarp();
+    }
+}
+
+template <int CR, bool FACTORED, int kWarpsPerBlock>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)     // 3 blocks / SM (80 registers) spills ~230 bytes per thread: slower
+ctc2d_head_bwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, const float *__restrict__ cls_logits,
+                           const float *__restrict__ dlp, const float *__restrict__ gfac, const float *__restrict__ go,
+                           int64_t go_stride, float tiny, float *__restrict__ dcls, float *__restrict__ gsum) {
+    constexpr int PITCH = CR + 1;
+    __shared__ float sm_all[kWarpsPerBlock][32 * PITCH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *sm = sm_all[warp];
+    const int wtiles = (g.W + 31) >> 5;
+    const int64_t nslabs = (int64_t)g.N * g.H * wtiles;
+    const int64_t HW = (int64_t)g.H * g.W;
+    for (int64_t slab = (int64_t)blockIdx.x * kWarpsPerBlock + warp; slab < nslabs; slab += (int64_t)gridDim.x * kWarpsPerBlock) {
+        // slab order: sample fastest -- the warps of a block (and neighbouring blocks) write the (T,H,N,C) rows of consecutive
+        // samples at the same time, so the 152-byte per-sample pieces of a row merge into full sectors in L2
+        const int n = (int)(slab % g.N);
+        const int64_t hw = slab / g.N;
+        const int wt = (int)(hw % wtiles);
+        const int h = (int)(hw / wtiles);
+        const int w0 = wt << 5, w = w0 + lane;
+        const bool valid = w < g.W;
+        // class logits of this lane's column first: C independent 128-byte-row loads in flight while the tile below is staged
+        const float *zp = cls_logits + ((int64_t)n * g.C * g.H + h) * g.W + w;
+        float zr[CR];
+        {
+            const float *p = zp;
+#pragma unroll
+            for (int c = 0; c < CR; ++c, p += HW) zr[c] = (valid && c < g.C) ? __ldg(p) : -INFINITY;
+        }
+        // upstream gradient (explicit [T,H,N,C]) or CTC factor ([T,N,C], shared by the heights): rows of C contiguous
+        // floats per column -> lanes over classes load (16 columns = 32 loads in flight), lanes over columns read back
+        {
+            const int ncol = min(32, g.W - w0);
+            const float *src = (FACTORED ? gfac + ((int64_t)w0 * g.N + n) * g.C : dlp + (((int64_t)w0 * g.H + h) * g.N + n) * g.C) + lane;
+            const int64_t cstep = FACTORED ? (int64_t)g.N * g.C : (int64_t)g.H * g.N * g.C;
+            const bool c0ok = lane < g.C, c1ok = lane + 32 < g.C;
+            float *d = sm + lane;
+#pragma unroll 1
+            for (int wl0 = 0; wl0 < 32; wl0 += 16, d += 16 * PITCH) {
+                float a[16], b[16];
+                const float *q = src + (int64_t)wl0 * cstep;
+#pragma unroll
+                for (int u = 0; u < 16; ++u, q += cstep) {
+                    const bool in = wl0 + u < ncol;
+                    a[u] = (in && c0ok) ? __ldg(q) : 0.f;
+                    b[u] = (in && c1ok) ? __ldg(q + 32) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    d[u * PITCH] = a[u];
+                    if (32 + lane < CR) d[u * PITCH + 32] = b[u];
+                }
+            }
+        }
+        const float maskp = ex2f(mask_logsoftmax_col(mask_logits + (int64_t)n * HW + w, g.H, g.W, h, valid) * kLog2e);
+        const float gout = (FACTORED && valid) ? __ldg(go + (int64_t)n * go_stride) : 1.f;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CR; ++c) mx = fmaxf(mx, zr[c]);
+        const float off = mx * kLog2e;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CR; c += 2) {
+            zr[c] = ex2f(fmaf(zr[c], kLog2e, -off));          // zr becomes the un-normalised class probability
+            s0 += zr[c];
+            if (c + 1 < CR) { zr[c + 1] = ex2f(fmaf(zr[c + 1], kLog2e, -off)); s1 += zr[c + 1]; }
+        }
+        const float inv = 1.f / (s0 + s1);
+        __syncwarp();
+        // probability domain: p = classify prob, q = mask * p (what the reference clamps at tiny); max(q, tiny) passes no
+        // gradient where q <= tiny.  With the CTC factor the upstream gradient is exp(log_probs) * gfac * go = q * gfac * go.
+        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CR; ++c) {                    // g_c replaces u_c in this lane's shared-memory row
+            zr[c] *= inv;
+            const float q = zr[c] * maskp;
+            const float u = sm[lane * PITCH + c];
+            const float gc = (c < g.C && q > tiny) ? (FACTORED ? q * u * gout : u) : 0.f;
+            sm[lane * PITCH + c] = gc;
+            if (c & 1) t1 += gc; else t0 += gc;
+        }
+        const float tot = t0 + t1;
+        if (valid) {
+            float *op = dcls + ((int64_t)n * g.C * g.H + h) * g.W + w;
+#pragma unroll
+            for (int c = 0; c < CR; ++c, op += HW)
+                if (c < g.C) *op = sm[lane * PITCH + c] - zr[c] * tot;
+            gsum[((int64_t)n * g.H + h) * g.W + w] = tot;
+        }
+        __syncwarp();
+    }
+}
+
+// =====================================================================================================
+// Any alphabet (ChineseCharset, concern/charsets.py:65-78: ~5 k classes) and any H, W: class-TILED kernels.  A block owns one
+// (sample, height, 32-column tile); warp k streams the classes k, k+8, ... (lane = column: 128-byte rows), keeping an online
+// (max, sum) per column; the block combines the eight partial results, then re-streams the logits (L2) and emits / consumes
+// the (T,H,N,C) side through a 32 x 32 transposing tile.  ~2x the algorithmic reads: a fallback, not the CRNN-2D path.
+// =====================================================================================================
+__device__ __forceinline__ void online_merge(float &m, float &s, float m2, float s2) {
+    const float nm = fmaxf(m, m2);
+    if (nm == -INFINITY) { m = nm; s = 0.f; return; }
+    s = s * ex2f((m - nm) * kLog2e) + s2 * ex2f((m2 - nm) * kLog2e);
+    m = nm;
+}
+
+template <int MODE>      // 0 = forward, 1 = backward with explicit gradient, 2 = backward with the CTC factor
+__global__ void __launch_bounds__(256)
+ctc2d_head_tiled_kernel(HeadGeo g, const float *__restrict__ mask_logits, const float *__restrict__ cls_logits,
+                        const float *__restrict__ dlp, const float *__restrict__ gfac, const float *__restrict__ go,
+                        int64_t go_stride, float tiny, float log_tiny, float *__restrict__ lp, float *__restrict__ dcls,
+                        float *__restrict__ gsum) {
+    __shared__ float red_m[8][32], red_s[8][32], tile[32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wtiles = (g.W + 31) >> 5;
+    const int wt = blockIdx.x % wtiles;
+    const int h = (blockIdx.x / wtiles) % g.H;
+    const int n = blockIdx.x / (wtiles * g.H);
+    const int w0 = wt << 5, w = w0 + lane;
+    const bool valid = w < g.W;
+    const int ncol = min(32, g.W - w0);
+    const int64_t HW = (int64_t)g.H * g.W;
+    const float *zp = cls_logits + ((int64_t)n * g.C * g.H + h) * g.W + w;
+    // pass 1: per-column (max, sum) over all classes
+    float m = -INFINITY, s = 0.f;
+    for (int c = warp; c < g.C; c += 8) {
+        const float z = valid ? __ldg(zp + (int64_t)c * HW) : -INFINITY;
+        online_merge(m, s, z, 1.f);
+    }
+    red_m[warp][lane] = m; red_s[warp][lane] = s;
+    __syncthreads();
+    m = red_m[0][lane]; s = red_s[0][lane];
+    for (int k = 1; k < 8; ++k) online_merge(m, s, red_m[k][lane], red_s[k][lane]);
+    const float mlog = mask_logsoftmax_col(mask_logits + (int64_t)n * HW + w, g.H, g.W, h, valid);
+    const float shift = mlog - m - lg2f(s) * kLn2;            // log_probs = z + shift (before the clamp)
+    const float inv = 1.f / s, maskp = ex2f(mlog * kLog2e);
+    const float gout = (MODE == 2 && valid) ? __ldg(go + (int64_t)n * go_stride) : 1.f;
+    const int64_t cstep_out = (int64_t)g.H * g.N * g.C;
+    if (MODE == 0) {
+        // pass 2: 32 classes x 32 columns at a time through the transposing tile
+        for (int c0 = 0; c0 < g.C; c0 += 32) {
+            for (int k = warp; k < 32; k += 8) {
+                const int c = c0 + k;
+                float v = 0.f;
+                if (valid && c < g.C) v = fmaxf(__ldg(zp + (int64_t)c * HW) + shift, log_tiny);
+                tile[k][lane] = v;
+            }
+            __syncthreads();
+            for (int wl = warp; wl < ncol; wl += 8) {
+                const int c = c0 + lane;
+                if (c < g.C) lp[((int64_t)(w0 + wl) * g.H + h) * g.N * g.C + (int64_t)n * g.C + c] = tile[lane][wl];
+            }
+            __syncthreads();
+        }
+        (void)cstep_out;
+    } else {
+        // pass 2a: tot = sum_c g_c ; pass 2b: d z_c = g_c - p_c * tot.  The upstream rows are re-read for 2b (L2).
+        float tot = 0.f;
+        for (int rep = 0; rep < 2; ++rep) {
+            float acc = 0.f;
+            for (int c0 = 0; c0 < g.C; c0 += 32) {
+                for (int wl = warp; wl < ncol; wl += 8) {     // lanes over classes: coalesced upstream rows
+                    const int c = c0 + lane;
+                    float u = 0.f;
+                    if (c < g.C)
+                        u = MODE == 2 ? __ldg(gfac + ((int64_t)(w0 + wl) * g.N + n) * g.C + c)
+                                      : __ldg(dlp + (((int64_t)(w0 + wl) * g.H + h) * g.N + n) * g.C + c);
+                    tile[lane][wl] = u;
+                }
+                __syncthreads();
+                for (int k = warp; k < 32; k += 8) {          // lanes over columns
+                    const int c = c0 + k;
+                    if (valid && c < g.C) {
+                        const float p = ex2f((__ldg(zp + (int64_t)c * HW) - m) * kLog2e) * inv;
+                        const float q = p * maskp;
+                        const float u = tile[k][lane];
+                        const float gg = q > tiny ? (MODE == 2 ? q * u * gout : u) : 0.f;
+                        if (rep == 0) acc += gg;
+                        else dcls[((int64_t)n * g.C + c) * HW + (int64_t)h * g.W + w] = gg - p * tot;
+                    }
+                }
+                __syncthreads();
+            }
+            if (rep == 0) {
+                red_s[warp][lane] = acc;
+                __syncthreads();
+                tot = 0.f;
+                for (int k = 0; k < 8; ++k) tot += red_s[k][lane];
+                if (warp == 0 && valid) gsum[((int64_t)n * g.H + h) * g.W + w] = tot;
+                __syncthreads();
+            }
+        }
+    }
+}
+
 int pick_nt(int C, int H, int tiles, size_t *smem) {
     // samples per block: as many as keep the logits tiles within 96 KB (so that >= 2 blocks share an SM), at most 8
     auto bytes = [&](int nt) { return (size_t)nt * ((size_t)C * tiles + H) * (kTW + 1) * sizeof(float); };
@@ -272,12 +558,28 @@ int mr_ctc2d_head_fwd_f32(const float *mask_logits, const float *cls_logits, int
     if (N == 0) return MR_OK;
     if (!mask_logits || !cls_logits || !log_probs) return MR_ERR_NULL_POINTER;
     HeadGeo g{N, C, H, W, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    static const bool old_only = getenv("MR_HEAD_BLOCK_TILE") != nullptr;
+    if (C <= 64 && !old_only) {
+        const int64_t nslabs = (int64_t)N * H * ceil_div(W, 32);
+        const int wpb = C <= 40 ? 8 : 4;
+        const int64_t blocks = std::min<int64_t>(ceil_div(nslabs, wpb), (int64_t)sm_count() * 32);
+        if (C <= 40) ctc2d_head_fwd_warp_kernel<40, 8><<<(unsigned)blocks, 256, 0, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
+        else ctc2d_head_fwd_warp_kernel<64, 4><<<(unsigned)blocks, 128, 0, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
+        return check_launch("ctc2d_head_fwd_warp_kernel");
+    }
     size_t smem;
     g.NT = pick_nt(C, H, 1, &smem);
-    if (!g.NT || H > 65535 || ceil_div(N, g.NT) > 65535) return MR_ERR_UNSUPPORTED;
+    if (!g.NT || H > 65535 || ceil_div(N, g.NT) > 65535) {
+        const int64_t blocks = (int64_t)N * H * ceil_div(W, 32);
+        if (blocks > 0x7fffffffLL) return MR_ERR_UNSUPPORTED;
+        ctc2d_head_tiled_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(g, mask_logits, cls_logits, nullptr, nullptr, nullptr, 0, tiny,
+                                                                    logf(tiny), log_probs, nullptr, nullptr);
+        return check_launch("ctc2d_head_tiled_kernel");
+    }
     { int rc_attr = ensure_dyn_smem((const void *)ctc2d_head_fwd_kernel, smem, "head fwd smem"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)ceil_div(W, kTW), (unsigned)H, (unsigned)ceil_div(N, g.NT));
-    ctc2d_head_fwd_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
+    ctc2d_head_fwd_kernel<<<grid, kThreads, smem, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
     return check_launch("ctc2d_head_fwd_kernel");
 }
 
@@ -291,10 +593,31 @@ int mr_ctc2d_head_bwd_f32(const float *mask_logits, const float *cls_logits, con
     const bool factored = grad_log_probs == nullptr;
     if (factored && (!gfac || !grad_out)) return MR_ERR_NULL_POINTER;
     HeadGeo g{N, C, H, W, 0};
-    size_t smem;
-    g.NT = pick_nt(C, H, 2, &smem);
-    if (!g.NT || H > 65535 || ceil_div(N, g.NT) > 65535) return MR_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool old_only = getenv("MR_HEAD_BLOCK_TILE") != nullptr;
+    size_t smem = 0;
+    g.NT = pick_nt(C, H, 2, &smem);
+    const bool tile_ok = g.NT && H <= 65535 && ceil_div(N, g.NT) <= 65535;
+    if (C <= 64 && !old_only) {
+        const int64_t nslabs = (int64_t)N * H * ceil_div(W, 32);
+        const int wpb = C <= 40 ? 8 : 4;
+        const int64_t blocks = std::min<int64_t>(ceil_div(nslabs, wpb), (int64_t)sm_count() * 32);
+#define MR_HEAD_BWD(CRV, FACV, WPB)                                                                                          \
+        ctc2d_head_bwd_warp_kernel<CRV, FACV, WPB><<<(unsigned)blocks, WPB * 32, 0, st>>>(                                     \
+            g, mask_logits, cls_logits, grad_log_probs, gfac, grad_out, grad_out_stride, tiny, grad_cls_logits, grad_mask_logits)
+        if (C <= 40) { if (factored) MR_HEAD_BWD(40, true, 8); else MR_HEAD_BWD(40, false, 8); }
+        else { if (factored) MR_HEAD_BWD(64, true, 4); else MR_HEAD_BWD(64, false, 4); }
+#undef MR_HEAD_BWD
+    } else if (!tile_ok) {
+        const int64_t blocks = (int64_t)N * H * ceil_div(W, 32);
+        if (blocks > 0x7fffffffLL) return MR_ERR_UNSUPPORTED;
+        if (factored)
+            ctc2d_head_tiled_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(g, mask_logits, cls_logits, nullptr, gfac, grad_out, grad_out_stride,
+                                                                        tiny, logf(tiny), nullptr, grad_cls_logits, grad_mask_logits);
+        else
+            ctc2d_head_tiled_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(g, mask_logits, cls_logits, grad_log_probs, nullptr, nullptr, 0,
+                                                                        tiny, logf(tiny), nullptr, grad_cls_logits, grad_mask_logits);
+    } else {
     {
         int rc_attr = factored ? ensure_dyn_smem((const void *)ctc2d_head_bwd_kernel<true>, smem, "head bwd smem")
                                : ensure_dyn_smem((const void *)ctc2d_head_bwd_kernel<false>, smem, "head bwd smem");
@@ -307,6 +630,7 @@ int mr_ctc2d_head_bwd_f32(const float *mask_logits, const float *cls_logits, con
     else
         ctc2d_head_bwd_kernel<false><<<grid, kThreads, smem, st>>>(g, mask_logits, cls_logits, grad_log_probs, nullptr, nullptr, 0,
                                                                     tiny, grad_cls_logits, grad_mask_logits);
+    }
     int rc = check_launch("ctc2d_head_bwd_kernel");
     if (rc) return rc;
     const int64_t cols = (int64_t)N * W;

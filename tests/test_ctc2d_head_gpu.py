@@ -43,7 +43,9 @@ def test_against_reference_golden(cuda, tag):
         assert _mismatch_fraction(m.grad, g[tag + ".grad_mask_logits"]) < 2e-3
 
 
-@pytest.mark.parametrize("shape", [(5, 38, 8, 32), (3, 38, 1, 37), (9, 100, 3, 65), (17, 7, 5, 1), (1, 38, 8, 32)])
+@pytest.mark.parametrize("shape", [(5, 38, 8, 32), (3, 38, 1, 37), (9, 100, 3, 65), (17, 7, 5, 1), (1, 38, 8, 32),
+                                   (3, 64, 4, 40), (2, 41, 3, 33),        # 64-register-row variant of the warp kernels
+                                   (2, 2000, 2, 37)])                     # large alphabet: class-tiled kernels
 def test_against_oracle_ragged(cuda, shape):
     N, C, H, W = shape
     rng = np.random.RandomState(N * 1000 + C)
@@ -83,6 +85,32 @@ def test_fused_loss_equals_composition(cuda):
     _close(nll1, nll2.detach().cpu().numpy(), "nll", 1e-6)
     _close(z1.grad, z2.grad.cpu().numpy(), "d classify logits", 2e-5)
     _close(m1.grad, m2.grad.cpu().numpy(), "d mask logits", 2e-5)
+
+
+def test_large_alphabet_fused_loss(cuda):
+    """ChineseCharset-sized head (concern/charsets.py:65-78): logits -> loss through the class-tiled epilogue kernels and the
+    CTC factor equals the unfused composition."""
+    torch.manual_seed(4)
+    N, C, H, W, S = 3, 5000, 2, 12, 8
+    m = torch.randn(N, 1, H, W, device=cuda)
+    z = torch.randn(N, C, H, W, device=cuda) * 2
+    lengths = torch.tensor([3, 5, 1], device=cuda)
+    targets = torch.zeros(N, S, dtype=torch.long, device=cuda)
+    for b in range(N):
+        targets[b, :lengths[b]] = torch.randint(2, C, (int(lengths[b]),), device=cuda)
+    il = torch.full((N,), W, dtype=torch.long, device=cuda)
+    m1, z1 = m.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    nll1, lp1 = ctc2d_head.head_loss(m1, z1, targets, il, lengths, 0)
+    nll1.sum().backward()
+    m2, z2 = m.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    lp2 = ctc2d_head.head_log_probs(m2, z2)
+    ref = head_port.head_log_probs(m.cpu().double(), z.cpu().double()).float()
+    _close(lp2, ref.numpy(), "log_probs")
+    nll2 = ctc2d.ctc_loss_2d(lp2, targets, il, lengths)
+    nll2.sum().backward()
+    _close(nll1, nll2.detach().cpu().numpy(), "nll", 1e-5)
+    _close(z1.grad, z2.grad.cpu().numpy(), "d classify logits", 5e-5)
+    _close(m1.grad, m2.grad.cpu().numpy(), "d mask logits", 5e-5)
 
 
 def test_full_size_normalisation_property(cuda):

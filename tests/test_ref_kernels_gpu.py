@@ -36,6 +36,8 @@ CTC_CASES = [
     (35, 64, 1, 5, 38, 32, 20, False, 0.0),     # H = 1 (1D CTC through the 2D op)
     (36, 8, 3, 3, 4001, 4, 4, False, 0.0),      # large alphabet
     (37, 32, 8, 2048, 38, 32, 12, False, 0.0),  # the CRNN-2D head's batch
+    (38, 32, 8, 6, 5000, 32, 32, True, 0.0),    # ChineseCharset-sized alphabet at the real T / H, targets up to 32 labels
+    (39, 32, 8, 11, 38, 32, 32, False, 0.0),    # longest targets (65 states: 3 states per lane, slot rounds)
 ]
 
 
