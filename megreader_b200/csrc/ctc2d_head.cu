@@ -31,6 +31,14 @@ struct HeadGeo { int N, C, H, W, NT; };
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+// base + i * stride_bytes with a 32 x 32 -> 64-bit multiply-add: ONE IMAD.WIDE.U32 per address (the plain pointer + int form
+// cost 5-7 integer instructions per access in these kernels: 55 % of all issued instructions, profiles/ctc2d_head_r2_summary.md)
+__device__ __forceinline__ const float *at(const float *base, unsigned i, unsigned stride_bytes) {
+    return reinterpret_cast<const float *>(reinterpret_cast<const char *>(base) + (uint64_t)i * stride_bytes);
+}
+__device__ __forceinline__ float *at(float *base, unsigned i, unsigned stride_bytes) {
+    return reinterpret_cast<float *>(reinterpret_cast<char *>(base) + (uint64_t)i * stride_bytes);
+}
 
 // mask tile mt[nl][k][w] <- mask_logits[n0+nl, 0, k, w0+w]: all heights of the block's samples / columns (the softmax over
 // H needs every height); loaded with the logits tile so that no thread waits on a chain of dependent global loads.
@@ -285,7 +293,8 @@ __device__ __forceinline__ float mask_logsoftmax_col(const float *__restrict__ m
     return mine - mx - lg2f(s) * kLn2;
 }
 
-template <int CR, int kWarpsPerBlock>
+// CX > 0: the alphabet size is exactly CX (compile time: every class predicate and address folds); CX = 0: runtime C <= CR.
+template <int CR, int kWarpsPerBlock, int CX>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, CR <= 40 ? 3 : 2)
 ctc2d_head_fwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, const float *__restrict__ cls_logits,
                            float log_tiny, float *__restrict__ lp) {
@@ -293,9 +302,11 @@ ctc2d_head_fwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, con
     __shared__ float sm_all[kWarpsPerBlock][32 * PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *sm = sm_all[warp];
+    const int C = CX > 0 ? CX : g.C;
     const int wtiles = (g.W + 31) >> 5;
     const int64_t nslabs = (int64_t)g.N * g.H * wtiles;
     const int64_t HW = (int64_t)g.H * g.W;
+    const unsigned HWB = (unsigned)(g.H * g.W) * 4u;       // byte strides; the host checks that they fit in 32 bits
     for (int64_t slab = (int64_t)blockIdx.x * kWarpsPerBlock + warp; slab < nslabs; slab += (int64_t)gridDim.x * kWarpsPerBlock) {
         // slab order: sample fastest -- the warps of a block (and neighbouring blocks) write the (T,H,N,C) rows of consecutive
         // samples at the same time, so the 152-byte per-sample pieces of a row merge into full sectors in L2
@@ -305,13 +316,10 @@ ctc2d_head_fwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, con
         const int h = (int)(hw / wtiles);
         const int w0 = wt << 5, w = w0 + lane;
         const bool valid = w < g.W;
-        const float *zp = cls_logits + ((int64_t)n * g.C * g.H + h) * g.W + w;      // + c * H * W
+        const float *zp = cls_logits + ((int64_t)n * C * g.H + h) * g.W + w;      // + c * H * W
         float zr[CR];
-        {
-            const float *p = zp;
 #pragma unroll
-            for (int c = 0; c < CR; ++c, p += HW) zr[c] = (valid && c < g.C) ? __ldg(p) : -INFINITY;
-        }
+        for (int c = 0; c < CR; ++c) zr[c] = (valid && c < C) ? __ldg(at(zp, c, HWB)) : -INFINITY;
         const float mlog = mask_logsoftmax_col(mask_logits + (int64_t)n * HW + w, g.H, g.W, h, valid);
         float mx = -INFINITY;
 #pragma unroll
@@ -327,24 +335,25 @@ ctc2d_head_fwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, con
         const float shift = mlog - mx - lg2f(s0 + s1) * kLn2;
 #pragma unroll
         for (int c = 0; c < CR; ++c)
-            if (c < g.C) sm[lane * PITCH + c] = fmaxf(zr[c] + shift, log_tiny);
+            if (c < C) sm[lane * PITCH + c] = fmaxf(zr[c] + shift, log_tiny);
         __syncwarp();
         // (T,H,N,C): column w0+wl of this slab = C contiguous floats at (((w0+wl)*H + h)*N + n)*C
         const int ncol = min(32, g.W - w0);
-        float *dst = lp + (((int64_t)w0 * g.H + h) * g.N + n) * g.C + lane;
-        const int64_t cstep = (int64_t)g.H * g.N * g.C;
-        const bool c0ok = lane < g.C, c1ok = lane + 32 < g.C;              // C <= CR <= 64: two class passes
+        float *dst = lp + (((int64_t)w0 * g.H + h) * g.N + n) * C + lane;
+        const unsigned cstepB = (unsigned)(g.H * g.N * C) * 4u;
+        const bool c0ok = lane < C, c1ok = lane + 32 < C;              // C <= CR <= 64: two class passes
         const float *src = sm + lane;
-#pragma unroll 4
-        for (int wl = 0; wl < ncol; ++wl, dst += cstep, src += PITCH) {
-            if (c0ok) dst[0] = src[0];
-            if (c1ok) dst[32] = src[32];
+#pragma unroll 8
+        for (int wl = 0; wl < ncol; ++wl) {
+            float *d = at(dst, wl, cstepB);
+            if (c0ok) d[0] = src[wl * PITCH];
+            if (c1ok) d[32] = src[wl * PITCH + 32];
         }
         __syncwarp();
     }
 }
 
-template <int CR, bool FACTORED, int kWarpsPerBlock>
+template <int CR, bool FACTORED, int kWarpsPerBlock, int CX>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)     // 3 blocks / SM (80 registers) spills ~230 bytes per thread: slower
 ctc2d_head_bwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, const float *__restrict__ cls_logits,
                            const float *__restrict__ dlp, const float *__restrict__ gfac, const float *__restrict__ go,
@@ -353,43 +362,38 @@ ctc2d_head_bwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, con
     __shared__ float sm_all[kWarpsPerBlock][32 * PITCH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *sm = sm_all[warp];
+    const int C = CX > 0 ? CX : g.C;
     const int wtiles = (g.W + 31) >> 5;
-    const int64_t nslabs = (int64_t)g.N * g.H * wtiles;
+    // explicit gradient: one slab = (sample, height, 32 columns).  CTC factor: the [T,N,C] tile is shared by all heights, so one
+    // slab = (sample, 32 columns) and the heights are an inner loop over the staged tile (one eighth of the tile traffic).
+    const int64_t nslabs = (int64_t)g.N * (FACTORED ? 1 : g.H) * wtiles;
     const int64_t HW = (int64_t)g.H * g.W;
+    const unsigned HWB = (unsigned)(g.H * g.W) * 4u;       // byte strides; the host checks that they fit in 32 bits
     for (int64_t slab = (int64_t)blockIdx.x * kWarpsPerBlock + warp; slab < nslabs; slab += (int64_t)gridDim.x * kWarpsPerBlock) {
-        // slab order: sample fastest -- the warps of a block (and neighbouring blocks) write the (T,H,N,C) rows of consecutive
-        // samples at the same time, so the 152-byte per-sample pieces of a row merge into full sectors in L2
         const int n = (int)(slab % g.N);
         const int64_t hw = slab / g.N;
         const int wt = (int)(hw % wtiles);
-        const int h = (int)(hw / wtiles);
+        const int h_first = FACTORED ? 0 : (int)(hw / wtiles);
+        const int h_end = FACTORED ? g.H : h_first + 1;
         const int w0 = wt << 5, w = w0 + lane;
         const bool valid = w < g.W;
-        // class logits of this lane's column first: C independent 128-byte-row loads in flight while the tile below is staged
-        const float *zp = cls_logits + ((int64_t)n * g.C * g.H + h) * g.W + w;
-        float zr[CR];
-        {
-            const float *p = zp;
-#pragma unroll
-            for (int c = 0; c < CR; ++c, p += HW) zr[c] = (valid && c < g.C) ? __ldg(p) : -INFINITY;
-        }
-        // upstream gradient (explicit [T,H,N,C]) or CTC factor ([T,N,C], shared by the heights): rows of C contiguous
-        // floats per column -> lanes over classes load (16 columns = 32 loads in flight), lanes over columns read back
+        // upstream gradient (explicit [T,H,N,C]) or CTC factor ([T,N,C]): rows of C contiguous floats per column -> lanes over
+        // classes load (16 columns = 32 loads in flight), lanes over columns read back
         {
             const int ncol = min(32, g.W - w0);
-            const float *src = (FACTORED ? gfac + ((int64_t)w0 * g.N + n) * g.C : dlp + (((int64_t)w0 * g.H + h) * g.N + n) * g.C) + lane;
-            const int64_t cstep = FACTORED ? (int64_t)g.N * g.C : (int64_t)g.H * g.N * g.C;
-            const bool c0ok = lane < g.C, c1ok = lane + 32 < g.C;
+            const float *src = (FACTORED ? gfac + ((int64_t)w0 * g.N + n) * C : dlp + (((int64_t)w0 * g.H + h_first) * g.N + n) * C) + lane;
+            const unsigned cstepB = (unsigned)(FACTORED ? g.N * C : g.H * g.N * C) * 4u;
+            const bool c0ok = lane < C, c1ok = lane + 32 < C;
             float *d = sm + lane;
 #pragma unroll 1
             for (int wl0 = 0; wl0 < 32; wl0 += 16, d += 16 * PITCH) {
                 float a[16], b[16];
-                const float *q = src + (int64_t)wl0 * cstep;
+                const float *q = at(src, wl0, cstepB);
 #pragma unroll
-                for (int u = 0; u < 16; ++u, q += cstep) {
+                for (int u = 0; u < 16; ++u) {
                     const bool in = wl0 + u < ncol;
-                    a[u] = (in && c0ok) ? __ldg(q) : 0.f;
-                    b[u] = (in && c1ok) ? __ldg(q + 32) : 0.f;
+                    a[u] = (in && c0ok) ? __ldg(at(q, u, cstepB)) : 0.f;
+                    b[u] = (in && c1ok) ? __ldg(at(q, u, cstepB) + 32) : 0.f;
                 }
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
@@ -398,40 +402,47 @@ ctc2d_head_bwd_warp_kernel(HeadGeo g, const float *__restrict__ mask_logits, con
                 }
             }
         }
-        const float maskp = ex2f(mask_logsoftmax_col(mask_logits + (int64_t)n * HW + w, g.H, g.W, h, valid) * kLog2e);
-        const float gout = (FACTORED && valid) ? __ldg(go + (int64_t)n * go_stride) : 1.f;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < CR; ++c) mx = fmaxf(mx, zr[c]);
-        const float off = mx * kLog2e;
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < CR; c += 2) {
-            zr[c] = ex2f(fmaf(zr[c], kLog2e, -off));          // zr becomes the un-normalised class probability
-            s0 += zr[c];
-            if (c + 1 < CR) { zr[c + 1] = ex2f(fmaf(zr[c + 1], kLog2e, -off)); s1 += zr[c + 1]; }
-        }
-        const float inv = 1.f / (s0 + s1);
         __syncwarp();
-        // probability domain: p = classify prob, q = mask * p (what the reference clamps at tiny); max(q, tiny) passes no
-        // gradient where q <= tiny.  With the CTC factor the upstream gradient is exp(log_probs) * gfac * go = q * gfac * go.
-        float t0 = 0.f, t1 = 0.f;
+        const float gout = (FACTORED && valid) ? __ldg(go + (int64_t)n * go_stride) : 1.f;
+#pragma unroll 1
+        for (int h = h_first; h < h_end; ++h) {
+            const float *zp = cls_logits + ((int64_t)n * C * g.H + h) * g.W + w;
+            float zr[CR];
 #pragma unroll
-        for (int c = 0; c < CR; ++c) {                    // g_c replaces u_c in this lane's shared-memory row
-            zr[c] *= inv;
-            const float q = zr[c] * maskp;
-            const float u = sm[lane * PITCH + c];
-            const float gc = (c < g.C && q > tiny) ? (FACTORED ? q * u * gout : u) : 0.f;
-            sm[lane * PITCH + c] = gc;
-            if (c & 1) t1 += gc; else t0 += gc;
-        }
-        const float tot = t0 + t1;
-        if (valid) {
-            float *op = dcls + ((int64_t)n * g.C * g.H + h) * g.W + w;
+            for (int c = 0; c < CR; ++c) zr[c] = (valid && c < C) ? __ldg(at(zp, c, HWB)) : -INFINITY;
+            const float maskp = ex2f(mask_logsoftmax_col(mask_logits + (int64_t)n * HW + w, g.H, g.W, h, valid) * kLog2e);
+            float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < CR; ++c, op += HW)
-                if (c < g.C) *op = sm[lane * PITCH + c] - zr[c] * tot;
-            gsum[((int64_t)n * g.H + h) * g.W + w] = tot;
+            for (int c = 0; c < CR; ++c) mx = fmaxf(mx, zr[c]);
+            const float off = mx * kLog2e;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < CR; c += 2) {
+                zr[c] = ex2f(fmaf(zr[c], kLog2e, -off));          // zr becomes the un-normalised class probability
+                s0 += zr[c];
+                if (c + 1 < CR) { zr[c + 1] = ex2f(fmaf(zr[c + 1], kLog2e, -off)); s1 += zr[c + 1]; }
+            }
+            const float inv = 1.f / (s0 + s1);
+            // probability domain: p = classify prob, q = mask * p (what the reference clamps at tiny); max(q, tiny) passes no
+            // gradient where q <= tiny.  With the CTC factor the upstream gradient is exp(log_probs) * gfac * go = q * gfac * go.
+            float t0 = 0.f, t1 = 0.f;
+            float gr[CR];
+#pragma unroll
+            for (int c = 0; c < CR; ++c) {
+                zr[c] *= inv;
+                const float q = zr[c] * maskp;
+                const float u = sm[lane * PITCH + c];
+                gr[c] = (c < C && q > tiny) ? (FACTORED ? q * u * gout : u) : 0.f;
+                if (c & 1) t1 += gr[c]; else t0 += gr[c];
+            }
+            const float tot = t0 + t1;
+            if (valid) {
+                float *op = dcls + ((int64_t)n * C * g.H + h) * g.W + w;
+#pragma unroll
+                for (int c = 0; c < CR; ++c)
+                    if (c < C) *at(op, c, HWB) = gr[c] - zr[c] * tot;
+                gsum[((int64_t)n * g.H + h) * g.W + w] = tot;
+            }
         }
         __syncwarp();
     }
@@ -560,12 +571,14 @@ int mr_ctc2d_head_fwd_f32(const float *mask_logits, const float *cls_logits, int
     HeadGeo g{N, C, H, W, 0};
     cudaStream_t st = (cudaStream_t)stream;
     static const bool old_only = getenv("MR_HEAD_BLOCK_TILE") != nullptr;
-    if (C <= 64 && !old_only) {
+    const bool fits32 = (int64_t)64 * H * W * 4 < (1LL << 32) && (int64_t)H * N * C * 4 < (1LL << 32);
+    if (C <= 64 && fits32 && !old_only) {
         const int64_t nslabs = (int64_t)N * H * ceil_div(W, 32);
         const int wpb = C <= 40 ? 8 : 4;
         const int64_t blocks = std::min<int64_t>(ceil_div(nslabs, wpb), (int64_t)sm_count() * 32);
-        if (C <= 40) ctc2d_head_fwd_warp_kernel<40, 8><<<(unsigned)blocks, 256, 0, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
-        else ctc2d_head_fwd_warp_kernel<64, 4><<<(unsigned)blocks, 128, 0, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
+        if (C == 38) ctc2d_head_fwd_warp_kernel<40, 8, 38><<<(unsigned)blocks, 256, 0, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);   // EnglishCharset
+        else if (C <= 40) ctc2d_head_fwd_warp_kernel<40, 8, 0><<<(unsigned)blocks, 256, 0, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
+        else ctc2d_head_fwd_warp_kernel<64, 4, 0><<<(unsigned)blocks, 128, 0, st>>>(g, mask_logits, cls_logits, logf(tiny), log_probs);
         return check_launch("ctc2d_head_fwd_warp_kernel");
     }
     size_t smem;
@@ -598,15 +611,17 @@ int mr_ctc2d_head_bwd_f32(const float *mask_logits, const float *cls_logits, con
     size_t smem = 0;
     g.NT = pick_nt(C, H, 2, &smem);
     const bool tile_ok = g.NT && H <= 65535 && ceil_div(N, g.NT) <= 65535;
-    if (C <= 64 && !old_only) {
-        const int64_t nslabs = (int64_t)N * H * ceil_div(W, 32);
+    const bool fits32 = (int64_t)64 * H * W * 4 < (1LL << 32) && (int64_t)H * N * C * 4 < (1LL << 32);
+    if (C <= 64 && fits32 && !old_only) {
+        const int64_t nslabs = (int64_t)N * (factored ? 1 : H) * ceil_div(W, 32);
         const int wpb = C <= 40 ? 8 : 4;
         const int64_t blocks = std::min<int64_t>(ceil_div(nslabs, wpb), (int64_t)sm_count() * 32);
-#define MR_HEAD_BWD(CRV, FACV, WPB)                                                                                          \
-        ctc2d_head_bwd_warp_kernel<CRV, FACV, WPB><<<(unsigned)blocks, WPB * 32, 0, st>>>(                                     \
+#define MR_HEAD_BWD(CRV, FACV, WPB, CXV)                                                                                     \
+        ctc2d_head_bwd_warp_kernel<CRV, FACV, WPB, CXV><<<(unsigned)blocks, WPB * 32, 0, st>>>(                                \
             g, mask_logits, cls_logits, grad_log_probs, gfac, grad_out, grad_out_stride, tiny, grad_cls_logits, grad_mask_logits)
-        if (C <= 40) { if (factored) MR_HEAD_BWD(40, true, 8); else MR_HEAD_BWD(40, false, 8); }
-        else { if (factored) MR_HEAD_BWD(64, true, 4); else MR_HEAD_BWD(64, false, 4); }
+        if (C == 38) { if (factored) MR_HEAD_BWD(40, true, 8, 38); else MR_HEAD_BWD(40, false, 8, 38); }
+        else if (C <= 40) { if (factored) MR_HEAD_BWD(40, true, 8, 0); else MR_HEAD_BWD(40, false, 8, 0); }
+        else { if (factored) MR_HEAD_BWD(64, true, 4, 0); else MR_HEAD_BWD(64, false, 4, 0); }
 #undef MR_HEAD_BWD
     } else if (!tile_ok) {
         const int64_t blocks = (int64_t)N * H * ceil_div(W, 32);
