@@ -68,12 +68,15 @@ _SIGS = {
     "mr_ctc_greedy_decode": [c_p, c_p] + [c_int] * 4 + [c_i64] * 7 + [c_int, c_int, c_p, c_p],
     "mr_blank_after_first_blank": [c_p, c_int, c_int, c_int, c_p],
     "mr_dcn_workspace_bytes": [c_i64] * 6,
+    "mr_dcn_fused_workspace_bytes": [c_i64] * 7,
+    "mr_dcn_forward_fused_f32": [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64] + [c_int] * 15 + [c_p],
     "mr_dcn_forward_f32": [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64] + [c_int] * 15 + [c_p],
     "mr_dcn_backward_f32": [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_f32,
                             c_p, c_i64] + [c_int] * 15 + [c_p],
 }
 _RESTYPES = {
     "mr_dcn_workspace_bytes": c_i64,
+    "mr_dcn_fused_workspace_bytes": c_i64,
     "mr_status_string": ctypes.c_char_p,
     "mr_last_cuda_error": ctypes.c_char_p,
     "mr_launch_count": c_i64,

@@ -239,6 +239,10 @@ int mr_dcn_forward_f32(const float *input, const float *weight, const float *bia
     if (rc) return rc;
     if (B == 0) return MR_OK;
     if (!input || !weight || !offset || !output || !workspace) return MR_ERR_NULL_POINTER;
+    // fused tcgen05 implicit GEMM (csrc/dcn_tcgen05.cu) when the shape qualifies and the workspace holds its scratch
+    rc = mr_dcn_forward_fused_f32(input, weight, bias, offset, offset_bstride, mask, mask_bstride, output, workspace,
+                                  workspace_bytes, B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, group, dg, stream);
+    if (rc != MR_ERR_UNSUPPORTED) return rc;
     g.off_bs = offset_bstride; g.mask_bs = mask_bstride;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t per = mr_dcn_workspace_bytes(1, C, kh, kw, g.Ho, g.Wo);

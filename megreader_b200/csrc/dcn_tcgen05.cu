@@ -1,0 +1,348 @@
+// Deformable convolution v1 / v2 FORWARD as ONE fused implicit GEMM on tcgen05 (round 2).
+//
+//   out[b, co, p] = sum_{k, c} W[co, c, k] * mask[b, k, p] * bilinear(x[b, c], pos(b, k, p))  (+ bias)
+//   (modulated_deform_conv_cuda_forward, assets/ops/dcn/src/deform_conv_cuda.cpp:486-564; K8 deform_conv_cuda_kernel.cu:569-632)
+//
+// Round 1 (csrc/dcn.cu) wrote the 9x column matrix to HBM and multiplied it with an fp32 SIMT SGEMM: 319 us for
+// B = 8, C = 128 @ 64 x 64, half of it in the GEMM (profiles/dcn_r1_summary.md).  Here the column matrix never exists:
+//
+//   GEMM view      M = output pixels (128-row tiles inside a sample), N = Cout, K = taps x channels, K index = k * C + c
+//                  (tap-major: a 64-wide K block is ONE tap and 64 consecutive channels, so the bilinear corner offsets and
+//                  weights of a (pixel, tap) are computed once per 64 channels).
+//   A operand      produced on the fly: 512 producer threads (8 lanes per pixel row, 2 rows each) read the four corners from an NHWC copy
+//                  of the input: a warp-wide float4 gather is 4 x 128 contiguous bytes; 16 gathers per thread are in flight, blend, fold the
+//                  modulation mask in, and store bf16 into the 128-byte-swizzled K-major tile that tcgen05.mma reads.
+//   precision      fp32 parity (1e-4, against the reference's own kernels) with tensor cores: every value is split
+//                  v = hi + lo (two bf16), and D += Ah Wh + Ah Wl + Al Wh -- three bf16 MMAs per K block, error ~2^-17 relative
+//                  (the dropped Al Wl term), fp32 accumulation in TMEM.
+//   B operand      weights re-packed per call to [Cout][k * C + c] bf16 (hi and lo), tiles by 2-D TMA.
+//   epilogue       TMEM -> registers -> NCHW output: a warp's 32 lanes are 32 consecutive pixels of one output channel, so
+//                  every store instruction is one coalesced 128-byte row; bias added on the way.
+//
+// Requirements of this path: group = 1, deformable_group = 1, C % 64 == 0, Cout % 128 == 0 (the ResNet-50 DCN units of
+// backbones/resnet.py:136-165 are C = Cout = 128 / 256 / 512); anything else uses the round-1 kernels in dcn.cu.
+// The offset / mask indexing quirk (flat (Ho,Wo) strides inside a possibly larger per-sample slab) is kept.
+#include "tcgen05.cuh"
+#include <math.h>
+#include <stdlib.h>
+#include <algorithm>
+
+namespace {
+
+struct DcnFArgs {
+    const float *xh;          // [B][H][W][C] fp32
+    const float *off, *msk;   // reference layout, per-sample slabs
+    const float *bias;
+    float *out;               // [B][Cout][Ho*Wo]
+    int64_t off_bs, mask_bs;
+    int B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, P;
+    int tiles_per_sample, ncb, nkb;     // ncb = C / 64 channel blocks per tap, nkb = kh*kw*ncb K blocks
+};
+
+template <int BN, int STAGES>
+struct DcnSmem {
+    static constexpr int A_BYTES = BM * BK * 2;               // one of (hi, lo)
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+constexpr int kProducerThreads = 512;      // 16 warps x (4 rows x 8 channel lanes) x 2 row quads = 128 rows
+constexpr int kDcnThreads = 64 + kProducerThreads;
+
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kDcnThreads, 1)
+dcn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, DcnFArgs a) {
+    using L = DcnSmem<BN, STAGES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x / a.tiles_per_sample;
+    const int p0 = (blockIdx.x - b * a.tiles_per_sample) * BM;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = a.nkb;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmWh);
+        tma_prefetch_desc(&tmWl);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1 + kProducerThreads); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ weight tiles (hi and lo) by TMA
+        if (elect_one()) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+                unsigned char *st = smem + s * L::STAGE_BYTES + 2 * L::A_BYTES;
+                mbar_expect_tx(full + s, 2 * L::B_BYTES);
+                tma_load_2d(&tmWh, full + s, st, i * BK, n0);
+                tma_load_2d(&tmWl, full + s, st + L::B_BYTES, i * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer: D += Ah Wh + Ah Wl + Al Wh
+        constexpr uint32_t idesc = make_idesc(BM, BN, 0, 0);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(full + s, (i / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t ah = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t al = ah + L::A_BYTES;
+                const uint32_t bh = al + L::A_BYTES;
+                const uint32_t bl = bh + L::B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_desc(ah + k * 32, 16, 1024), make_desc(bh + k * 32, 16, 1024), idesc, (i | k) != 0);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_desc(ah + k * 32, 16, 1024), make_desc(bl + k * 32, 16, 1024), idesc, 1);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16(tmem_base, make_desc(al + k * 32, 16, 1024), make_desc(bh + k * 32, 16, 1024), idesc, 1);
+                umma_commit(empty + s);
+                if (i == nkb - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ producers: bilinear gather -> swizzled bf16 tiles
+        // Thread mapping: 8 lanes share a pixel row and split its 64 channels (lane j: channels 4j..4j+3 and 32+4j..32+4j+3),
+        // 4 rows per warp instruction, 2 such row quads per warp.  A warp-wide float4 gather therefore touches 4 x 128
+        // contiguous bytes (4 L1 wavefronts); with lanes = 32 different pixels it was 32 separate half-used sectors and
+        // the kernel was bound by the L1 data stage (ncu: l1tex 78 % busy, 27 sectors / request, profiles/dcn_r2_summary.md).
+        const int pwp = warp - 2;                             // producer warp 0..15
+        const int sub = lane >> 3, j = lane & 7;
+        struct Row { const float4 *q1, *q2, *q3, *q4; float w1, w2, w3, w4; };
+        const float *xb = a.xh + (int64_t)b * a.H * a.W * a.C + j * 4;
+        int rrow[2], pcl[2], hov[2], wov[2];
+        bool rok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            rrow[u] = pwp * 8 + u * 4 + sub;
+            const int p = p0 + rrow[u];
+            rok[u] = p < a.P;
+            pcl[u] = rok[u] ? p : a.P - 1;
+            hov[u] = pcl[u] / a.Wo; wov[u] = pcl[u] - hov[u] * a.Wo;
+        }
+        const float *offb = a.off + (int64_t)b * a.off_bs;
+        const float *mskb = a.msk ? a.msk + (int64_t)b * a.mask_bs : nullptr;
+        int kb = 0;
+        for (int k = 0; k < a.kh * a.kw; ++k) {
+            const int ti = k / a.kw, tj = k - ti * a.kw;
+            Row rw[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float oh = __ldg(offb + (int64_t)(2 * k) * a.P + pcl[u]);
+                const float ow = __ldg(offb + (int64_t)(2 * k + 1) * a.P + pcl[u]);
+                const float m = mskb ? __ldg(mskb + (int64_t)k * a.P + pcl[u]) : 1.f;
+                const float hy = (float)(hov[u] * a.sh - a.ph + ti * a.dh) + oh;
+                const float wx = (float)(wov[u] * a.sw - a.pw + tj * a.dw) + ow;
+                // dmcn_im2col_bilinear (deform_conv_cuda_kernel.cu:466-496): zero outside (-1,H) x (-1,W), corners outside dropped
+                const bool inside = rok[u] && hy > -1.f && wx > -1.f && hy < (float)a.H && wx < (float)a.W;
+                const int hl = (int)floorf(hy), wl = (int)floorf(wx);
+                const int hh = hl + 1, wh = wl + 1;
+                const float lh = hy - hl, lw = wx - wl, uh = 1.f - lh, uw = 1.f - lw;
+                const bool m1 = inside && hl >= 0 && wl >= 0, m2 = inside && hl >= 0 && wh <= a.W - 1;
+                const bool m3 = inside && hh <= a.H - 1 && wl >= 0, m4 = inside && hh <= a.H - 1 && wh <= a.W - 1;
+                rw[u].w1 = m1 ? uh * uw * m : 0.f; rw[u].w2 = m2 ? uh * lw * m : 0.f;
+                rw[u].w3 = m3 ? lh * uw * m : 0.f; rw[u].w4 = m4 ? lh * lw * m : 0.f;
+                rw[u].q1 = reinterpret_cast<const float4 *>(xb + (int64_t)(m1 ? hl * a.W + wl : 0) * a.C);
+                rw[u].q2 = reinterpret_cast<const float4 *>(xb + (int64_t)(m2 ? hl * a.W + wh : 0) * a.C);
+                rw[u].q3 = reinterpret_cast<const float4 *>(xb + (int64_t)(m3 ? hh * a.W + wl : 0) * a.C);
+                rw[u].q4 = reinterpret_cast<const float4 *>(xb + (int64_t)(m4 ? hh * a.W + wh : 0) * a.C);
+            }
+            for (int cc = 0; cc < a.ncb; ++cc, ++kb) {
+                // all 16 gathers of this thread are issued before the slot wait and before any use
+                float4 x1[2][2], x2[2][2], x3[2][2], x4[2][2];
+                const int c4 = cc * (BK / 4);
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        x1[u][e] = __ldg(rw[u].q1 + c4 + e * 8); x2[u][e] = __ldg(rw[u].q2 + c4 + e * 8);
+                        x3[u][e] = __ldg(rw[u].q3 + c4 + e * 8); x4[u][e] = __ldg(rw[u].q4 + c4 + e * 8);
+                    }
+                const int s = kb % STAGES;
+                mbar_wait(empty + s, ((kb / STAGES) & 1) ^ 1);
+                unsigned char *ah = smem + s * L::STAGE_BYTES;
+                unsigned char *al = ah + L::A_BYTES;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const uint32_t row_off = (uint32_t)rrow[u] * 128u, sw = (uint32_t)(rrow[u] & 7);
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float v0 = rw[u].w1 * x1[u][e].x + rw[u].w2 * x2[u][e].x + rw[u].w3 * x3[u][e].x + rw[u].w4 * x4[u][e].x;
+                        const float v1 = rw[u].w1 * x1[u][e].y + rw[u].w2 * x2[u][e].y + rw[u].w3 * x3[u][e].y + rw[u].w4 * x4[u][e].y;
+                        const float v2 = rw[u].w1 * x1[u][e].z + rw[u].w2 * x2[u][e].z + rw[u].w3 * x3[u][e].z + rw[u].w4 * x4[u][e].z;
+                        const float v3 = rw[u].w1 * x1[u][e].w + rw[u].w2 * x2[u][e].w + rw[u].w3 * x3[u][e].w + rw[u].w4 * x4[u][e].w;
+                        uint2 hi, lo;
+                        __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&hi);
+                        __nv_bfloat162 *l2 = reinterpret_cast<__nv_bfloat162 *>(&lo);
+                        h2[0] = __floats2bfloat162_rn(v0, v1);
+                        h2[1] = __floats2bfloat162_rn(v2, v3);
+                        const float2 f0 = __bfloat1622float2(h2[0]), f1 = __bfloat1622float2(h2[1]);
+                        l2[0] = __floats2bfloat162_rn(v0 - f0.x, v1 - f0.y);
+                        l2[1] = __floats2bfloat162_rn(v2 - f1.x, v3 - f1.y);
+                        // channels e*32 + 4j .. +3 -> 16-byte chunk e*4 + j/2 of the row (swizzled), 8-byte half j & 1
+                        const uint32_t o = row_off + ((((uint32_t)(e * 4 + (j >> 1))) ^ sw) << 4) + (uint32_t)(j & 1) * 8u;
+                        *reinterpret_cast<uint2 *>(ah + o) = hi;
+                        *reinterpret_cast<uint2 *>(al + o) = lo;
+                    }
+                }
+                fence_proxy_async();                          // generic-proxy smem writes -> visible to tcgen05
+                mbar_arrive_cta(full + s);
+            }
+        }
+        // ------------------------------------------------------------ epilogue: TMEM -> NCHW (+ bias); 4 warps per TMEM quarter
+        const int q = warp & 3;                               // TMEM lane quarter this warp may access
+        const int part = (warp - 2) >> 2;                     // which quarter of the BN columns (4 warps share a TMEM quarter)
+        const int prow = p0 + q * 32 + lane;
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        float *ob = a.out + ((int64_t)b * a.Cout + n0) * a.P + prow;
+#pragma unroll 1
+        for (int c = part * (BN / 128); c < (part + 1) * (BN / 128); ++c) {
+            uint32_t rr[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), rr);
+            if (prow < a.P) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = c * 32 + j;
+                    float v = __uint_as_float(rr[j]);
+                    if (a.bias) v += __ldg(a.bias + n0 + co);
+                    ob[(int64_t)co * a.P] = v;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// x [B][C][P] -> y [B][P][C] (fp32), 32 x 32 tiles through shared memory; both sides 128-byte rows
+__global__ void __launch_bounds__(256)
+dcn_nchw_to_nhwc_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int P) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *xb = x + (int64_t)b * C * P;
+    float *yb = y + (int64_t)b * C * P;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j, p = p0 + tx;
+        tile[ty + 8 * j][tx] = (c < C && p < P) ? __ldg(xb + (int64_t)c * P + p) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = p0 + ty + 8 * j, c = c0 + tx;
+        if (p < P && c < C) yb[(int64_t)p * C + c] = tile[tx][ty + 8 * j];
+    }
+}
+
+// weight [Cout][C][K] fp32 -> hi / lo bf16 [Cout][k * C + c]
+__global__ void dcn_weight_pack_kernel(const float *__restrict__ w, int Cout, int C, int K, bf16 *__restrict__ hi, bf16 *__restrict__ lo) {
+    const int64_t n = (int64_t)Cout * C * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t t = i / C;
+        const int k = (int)(t % K);
+        const int co = (int)(t / K);
+        const float v = w[((int64_t)co * C + c) * K + k];
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+template <int BN, int STAGES>
+int launch_dcn_fwd(const CUtensorMap &th, const CUtensorMap &tl, const DcnFArgs &a, cudaStream_t st) {
+    using L = DcnSmem<BN, STAGES>;
+    auto kern = dcn_fwd_tcgen05_kernel<BN, STAGES>;
+    { int rc_attr = ensure_dyn_smem((const void *)kern, L::TOTAL, "dcn_fwd_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
+    dim3 grid((unsigned)(a.B * a.tiles_per_sample), (unsigned)(a.Cout / BN), 1);
+    kern<<<grid, kDcnThreads, L::TOTAL, st>>>(th, tl, a);
+    return check_launch("dcn_fwd_tcgen05_kernel");
+}
+
+}  // namespace
+
+extern "C" {
+
+/* scratch the fused forward needs: NHWC copy of the input + hi/lo packed weights (256-byte aligned pieces) */
+int64_t mr_dcn_fused_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t Cout, int64_t kh, int64_t kw) {
+    const int64_t x = round_up(B * H * W * C * 4, 256);
+    const int64_t w = round_up(Cout * C * kh * kw * 2, 256);
+    return x + 2 * w;
+}
+
+/* MR_ERR_UNSUPPORTED when the shape is outside the fused path (the caller then runs the unfused kernels of dcn.cu). */
+int mr_dcn_forward_fused_f32(const float *input, const float *weight, const float *bias, const float *offset,
+                             int64_t offset_bstride, const float *mask, int64_t mask_bstride, float *output,
+                             float *workspace, int64_t workspace_bytes, int B, int C, int H, int W, int Cout, int kh, int kw,
+                             int sh, int sw, int ph, int pw, int dh, int dw, int group, int dg, void *stream) {
+    if (group != 1 || dg != 1 || C % 64 || Cout % 128 || B <= 0) return MR_ERR_UNSUPPORTED;
+    if (getenv("MR_DCN_UNFUSED")) return MR_ERR_UNSUPPORTED;
+    if (!input || !weight || !offset || !output || !workspace) return MR_ERR_NULL_POINTER;
+    if (workspace_bytes < mr_dcn_fused_workspace_bytes(B, C, H, W, Cout, kh, kw) || ((uintptr_t)workspace % 256)) return MR_ERR_UNSUPPORTED;
+    DcnFArgs a;
+    a.B = B; a.C = C; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.sh = sh; a.sw = sw; a.ph = ph; a.pw = pw;
+    a.dh = dh; a.dw = dw;
+    a.Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
+    a.Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+    if (a.Ho <= 0 || a.Wo <= 0) return MR_ERR_BAD_SHAPE;
+    a.P = a.Ho * a.Wo;
+    a.tiles_per_sample = (int)ceil_div(a.P, BM);
+    a.ncb = C / BK; a.nkb = kh * kw * a.ncb;
+    if ((int64_t)B * a.tiles_per_sample > 0x7fffffffLL) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    float *xh = (float *)ws;
+    const int64_t xbytes = round_up((int64_t)B * H * W * C * 4, 256), wbytes = round_up((int64_t)Cout * C * kh * kw * 2, 256);
+    bf16 *whi = (bf16 *)(ws + xbytes), *wlo = (bf16 *)(ws + xbytes + wbytes);
+    {
+        dim3 tg((unsigned)ceil_div((int64_t)H * W, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+        dcn_nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(input, xh, C, H * W);
+    }
+    int rc = check_launch("dcn_nchw_to_nhwc_kernel");
+    if (rc) return rc;
+    const int64_t nw = (int64_t)Cout * C * kh * kw;
+    dcn_weight_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nw, 256), 148 * 8), 256, 0, st>>>(weight, Cout, C, kh * kw, whi, wlo);
+    rc = check_launch("dcn_weight_pack_kernel");
+    if (rc) return rc;
+    a.xh = xh; a.off = offset; a.msk = mask; a.bias = bias; a.out = output; a.off_bs = offset_bstride; a.mask_bs = mask_bstride;
+    const int64_t Kt = (int64_t)kh * kw * C;
+    /* BN = 256 halves the number of times a pixel tile is gathered when Cout >= 256, as long as the grid still covers the SMs */
+    const bool wide = Cout % 256 == 0 && (int64_t)B * a.tiles_per_sample * (Cout / 256) >= sm_count();
+    CUtensorMap th, tl;
+    rc = make_map(&th, whi, Kt, Cout, Kt, BK, wide ? 256 : 128);
+    if (rc) return rc;
+    rc = make_map(&tl, wlo, Kt, Cout, Kt, BK, wide ? 256 : 128);
+    if (rc) return rc;
+    if (wide) return launch_dcn_fwd<256, 2>(th, tl, a, st);
+    return launch_dcn_fwd<128, 3>(th, tl, a, st);
+}
+
+}  // extern "C"

@@ -31,10 +31,16 @@ def _slab(t):
     return t, (t.stride(0) if t.size(0) > 1 else t[0].numel() if t.size(0) else 0)
 
 
-def _workspace(x, C, kh, kw, Ho, Wo):
+def _workspace(x, C, kh, kw, Ho, Wo, Cout=0):
+    """Scratch for the op: room for the column matrix of nb samples (unfused kernels) and, when Cout is given, for the fused
+    forward's NHWC input copy + packed weights (csrc/dcn_tcgen05.cu) -- whichever is larger."""
     per = C * kh * kw * Ho * Wo * 4
     nb = max(1, min(x.size(0), WORKSPACE_CAP_BYTES // max(per, 1)))
-    return torch.empty(nb * per // 4, dtype=torch.float32, device=x.device), nb * per
+    nbytes = nb * per
+    if Cout:
+        nbytes = max(nbytes, int(_lib.lib().mr_dcn_fused_workspace_bytes(x.size(0), C, x.size(2), x.size(3), Cout, kh, kw)))
+    nbytes = (nbytes + 255) // 256 * 256
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=x.device), nbytes
 
 
 def _check(x, weight):
@@ -63,7 +69,7 @@ def _forward(x, weight, bias, offset, mask, output, kh, kw, sh, sw, ph, pw, dh, 
     if mask is not None:
         mask, mbs = _slab(mask)
     assert output.is_contiguous() and output.numel() == B * Cout * Ho * Wo
-    ws, ws_bytes = _workspace(x, C, kh, kw, Ho, Wo)
+    ws, ws_bytes = _workspace(x, C, kh, kw, Ho, Wo, Cout)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().mr_dcn_forward_f32(
             x.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None, offset.data_ptr(), obs,
