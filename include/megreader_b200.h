@@ -227,6 +227,14 @@ int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N,
  * flipped/transposed weights and padding (k-1-p) the same entry computes the input gradient. */
 int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, int W, int C, int Cout, int kh, int kw,
                           int ph, int pw, int out_dtype, const float *bias, int relu, void *stream);
+/* General forms with stride and dilation (the trunk convolutions of backbones/resnet.py:110-256, resnet_dilated.py:50-69,
+ * ppm.py:6-44, fpn_top_down.py:6-30 and the 2D-CTC head branches decoders/ctc_decoder2d.py:16-27): same kernels, the stride is
+ * the activation tensor map's traversal stride, the dilation scales the tap's coordinate offset. */
+int mr_conv2d_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, int W, int C, int Cout, int kh, int kw,
+                            int sh, int sw, int ph, int pw, int dh, int dw, int out_dtype, const float *bias, int relu,
+                            void *stream);
+int mr_conv2d_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int H, int W, int C, int Cout, int kh, int kw,
+                            int sh, int sw, int ph, int pw, int dh, int dw, int splits, void *stream);
 /* Implicit-GEMM weight gradient: dWm[Cout, kh*kw*C] fp32 += dz[N,Ho,Wo,Cout]^T (*) x[N,H,W,C] (atomic, split-K). */
 int mr_conv_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int H, int W, int C, int Cout, int kh, int kw,
                           int ph, int pw, int splits, void *stream);

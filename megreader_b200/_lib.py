@@ -52,6 +52,8 @@ _SIGS = {
     "mr_gemm_tcgen05": [c_p] * 3 + [c_i64] * 6 + [c_int] * 3 + [c_p, c_int, c_f32, c_int, c_p],
     "mr_conv_fprop_tcgen05": [c_p] * 3 + [c_int] * 10 + [c_p, c_int, c_p],
     "mr_conv_wgrad_tcgen05": [c_p] * 3 + [c_int] * 10 + [c_p],
+    "mr_conv2d_fprop_tcgen05": [c_p] * 3 + [c_int] * 14 + [c_p, c_int, c_p],
+    "mr_conv2d_wgrad_tcgen05": [c_p] * 3 + [c_int] * 14 + [c_p],
     "mr_lstm_step_fwd_tcgen05": [c_p] * 7 + [c_i64, c_p, c_int, c_int, c_int, c_p],
     "mr_lstm_step_bwd_tcgen05": [c_p] * 6 + [c_i64, c_p, c_p, c_int, c_int, c_int, c_p],
     "mr_lstm_seq_fwd_tcgen05": [c_p] * 6 + [c_int] * 3 + [c_p],

@@ -1,0 +1,172 @@
+"""General 2-D convolution on the tcgen05 implicit-GEMM kernels (csrc/gemm_tcgen05.cu) as an autograd Function, and the module
+swap that puts the reference-named trunks on it.
+
+    conv2d(x, weight, bias, stride, padding, dilation)            x, result: (N, C, H, W) bf16 in channels_last memory
+    EngineConv2d                                                   nn.Conv2d subclass (same parameters / state-dict keys)
+    use_engine_convs(module)                                       swaps every eligible nn.Conv2d of a trunk in place
+
+Covers what the ResNet-50 / dilated / PPM / FPN trunks and the 2D-CTC head branches use (backbones/resnet.py:110-256,
+resnet_dilated.py:50-69, ppm.py:6-44, fpn_top_down.py:6-30, decoders/ctc_decoder2d.py:16-27): 1x1 and 3x3 kernels, stride 1 / 2,
+any dilation, groups = 1, C_in % 64 == 0; the stem (C_in = 3, 7x7 stride 2) is an unfold + the same tensor-core GEMM.
+bf16 operands, fp32 accumulation, fp32 master weights.  Forward = implicit GEMM; input gradient = implicit GEMM of dz with the
+flipped / transposed weights (stride 2: over the zero-upsampled dz); weight gradient = implicit GEMM over pixels (split-K).
+CUDA only -- there is no CPU fallback."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import nnops as ops
+
+
+def _pad_to(n, m):
+    return -(-n // m) * m
+
+
+class _Conv2dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation):
+        if not x.is_cuda:
+            raise NotImplementedError("megreader_b200.conv_engine: CUDA tensors only (no CPU fallback)")
+        Cout, Cin, kh, kw = weight.shape
+        sh, sw = stride
+        ph, pw = padding
+        dh, dw = dilation
+        N, C, H, W = x.shape
+        assert C == Cin and Cin % 64 == 0
+        xh = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).contiguous()   # NHWC
+        Cp = _pad_to(Cout, 8)                                   # weight-gradient kernel wants Cout % 8 == 0
+        Wm = ops.conv_weight_pack(weight.detach().float().contiguous(), Cin, kh * kw * Cin, torch.bfloat16, 0)   # [Cout, K]
+        if Cp != Cout:
+            Wm = F.pad(Wm, (0, 0, 0, Cp - Cout))
+        bz = None
+        if bias is not None:
+            bz = bias.detach().float()
+            if Cp != Cout:
+                bz = F.pad(bz, (0, Cp - Cout))
+        y, Ho, Wo = ops.conv2d_fprop_tc(xh, Wm, kh, kw, sh, sw, ph, pw, dh, dw, bias=bz)
+        ctx.save_for_backward(xh, weight)
+        ctx.geo = (N, H, W, Cin, Cout, Cp, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, bias is not None, x.dtype)
+        out = y.view(N, Ho, Wo, Cp)
+        if Cp != Cout:
+            out = out[..., :Cout]
+        return out.permute(0, 3, 1, 2)                          # (N, Cout, Ho, Wo) view, channels_last memory
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, weight = ctx.saved_tensors
+        N, H, W, Cin, Cout, Cp, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, has_bias, in_dtype = ctx.geo
+        dz = dy.permute(0, 2, 3, 1).to(torch.bfloat16)
+        if Cp != Cout:
+            dz = F.pad(dz, (0, Cp - Cout))
+        dz = dz.contiguous()                                    # [N, Ho, Wo, Cp]
+        dx = dw_ = db = None
+        if ctx.needs_input_grad[1]:
+            dWm = ops.conv2d_wgrad_tc(dz, xh, kh, kw, sh, sw, ph, pw, dh, dw)               # [Cp, kh*kw*Cin] fp32
+            dw_ = dWm[:Cout].view(Cout, kh, kw, Cin).permute(0, 3, 1, 2).contiguous().to(weight.dtype)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dz.view(-1, Cp)[:, :Cout].float().sum(0)
+        if ctx.needs_input_grad[0]:
+            # dgrad = stride-1 convolution of (zero-upsampled) dz with the flipped, transposed weights, padding d*(k-1) - p
+            w = weight.detach().float()
+            Wd = w.flip(2, 3).permute(1, 2, 3, 0)               # [Cin, kh, kw, Cout]
+            if Cp != Cout:
+                Wd = F.pad(Wd, (0, Cp - Cout))
+            Kp = _pad_to(Cp, 64)                                # the forward kernel wants its channel count % 64 == 0
+            if Kp != Cp:
+                Wd = F.pad(Wd, (0, Kp - Cp))
+                dz = F.pad(dz, (0, Kp - Cp))
+            Wd = Wd.reshape(Cin, kh * kw * Kp).to(torch.bfloat16).contiguous()
+            if sh > 1 or sw > 1:
+                Hu, Wu = (Ho - 1) * sh + 1, (Wo - 1) * sw + 1
+                up = torch.zeros((N, Hu, Wu, Kp), dtype=torch.bfloat16, device=dz.device)
+                up[:, ::sh, ::sw] = dz
+                dz = up
+            qh, qw = dh * (kh - 1) - ph, dw * (kw - 1) - pw
+            # output size of the transposed problem must be (H, W): rows lost to the stride's floor come back as extra padding
+            Hd, Wd_ = dz.size(1), dz.size(2)
+            eh, ew = H - (Hd + 2 * qh - dh * (kh - 1)), W - (Wd_ + 2 * qw - dw * (kw - 1))
+            if qh < 0 or qw < 0 or eh or ew:
+                # asymmetric / negative padding: materialise it (rare: only when p > d*(k-1) or the stride drops rows)
+                dz = F.pad(dz, (0, 0, max(qw, 0), max(qw, 0) + max(ew, 0), max(qh, 0), max(qh, 0) + max(eh, 0)))
+                if qh < 0 or qw < 0:
+                    dz = dz[:, -qh if qh < 0 else 0:, -qw if qw < 0 else 0:]
+                dz = dz.contiguous()
+                qh = qw = 0
+            g, Hg, Wg = ops.conv2d_fprop_tc(dz.contiguous(), Wd, kh, kw, 1, 1, qh, qw, dh, dw)
+            assert (Hg, Wg) == (H, W), ((Hg, Wg), (H, W))
+            dx = g.view(N, H, W, Cin).permute(0, 3, 1, 2).to(in_dtype)
+        return dx, dw_, db, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1)):
+    return _Conv2dFn.apply(x, weight, bias, tuple(stride), tuple(padding), tuple(dilation))
+
+
+class _StemFn(torch.autograd.Function):
+    """Convolutions whose input has few channels (the 7x7 stride-2 stem on RGB, backbones/resnet.py:198): unfold + one
+    tensor-core GEMM (K = C*kh*kw padded to 64).  The images need no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation):
+        Cout, Cin, kh, kw = weight.shape
+        N, C, H, W = x.shape
+        cols = F.unfold(x.float(), (kh, kw), dilation, padding, stride)           # [N, C*kh*kw, L]
+        L = cols.size(2)
+        K = Cin * kh * kw
+        Kp = _pad_to(K, 64)
+        A = torch.zeros((N * L, Kp), dtype=torch.bfloat16, device=x.device)
+        A[:, :K] = cols.transpose(1, 2).reshape(N * L, K)
+        Wm = torch.zeros((Cout, Kp), dtype=torch.bfloat16, device=x.device)
+        Wm[:, :K] = weight.detach().reshape(Cout, K)
+        y = ops.gemm_tc(A, Wm, transB=True, out_dtype=torch.bfloat16, bias=bias.detach().float() if bias is not None else None)
+        Ho = (H + 2 * padding[0] - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+        Wo = L // Ho
+        ctx.save_for_backward(A)
+        ctx.geo = (Cout, Cin, kh, kw, K, bias is not None, weight.dtype)
+        return y.view(N, Ho, Wo, Cout).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (A,) = ctx.saved_tensors
+        Cout, Cin, kh, kw, K, has_bias, wdtype = ctx.geo
+        dz = dy.permute(0, 2, 3, 1).reshape(-1, Cout).to(torch.bfloat16).contiguous()
+        dWm = ops.gemm_tc(dz, A, transA=True, transB=False, out_dtype=torch.float32)  # [Cout, Kp] = dz^T A
+        dw_ = dWm[:, :K].reshape(Cout, Cin, kh, kw).to(wdtype)
+        db = dz.float().sum(0) if has_bias else None
+        return None, dw_, db, None, None, None
+
+
+class EngineConv2d(nn.Conv2d):
+    """nn.Conv2d whose arithmetic runs on megreader_b200's tcgen05 kernels (same parameters, same state-dict keys)."""
+
+    def forward(self, x):
+        if self.groups != 1 or self.padding_mode != "zeros" or isinstance(self.padding, str):
+            raise NotImplementedError("EngineConv2d: groups = 1, zero padding only")
+        if self.in_channels % 64 == 0:
+            return conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation)
+        return _StemFn.apply(x, self.weight, self.bias, self.stride, self.padding, self.dilation)
+
+
+def eligible(m):
+    return (type(m) is nn.Conv2d and m.groups == 1 and m.padding_mode == "zeros" and not isinstance(m.padding, str)
+            and (m.in_channels % 64 == 0 or m.in_channels <= 4))
+
+
+def use_engine_convs(module):
+    """Re-class every eligible nn.Conv2d below `module` to EngineConv2d (parameters stay the same objects).  Returns the
+    number of layers switched.  Undo with restore_library_convs()."""
+    n = 0
+    for m in module.modules():
+        if eligible(m):
+            m.__class__ = EngineConv2d
+            n += 1
+    return n
+
+
+def restore_library_convs(module):
+    n = 0
+    for m in module.modules():
+        if type(m) is EngineConv2d:
+            m.__class__ = nn.Conv2d
+            n += 1
+    return n

@@ -210,6 +210,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 struct ConvArgs {
     const bf16 *x;
     int N, H, W, C, kh, kw, ph, pw, Ho, Wo;
+    int sh, sw, dh, dw;                 // stride and dilation (round 2: ResNet trunks; 1 / 1 for the CRNN layers)
     // TMA-A variant: the output space [N, Ho, Wo] is tiled by boxes of bw x bh x bn = 128 pixels; the width is cut
     // into segments of power-of-two widths (e.g. Wo = 65 -> one 64-wide segment + one 1-wide segment).
     struct Seg { int w0, bw, bh, bn, h_blocks, tile_begin; } seg[4];
@@ -307,7 +308,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
 #pragma unroll
                     for (int sub = 0; sub < MT; ++sub)
                         tma_load_4d(tmX[sub], full + s, smem + s * L::STAGE_BYTES + sub * (BM * BK * 2), cc * BK,
-                                    tw0[sub] + tj - a.pw, th0[sub] + ti - a.ph, tn[sub]);
+                                    tw0[sub] * a.sw + tj * a.dw - a.pw, th0[sub] * a.sh + ti * a.dh - a.ph, tn[sub]);
                     if (++cc == cchunks) { cc = 0; if (++tj == a.kw) { tj = 0; ++ti; } }
                 }
                 tma_load_2d(&tmB, full + s, smem + s * L::STAGE_BYTES + L::A_BYTES, i * BK, n0);
@@ -380,7 +381,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
             mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
 #pragma unroll
             for (int sub = 0; sub < MT; ++sub) {
-                const int h = ho[sub] + ti - a.ph, w = wo[sub] + tj - a.pw;
+                const int h = ho[sub] * a.sh + ti * a.dh - a.ph, w = wo[sub] * a.sw + tj * a.dw - a.pw;
                 const bool ok = valid[sub] && h >= 0 && h < a.H && w >= 0 && w < a.W;
                 const bf16 *src = ok ? a.x + ((((int64_t)n[sub] * a.H + h) * a.W + w) * a.C + cc * BK) : a.x;
                 const uint32_t dst = smem_u32(smem + s * L::STAGE_BYTES + sub * (BM * BK * 2)) + row_off;
@@ -419,6 +420,7 @@ conv_fprop_tcgen05_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_
 // =====================================================================================================
 struct WgradArgs {
     int N, H, W, C, kh, kw, ph, pw, Ho, Wo, Cout;
+    int sh, sw, dh, dw;
     int wboxes;                 // ceil(Wo / RB)
     int kb_total, kblocks_per_split;
     GemmArgs g;                 // M = Cout, N = kh*kw*C, C = dW, atomic = 1
@@ -492,9 +494,10 @@ conv_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmDz, const __grid
 #pragma unroll
                 for (int q = 0; q < BN / 64; ++q) {
                     if (n0 + 64 * q < g.N)
-                        tma_load_4d(&tmX, full + s, b_dst + q * RB * 128, at_c[q], wb * RB + at_j[q] - a.pw, ho + at_i[q] - a.ph, n);
+                        tma_load_4d(&tmX, full + s, b_dst + q * RB * 128, at_c[q], wb * RB * a.sw + at_j[q] * a.dw - a.pw,
+                                    ho * a.sh + at_i[q] * a.dh - a.ph, n);
                     else   // column atom beyond kh*kw*C: keep the transaction count with an all-out-of-bounds box
-                        tma_load_4d(&tmX, full + s, b_dst + q * RB * 128, 0, -RB - 8, 0, n);
+                        tma_load_4d(&tmX, full + s, b_dst + q * RB * 128, 0, -RB * a.sw - 8, 0, n);
                 }
             }
         }
@@ -848,14 +851,17 @@ int launch(const CUtensorMap &ta, const CUtensorMap &tb, const GemmArgs &g, int 
 }
 
 // 4-D bf16 NHWC tensor map {C, W, H, N}, box {64, box_w, 1, 1}
+// sw / sh > 1: strided traversal (every sw-th column, sh-th row) -- the box then spans box_w * sw columns of the tensor and
+// delivers box_w of them (cuTensorMapEncodeTiled elementStrides)
 int make_map_nhwc(CUtensorMap *m, const void *base, int64_t C, int64_t W, int64_t H, int64_t N, int box_w, int box_h = 1,
-                  int box_n = 1) {
+                  int box_n = 1, int sw = 1, int sh = 1) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_cuda_error(cudaErrorUnknown, "cuTensorMapEncodeTiled entry point"); return MR_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_n};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)(box_w * sw), (cuuint32_t)(box_h * sh), (cuuint32_t)box_n};
+    cuuint32_t estr[4] = {1, (cuuint32_t)sw, (cuuint32_t)sh, 1};
+    if (box[1] > 256 || box[2] > 256) { set_cuda_error(cudaErrorInvalidValue, "conv tensor map: strided box too large"); return MR_ERR_UNSUPPORTED; }
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -943,14 +949,25 @@ int mr_gemm_tcgen05(const void *A, const void *B, void *C, int64_t M, int64_t N,
  * C % 64 == 0, Wm row pitch = kh*kw*C.  With flipped/transposed weights and padding (k-1-p) it is the input gradient. */
 int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, int W, int C, int Cout, int kh, int kw,
                           int ph, int pw, int out_dtype, const float *bias, int relu, void *stream) {
-    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || ph < 0 || pw < 0) return MR_ERR_BAD_SHAPE;
+    return mr_conv2d_fprop_tcgen05(x, Wm, y, N, H, W, C, Cout, kh, kw, 1, 1, ph, pw, 1, 1, out_dtype, bias, relu, stream);
+}
+
+/* General form: stride (sh, sw) and dilation (dh, dw) -- nn.Conv2d of the ResNet / PPM / FPN trunks (backbones/resnet.py:110-256,
+ * resnet_dilated.py:50-69).  The tap shift is a TMA coordinate offset scaled by the dilation; a stride is the tensor map's
+ * traversal stride (every s-th column / row of the box is delivered), so the kernel itself is unchanged. */
+int mr_conv2d_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, int W, int C, int Cout, int kh, int kw,
+                            int sh, int sw, int ph, int pw, int dh, int dw, int out_dtype, const float *bias, int relu,
+                            void *stream) {
+    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || ph < 0 || pw < 0 || sh <= 0 || sw <= 0 ||
+        dh <= 0 || dw <= 0) return MR_ERR_BAD_SHAPE;
     if (N == 0) return MR_OK;
     if (!x || !Wm || !y) return MR_ERR_NULL_POINTER;
     if (C % 64 || ((uintptr_t)x % 16) || ((uintptr_t)Wm % 16)) return MR_ERR_UNSUPPORTED;
     ConvArgs a;
     a.x = (const bf16 *)x; a.N = N; a.H = H; a.W = W; a.C = C; a.kh = kh; a.kw = kw; a.ph = ph; a.pw = pw;
-    a.Ho = H + 2 * ph - kh + 1; a.Wo = W + 2 * pw - kw + 1;
-    if (a.Ho <= 0 || a.Wo <= 0) return MR_ERR_BAD_SHAPE;
+    a.sh = sh; a.sw = sw; a.dh = dh; a.dw = dw;
+    a.Ho = (H + 2 * ph - dh * (kh - 1) - 1) / sh + 1; a.Wo = (W + 2 * pw - dw * (kw - 1) - 1) / sw + 1;
+    if (a.Ho <= 0 || a.Wo <= 0 || H + 2 * ph < dh * (kh - 1) + 1 || W + 2 * pw < dw * (kw - 1) + 1) return MR_ERR_BAD_SHAPE;
     const int64_t P = (int64_t)N * a.Ho * a.Wo, K = (int64_t)kh * kw * C;
     if (P > (1LL << 31) - 256) return MR_ERR_UNSUPPORTED;
     a.g.M = (int)P; a.g.N = Cout; a.g.K = (int)K; a.g.ldc = Cout; a.g.C = y; a.g.bias = bias; a.g.relu = relu;
@@ -985,7 +1002,8 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
                 if (a.nseg == 4) { ok = false; break; }
                 ConvArgs::Seg &sg = a.seg[a.nseg];
                 sg.w0 = w0; sg.bw = bw; sg.bh = bh; sg.bn = bn; sg.h_blocks = h_blocks; sg.tile_begin = tiles;
-                rc = make_map_nhwc(&tx[a.nseg], x, C, W, H, N, bw, bh, bn);
+                rc = make_map_nhwc(&tx[a.nseg], x, C, W, H, N, bw, bh, bn, sw, sh);
+                if (rc == MR_ERR_UNSUPPORTED) { ok = false; break; }
                 if (rc) return rc;
                 tiles += h_blocks * n_blocks;
                 ++a.nseg;
@@ -1026,14 +1044,21 @@ int mr_conv_fprop_tcgen05(const void *x, const void *Wm, void *y, int N, int H, 
  * dz[N,Ho,Wo,Cout] and x[N,H,W,C] (NHWC bf16, stride-1 geometry).  C % 64 == 0 and Cout % 8 == 0. */
 int mr_conv_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int H, int W, int C, int Cout, int kh, int kw,
                           int ph, int pw, int splits, void *stream) {
-    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || ph < 0 || pw < 0) return MR_ERR_BAD_SHAPE;
+    return mr_conv2d_wgrad_tcgen05(dz, x, dWm, N, H, W, C, Cout, kh, kw, 1, 1, ph, pw, 1, 1, splits, stream);
+}
+
+int mr_conv2d_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int H, int W, int C, int Cout, int kh, int kw,
+                            int sh, int sw, int ph, int pw, int dh, int dw, int splits, void *stream) {
+    if (N < 0 || H <= 0 || W <= 0 || C <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || ph < 0 || pw < 0 || sh <= 0 || sw <= 0 ||
+        dh <= 0 || dw <= 0) return MR_ERR_BAD_SHAPE;
     if (N == 0) return MR_OK;
     if (!dz || !x || !dWm) return MR_ERR_NULL_POINTER;
     if (C % 64 || Cout % 8 || ((uintptr_t)x % 16) || ((uintptr_t)dz % 16)) return MR_ERR_UNSUPPORTED;
     WgradArgs a;
     a.N = N; a.H = H; a.W = W; a.C = C; a.kh = kh; a.kw = kw; a.ph = ph; a.pw = pw; a.Cout = Cout;
-    a.Ho = H + 2 * ph - kh + 1; a.Wo = W + 2 * pw - kw + 1;
-    if (a.Ho <= 0 || a.Wo <= 0) return MR_ERR_BAD_SHAPE;
+    a.sh = sh; a.sw = sw; a.dh = dh; a.dw = dw;
+    a.Ho = (H + 2 * ph - dh * (kh - 1) - 1) / sh + 1; a.Wo = (W + 2 * pw - dw * (kw - 1) - 1) / sw + 1;
+    if (a.Ho <= 0 || a.Wo <= 0 || H + 2 * ph < dh * (kh - 1) + 1 || W + 2 * pw < dw * (kw - 1) + 1) return MR_ERR_BAD_SHAPE;
     const int K = kh * kw * C;
     const bool rb80 = (a.Wo > 64 && a.Wo <= 80);
     const int RB = rb80 ? 80 : 64;
@@ -1048,7 +1073,7 @@ int mr_conv_wgrad_tcgen05(const void *dz, const void *x, float *dWm, int N, int 
     CUtensorMap tdz, tx;
     int rc = make_map_nhwc(&tdz, dz, Cout, a.Wo, a.Ho, N, RB);
     if (rc) return rc;
-    rc = make_map_nhwc(&tx, x, C, W, H, N, RB);
+    rc = make_map_nhwc(&tx, x, C, W, H, N, RB, 1, 1, sw, 1);      /* rows are addressed one at a time: only the width strides */
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int BN = K > 128 ? 256 : (K > 64 ? 128 : 64);

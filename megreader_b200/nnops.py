@@ -228,6 +228,32 @@ def conv_wgrad_tc(dz, x, kh, kw, ph, pw, splits=0, out=None):
     return dWm
 
 
+def conv2d_fprop_tc(x, Wm, kh, kw, sh, sw, ph, pw, dh, dw, out_dtype=torch.bfloat16, bias=None, relu=False):
+    """General implicit-GEMM conv (stride, dilation): x NHWC bf16 [N,H,W,C] -> ([N*Ho*Wo, Cout], Ho, Wo)."""
+    N, H, W, C = x.shape
+    Cout = Wm.size(0)
+    assert x.is_contiguous() and Wm.is_contiguous() and Wm.size(1) == kh * kw * C
+    Ho, Wo = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1, (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    y = torch.empty((N * Ho * Wo, Cout), dtype=out_dtype, device=x.device)
+    _chk(_lib.lib().mr_conv2d_fprop_tcgen05(_p(x), _p(Wm), _p(y), N, H, W, C, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
+                                            code(out_dtype), _p(bias), int(relu), _st()), "conv2d_fprop_tcgen05")
+    return y, Ho, Wo
+
+
+def conv2d_wgrad_tc(dz, x, kh, kw, sh, sw, ph, pw, dh, dw, splits=0, out=None):
+    """dWm [Cout, kh*kw*C] fp32 from dz [N,Ho,Wo,Cout] and x [N,H,W,C] (NHWC bf16), stride / dilation as the forward."""
+    N, H, W, C = x.shape
+    Cout = dz.size(-1)
+    K = kh * kw * C
+    dWm = out if out is not None else torch.zeros((Cout, K), dtype=torch.float32, device=x.device)
+    if splits <= 0:
+        tiles = ((Cout + 127) // 128) * ((K + 255) // 256)
+        splits = max(1, -(-288 // tiles))
+    _chk(_lib.lib().mr_conv2d_wgrad_tcgen05(_p(dz), _p(x), _p(dWm), N, H, W, C, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
+                                            int(splits), _st()), "conv2d_wgrad_tcgen05")
+    return dWm
+
+
 def lstm_step_fwd_tc(h_prev, Whh, gates, bias, c_prev, c_out, h_out, ldh, h_next, have_h):
     """Fused recurrent GEMM + LSTM cell, both directions (lists of 2 tensors each), unit-major gate layout."""
     B, H4 = gates[0].shape

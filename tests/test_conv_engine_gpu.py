@@ -1,0 +1,67 @@
+"""GPU: the general tcgen05 convolution (stride, dilation, 1x1 / 3x3 / stem) behind megreader_b200.conv_engine against
+torch's conv2d in fp32 on the same bf16-rounded operands -- forward, input gradient, weight gradient, bias gradient -- at the
+geometries of the ResNet-50 / dilated / PPM / FPN trunks and the 2D-CTC head."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # Cin, Cout, k, s, p, d, N, H, W, bias
+    (64, 64, 1, 1, 0, 1, 2, 16, 64, False),      # bottleneck conv1
+    (64, 256, 1, 1, 0, 1, 2, 16, 64, False),     # bottleneck conv3 / downsample
+    (128, 128, 3, 2, 1, 1, 2, 16, 64, False),    # layer2.0.conv2 (stride 2)
+    (256, 512, 1, 2, 0, 1, 2, 16, 64, False),    # layer2.0.downsample (1x1 stride 2)
+    (256, 256, 3, 1, 2, 2, 2, 8, 32, False),     # dilated layer3
+    (512, 512, 3, 1, 4, 4, 1, 8, 32, False),     # dilated layer4
+    (256, 256, 3, 1, 1, 1, 3, 8, 32, True),      # CTCDecoder2D branch 3x3 (with bias)
+    (256, 38, 1, 1, 0, 1, 3, 8, 32, True),       # classify 1x1
+    (256, 1, 1, 1, 0, 1, 3, 8, 32, True),        # mask 1x1 (one output channel)
+    (128, 128, 3, 2, 1, 1, 2, 15, 33, False),    # odd sizes under stride 2
+    (64, 64, 3, 1, 1, 1, 2, 12, 65, True),       # width with a 1-wide TMA segment
+    (3, 64, 7, 2, 3, 1, 2, 64, 96, False),       # stem (unfold + GEMM)
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_conv2d_forward_backward(cuda, case):
+    from megreader_b200 import conv_engine
+    Cin, Cout, k, s, p, d, N, H, W, with_bias = case
+    torch.manual_seed(sum(case[:9]))
+    x = torch.randn(N, Cin, H, W, device=cuda).bfloat16().float()
+    w = (torch.randn(Cout, Cin, k, k, device=cuda) / (Cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(Cout, device=cuda) if with_bias else None
+    xr, wr = x.clone().requires_grad_(Cin % 64 == 0), w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if with_bias else None
+    ref = F.conv2d(xr, wr, br, s, p, d)
+    go = torch.randn_like(ref).bfloat16().float()
+    ref.backward(go)
+    conv = torch.nn.Conv2d(Cin, Cout, k, s, p, d, bias=with_bias).to(cuda)
+    conv.weight.data.copy_(w)
+    if with_bias:
+        conv.bias.data.copy_(b)
+    assert conv_engine.use_engine_convs(conv) == 1
+    xe = x.clone().requires_grad_(Cin % 64 == 0)
+    out = conv(xe)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == tuple(ref.shape)
+    out.backward(go.to(out.dtype))
+
+    def rel(a, r):
+        return float((a.float() - r).norm() / (r.norm() + 1e-12))
+    assert rel(out, ref) < 6e-3, rel(out, ref)
+    assert rel(conv.weight.grad, wr.grad) < 1e-2, rel(conv.weight.grad, wr.grad)
+    if with_bias:
+        assert rel(conv.bias.grad, br.grad) < 1e-2
+    if Cin % 64 == 0:
+        assert rel(xe.grad, xr.grad) < 1e-2, rel(xe.grad, xr.grad)
+
+
+def test_trunk_switch_counts_and_restores(cuda):
+    from megreader_b200 import conv_engine
+    m = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 7, 2, 3), torch.nn.Conv2d(64, 64, 3, padding=1),
+                            torch.nn.Conv2d(64, 32, 1), torch.nn.Conv2d(32, 32, 3, groups=2))
+    assert conv_engine.use_engine_convs(m) == 3            # 32 -> 32 grouped stays with the library
+    assert conv_engine.restore_library_convs(m) == 3
+    with pytest.raises(NotImplementedError):
+        conv_engine.conv2d(torch.zeros(1, 64, 4, 4), torch.zeros(64, 64, 1, 1))
