@@ -275,6 +275,14 @@ def run_ours(args):
         out["ctc2d"], ctc_roof = bench_ctc2d(dev)
         out["roofline"] = bench_conv_roofline(dev)
         out["roofline_ctc2d"] = ctc_roof
+        try:
+            out["roofline_dcn"] = bench_dcn(dev)
+        except Exception as e:                                # an extra arm never takes the headline down, but says why
+            out["roofline_dcn"] = {"error": str(e)[:200]}
+        try:
+            out["parity"] = bench_parity(dev, lambda: net)
+        except Exception as e:
+            out["parity"] = {"error": str(e)[:200]}
         out["cpu_baseline"] = cpu_arm(steps=3, warmup=1, sample_n=16)
         out["stages"] = {"conv": "megreader_b200 tcgen05 implicit-GEMM kernels (fprop, dgrad, wgrad); conv0 (Cin=3): im2col kernel + cuBLAS",
                          "bias+ReLU+MaxPool, BatchNorm": "megreader_b200 CUDA (fused NHWC kernels)",
@@ -290,72 +298,175 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------- 2D-CTC micro arm
-def bench_ctc2d(dev, N=16384, iters=10):
-    """cfg-3 shape (T32,H8,C38,S32) fwd+bwd through ops.ctc_loss_2d's training pair at a saturating batch; inputs
-    (637 MB) exceed L2.  Algorithmic bytes: SURVEY.md §8(d) '3*|lp| + 2*iota + 12' = 117,292 B/sample."""
+def _graph_time(fn, iters=20):
+    """device time of one call without the host launch gap: `iters` calls captured in a CUDA graph, replayed once"""
+    fn(); fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) * 1e-3 / iters
+
+
+def bench_ctc2d(dev, iters=10):
+    """cfg-3 shape (T32,H8,C38,S32) fwd+bwd through ops.ctc_loss_2d's training pair at N in {32, 256, 2048, 16384}
+    (SURVEY.md section 8d).  N = 16384: inputs (637 MB) exceed L2, CUDA events around back-to-back launches.  Smaller batches fit
+    in L2 and a single launch is shorter than the host's launch gap, so they are timed as 20 launches inside one CUDA graph.
+    Algorithmic bytes: SURVEY.md section 8(d) '3*|lp| + 2*iota + 12' = 117,292 B/sample."""
     from megreader_b200 import ctc2d
     from tests.cases import ctc2d_case
     T, H, C, S = 32, 8, 38, 32
-    base = 256
-    lp, tg, il, tl = ctc2d_case(3, T, H, base, C, S, 12)
-    rep = N // base
-    d_lp = torch.from_numpy(np.ascontiguousarray(np.tile(lp, (1, 1, rep, 1)))).to(dev)
-    d_tg = torch.from_numpy(np.tile(tg, (rep, 1))).to(dev)
-    d_il = torch.from_numpy(np.tile(il, rep)).to(dev)
-    d_tl = torch.from_numpy(np.tile(tl, rep)).to(dev)
-    go = 1.0 / d_tl.float()
-    def fwd():
-        return ctc2d.ctc2d_forward_train(d_lp, d_tg, d_il, d_tl, 0)
-
-    def bwd(gf):
-        return ctc2d.ctc2d_backward_apply(go, d_lp, gf)
-    for _ in range(3):
-        _, gf = fwd(); bwd(gf)
-    torch.cuda.synchronize()
-    tf = tb = 0.0
-    for _ in range(iters):
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record(); _, gf = fwd(); b.record(); bwd(gf); c.record()
-        torch.cuda.synchronize()
-        tf += a.elapsed_time(b); tb += b.elapsed_time(c)
-    tf, tb = tf / iters * 1e-3, tb / iters * 1e-3
     lp_b, idx_b = T * H * C * 4, 8 * S + 16
-    fwd_bytes, bwd_bytes = lp_b + T * C * 4 + idx_b + 4, 2 * lp_b + T * C * 4 + 4
+    fwd_bytes, bwd_bytes, pair_bytes = lp_b + T * C * 4 + idx_b + 4, 2 * lp_b + T * C * 4 + 4, 3 * lp_b + 2 * idx_b + 12
     pk = peaks()
-    ctc = {"shape": {"T": T, "H": H, "C": C, "S": S, "N": N}, "fwd_us": tf * 1e6, "bwd_us": tb * 1e6,
-           "alg_bytes_per_sample_fwd_bwd": 3 * lp_b + 2 * idx_b + 12,
-           "fwd_bwd_GBps": N * (3 * lp_b + 2 * idx_b + 12) / (tf + tb) / 1e9,
-           "frac_of_hbm_peak": N * (3 * lp_b + 2 * idx_b + 12) / (tf + tb) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"]}
-    # head epilogue in front of the loss (decoders/ctc_decoder2d.py:37-45): logits -> log_probs, and the fused backward
-    try:
-        from megreader_b200 import ctc2d_head
-        m = torch.randn(N, 1, H, T, device=dev)
-        z = torch.randn(N, C, H, T, device=dev)
+    base = 256
+    lp0, tg0, il0, tl0 = ctc2d_case(3, T, H, base, C, S, 12)
+    sweep = {}
+    ctc = roof = None
+    for N in (32, 256, 2048, 16384):
+        rep = max(1, N // base)
+        sl = slice(0, min(N, base))
+        d_lp = torch.from_numpy(np.ascontiguousarray(np.tile(lp0[:, :, sl], (1, 1, rep, 1)))).to(dev)
+        d_tg = torch.from_numpy(np.tile(tg0[sl], (rep, 1))).to(dev)
+        d_il = torch.from_numpy(np.tile(il0[sl], rep)).to(dev)
+        d_tl = torch.from_numpy(np.tile(tl0[sl], rep)).to(dev)
+        go = 1.0 / d_tl.float()
+        fwd = lambda: ctc2d.ctc2d_forward_train(d_lp, d_tg, d_il, d_tl, 0)  # noqa: E731
         _, gf = fwd()
-        for _ in range(2):
-            ctc2d_head.head_forward(m, z); ctc2d_head.head_backward(m, z, gfac=gf, grad_out=go)
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        bwd = lambda: ctc2d.ctc2d_backward_apply(go, d_lp, gf)  # noqa: E731
+        if N < 16384:
+            tf, tb = _graph_time(fwd), _graph_time(bwd)
+            how = "20 launches in one CUDA graph (inputs L2-resident)"
+        else:
+            for _ in range(3):
+                fwd(); bwd()
+            torch.cuda.synchronize()
+            tf = tb = 0.0
+            for _ in range(iters):
+                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record(); fwd(); b.record(); bwd(); c.record()
+                torch.cuda.synchronize()
+                tf += a.elapsed_time(b); tb += b.elapsed_time(c)
+            tf, tb = tf / iters * 1e-3, tb / iters * 1e-3
+            how = "CUDA events, back-to-back launches, inputs exceed L2"
+        sweep[str(N)] = {"fwd_us": tf * 1e6, "bwd_us": tb * 1e6, "fwd_bwd_GBps": N * pair_bytes / (tf + tb) / 1e9,
+                         "frac_of_hbm_peak": N * pair_bytes / (tf + tb) / 1e9 / pk["hbm_gbs"], "timing": how}
+        if N == 16384:
+            ctc = {"shape": {"T": T, "H": H, "C": C, "S": S, "N": N}, "fwd_us": tf * 1e6, "bwd_us": tb * 1e6,
+                   "alg_bytes_per_sample_fwd_bwd": pair_bytes, "fwd_bwd_GBps": N * pair_bytes / (tf + tb) / 1e9,
+                   "frac_of_hbm_peak": N * pair_bytes / (tf + tb) / 1e9 / pk["hbm_gbs"], "peak_source": pk["source"]}
+            roof = {"kernel": "ctc2d_dp4_kernel<FAC> (2D-CTC training forward: Q, interleaved alpha/beta sweeps, factors)",
+                    "bound": "hbm", "achieved": N * fwd_bytes / tf / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": N * fwd_bytes / tf / 1e9 / pk["hbm_gbs"], "traffic": _measured("ctc2d_dp4", "dram_bytes_per_launch"),
+                    "peak_source": pk["source"], "alg_bytes_per_launch": N * fwd_bytes,
+                    "note": "2D-CTC training forward (BASELINE.json metric, second half)"}
+            # head epilogue in front of the loss (decoders/ctc_decoder2d.py:37-45): logits -> log_probs, and the fused backward
+            try:
+                from megreader_b200 import ctc2d_head
+                m = torch.randn(N, 1, H, T, device=dev)
+                z = torch.randn(N, C, H, T, device=dev)
+                for _ in range(2):
+                    ctc2d_head.head_forward(m, z); ctc2d_head.head_backward(m, z, gfac=gf, grad_out=go)
+                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record()
+                for _ in range(iters):
+                    ctc2d_head.head_forward(m, z)
+                b.record()
+                for _ in range(iters):
+                    ctc2d_head.head_backward(m, z, gfac=gf, grad_out=go)
+                c.record()
+                torch.cuda.synchronize()
+                hf, hb = a.elapsed_time(b) / iters * 1e-3, b.elapsed_time(c) / iters * 1e-3
+                ctc["head_epilogue"] = {"fwd_us": hf * 1e6, "bwd_factored_us": hb * 1e6,
+                                        "fwd_GBps": N * (2 * lp_b + H * T * 4) / hf / 1e9,
+                                        "bwd_GBps": N * (2 * lp_b + T * C * 4) / hb / 1e9,
+                                        "fwd_frac_of_hbm_peak": N * (2 * lp_b + H * T * 4) / hf / 1e9 / pk["hbm_gbs"],
+                                        "bwd_frac_of_hbm_peak": N * (2 * lp_b + T * C * 4) / hb / 1e9 / pk["hbm_gbs"]}
+                del m, z
+            except Exception as e:
+                ctc["head_epilogue"] = {"error": str(e)[:200]}
+        del d_lp, gf
+    ctc["batches"] = sweep
+    return ctc, roof
+
+
+def _measured(kernel, key):
+    """A number taken from the committed ncu summary of the current revision (profiles/measured_r2.json, written from the
+    `ncu --set full` captures listed in profiles/); None when no capture of that kernel is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "measured_r2.json")))
+        return d[kernel][key]
+    except Exception:
+        return None
+
+
+def bench_dcn(dev, iters=10):
+    """DCNv2 forward at SURVEY.md section 8d's shapes (B = 8): fused tcgen05 implicit GEMM (csrc/dcn_tcgen05.cu), timed through the
+    autograd surface (NHWC copy + weight pack + the GEMM).  Roofline: tensor pipe, 2*C*9*Cout*Ho*Wo flops per sample."""
+    from megreader_b200 import dcn
+    pk = peaks()
+    out = {}
+    for C, H in ((128, 64), (256, 32), (512, 16)):
+        B = 8
+        x = torch.randn(B, C, H, H, device=dev)
+        w = torch.randn(C, C, 3, 3, device=dev) / (3 * C ** 0.5)
+        off = 2 * torch.randn(B, 18, H, H, device=dev)
+        m = torch.sigmoid(torch.randn(B, 9, H, H, device=dev))
+        fn = lambda: dcn.modulated_deform_conv(x, off, m, w, None, 1, 1, 1, 1, 1)  # noqa: E731
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(iters):
-            ctc2d_head.head_forward(m, z)
+            fn()
         b.record()
-        for _ in range(iters):
-            ctc2d_head.head_backward(m, z, gfac=gf, grad_out=go)
-        c.record()
         torch.cuda.synchronize()
-        hf, hb = a.elapsed_time(b) / iters * 1e-3, b.elapsed_time(c) / iters * 1e-3
-        ctc["head_epilogue"] = {"fwd_us": hf * 1e6, "bwd_factored_us": hb * 1e6,
-                                "fwd_GBps": N * (2 * lp_b + H * T * 4) / hf / 1e9,
-                                "bwd_GBps": N * (2 * lp_b + T * C * 4) / hb / 1e9}
-        del m, z
-    except Exception as e:                                   # never let the extra arm take the headline down
-        ctc["head_epilogue"] = {"error": str(e)[:200]}
-    roof = {"kernel": "ctc2d_dp_warp_kernel<FAC> (2D-CTC training forward: Q, alpha/beta sweeps, factors)",
-            "bound": "hbm", "achieved": N * fwd_bytes / tf / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "frac": N * fwd_bytes / tf / 1e9 / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
-            "alg_bytes_per_launch": N * fwd_bytes,
-            "note": "2D-CTC training forward (BASELINE.json metric, second half)"}
-    return ctc, roof
+        sec = a.elapsed_time(b) / iters * 1e-3
+        flops = 2.0 * B * C * 9 * C * H * H
+        out["C%d@%dx%d" % (C, H, H)] = {"fwd_us": sec * 1e6, "alg_TFLOPs": flops / sec / 1e12,
+                                        "frac_of_tensor_peak": flops / sec / 1e12 / pk["bf16_tflops"],
+                                        "mma_TFLOPs_issued": 3 * flops / sec / 1e12}
+    return {"kernel": "dcn_fwd_tcgen05_kernel (bilinear gather = A-operand producer, bf16 hi/lo split: 3 MMAs per K block)",
+            "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops"], "peak_source": pk["source"], "B": 8, "shapes": out,
+            "round1_fwd_us": {"C128@64x64": 319.2, "C256@32x32": 264.5, "C512@16x16": 215.3}}
+
+
+def bench_parity(dev, model_fn):
+    """bf16 engine (the timed mode) against the fp32 engine on one 512-line bench batch: what tests/test_bench_shape_parity_gpu.py
+    asserts, recomputed live."""
+    from megreader_b200 import crnn_engine
+    net = model_fn()
+    x, y, l = [t.to(dev) for t in synth_batch(0, BATCH_PER_GPU)]
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    res = {}
+    for name, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        crnn_engine.set_compute_dtype(dt)
+        with torch.no_grad():
+            net.train()
+            loss, lp = net(x, y, l)
+        net.load_state_dict(state)
+        res[name] = (float(loss), lp.float())
+    crnn_engine.set_compute_dtype(torch.bfloat16)
+    l32, p32 = res["fp32"]
+    l16, p16 = res["bf16"]
+    dmax = float((p16 - p32).abs().max())
+    top2 = p32.topk(2, dim=2).values
+    decided = (top2[..., 0] - top2[..., 1]) > 4 * dmax
+    same = p16.argmax(2) == p32.argmax(2)
+    return {"shape": "N=512, 3x32x256, T=65", "loss_rel_delta_bf16_vs_fp32": abs(l16 - l32) / abs(l32),
+            "max_abs_logprob_delta": dmax, "argmax_agreement": float(same.float().mean()),
+            "argmax_agreement_where_fp32_margin_gt_4x_delta": float(same[decided].float().mean()) if bool(decided.any()) else None,
+            "decided_fraction": float(decided.float().mean()),
+            "fp32_engine_vs_cpu_oracle": "tests/test_bench_shape_parity_gpu.py (loss / log-probs 1e-4, labels bit-exact)"}
 
 
 def bench_conv_roofline(dev, iters=10):
@@ -381,7 +492,7 @@ def bench_conv_roofline(dev, iters=10):
     return {"kernel": "conv_fprop_tcgen05_kernel<256,2,1,1> (implicit-GEMM 3x3 conv via 4-D TMA, conv5 shape, bf16 in / fp32 acc)",
             "bound": "tensor", "achieved": flops / sec / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
             "frac": flops / sec / 1e12 / pk["bf16_tflops"],
-            "traffic": 388.5e6,   # dram__bytes_read+write per launch, ncu --set full (profiles/conv_fprop_r1b_summary.md)
+            "traffic": _measured("conv_fprop_conv5", "dram_bytes_per_launch"),   # ncu --set full of this revision, or None
             "traffic_algorithmic": 2.0 * N * H * W * C + 2.0 * N * H * W * Cout + 2.0 * Cout * k * k * C,
             "peak_source": pk["source"],
             "alg_flops_per_launch": flops, "us_per_launch": sec * 1e6}
@@ -492,9 +603,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json configuration: 2 = CRNN + 1D CTC (headline, default); 3 = ResNet50-PPM + 2D CTC; "
+                         "4 = FPN50 + attention decoder (bench_trunks.py)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch for --config 3 / 4 (default 32)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != 2:
+        import bench_trunks
+        bench_trunks.run(args, peaks(), ClockSampler, emit_json)
     else:
         run_ours(args)
 

@@ -33,6 +33,9 @@ class _Conv2dFn(torch.autograd.Function):
         dh, dw = dilation
         N, C, H, W = x.shape
         assert C == Cin and Cin % 64 == 0
+        if x.numel() == 0 or (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1 <= 0 or (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1 <= 0:
+            raise RuntimeError("megreader_b200.conv_engine: empty convolution problem: input %s, kernel %s, stride %s, padding %s, "
+                               "dilation %s" % (tuple(x.shape), (kh, kw), stride, padding, dilation))
         xh = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).contiguous()   # NHWC
         Cp = _pad_to(Cout, 8)                                   # weight-gradient kernel wants Cout % 8 == 0
         Wm = ops.conv_weight_pack(weight.detach().float().contiguous(), Cin, kh * kw * Cin, torch.bfloat16, 0)   # [Cout, K]

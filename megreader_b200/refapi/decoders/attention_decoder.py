@@ -131,12 +131,13 @@ class AttentionDecoder(nn.Module):
     def forward(self, feature, targets=None, lengths=None, train=False):
         device = feature.device
         n = feature.shape[0]
-        grid = torch.cat([self.encode(feature), self._positions(n, device)], dim=1)
+        # the conv encoder may run in bf16 (megreader_b200.conv_engine); the recurrent part is fp32 like its parameters
+        grid = torch.cat([self.encode(feature).float(), self._positions(n, device)], dim=1)
         memory = grid.reshape(n, grid.shape[1], -1).permute(2, 0, 1)            # (L,N,H+E), L = height*max_size
         memory_bt = memory.transpose(0, 1)
         projected = self.decoder.attn.project_encoder(memory)
         blank = self.charset.blank
-        hidden = feature.new_zeros(n, self.inner_channels)
+        hidden = grid.new_zeros(n, self.inner_channels)
         word = torch.full((n,), blank, dtype=torch.long, device=device)
         vocab = len(self.charset)
 
