@@ -615,9 +615,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
                     help="BASELINE.json configuration: 2 = CRNN + 1D CTC (headline, default); 3 = ResNet50-PPM + 2D CTC; "
-                         "4 = FPN50 + attention decoder (bench_trunks.py)")
+                         "4 = FPN50 + attention decoder; 5 = deformable ResNet50 + FPN + EAST (bench_trunks.py)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch for --config 3 / 4 (default 32)")
     ap.add_argument("--strong", action="store_true",
                     help="reference semantics (data/data_loader.py:40-43): global batch 512 split over the ranks (strong scaling) "

@@ -21,7 +21,18 @@ CFG = {
     # decoders/attention_decoder.py:41-66) needs a 16-row feature map = 64 input rows at the FPN's stride 4
     4: dict(name="ResNet50-FPN + attention decoder (fpn50-attention-decoder.yaml)", hw=(64, 256), backbone="Resnet50FPN",
             decoder="AttentionDecoder", l_max=12),
+    # no EAST yaml exists in the reference; SURVEY.md D4: FeaturePyramid(deformable_resnet50, FPNTopDown) -> EASTDecoder
+    5: dict(name="deformable ResNet50 (DCNv2) + FPN + EAST head (SURVEY.md D4 composition)", hw=(512, 512), backbone="deformable_resnet50+FPN",
+            decoder="EASTDecoder", l_max=0),
 }
+
+
+def synth_east(seed, n, hw):
+    """uint8-like scenes, all-zero heat maps / dense boxes with unit weights (loss arithmetic only)."""
+    rng = np.random.RandomState(seed)
+    x = (rng.standard_normal((n, 3, hw[0], hw[1])) * 60 + 110).clip(0, 255).astype(np.float32)
+    z = lambda c: torch.zeros(n, c, hw[0], hw[1])  # noqa: E731
+    return torch.from_numpy(x), {"heatmap": z(1), "heatmap_weight": z(1) + 1, "densebox": z(8), "densebox_weight": z(8) + 1}
 
 
 def synth(seed, n, hw, l_max, S=32, n_classes=38):
@@ -34,6 +45,30 @@ def synth(seed, n, hw, l_max, S=32, n_classes=38):
     return torch.from_numpy(x), torch.from_numpy(labels), torch.from_numpy(lengths)
 
 
+def _map(t, fn):
+    if t is None:
+        return None
+    if isinstance(t, dict):
+        return {k: fn(v) for k, v in t.items()}
+    return fn(t)
+
+
+def _nbytes(t):
+    if t is None:
+        return 0
+    if isinstance(t, dict):
+        return sum(v.numel() * v.element_size() for v in t.values())
+    return t.numel() * t.element_size()
+
+
+def make_batch(cfg, seed, n):
+    c = CFG[cfg]
+    if cfg == 5:
+        x, lab = synth_east(seed, n, c["hw"])
+        return x, lab, None
+    return synth(seed, n, c["hw"], c["l_max"])
+
+
 def build(cfg, device, engine=True):
     import megreader_b200
     megreader_b200.install_reference_api()
@@ -41,9 +76,14 @@ def build(cfg, device, engine=True):
     import decoders
     from tests.weights import fill_state_dict
     c = CFG[cfg]
-    kw = {"resnet_pretrained": False}
-    bb = getattr(backbones, c["backbone"])(**kw)
-    dec = getattr(decoders, c["decoder"])(in_channels=256)
+    if cfg == 5:
+        from backbones.feature_pyramid import FeaturePyramid
+        from backbones.fpn_top_down import FPNTopDown
+        bb = FeaturePyramid(backbones.deformable_resnet50(pretrained=False), FPNTopDown([2048, 1024, 512, 256], 256))
+        dec = decoders.EASTDecoder(channels=256)
+    else:
+        bb = getattr(backbones, c["backbone"])(resnet_pretrained=False)
+        dec = getattr(decoders, c["decoder"])(in_channels=256)
 
     class Net(torch.nn.Module):          # structure/model.py:16-24 BasicModel: decoder(backbone(x), **kw)
         def __init__(self):
@@ -52,6 +92,9 @@ def build(cfg, device, engine=True):
             self.decoder = fill_state_dict(dec, "dec%d." % cfg)
 
         def forward(self, images, targets, lengths):
+            if cfg == 5:                 # structure/model.py:63-87 DetectionModel: decoder(feature, label, meta, train)
+                loss, pred, _ = self.decoder(self.backbone(images), targets, None, True)
+                return loss, pred
             return self.decoder(self.backbone(images), targets=targets, lengths=lengths, train=True)
     net = Net().to(device).train()
     n_engine = 0
@@ -66,7 +109,7 @@ def conv_roofline(dev, peaks, cfg):
     8x32 map) / the 3x3 512->512 of layer4 at stride-32 resolution (config 4), timed alone with CUDA events."""
     from megreader_b200 import nnops
     N = 256
-    H, W, C, d = (8, 32, 512, 4) if cfg == 3 else (6, 20, 512, 1)
+    H, W, C, d = (8, 32, 512, 4) if cfg == 3 else ((16, 16, 512, 1) if cfg == 5 else (6, 20, 512, 1))
     x = torch.randn(N, H, W, C, device=dev).bfloat16()
     wm = (torch.randn(C, 9 * C, device=dev) / 68).bfloat16()
     fn = lambda: nnops.conv2d_fprop_tc(x, wm, 3, 3, 1, 1, d, d, d, d)  # noqa: E731
@@ -98,6 +141,9 @@ def cpu_arm(cfg, sample_n, steps, budget_s=25.0):
     c = CFG[cfg]
     cores = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
     torch.set_num_threads(cores)
+    if cfg == 5:
+        return {"value": None, "unit": "lines/s", "cores": cores, "kind": "port",
+                "sample": "not timed: the reference has no CPU implementation of the DCN op (functions/deform_conv.py:40-41 raises)"}
     bb = fill_state_dict(getattr(backbones, c["backbone"])(resnet_pretrained=False), "bb%d." % cfg).train()
     x, _, _ = synth(0, sample_n, c["hw"], c["l_max"])
     opt = torch.optim.Adam(bb.parameters(), lr=1e-3)
@@ -136,15 +182,15 @@ def run(args, peaks, ClockSampler, emit_json):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
-    batch = args.batch or 32
+    batch = args.batch or (8 if cfg == 5 else 32)           # BASELINE.json: 256 (cfg 3/4) and 64 (cfg 5) over 8 GPUs
     net, n_engine = build(cfg, dev)
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3, fused=True)
     host = []
     for i in range(3):
-        x, y, l = synth(100 * rank + i, batch, c["hw"], c["l_max"])
-        host.append((x.pin_memory(), y.pin_memory(), l.pin_memory()))
-    dev_batches = [tuple(t.to(dev) for t in hb) for hb in host]
+        hb = make_batch(cfg, 100 * rank + i, batch)
+        host.append(tuple(_map(t, lambda v: v.pin_memory()) for t in hb))
+    dev_batches = [tuple(_map(t, lambda v: v.to(dev)) for t in hb) for hb in host]
 
     def step(x, y, l):
         opt.zero_grad(set_to_none=True)
@@ -182,11 +228,11 @@ def run(args, peaks, ClockSampler, emit_json):
     final_loss = float(loss.item())
     # end to end: pinned host batches, copies inside the timed region, loss read back every step
     copy_stream = torch.cuda.Stream()
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    h2d = sum(_nbytes(t) for t in host[0])
 
     def fetch(i):
         with torch.cuda.stream(copy_stream):
-            b = tuple(t.to(dev, non_blocking=True) for t in host[i % 3])
+            b = tuple(_map(t, lambda v: v.to(dev, non_blocking=True)) for t in host[i % 3])
             ev = torch.cuda.Event()
             ev.record(copy_stream)
         return b, ev
@@ -213,14 +259,14 @@ def run(args, peaks, ClockSampler, emit_json):
     ms, ms_e2e = float(t[0]), float(t[1])
     lines = batch * world * args.steps
     out = {
-        "metric": "text-lines/sec %s train step (fwd+bwd+Adam), %dx%d lines, batch %d/GPU" % (c["name"], c["hw"][0], c["hw"][1], batch),
-        "value": lines / (ms / 1e3), "unit": "lines/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": "%s/sec %s train step (fwd+bwd+Adam), %dx%d inputs, batch %d/GPU" % ("scenes" if cfg == 5 else "text-lines", c["name"], c["hw"][0], c["hw"][1], batch),
+        "value": lines / (ms / 1e3), "unit": "scenes/s" if cfg == 5 else "lines/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": "%s, 3x%dx%d fp32 input, bf16 compute, Adam lr 1e-3" % (c["name"], c["hw"][0], c["hw"][1]),
                    "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": "dp%d" % world,
                    "l2": "3 rotating input batches; weights + gradients + Adam state (> 400 MB) and activations exceed the 126 MB L2"},
-        "e2e": {"value": lines / (ms_e2e / 1e3), "unit": "lines/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+        "e2e": {"value": lines / (ms_e2e / 1e3), "unit": "scenes/s" if cfg == 5 else "lines/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps, "final_loss": final_loss, "clocks": clocks,
         "engine_convs": n_engine,
@@ -231,7 +277,9 @@ def run(args, peaks, ClockSampler, emit_json):
         out["stages"] = {"convolutions (trunk + head, %d layers)" % n_engine: "megreader_b200 tcgen05 implicit-GEMM kernels (fprop, dgrad, wgrad)",
                          "BatchNorm / ReLU / pooling / interpolation": "library (ATen, channels_last bf16)",
                          "head": ("megreader_b200 fused 2D-CTC epilogue + DP kernels" if cfg == 3 else
-                                  "attention decoder: library (ATen) per-step arithmetic, hoisted encoder projection"),
+                                  "attention decoder: library (ATen) per-step arithmetic, hoisted encoder projection" if cfg == 4 else
+                                  "EAST head: 3x3 / 1x1 convolutions on the conv engine, transposed convolutions + losses library; "
+                                  "DCNv2 units: fused tcgen05 forward (csrc/dcn_tcgen05.cu), round-1 backward kernels + cuBLAS"),
                          "Adam": "library (torch fused)", "launch": "eager (no CUDA graph for these configurations)"}
         emit_json(out)
     if world > 1:

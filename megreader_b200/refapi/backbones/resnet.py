@@ -82,6 +82,10 @@ class _DeformableSlot:
             return self.conv2(x)
         # NB the reference takes this branch even when fallback_on_stride built a dense conv2; so do we.
         field = self.conv2_offset(x)
+        if x.dtype != torch.float32:
+            # bf16 trunk (megreader_b200.conv_engine): the deformable op is the reference's fp32 NCHW op (its fused forward
+            # splits every operand into two bf16 halves internally), so hand it fp32 NCHW tensors
+            x, field = x.float().contiguous(), field.float().contiguous()
         if self.with_modulated_dcn:
             return self.conv2(x, field[:, :18], field[:, -9:].sigmoid())
         return self.conv2(x, field)

@@ -4,3 +4,4 @@ from .ctc_decoder import CTCDecoder  # noqa: F401
 from .crnn import CRNNDecoder  # noqa: F401
 from .ctc_decoder2d import CTCDecoder2D  # noqa: F401
 from .ctc_loss2d import CTCLoss2D, CTC2DLoss  # noqa: F401
+from .east import EASTDecoder  # noqa: F401

@@ -68,7 +68,7 @@ def test_public_names_match_the_reference_inits(api):
     for name in ("Resnet18FPN", "Resnet34FPN", "Resnet50FPN", "Resnet101FPN", "Resnet152FPN", "resnet18", "resnet34",
                  "resnet50", "resnet101", "deformable_resnet50", "crnn_backbone", "resnet50dilated_ppm"):
         assert callable(getattr(backbones, name)), name           # backbones/__init__.py:1-4
-    for name in ("AttentionDecoder", "CTCDecoder2D", "CTCDecoder", "CRNNDecoder", "CTCLoss2D", "CTC2DLoss"):
+    for name in ("AttentionDecoder", "CTCDecoder2D", "CTCDecoder", "CRNNDecoder", "CTCLoss2D", "CTC2DLoss", "EASTDecoder"):
         assert callable(getattr(decoders, name)), name
     import assets.ops.dcn as dcn
     assert sorted(dcn.__all__) == sorted(['DeformConv', 'DeformConvPack', 'ModulatedDeformConv', 'ModulatedDeformConvPack',

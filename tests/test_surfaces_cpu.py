@@ -50,7 +50,8 @@ def test_state_dict_keys_equal_reference():
              (rb.resnet50dilated_ppm(inner_channels=128), mb.resnet50dilated_ppm(inner_channels=128)),
              (rd.AttentionDecoder(64, inner_channels=128, max_size=16, height=2),
               md.AttentionDecoder(64, inner_channels=128, max_size=16, height=2)),
-             (rd.CTCDecoder(64, inner_channels=96), md.CTCDecoder(64, inner_channels=96))]
+             (rd.CTCDecoder(64, inner_channels=96), md.CTCDecoder(64, inner_channels=96)),
+             (rd.EASTDecoder(channels=64), md.EASTDecoder(channels=64))]
     for r, m in pairs:
         assert _keys(r) == _keys(m)
     # deformable trunk: our modules resolve `assets.ops.dcn` lazily; bind it to megreader_b200.dcn for this process
@@ -83,3 +84,28 @@ def test_state_dict_keys_equal_reference():
     rp, mp = rb.resnet50dilated_ppm(), mb.resnet50dilated_ppm()
     geo = lambda net: [(n, c.stride, c.dilation, c.padding) for n, c in net.named_modules() if isinstance(c, torch.nn.Conv2d)]
     assert geo(rp) == geo(mp)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+def test_east_decoder_equals_reference_module():
+    """decoders/east.py:7-60 on CPU: same parameters -> same loss, metrics and predictions (train and eval branches)."""
+    ref_loader.install()
+    import decoders as rd
+    import megreader_b200.refapi.decoders as md
+    torch.manual_seed(0)
+    r, m = rd.EASTDecoder(channels=32).train(), md.EASTDecoder(channels=32).train()
+    m.load_state_dict(r.state_dict())
+    x = torch.randn(2, 32, 6, 10)
+    label = {"heatmap": (torch.rand(2, 1, 24, 40) > 0.7).float(), "heatmap_weight": torch.rand(2, 1, 24, 40),
+             "densebox": torch.randn(2, 8, 24, 40) * 50, "densebox_weight": torch.rand(2, 8, 24, 40)}
+    lr, pr, mr_ = r(x, label, None, True)
+    lm, pm, mm = m(x, label, None, True)
+    torch.testing.assert_close(lm, lr)
+    for k in pr:
+        torch.testing.assert_close(pm[k], pr[k])
+    for k in mr_:
+        torch.testing.assert_close(mm[k], mr_[k])
+    r.eval(); m.eval()
+    pe_r, pe_m = r(x, label, None, False), m(x, label, None, False)
+    for k in pe_r:
+        torch.testing.assert_close(pe_m[k], pe_r[k])
