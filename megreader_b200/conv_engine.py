@@ -155,14 +155,25 @@ def eligible(m):
             and (m.in_channels % 64 == 0 or m.in_channels <= 4))
 
 
+def _cast_input_hook(mod, args):
+    x = args[0]
+    if torch.is_tensor(x) and x.is_floating_point() and x.dtype != mod.weight.dtype:
+        return (x.to(mod.weight.dtype),) + tuple(args[1:])
+    return None
+
+
 def use_engine_convs(module):
     """Re-class every eligible nn.Conv2d below `module` to EngineConv2d (parameters stay the same objects).  Returns the
-    number of layers switched.  Undo with restore_library_convs()."""
+    number of layers switched.  Undo with restore_library_convs().  The layers that stay with the library (transposed and grouped
+    convolutions, Linear) get a pre-hook that casts the bf16 activations arriving from engine layers to their weights' dtype."""
     n = 0
     for m in module.modules():
         if eligible(m):
             m.__class__ = EngineConv2d
             n += 1
+        elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)) and type(m) is not EngineConv2d \
+                and not hasattr(m, "_mr_cast_hook"):
+            m._mr_cast_hook = m.register_forward_pre_hook(_cast_input_hook)
     return n
 
 
@@ -172,4 +183,7 @@ def restore_library_convs(module):
         if type(m) is EngineConv2d:
             m.__class__ = nn.Conv2d
             n += 1
+        if hasattr(m, "_mr_cast_hook"):
+            m._mr_cast_hook.remove()
+            del m._mr_cast_hook
     return n
