@@ -291,6 +291,10 @@ def run_ours(args):
         except Exception as e:                                # an extra arm never takes the headline down, but says why
             out["roofline_dcn"] = {"error": str(e)[:200]}
         try:
+            out["input_step"] = bench_input_step(dev)
+        except Exception as e:
+            out["input_step"] = {"error": str(e)[:200]}
+        try:
             out["parity"] = bench_parity(dev, lambda: net)
         except Exception as e:
             out["parity"] = {"error": str(e)[:200]}
@@ -450,6 +454,30 @@ def bench_dcn(dev, iters=10):
     return {"kernel": "dcn_fwd_tcgen05_kernel (bilinear gather = A-operand producer, bf16 hi/lo split: 3 MMAs per K block)",
             "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops"], "peak_source": pk["source"], "B": 8, "shapes": out,
             "round1_fwd_us": {"C128@64x64": 319.2, "C256@32x32": 264.5, "C512@16x16": 215.3}}
+
+
+def bench_input_step(dev, n=512, reps=5):
+    """Input step of SURVEY.md section 8 row N3 on the GPU: a ragged batch of decoded uint8 HWC line images -> resize to 32x256,
+    normalise, CHW fp32 (one launch) + label strings -> class indices (one launch).  `e2e` includes the host-side concatenation of
+    the ragged batch and the pinned H2D copies; `device` is the two kernels alone (CUDA events)."""
+    from megreader_b200 import input_pipeline as ip
+    rng = np.random.RandomState(0)
+    images = [rng.randint(0, 256, size=(int(rng.randint(24, 49)), int(rng.randint(60, 301)), 3), dtype=np.uint8) for _ in range(n)]
+    alphabet = "0123456789abcdefghijklmnopqrstuvwxyz"
+    texts = ["".join(alphabet[int(c)] for c in rng.randint(0, 36, size=int(rng.randint(1, 17)))) for _ in range(n)]
+    for _ in range(2):
+        ip.resize_normalize(images, (32, IMG_W), "resize", dev); ip.pack_labels(texts, None, 32, dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        x = ip.resize_normalize(images, (32, IMG_W), "resize", dev)
+        y, l = ip.pack_labels(texts, None, 32, dev)
+    torch.cuda.synchronize()
+    e2e = (time.perf_counter() - t0) / reps
+    src_bytes = sum(im.size for im in images)
+    return {"batch": n, "e2e_lines_per_s": n / e2e, "e2e_ms": e2e * 1e3, "src_bytes": src_bytes, "out_bytes": int(x.numel() * 4),
+            "note": "host: numpy concatenation of the ragged uint8 batch + pinned copies; device: csrc/input_pipeline.cu; JPEG "
+                    "decode and the LMDB read stay on the host (not timed)"}
 
 
 def bench_parity(dev, model_fn):

@@ -65,6 +65,11 @@ def resize_normalize(images, image_size, mode="resize", device=None, mean=RGB_ME
 def charset_lut(charset=None):
     """256-entry byte -> class-index table of a charset (`Charset.index`, concern/charsets.py: unknown for anything else)."""
     charset = charset if charset is not None else default_charset()
+    chars = getattr(charset, "_charset", None)          # the reference's Charset keeps its alphabet in `_charset` (concern/charsets.py)
+    if chars is not None and any(ord(ch) > 255 for ch in chars if isinstance(ch, str) and len(ch) == 1):
+        # e.g. the reference's ChineseCharset: a byte table would silently map every such character to `unknown`
+        raise NotImplementedError("megreader_b200.input_pipeline.pack_labels: the charset has characters outside Latin-1; "
+                                  "the GPU label packer works on a 256-entry byte table")
     return np.array([charset.index(chr(b)) for b in range(256)], dtype=np.int32)
 
 
