@@ -418,7 +418,10 @@ def _bilstm_backward_fused(dE, sv):
                 else torch.zeros(4 * H, H, device=dev))[inv]
         db = ops.colsum(dG2)[inv]
         grads += [dWih, dWhh, db, db.clone()]
-        ops.gemm(dG2, sv["Wih"][d], out=dX, beta=0.0 if d == 0 else 1.0)
+        if d == 0 or ops.GEMM_BACKEND != "tc":
+            ops.gemm(dG2, sv["Wih"][d], out=dX, beta=0.0 if d == 0 else 1.0)
+        else:
+            dX.add_(ops.gemm(dG2, sv["Wih"][d]))       # tcgen05 kernel: no bf16 accumulate form -> own GEMM + one add
     return dX.view(T, N, I), grads + [dWemb, dbemb]
 
 

@@ -139,8 +139,47 @@ def cast(x, dtype):
     return y
 
 
+# bf16 GEMMs of the engine: "tc" = the repo's tcgen05 kernel (csrc/gemm_tcgen05.cu) wherever it covers the form, "cublas" = library
+# Default "cublas": measured on the cfg-2 step (profiles/r2_gemm_routing.md) 8.95 ms with library GEMMs for the LSTM projections /
+# Linear / conv0 / weight gradients, 9.34 ms with the tcgen05 kernel on the large NT / NN forms, 10.46 ms on all forms.
+GEMM_BACKEND = __import__("os").environ.get("MEGREADER_B200_GEMM", "cublas")
+GEMM_POLICY = __import__("os").environ.get("MEGREADER_B200_GEMM_POLICY", "big")      # "big" | "all"
+
+
+def _gemm_tc_try(A, B, out, M, N, K, transA, transB, alpha, beta):
+    """Route one bf16 GEMM to the hand-written kernel.  Returns True when it ran."""
+    if alpha != 1.0 or (transA and transB):
+        return False
+    if GEMM_POLICY == "big" and (transA or K < 256 or N < 128):
+        return False      # measured (profiles/r2_gemm_routing.md): the K = 32 conv0 GEMM and the split-K weight-gradient forms are
+                          # slower on the hand-written kernel than on the library one; they stay library GEMMs
+    lib = _lib.lib()
+    if transA:
+        # weight-gradient form dW[M,N] = A^T B over a long K: split-K with fp32 atomic accumulation into a zeroed output
+        if out.dtype != torch.float32:
+            return False
+        if beta == 0.0:
+            out.zero_()
+        elif beta != 1.0:
+            return False
+        tiles = ((M + 127) // 128) * ((N + 255) // 256)
+        splits = max(1, min(-(-296 // tiles), (K + 63) // 64))
+        rc = lib.mr_gemm_tcgen05(_p(A), _p(B), _p(out), M, N, K, A.stride(0), B.stride(0), out.stride(0), 1, 0,
+                                 code(out.dtype), None, 0, 1.0, int(splits), _st())
+    else:
+        if beta != 0.0:
+            return False
+        rc = lib.mr_gemm_tcgen05(_p(A), _p(B), _p(out), M, N, K, A.stride(0), B.stride(0), out.stride(0), 0, int(transB),
+                                 code(out.dtype), None, 0, 0.0, 1, _st())
+    if rc == _lib.MR_ERR_UNSUPPORTED:
+        return False
+    _chk(rc, "gemm_tcgen05")
+    return True
+
+
 def gemm(A, B, transA=False, transB=False, out=None, out_dtype=None, alpha=1.0, beta=0.0):
-    """Row-major out[M,N] = alpha * op(A) op(B) + beta * out.  A, B: 2-D, unit inner stride (row stride = ld)."""
+    """Row-major out[M,N] = alpha * op(A) op(B) + beta * out.  A, B: 2-D, unit inner stride (row stride = ld).  bf16 operands go
+    to the tcgen05 kernel when it covers the form (NT / NN, TN with fp32 output); everything else is a plain library GEMM."""
     assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1 and A.dtype == B.dtype
     M, K = (A.size(1), A.size(0)) if transA else (A.size(0), A.size(1))
     Kb, N = (B.size(1), B.size(0)) if transB else (B.size(0), B.size(1))
@@ -148,6 +187,8 @@ def gemm(A, B, transA=False, transB=False, out=None, out_dtype=None, alpha=1.0, 
     if out is None:
         out = torch.empty((M, N), dtype=out_dtype or A.dtype, device=A.device)
     assert out.stride(1) == 1 and out.shape == (M, N)
+    if GEMM_BACKEND == "tc" and A.dtype == torch.bfloat16 and _gemm_tc_try(A, B, out, M, N, K, transA, transB, alpha, beta):
+        return out
     _chk(_lib.lib().mr_gemm(_p(A), _p(B), _p(out), M, N, K, A.stride(0), B.stride(0), out.stride(0), int(transA),
                             int(transB), code(A.dtype), code(out.dtype), float(alpha), float(beta), _st()), "gemm")
     return out
