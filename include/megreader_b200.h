@@ -148,6 +148,15 @@ int mr_dcn_forward_fused_f32(const float *input, const float *weight, const floa
                              float *workspace, int64_t workspace_bytes, int B, int C, int H, int W, int Cout, int kh, int kw,
                              int sh, int sw, int ph, int pw, int dh, int dw, int group, int dg, void *stream);
 
+/* Fused weight gradient (csrc/dcn_tcgen05.cu), the deform_conv_cuda.cpp:645-658 step (im2col + SGEMM per sample in the reference)
+ * as one tcgen05 GEMM over the pixels whose B operand is the bilinear gather itself: grad_weight += scale * go (*) columns.
+ * Same eligibility as the fused forward; workspace >= mr_dcn_fused_wgrad_workspace_bytes(...).  mr_dcn_backward_f32 tries it first. */
+int64_t mr_dcn_fused_wgrad_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t Cout, int64_t Ho, int64_t Wo);
+int mr_dcn_wgrad_fused_f32(const float *input, const float *offset, int64_t offset_bstride, const float *mask, int64_t mask_bstride,
+                           const float *grad_output, float *grad_weight, float scale, float *workspace, int64_t workspace_bytes,
+                           int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                           int group, int dg, void *stream);
+
 /* modulated_deform_conv_cuda_backward (deform_conv_cuda.cpp:566-679) / deform_conv_backward_input_cuda (:260-371)
  * + deform_conv_backward_parameters_cuda (:373-484).  grad_input / grad_weight / grad_bias are ACCUMULATED into
  * (the caller zero-fills them, functions/deform_conv.py:150-154); grad_offset / grad_mask entries are assigned with

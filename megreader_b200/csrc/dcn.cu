@@ -299,6 +299,14 @@ int mr_dcn_backward_f32(const float *input, const float *weight, const float *of
     const int Cg = C / group, Og = Cout / group, CgK = Cg * g.K;
     const float one = 1.f, zero = 0.f;
     const bool want_data = grad_input || grad_offset || grad_mask;
+    bool wgrad_done = false;
+    if (grad_weight) {
+        // fused tcgen05 weight gradient (csrc/dcn_tcgen05.cu): uses the workspace first; the loop below reuses it afterwards
+        rc = mr_dcn_wgrad_fused_f32(input, offset, offset_bstride, mask, mask_bstride, grad_output, grad_weight, weight_grad_scale,
+                                    workspace, workspace_bytes, B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, group, dg, stream);
+        if (rc == MR_OK) wgrad_done = true;
+        else if (rc != MR_ERR_UNSUPPORTED) return rc;
+    }
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = (B - b0 < chunk) ? B - b0 : chunk;
         if (want_data) {
@@ -315,7 +323,7 @@ int mr_dcn_backward_f32(const float *input, const float *weight, const float *of
             rc = check_launch("dcn_col2im_kernel");
             if (rc) return rc;
         }
-        if (grad_weight) {
+        if (grad_weight && !wgrad_done) {
             const int cs = pick_csplit(g, nb);
             dcn_im2col_kernel<<<grid_for((int64_t)nb * cs * g.dg * g.K * g.P, 256), 256, 0, st>>>(g, b0, nb, cs, input, offset, mask, workspace);
             rc = check_launch("dcn_im2col_kernel");

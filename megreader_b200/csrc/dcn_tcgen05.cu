@@ -265,6 +265,236 @@ dcn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_co
     }
 }
 
+// =====================================================================================================
+// Fused WEIGHT GRADIENT (round 2):  gw[co, c, k] += scale * sum_{b,p} go[b, co, p] * col[b, p, (c, k)]
+//   (deform_conv_cuda.cpp:645-658 / :373-484: im2col of every sample + one SGEMM per sample in the reference)
+// The column matrix is produced exactly as in the forward (same producer threads, same swizzled tile [128 pixels][64 (tap, channels)])
+// but now it is the MN-major B operand of  D[co (128), kc (64)] += go^T[co, p] * col[p, kc]  with the PIXELS as the reduction
+// dimension.  One CTA owns one 64-wide (tap, channel block) slice and one 128-channel slice of Cout and walks over a strided subset
+// of the pixel tiles (split-K); the A operand is grad_output re-tiled to [b * tiles + tile][co][128 pixels in tile order] and split
+// into bf16 hi / lo by a small pre-pass, so that one pixel tile of it is a plain 2-D TMA box.  fp32 atomics at the end.
+// =====================================================================================================
+struct DcnWArgs {
+    const float *xh, *off, *msk;
+    float *gw;                // [Cout][C][kh*kw] fp32, accumulated
+    int64_t off_bs, mask_bs;
+    float scale;
+    int B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, P;
+    int tiles_per_sample, tiles_x, ncb, nkb, ntiles, splits;
+};
+
+struct DcnWSmem {
+    static constexpr int B_BYTES = BM * BK * 2;               // produced tile, one of (hi, lo): [128 pixels][64 kc]
+    static constexpr int A_BYTES = BM * BM * 2;               // go tile, one of (hi, lo): [128 co][128 pixels] = two 64-pixel atoms
+    static constexpr int STAGE_BYTES = 2 * B_BYTES + 2 * A_BYTES;     // 96 KB
+    static constexpr int STAGES = 2;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TAP_OFF = BAR_OFF + 128;
+    static constexpr int TOTAL = TAP_OFF + STAGES * BM * 24 + 1024;   // one tap-table row set per stage
+};
+
+__global__ void __launch_bounds__(kDcnThreads, 1)
+dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl, DcnWArgs a) {
+    using L = DcnWSmem;
+    constexpr int STAGES = L::STAGES;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
+    float4 *tapw_all = (float4 *)(smem + L::TAP_OFF);         // [STAGES][128]
+    uint2 *tapc_all = (uint2 *)(tapw_all + STAGES * BM);      // [STAGES][128]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb = blockIdx.x;                                // K block of the forward GEMM: (channel block, tap)
+    const int cc = kb / (a.kh * a.kw), k = kb - cc * (a.kh * a.kw);
+    const int co0 = blockIdx.z * BM;
+    const int nt = (a.ntiles - (int)blockIdx.y + a.splits - 1) / a.splits;      // pixel tiles of this CTA: y, y + splits, ...
+    constexpr uint32_t BN = 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmGh);
+        tma_prefetch_desc(&tmGl);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1 + kProducerThreads); mbar_init(empty + s, 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int i = 0; i < nt; ++i) {
+                const int s = i % STAGES;
+                const int gt = (int)blockIdx.y + i * a.splits;
+                mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+                unsigned char *st = smem + s * L::STAGE_BYTES + 2 * L::B_BYTES;
+                mbar_expect_tx(full + s, 2 * L::A_BYTES);
+                const int row = gt * a.Cout + co0;                        // rows of the re-tiled grad_output: (tile, co)
+                tma_load_2d(&tmGh, full + s, st, 0, row);
+                tma_load_2d(&tmGh, full + s, st + BM * 128, 64, row);
+                tma_load_2d(&tmGl, full + s, st + L::A_BYTES, 0, row);
+                tma_load_2d(&tmGl, full + s, st + L::A_BYTES + BM * 128, 64, row);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, 0, 1);              // A K-major (pixels contiguous), B MN-major (kc contiguous)
+        for (int i = 0; i < nt; ++i) {
+            const int s = i % STAGES;
+            mbar_wait(full + s, (i / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t bh = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t bl = bh + L::B_BYTES;
+                const uint32_t ah = bl + L::B_BYTES;
+                const uint32_t al = ah + L::A_BYTES;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint32_t aa = pass == 2 ? al : ah, bb = pass == 1 ? bl : bh;       // Ah Bh, Ah Bl, Al Bh
+#pragma unroll
+                    for (int j = 0; j < BM / UMMA_K; ++j)                                     // 8 steps of 16 pixels
+                        umma_bf16(tmem_base, make_desc(aa + (j >> 2) * (BM * 128) + (j & 3) * 32, 16, 1024),
+                                  make_desc(bb + j * 2048, BM * 128, 1024), idesc, (i | pass | j) != 0);
+                }
+                umma_commit(empty + s);
+                if (i == nt - 1) umma_commit(tmem_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int pwp = warp - 2;
+        const int sub = lane >> 3, j = lane & 7;
+        const int ptid = threadIdx.x - 64;
+        int rrow[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) rrow[u] = pwp * 8 + u * 4 + sub;
+        const int ti = k / a.kw, tj = k - ti * a.kw;
+        for (int i = 0; i < nt; ++i) {
+            const int s = i % STAGES;
+            const int gt = (int)blockIdx.y + i * a.splits;
+            const int b = gt / a.tiles_per_sample;
+            const int tile = gt - b * a.tiles_per_sample;
+            const int ty0 = (tile / a.tiles_x) * 8, tx0 = (tile % a.tiles_x) * 16;
+            float4 *tapw = tapw_all + s * BM;
+            uint2 *tapc = tapc_all + s * BM;
+            // the stage's previous tile (i - STAGES) has been consumed by every producer before anybody reached this point:
+            // its readers passed the named barrier of tile i - 1 ... but not necessarily of this stage; wait for the slot first
+            mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+            if (ptid < BM) {
+                const int r = ptid;
+                const int py = ty0 + (r >> 4), px = tx0 + (r & 15);
+                const bool rok = py < a.Ho && px < a.Wo;
+                const int ho = rok ? py : a.Ho - 1, wo = rok ? px : a.Wo - 1;
+                const int pc = ho * a.Wo + wo;
+                const float *offb = a.off + (int64_t)b * a.off_bs;
+                const float oh = __ldg(offb + (int64_t)(2 * k) * a.P + pc);
+                const float ow = __ldg(offb + (int64_t)(2 * k + 1) * a.P + pc);
+                const float m = a.msk ? __ldg(a.msk + (int64_t)b * a.mask_bs + (int64_t)k * a.P + pc) : 1.f;
+                const float hy = (float)(ho * a.sh - a.ph + ti * a.dh) + oh;
+                const float wx = (float)(wo * a.sw - a.pw + tj * a.dw) + ow;
+                const bool inside = rok && hy > -1.f && wx > -1.f && hy < (float)a.H && wx < (float)a.W;
+                const int hl = (int)floorf(hy), wl = (int)floorf(wx);
+                const int hh = hl + 1, wh = wl + 1;
+                const float lh = hy - hl, lw = wx - wl, uh = 1.f - lh, uw = 1.f - lw;
+                const bool m1 = inside && hl >= 0 && wl >= 0, m2 = inside && hl >= 0 && wh <= a.W - 1;
+                const bool m3 = inside && hh <= a.H - 1 && wl >= 0, m4 = inside && hh <= a.H - 1 && wh <= a.W - 1;
+                tapw[r] = make_float4(m1 ? uh * uw * m : 0.f, m2 ? uh * lw * m : 0.f, m3 ? lh * uw * m : 0.f, m4 ? lh * lw * m : 0.f);
+                const int y0 = min(max(hl, 0), a.H - 1), y1 = min(max(hh, 0), a.H - 1);
+                const int x0 = min(max(wl, 0), a.W - 1), x1 = min(max(wh, 0), a.W - 1);
+                tapc[r] = make_uint2((unsigned)y0 | ((unsigned)y1 << 16), (unsigned)x0 | ((unsigned)x1 << 16));
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+            const float *xb = a.xh + (int64_t)b * a.H * a.W * a.C + j * 4;
+            const int c4 = cc * (BK / 4);
+            float4 x1[2][2], x2[2][2], x3[2][2], x4[2][2];
+            float4 wv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                wv[u] = tapw[rrow[u]];
+                const uint2 cv = tapc[rrow[u]];
+                const int y0 = (int)(cv.x & 0xffffu) * a.W, y1 = (int)(cv.x >> 16) * a.W;
+                const int x0 = (int)(cv.y & 0xffffu), xx1 = (int)(cv.y >> 16);
+                const float4 *q1 = reinterpret_cast<const float4 *>(xb + (int64_t)(y0 + x0) * a.C);
+                const float4 *q2 = reinterpret_cast<const float4 *>(xb + (int64_t)(y0 + xx1) * a.C);
+                const float4 *q3 = reinterpret_cast<const float4 *>(xb + (int64_t)(y1 + x0) * a.C);
+                const float4 *q4 = reinterpret_cast<const float4 *>(xb + (int64_t)(y1 + xx1) * a.C);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    x1[u][e] = __ldg(q1 + c4 + e * 8); x2[u][e] = __ldg(q2 + c4 + e * 8);
+                    x3[u][e] = __ldg(q3 + c4 + e * 8); x4[u][e] = __ldg(q4 + c4 + e * 8);
+                }
+            }
+            const uint32_t bh_s = smem_u32(smem + s * L::STAGE_BYTES);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t row_off = (uint32_t)rrow[u] * 128u, sw = (uint32_t)(rrow[u] & 7);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float v0 = wv[u].x * x1[u][e].x + wv[u].y * x2[u][e].x + wv[u].z * x3[u][e].x + wv[u].w * x4[u][e].x;
+                    const float v1 = wv[u].x * x1[u][e].y + wv[u].y * x2[u][e].y + wv[u].z * x3[u][e].y + wv[u].w * x4[u][e].y;
+                    const float v2 = wv[u].x * x1[u][e].z + wv[u].y * x2[u][e].z + wv[u].z * x3[u][e].z + wv[u].w * x4[u][e].z;
+                    const float v3 = wv[u].x * x1[u][e].w + wv[u].y * x2[u][e].w + wv[u].z * x3[u][e].w + wv[u].w * x4[u][e].w;
+                    uint2 hi, lo;
+                    __nv_bfloat162 *h2 = reinterpret_cast<__nv_bfloat162 *>(&hi);
+                    __nv_bfloat162 *l2 = reinterpret_cast<__nv_bfloat162 *>(&lo);
+                    h2[0] = __floats2bfloat162_rn(v0, v1);
+                    h2[1] = __floats2bfloat162_rn(v2, v3);
+                    const float2 f0 = __bfloat1622float2(h2[0]), f1 = __bfloat1622float2(h2[1]);
+                    l2[0] = __floats2bfloat162_rn(v0 - f0.x, v1 - f0.y);
+                    l2[1] = __floats2bfloat162_rn(v2 - f1.x, v3 - f1.y);
+                    const uint32_t o = row_off + ((((uint32_t)(e * 4 + (j >> 1))) ^ sw) << 4) + (uint32_t)(j & 1) * 8u;
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bh_s + o), "r"(hi.x), "r"(hi.y) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bh_s + (uint32_t)L::B_BYTES + o), "r"(lo.x), "r"(lo.y) : "memory");
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive_cta(full + s);
+        }
+        // ---- epilogue: D[co][kc] -> gw[co][c][k] (fp32 atomics; 4 warps per TMEM quarter, 16 columns each)
+        const int q = warp & 3, part = (warp - 2) >> 2;
+        const int co = co0 + q * 32 + lane;
+        if (nt > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+            uint32_t rr[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 16), rr);
+            if (co < a.Cout) {
+                float *gp = a.gw + ((int64_t)co * a.C + cc * BK + part * 16) * (a.kh * a.kw) + k;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) atomicAdd(gp + (int64_t)e * (a.kh * a.kw), a.scale * __uint_as_float(rr[e]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+// grad_output [B][Cout][P] fp32 -> hi / lo bf16 [B * tiles][Cout][128] in the 8 x 16 tile order of the kernels (0 outside the map)
+__global__ void dcn_go_retile_kernel(const float *__restrict__ go, int B, int Cout, int Ho, int Wo, int tiles_x, int tiles_per_sample,
+                                     bf16 *__restrict__ hi, bf16 *__restrict__ lo) {
+    const int64_t n = (int64_t)B * tiles_per_sample * Cout * BM;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i % BM);
+        int64_t t = i / BM;
+        const int co = (int)(t % Cout); t /= Cout;
+        const int tile = (int)(t % tiles_per_sample);
+        const int b = (int)(t / tiles_per_sample);
+        const int py = (tile / tiles_x) * 8 + (r >> 4), px = (tile % tiles_x) * 16 + (r & 15);
+        float v = 0.f;
+        if (py < Ho && px < Wo) v = go[((int64_t)b * Cout + co) * Ho * Wo + (int64_t)py * Wo + px];
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
 // x [B][C][P] -> y [B][P][C] (fp32), 32 x 32 tiles through shared memory; both sides 128-byte rows
 __global__ void __launch_bounds__(256)
 dcn_nchw_to_nhwc_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int P) {
@@ -376,6 +606,66 @@ int mr_dcn_forward_fused_f32(const float *input, const float *weight, const floa
     static const bool three = getenv("MR_DCN_STAGES3") != nullptr;
     if (three) return launch_dcn_fwd<128, 3>(th, tl, a, st);
     return launch_dcn_fwd<128, 2>(th, tl, a, st);
+}
+
+/* scratch of the fused weight gradient: NHWC copy of the input + re-tiled hi / lo grad_output */
+int64_t mr_dcn_fused_wgrad_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t Cout, int64_t Ho, int64_t Wo) {
+    const int64_t tiles = ceil_div(Wo, 16) * ceil_div(Ho, 8);
+    return round_up(B * H * W * C * 4, 256) + 2 * round_up(B * tiles * Cout * BM * 2, 256);
+}
+
+/* grad_weight [Cout][C][kh*kw] += scale * (grad_output (*) deformable columns); MR_ERR_UNSUPPORTED outside the fused path. */
+int mr_dcn_wgrad_fused_f32(const float *input, const float *offset, int64_t offset_bstride, const float *mask, int64_t mask_bstride,
+                           const float *grad_output, float *grad_weight, float scale, float *workspace, int64_t workspace_bytes,
+                           int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                           int group, int dg, void *stream) {
+    if (group != 1 || dg != 1 || C % 64 || Cout % 128 || B <= 0 || H > 65535 || W > 65535) return MR_ERR_UNSUPPORTED;
+    if (getenv("MR_DCN_UNFUSED") || getenv("MR_DCN_UNFUSED_WGRAD")) return MR_ERR_UNSUPPORTED;
+    if (!input || !offset || !grad_output || !grad_weight || !workspace) return MR_ERR_NULL_POINTER;
+    DcnWArgs a;
+    a.B = B; a.C = C; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.sh = sh; a.sw = sw; a.ph = ph; a.pw = pw;
+    a.dh = dh; a.dw = dw;
+    a.Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1;
+    a.Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+    if (a.Ho <= 0 || a.Wo <= 0) return MR_ERR_BAD_SHAPE;
+    if (workspace_bytes < mr_dcn_fused_wgrad_workspace_bytes(B, C, H, W, Cout, a.Ho, a.Wo) || ((uintptr_t)workspace % 256)) return MR_ERR_UNSUPPORTED;
+    a.P = a.Ho * a.Wo;
+    a.tiles_x = (int)ceil_div(a.Wo, 16);
+    a.tiles_per_sample = a.tiles_x * (int)ceil_div(a.Ho, 8);
+    a.ncb = C / BK; a.nkb = kh * kw * a.ncb;
+    a.ntiles = B * a.tiles_per_sample;
+    if ((int64_t)a.ntiles * Cout > 0x7fffffffLL) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    float *xh = (float *)ws;
+    const int64_t xbytes = round_up((int64_t)B * H * W * C * 4, 256), gbytes = round_up((int64_t)a.ntiles * Cout * BM * 2, 256);
+    bf16 *ghi = (bf16 *)(ws + xbytes), *glo = (bf16 *)(ws + xbytes + gbytes);
+    {
+        dim3 tg((unsigned)ceil_div((int64_t)H * W, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+        dcn_nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(input, xh, C, H * W);
+    }
+    int rc = check_launch("dcn_nchw_to_nhwc_kernel");
+    if (rc) return rc;
+    const int64_t ng = (int64_t)a.ntiles * Cout * BM;
+    dcn_go_retile_kernel<<<(unsigned)std::min<int64_t>(ceil_div(ng, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(
+        grad_output, B, Cout, a.Ho, a.Wo, a.tiles_x, a.tiles_per_sample, ghi, glo);
+    rc = check_launch("dcn_go_retile_kernel");
+    if (rc) return rc;
+    a.xh = xh; a.off = offset; a.msk = mask; a.off_bs = offset_bstride; a.mask_bs = mask_bstride; a.gw = grad_weight; a.scale = scale;
+    CUtensorMap th, tl;
+    rc = make_map(&th, ghi, BM, (int64_t)a.ntiles * Cout, BM, BK, BM);
+    if (rc) return rc;
+    rc = make_map(&tl, glo, BM, (int64_t)a.ntiles * Cout, BM, BK, BM);
+    if (rc) return rc;
+    const int ctas_fixed = a.nkb * (Cout / BM);
+    int splits = (int)ceil_div(2 * sm_count(), ctas_fixed);
+    if (splits > a.ntiles) splits = a.ntiles;
+    if (splits < 1) splits = 1;
+    a.splits = splits;
+    { int rc_attr = ensure_dyn_smem((const void *)dcn_wgrad_tcgen05_kernel, DcnWSmem::TOTAL, "dcn_wgrad_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
+    dim3 grid((unsigned)a.nkb, (unsigned)splits, (unsigned)(Cout / BM));
+    dcn_wgrad_tcgen05_kernel<<<grid, kDcnThreads, DcnWSmem::TOTAL, st>>>(th, tl, a);
+    return check_launch("dcn_wgrad_tcgen05_kernel");
 }
 
 }  // extern "C"

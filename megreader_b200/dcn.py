@@ -31,13 +31,15 @@ def _slab(t):
     return t, (t.stride(0) if t.size(0) > 1 else t[0].numel() if t.size(0) else 0)
 
 
-def _workspace(x, C, kh, kw, Ho, Wo, Cout=0):
+def _workspace(x, C, kh, kw, Ho, Wo, Cout=0, backward=False):
     """Scratch for the op: room for the column matrix of nb samples (unfused kernels) and, when Cout is given, for the fused
     forward's NHWC input copy + packed weights (csrc/dcn_tcgen05.cu) -- whichever is larger."""
     per = C * kh * kw * Ho * Wo * 4
     nb = max(1, min(x.size(0), WORKSPACE_CAP_BYTES // max(per, 1)))
     nbytes = nb * per
-    if Cout:
+    if Cout and backward:
+        nbytes = max(nbytes, int(_lib.lib().mr_dcn_fused_wgrad_workspace_bytes(x.size(0), C, x.size(2), x.size(3), Cout, Ho, Wo)))
+    elif Cout:
         nbytes = max(nbytes, int(_lib.lib().mr_dcn_fused_workspace_bytes(x.size(0), C, x.size(2), x.size(3), Cout, kh, kw)))
     nbytes = (nbytes + 255) // 256 * 256
     return torch.empty(nbytes // 4, dtype=torch.float32, device=x.device), nbytes
@@ -94,7 +96,7 @@ def _backward(x, weight, offset, mask, grad_output, grad_input, grad_weight, gra
         assert grad_mask.size(0) == 0 or grad_mask[0].is_contiguous()
         gmbs = _slab(grad_mask)[1]
     grad_output = grad_output.contiguous()
-    ws, ws_bytes = _workspace(x, C, kh, kw, Ho, Wo)
+    ws, ws_bytes = _workspace(x, C, kh, kw, Ho, Wo, Cout, backward=True)
     p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().mr_dcn_backward_f32(
