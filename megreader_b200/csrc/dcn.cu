@@ -300,14 +300,20 @@ int mr_dcn_backward_f32(const float *input, const float *weight, const float *of
     const float one = 1.f, zero = 0.f;
     const bool want_data = grad_input || grad_offset || grad_mask;
     bool wgrad_done = false;
-    if (grad_weight) {
+    // everything but grad_bias on the fused tcgen05 kernels when the shape allows (csrc/dcn_tcgen05.cu)
+    rc = mr_dcn_backward_fused_f32(input, weight, offset, offset_bstride, mask, mask_bstride, grad_output, grad_input, grad_weight,
+                                   grad_offset, grad_offset_bstride, grad_mask, grad_mask_bstride, weight_grad_scale, workspace,
+                                   workspace_bytes, B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, group, dg, stream);
+    if (rc != MR_OK && rc != MR_ERR_UNSUPPORTED) return rc;
+    const bool fused_all = rc == MR_OK;
+    if (grad_weight && !fused_all) {
         // fused tcgen05 weight gradient (csrc/dcn_tcgen05.cu): uses the workspace first; the loop below reuses it afterwards
         rc = mr_dcn_wgrad_fused_f32(input, offset, offset_bstride, mask, mask_bstride, grad_output, grad_weight, weight_grad_scale,
                                     workspace, workspace_bytes, B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, group, dg, stream);
         if (rc == MR_OK) wgrad_done = true;
         else if (rc != MR_ERR_UNSUPPORTED) return rc;
     }
-    for (int b0 = 0; b0 < B; b0 += chunk) {
+    for (int b0 = 0; b0 < B && !fused_all; b0 += chunk) {
         const int nb = (B - b0 < chunk) ? B - b0 : chunk;
         if (want_data) {
             for (int gr = 0; gr < group; ++gr) {

@@ -476,6 +476,284 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
     }
 }
 
+// =====================================================================================================
+// Fused DATA GRADIENT (round 2): grad_input, grad_offset, grad_mask without the column-gradient matrix
+//   colg[b, p, (k, c)] = sum_co go[b, co, p] * W[co, c, k]          (deform_conv_cuda.cpp:611-614, an SGEMM per sample in the reference)
+//   grad_input  += bilinear scatter of colg * mask                  (K9,  deform_conv_cuda_kernel.cu:634-692)
+//   grad_offset  = sum_c colg * mask * d bilinear / d position      (K10, :694-766)
+//   grad_mask    = sum_c colg * bilinear(x)                         (K10, :752)
+// One CTA owns one 8 x 16 pixel tile and a subset of the taps.  For a tap and a 128-channel chunk the 128 x 128 block of colg is one
+// tcgen05 GEMM over Cout (A = re-tiled grad_output, MN-major: pixels contiguous; B = the forward's packed weights read MN-major:
+// (tap, channel) contiguous; bf16 hi / lo, three MMAs per K block) into one of two TMEM accumulators.  The 16 epilogue warps move
+// it through a swizzled fp32 staging tile to the forward's 8-lanes-per-pixel mapping, gather the four corners from the NHWC input
+// (128 contiguous bytes per 8 lanes), form the three per-pixel sums and scatter into an NHWC fp32 copy of grad_input with 16-byte
+// vector reductions (red.global.add.v4.f32), which a transpose-add folds into the caller's NCHW tensor.
+// =====================================================================================================
+struct DcnDArgs {
+    const float *xh, *off, *msk;
+    float *gxh;                // [B][H][W][C] fp32, zero-filled; nullptr = no grad_input wanted
+    float *goff, *gmask;       // reference layouts (flat (Ho, Wo) strides inside per-sample slabs); either may be nullptr
+    int64_t off_bs, mask_bs, goff_bs, gmask_bs;
+    int B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, P;
+    int tiles_per_sample, tiles_x, nch, nkk, tap_splits;     // nch = C / 128 channel chunks, nkk = Cout / 64 K blocks
+};
+
+struct DcnDSmem {
+    static constexpr int BN = 128;
+    static constexpr int OP_BYTES = BK * 128 * 2;             // one operand tile, one of (hi, lo): [64 co][128 (pixels | kc)] = 16 KB
+    static constexpr int STAGE_BYTES = 4 * OP_BYTES;          // A hi, A lo, B hi, B lo
+    static constexpr int STAGES = 2;
+    static constexpr int STG_OFF = STAGES * STAGE_BYTES;      // fp32 staging tile [128 pixels][128 channels], 16-byte chunks XOR-swizzled
+    static constexpr int STG_BYTES = BM * BN * 4;
+    static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
+    static constexpr int TAB_OFF = BAR_OFF + 128;
+    static constexpr int TAB_BYTES = BM * (3 * 16 + 8 + 4);
+    static constexpr int TOTAL = TAB_OFF + TAB_BYTES + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kDcnThreads, 1)
+dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_constant__ CUtensorMap tmGl,
+                         const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl, DcnDArgs a) {
+    using L = DcnDSmem;
+    constexpr int STAGES = L::STAGES;
+    constexpr uint32_t BN = L::BN;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *empty = full + STAGES;
+    uint64_t *acc_full = empty + STAGES;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
+    float4 *tabw = (float4 *)(smem + L::TAB_OFF);      // bilinear weights of the valid corners (no mask)
+    float4 *tabh = tabw + BM;                          // mask * d/dh coefficients of the four corner values
+    float4 *tabv = tabh + BM;                          // mask * d/dw coefficients
+    uint2 *tabc = (uint2 *)(tabv + BM);                // clamped corner rows / columns
+    float *tabm = (float *)(tabc + BM);                // modulation mask of the (pixel, tap)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gt = blockIdx.x;
+    const int b = gt / a.tiles_per_sample;
+    const int tile = gt - b * a.tiles_per_sample;
+    const int ty0 = (tile / a.tiles_x) * 8, tx0 = (tile % a.tiles_x) * 16;
+    const int K = a.kh * a.kw;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmGh); tma_prefetch_desc(&tmGl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int i = 0;
+            for (int kk = blockIdx.y; kk < K; kk += a.tap_splits)
+                for (int h = 0; h < a.nch; ++h)
+                    for (int kb = 0; kb < a.nkk; ++kb, ++i) {
+                        const int s = i % STAGES;
+                        mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
+                        unsigned char *st = smem + s * L::STAGE_BYTES;
+                        mbar_expect_tx(full + s, L::STAGE_BYTES);
+                        const int grow = gt * a.Cout + kb * BK;                          // (tile, co) rows of the re-tiled grad_output
+                        tma_load_2d(&tmGh, full + s, st, 0, grow);
+                        tma_load_2d(&tmGh, full + s, st + BK * 128, 64, grow);
+                        tma_load_2d(&tmGl, full + s, st + L::OP_BYTES, 0, grow);
+                        tma_load_2d(&tmGl, full + s, st + L::OP_BYTES + BK * 128, 64, grow);
+                        const int kc0 = ((2 * h) * K + kk) * BK, kc1 = ((2 * h + 1) * K + kk) * BK;   // the chunk's two channel blocks
+                        tma_load_2d(&tmWh, full + s, st + 2 * L::OP_BYTES, kc0, kb * BK);
+                        tma_load_2d(&tmWh, full + s, st + 2 * L::OP_BYTES + BK * 128, kc1, kb * BK);
+                        tma_load_2d(&tmWl, full + s, st + 3 * L::OP_BYTES, kc0, kb * BK);
+                        tma_load_2d(&tmWl, full + s, st + 3 * L::OP_BYTES + BK * 128, kc1, kb * BK);
+                    }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(BM, BN, 1, 1);                             // both operands MN-major
+        int i = 0, n = 0;
+        for (int kk = blockIdx.y; kk < K; kk += a.tap_splits)
+            for (int h = 0; h < a.nch; ++h, ++n) {
+                const int buf = n & 1;
+                mbar_wait(acc_empty + buf, ((n >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < a.nkk; ++kb, ++i) {
+                    const int s = i % STAGES;
+                    mbar_wait(full + s, (i / STAGES) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t ah = smem_u32(smem + s * L::STAGE_BYTES);
+                        const uint32_t al = ah + L::OP_BYTES, bh = ah + 2 * L::OP_BYTES, bl = ah + 3 * L::OP_BYTES;
+#pragma unroll
+                        for (int pass = 0; pass < 3; ++pass) {
+                            const uint32_t aa = pass == 2 ? al : ah, bb = pass == 1 ? bl : bh;
+#pragma unroll
+                            for (int k4 = 0; k4 < BK / UMMA_K; ++k4)
+                                umma_bf16(tmem_base + buf * BN, make_desc(aa + k4 * 2048, BK * 128, 1024),
+                                          make_desc(bb + k4 * 2048, BK * 128, 1024), idesc, (kb | pass | k4) != 0);
+                        }
+                        umma_commit(empty + s);
+                        if (kb == a.nkk - 1) umma_commit(acc_full + buf);
+                    }
+                    __syncwarp();
+                }
+            }
+    } else {
+        const int pwp = warp - 2;
+        const int sub = lane >> 3, j = lane & 7;
+        const int ptid = threadIdx.x - 64;
+        const int q = warp & 3, part = pwp >> 2;                  // TMEM quarter of this warp, 32-column slice it drains
+        int rrow[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) rrow[u] = pwp * 8 + u * 4 + sub;
+        const uint32_t stg = smem_u32(smem + L::STG_OFF);
+        const float *xb = a.xh + (int64_t)b * a.H * a.W * a.C + j * 4;
+        float *gxb = a.gxh ? a.gxh + (int64_t)b * a.H * a.W * a.C + j * 4 : nullptr;
+        int n = 0;
+        for (int kk = blockIdx.y; kk < K; kk += a.tap_splits) {
+            if (ptid < BM) {
+                const int r = ptid;
+                const int ti = kk / a.kw, tj = kk - ti * a.kw;
+                const int py = ty0 + (r >> 4), px = tx0 + (r & 15);
+                const bool rok = py < a.Ho && px < a.Wo;
+                const int ho = rok ? py : a.Ho - 1, wo = rok ? px : a.Wo - 1;
+                const int pc = ho * a.Wo + wo;
+                const float *offb = a.off + (int64_t)b * a.off_bs;
+                const float oh = __ldg(offb + (int64_t)(2 * kk) * a.P + pc);
+                const float ow = __ldg(offb + (int64_t)(2 * kk + 1) * a.P + pc);
+                const float m = a.msk ? __ldg(a.msk + (int64_t)b * a.mask_bs + (int64_t)kk * a.P + pc) : 1.f;
+                const float hy = (float)(ho * a.sh - a.ph + ti * a.dh) + oh;
+                const float wx = (float)(wo * a.sw - a.pw + tj * a.dw) + ow;
+                const bool inside = rok && hy > -1.f && wx > -1.f && hy < (float)a.H && wx < (float)a.W;
+                const int hl = (int)floorf(hy), wl = (int)floorf(wx);
+                const int hh = hl + 1, wh = wl + 1;
+                const float lh = hy - hl, lw = wx - wl, uh = 1.f - lh, uw = 1.f - lw;
+                const float f1 = (inside && hl >= 0 && wl >= 0) ? 1.f : 0.f, f2 = (inside && hl >= 0 && wh <= a.W - 1) ? 1.f : 0.f;
+                const float f3 = (inside && hh <= a.H - 1 && wl >= 0) ? 1.f : 0.f, f4 = (inside && hh <= a.H - 1 && wh <= a.W - 1) ? 1.f : 0.f;
+                tabw[r] = make_float4(f1 * uh * uw, f2 * uh * lw, f3 * lh * uw, f4 * lh * lw);
+                tabh[r] = make_float4(-m * uw * f1, -m * lw * f2, m * uw * f3, m * lw * f4);      // dmcn_get_coordinate_weight :527-567
+                tabv[r] = make_float4(-m * uh * f1, m * uh * f2, -m * lh * f3, m * lh * f4);
+                const int y0 = min(max(hl, 0), a.H - 1), y1 = min(max(hh, 0), a.H - 1);
+                const int x0 = min(max(wl, 0), a.W - 1), x1 = min(max(wh, 0), a.W - 1);
+                tabc[r] = make_uint2((unsigned)y0 | ((unsigned)y1 << 16), (unsigned)x0 | ((unsigned)x1 << 16));
+                tabm[r] = m;
+            }
+            float vh[2] = {0.f, 0.f}, vw[2] = {0.f, 0.f}, vm[2] = {0.f, 0.f};
+            for (int h = 0; h < a.nch; ++h, ++n) {
+                const int buf = n & 1;
+                mbar_wait(acc_full + buf, (n >> 1) & 1);
+                tc_fence_after();
+                {
+                    uint32_t rr[32];
+                    tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 32), rr);
+                    const int r = q * 32 + lane;
+                    const uint32_t rb = stg + (uint32_t)r * 512u;
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rb + ((((uint32_t)(part * 8 + c4)) ^ (uint32_t)(r & 31)) << 4)),
+                                     "r"(rr[4 * c4]), "r"(rr[4 * c4 + 1]), "r"(rr[4 * c4 + 2]), "r"(rr[4 * c4 + 3]) : "memory");
+                }
+                tc_fence_before();
+                asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
+                if (ptid == 0) mbar_arrive_cta(acc_empty + buf);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int r = rrow[u];
+                    const float4 w = tabw[r], ch = tabh[r], cv = tabv[r];
+                    const uint2 cc = tabc[r];
+                    const int y0 = (int)(cc.x & 0xffffu) * a.W, y1 = (int)(cc.x >> 16) * a.W;
+                    const int x0 = (int)(cc.y & 0xffffu), x1 = (int)(cc.y >> 16);
+                    const int64_t o1 = (int64_t)(y0 + x0) * a.C + h * 128, o2 = (int64_t)(y0 + x1) * a.C + h * 128;
+                    const int64_t o3 = (int64_t)(y1 + x0) * a.C + h * 128, o4 = (int64_t)(y1 + x1) * a.C + h * 128;
+                    const float mk = tabm[r];          // ch / cv carry the mask already; the scatter needs it separately
+#pragma unroll 1
+                    for (int eh = 0; eh < 4; eh += 2) {         // two 16-byte channel chunks at a time (register budget: 96)
+                        float4 g[2], v1[2], v2[2], v3[2], v4[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            v1[e] = __ldg(reinterpret_cast<const float4 *>(xb + o1) + (eh + e) * 8);
+                            v2[e] = __ldg(reinterpret_cast<const float4 *>(xb + o2) + (eh + e) * 8);
+                            v3[e] = __ldg(reinterpret_cast<const float4 *>(xb + o3) + (eh + e) * 8);
+                            v4[e] = __ldg(reinterpret_cast<const float4 *>(xb + o4) + (eh + e) * 8);
+                            const uint32_t ad = stg + (uint32_t)r * 512u + ((((uint32_t)(j + 8 * (eh + e))) ^ (uint32_t)(r & 31)) << 4);
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(g[e].x), "=f"(g[e].y), "=f"(g[e].z), "=f"(g[e].w) : "r"(ad));
+                        }
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+#define MR_DCN_CH(F)                                                                                              \
+                            {                                                                                         \
+                                const float gg = g[e].F;                                                              \
+                                vm[u] = fmaf(gg, w.x * v1[e].F + w.y * v2[e].F + w.z * v3[e].F + w.w * v4[e].F, vm[u]);      \
+                                vh[u] = fmaf(gg, ch.x * v1[e].F + ch.y * v2[e].F + ch.z * v3[e].F + ch.w * v4[e].F, vh[u]);  \
+                                vw[u] = fmaf(gg, cv.x * v1[e].F + cv.y * v2[e].F + cv.z * v3[e].F + cv.w * v4[e].F, vw[u]);  \
+                            }
+                            MR_DCN_CH(x) MR_DCN_CH(y) MR_DCN_CH(z) MR_DCN_CH(w)
+#undef MR_DCN_CH
+                            if (gxb) {
+                                const float gx = g[e].x * mk, gy = g[e].y * mk, gz = g[e].z * mk, gw = g[e].w * mk;
+                                const int eo = (eh + e) * 32;
+                                if (w.x != 0.f) red_add_v4(gxb + o1 + eo, w.x * gx, w.x * gy, w.x * gz, w.x * gw);
+                                if (w.y != 0.f) red_add_v4(gxb + o2 + eo, w.y * gx, w.y * gy, w.y * gz, w.y * gw);
+                                if (w.z != 0.f) red_add_v4(gxb + o3 + eo, w.z * gx, w.z * gy, w.z * gz, w.z * gw);
+                                if (w.w != 0.f) red_add_v4(gxb + o4 + eo, w.w * gx, w.w * gy, w.w * gz, w.w * gw);
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+            }
+            // the tap is complete: fold the 8 channel lanes of each pixel row and write its three gradients
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+#pragma unroll
+                for (int sft = 1; sft < 8; sft <<= 1) {
+                    vh[u] += __shfl_xor_sync(0xffffffffu, vh[u], sft);
+                    vw[u] += __shfl_xor_sync(0xffffffffu, vw[u], sft);
+                    vm[u] += __shfl_xor_sync(0xffffffffu, vm[u], sft);
+                }
+                const int r = rrow[u];
+                const int py = ty0 + (r >> 4), px = tx0 + (r & 15);
+                if (j == 0 && py < a.Ho && px < a.Wo) {
+                    const int pc = py * a.Wo + px;
+                    if (a.goff) {
+                        float *gp = a.goff + (int64_t)b * a.goff_bs;
+                        gp[(int64_t)(2 * kk) * a.P + pc] = vh[u];
+                        gp[(int64_t)(2 * kk + 1) * a.P + pc] = vw[u];
+                    }
+                    if (a.gmask) a.gmask[(int64_t)b * a.gmask_bs + (int64_t)kk * a.P + pc] = vm[u];
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// y [B][C][P] += x [B][P][C]   (the NHWC gradient scratch folded into the caller's NCHW grad_input, which is accumulated into)
+__global__ void __launch_bounds__(256) dcn_nhwc_to_nchw_add_kernel(const float *__restrict__ x, float *__restrict__ y, int C, int P) {
+    __shared__ float t[32][33];
+    const int b = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int p = p0 + i, c = c0 + tx;
+        t[i][tx] = (p < P && c < C) ? x[((int64_t)b * P + p) * C + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, p = p0 + tx;
+        if (p < P && c < C) y[((int64_t)b * C + c) * P + p] += t[tx][i];
+    }
+}
+
 // grad_output [B][Cout][P] fp32 -> hi / lo bf16 [B * tiles][Cout][128] in the 8 x 16 tile order of the kernels (0 outside the map)
 __global__ void dcn_go_retile_kernel(const float *__restrict__ go, int B, int Cout, int Ho, int Wo, int tiles_x, int tiles_per_sample,
                                      bf16 *__restrict__ hi, bf16 *__restrict__ lo) {
@@ -532,6 +810,24 @@ __global__ void dcn_weight_pack_kernel(const float *__restrict__ w, int Cout, in
         hi[i] = h;
         lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
+}
+
+// launch of the fused weight gradient once the NHWC input and the re-tiled grad_output exist
+int launch_dcn_wgrad(DcnWArgs &a, const bf16 *ghi, const bf16 *glo, cudaStream_t st) {
+    CUtensorMap th, tl;
+    int rc = make_map(&th, ghi, BM, (int64_t)a.ntiles * a.Cout, BM, BK, BM);
+    if (rc) return rc;
+    rc = make_map(&tl, glo, BM, (int64_t)a.ntiles * a.Cout, BM, BK, BM);
+    if (rc) return rc;
+    const int ctas_fixed = a.nkb * (a.Cout / BM);
+    int splits = (int)ceil_div(2 * sm_count(), ctas_fixed);
+    if (splits > a.ntiles) splits = a.ntiles;
+    if (splits < 1) splits = 1;
+    a.splits = splits;
+    { int rc_attr = ensure_dyn_smem((const void *)dcn_wgrad_tcgen05_kernel, DcnWSmem::TOTAL, "dcn_wgrad_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
+    dim3 grid((unsigned)a.nkb, (unsigned)splits, (unsigned)(a.Cout / BM));
+    dcn_wgrad_tcgen05_kernel<<<grid, kDcnThreads, DcnWSmem::TOTAL, st>>>(th, tl, a);
+    return check_launch("dcn_wgrad_tcgen05_kernel");
 }
 
 template <int BN, int STAGES>
@@ -608,6 +904,94 @@ int mr_dcn_forward_fused_f32(const float *input, const float *weight, const floa
     return launch_dcn_fwd<128, 2>(th, tl, a, st);
 }
 
+/* scratch of the fused backward: NHWC copies of the input and of grad_input, re-tiled hi / lo grad_output, packed hi / lo weights */
+int64_t mr_dcn_fused_backward_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t Cout, int64_t Ho, int64_t Wo,
+                                              int64_t kh, int64_t kw) {
+    const int64_t tiles = ceil_div(Wo, 16) * ceil_div(Ho, 8);
+    return 2 * round_up(B * H * W * C * 4, 256) + 2 * round_up(B * tiles * Cout * BM * 2, 256) + 2 * round_up(Cout * C * kh * kw * 2, 256);
+}
+
+/* The whole of mr_dcn_backward_f32 except grad_bias on the fused kernels (weight gradient + data gradient); MR_ERR_UNSUPPORTED
+ * outside group = deformable_group = 1, C % 128 == 0, Cout % 128 == 0 or when the workspace is too small. */
+int mr_dcn_backward_fused_f32(const float *input, const float *weight, const float *offset, int64_t offset_bstride, const float *mask,
+                              int64_t mask_bstride, const float *grad_output, float *grad_input, float *grad_weight,
+                              float *grad_offset, int64_t grad_offset_bstride, float *grad_mask, int64_t grad_mask_bstride,
+                              float weight_grad_scale, float *workspace, int64_t workspace_bytes, int B, int C, int H, int W, int Cout,
+                              int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw, int group, int dg, void *stream) {
+    if (group != 1 || dg != 1 || C % 128 || Cout % 128 || B <= 0 || H > 65535 || W > 65535) return MR_ERR_UNSUPPORTED;
+    if (getenv("MR_DCN_UNFUSED") || getenv("MR_DCN_UNFUSED_DGRAD")) return MR_ERR_UNSUPPORTED;
+    if (!input || !weight || !offset || !grad_output || !workspace) return MR_ERR_NULL_POINTER;
+    const int Ho = (H + 2 * ph - (dh * (kh - 1) + 1)) / sh + 1, Wo = (W + 2 * pw - (dw * (kw - 1) + 1)) / sw + 1;
+    if (Ho <= 0 || Wo <= 0) return MR_ERR_BAD_SHAPE;
+    if (workspace_bytes < mr_dcn_fused_backward_workspace_bytes(B, C, H, W, Cout, Ho, Wo, kh, kw) || ((uintptr_t)workspace % 256)) return MR_ERR_UNSUPPORTED;
+    const int tiles_x = (int)ceil_div(Wo, 16), tiles_per_sample = tiles_x * (int)ceil_div(Ho, 8), ntiles = B * tiles_per_sample;
+    if ((int64_t)ntiles * Cout > 0x7fffffffLL) return MR_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned char *ws = (unsigned char *)workspace;
+    const int64_t xbytes = round_up((int64_t)B * H * W * C * 4, 256), gbytes = round_up((int64_t)ntiles * Cout * BM * 2, 256);
+    const int64_t wbytes = round_up((int64_t)Cout * C * kh * kw * 2, 256);
+    float *xh = (float *)ws, *gxh = (float *)(ws + xbytes);
+    bf16 *ghi = (bf16 *)(ws + 2 * xbytes), *glo = (bf16 *)(ws + 2 * xbytes + gbytes);
+    bf16 *whi = (bf16 *)(ws + 2 * xbytes + 2 * gbytes), *wlo = (bf16 *)(ws + 2 * xbytes + 2 * gbytes + wbytes);
+    const bool want_data = grad_input || grad_offset || grad_mask;
+    if (!want_data && !grad_weight) return MR_OK;
+    {
+        dim3 tg((unsigned)ceil_div((int64_t)H * W, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+        dcn_nchw_to_nhwc_kernel<<<tg, 256, 0, st>>>(input, xh, C, H * W);
+    }
+    int rc = check_launch("dcn_nchw_to_nhwc_kernel");
+    if (rc) return rc;
+    const int64_t ng = (int64_t)ntiles * Cout * BM;
+    dcn_go_retile_kernel<<<(unsigned)std::min<int64_t>(ceil_div(ng, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(
+        grad_output, B, Cout, Ho, Wo, tiles_x, tiles_per_sample, ghi, glo);
+    rc = check_launch("dcn_go_retile_kernel");
+    if (rc) return rc;
+    if (grad_weight) {
+        DcnWArgs a;
+        a.B = B; a.C = C; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.sh = sh; a.sw = sw; a.ph = ph; a.pw = pw; a.dh = dh; a.dw = dw;
+        a.Ho = Ho; a.Wo = Wo; a.P = Ho * Wo; a.tiles_x = tiles_x; a.tiles_per_sample = tiles_per_sample; a.ncb = C / BK; a.nkb = kh * kw * a.ncb;
+        a.ntiles = ntiles;
+        a.xh = xh; a.off = offset; a.msk = mask; a.off_bs = offset_bstride; a.mask_bs = mask_bstride; a.gw = grad_weight; a.scale = weight_grad_scale;
+        rc = launch_dcn_wgrad(a, ghi, glo, st);
+        if (rc) return rc;
+    }
+    if (want_data) {
+        const int64_t nw = (int64_t)Cout * C * kh * kw;
+        dcn_weight_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nw, 256), 148 * 8), 256, 0, st>>>(weight, Cout, C, kh * kw, whi, wlo);
+        rc = check_launch("dcn_weight_pack_kernel");
+        if (rc) return rc;
+        if (grad_input) MR_CUDA_TRY(cudaMemsetAsync(gxh, 0, (size_t)B * H * W * C * 4, st), "cudaMemsetAsync(dcn grad_input scratch)");
+        DcnDArgs a;
+        a.B = B; a.C = C; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.sh = sh; a.sw = sw; a.ph = ph; a.pw = pw; a.dh = dh; a.dw = dw;
+        a.Ho = Ho; a.Wo = Wo; a.P = Ho * Wo; a.tiles_x = tiles_x; a.tiles_per_sample = tiles_per_sample; a.nch = C / 128; a.nkk = Cout / BK;
+        a.xh = xh; a.off = offset; a.msk = mask; a.gxh = grad_input ? gxh : nullptr; a.goff = grad_offset; a.gmask = grad_mask;
+        a.off_bs = offset_bstride; a.mask_bs = mask_bstride; a.goff_bs = grad_offset_bstride; a.gmask_bs = grad_mask_bstride;
+        const int K = kh * kw;
+        int splits = 1;                                   // taps are spread over grid.y until the grid covers the SMs
+        while (splits < K && (int64_t)ntiles * splits < sm_count()) ++splits;
+        while (K % splits) ++splits;
+        a.tap_splits = splits;
+        CUtensorMap gh, gl, wh, wl;
+        const int64_t Kt = (int64_t)K * C;
+        if ((rc = make_map(&gh, ghi, BM, (int64_t)ntiles * Cout, BM, BK, BK))) return rc;
+        if ((rc = make_map(&gl, glo, BM, (int64_t)ntiles * Cout, BM, BK, BK))) return rc;
+        if ((rc = make_map(&wh, whi, Kt, Cout, Kt, BK, BK))) return rc;
+        if ((rc = make_map(&wl, wlo, Kt, Cout, Kt, BK, BK))) return rc;
+        { int rc_attr = ensure_dyn_smem((const void *)dcn_dgrad_tcgen05_kernel, DcnDSmem::TOTAL, "dcn_dgrad_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
+        dim3 grid((unsigned)ntiles, (unsigned)splits);
+        dcn_dgrad_tcgen05_kernel<<<grid, kDcnThreads, DcnDSmem::TOTAL, st>>>(gh, gl, wh, wl, a);
+        rc = check_launch("dcn_dgrad_tcgen05_kernel");
+        if (rc) return rc;
+        if (grad_input) {
+            dim3 tg((unsigned)ceil_div((int64_t)H * W, 32), (unsigned)ceil_div(C, 32), (unsigned)B);
+            dcn_nhwc_to_nchw_add_kernel<<<tg, 256, 0, st>>>(gxh, grad_input, C, H * W);
+            rc = check_launch("dcn_nhwc_to_nchw_add_kernel");
+            if (rc) return rc;
+        }
+    }
+    return MR_OK;
+}
+
 /* scratch of the fused weight gradient: NHWC copy of the input + re-tiled hi / lo grad_output */
 int64_t mr_dcn_fused_wgrad_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W, int64_t Cout, int64_t Ho, int64_t Wo) {
     const int64_t tiles = ceil_div(Wo, 16) * ceil_div(Ho, 8);
@@ -652,20 +1036,7 @@ int mr_dcn_wgrad_fused_f32(const float *input, const float *offset, int64_t offs
     rc = check_launch("dcn_go_retile_kernel");
     if (rc) return rc;
     a.xh = xh; a.off = offset; a.msk = mask; a.off_bs = offset_bstride; a.mask_bs = mask_bstride; a.gw = grad_weight; a.scale = scale;
-    CUtensorMap th, tl;
-    rc = make_map(&th, ghi, BM, (int64_t)a.ntiles * Cout, BM, BK, BM);
-    if (rc) return rc;
-    rc = make_map(&tl, glo, BM, (int64_t)a.ntiles * Cout, BM, BK, BM);
-    if (rc) return rc;
-    const int ctas_fixed = a.nkb * (Cout / BM);
-    int splits = (int)ceil_div(2 * sm_count(), ctas_fixed);
-    if (splits > a.ntiles) splits = a.ntiles;
-    if (splits < 1) splits = 1;
-    a.splits = splits;
-    { int rc_attr = ensure_dyn_smem((const void *)dcn_wgrad_tcgen05_kernel, DcnWSmem::TOTAL, "dcn_wgrad_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
-    dim3 grid((unsigned)a.nkb, (unsigned)splits, (unsigned)(Cout / BM));
-    dcn_wgrad_tcgen05_kernel<<<grid, kDcnThreads, DcnWSmem::TOTAL, st>>>(th, tl, a);
-    return check_launch("dcn_wgrad_tcgen05_kernel");
+    return launch_dcn_wgrad(a, ghi, glo, st);
 }
 
 }  // extern "C"

@@ -38,7 +38,8 @@ def _workspace(x, C, kh, kw, Ho, Wo, Cout=0, backward=False):
     nb = max(1, min(x.size(0), WORKSPACE_CAP_BYTES // max(per, 1)))
     nbytes = nb * per
     if Cout and backward:
-        nbytes = max(nbytes, int(_lib.lib().mr_dcn_fused_wgrad_workspace_bytes(x.size(0), C, x.size(2), x.size(3), Cout, Ho, Wo)))
+        nbytes = max(nbytes, int(_lib.lib().mr_dcn_fused_wgrad_workspace_bytes(x.size(0), C, x.size(2), x.size(3), Cout, Ho, Wo)),
+                     int(_lib.lib().mr_dcn_fused_backward_workspace_bytes(x.size(0), C, x.size(2), x.size(3), Cout, Ho, Wo, kh, kw)))
     elif Cout:
         nbytes = max(nbytes, int(_lib.lib().mr_dcn_fused_workspace_bytes(x.size(0), C, x.size(2), x.size(3), Cout, kh, kw)))
     nbytes = (nbytes + 255) // 256 * 256

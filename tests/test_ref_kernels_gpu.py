@@ -110,6 +110,7 @@ DCN_CASES = [
     (4, 128, 16, 16, 128, 3, 1, 1, 1, 1, 1, False, False),
     (2, 256, 16, 16, 256, 3, 2, 1, 1, 1, 1, False, True),  # layer-3 first block geometry (stride 2, big offset)
     (2, 64, 12, 20, 64, 3, 1, 1, 1, 1, 1, True, False),
+    (2, 128, 13, 19, 256, 3, 1, 1, 1, 1, 1, True, False),  # fused backward, ragged 8 x 16 tiles, Cout = 2 x 128
 ]
 
 
