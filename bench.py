@@ -447,13 +447,31 @@ def bench_dcn(dev, iters=10):
         b.record()
         torch.cuda.synchronize()
         sec = a.elapsed_time(b) / iters * 1e-3
+        # backward through the reference's pybind-style entry (deform_conv_cuda.cpp:566-679): fused weight + data gradient kernels
+        go = torch.randn(B, C, H, H, device=dev)
+        gi, gw, goff, gm = torch.zeros_like(x), torch.zeros_like(w), torch.zeros_like(off), torch.zeros_like(m)
+        bw = lambda: dcn.modulated_deform_conv_cuda_backward(x, w, None, None, off, m, None, gi, gw, None, goff, gm, go,  # noqa: E731
+                                                            3, 3, 1, 1, 1, 1, 1, 1, 1, 1, False)
+        for _ in range(3):
+            bw()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            bw()
+        b.record()
+        torch.cuda.synchronize()
+        bsec = a.elapsed_time(b) / iters * 1e-3
         flops = 2.0 * B * C * 9 * C * H * H
         out["C%d@%dx%d" % (C, H, H)] = {"fwd_us": sec * 1e6, "alg_TFLOPs": flops / sec / 1e12,
                                         "frac_of_tensor_peak": flops / sec / 1e12 / pk["bf16_tflops"],
-                                        "mma_TFLOPs_issued": 3 * flops / sec / 1e12}
-    return {"kernel": "dcn_fwd_tcgen05_kernel (bilinear gather = A-operand producer, bf16 hi/lo split: 3 MMAs per K block)",
+                                        "mma_TFLOPs_issued": 3 * flops / sec / 1e12,
+                                        "bwd_us": bsec * 1e6, "bwd_alg_TFLOPs": 2 * flops / bsec / 1e12,
+                                        "bwd_frac_of_tensor_peak": 2 * flops / bsec / 1e12 / pk["bf16_tflops"]}
+    return {"kernel": "dcn_fwd_tcgen05_kernel (bilinear gather = A-operand producer, bf16 hi/lo split: 3 MMAs per K block); backward = "
+                      "dcn_wgrad_tcgen05_kernel + dcn_dgrad_tcgen05_kernel (no column matrices in HBM)",
             "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops"], "peak_source": pk["source"], "B": 8, "shapes": out,
-            "round1_fwd_us": {"C128@64x64": 319.2, "C256@32x32": 264.5, "C512@16x16": 215.3}}
+            "round1_fwd_us": {"C128@64x64": 319.2, "C256@32x32": 264.5, "C512@16x16": 215.3},
+            "round1_fwd_bwd_us": {"C128@64x64": 1611.0, "C256@32x32": 1115.3, "C512@16x16": 944.9}}
 
 
 def bench_input_step(dev, n=512, reps=5):

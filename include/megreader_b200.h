@@ -340,6 +340,23 @@ int mr_ctc_greedy_decode(const float *prob, const float *mask, int N, int C, int
                          void *stream);
 int mr_blank_after_first_blank(int *pred, int N, int W, int blank, void *stream);
 
+/* ---- attention recogniser head: the greedy decoding loop (decoders/attention_decoder.py:119-131, AttentionRNNCell.forward :187-231)
+ * as ONE persistent cooperative kernel (csrc/attn_decode.cu).  All tensors fp32, contiguous unless a stride is given:
+ *   projected [N][L][H]   = attn.attn.weight[:, H:] . memory + attn.attn.bias   (step-invariant half of the energies, caller-computed)
+ *   memory    [N][L][H+E] = encoder grid with the position one-hots appended (decoder_input of the reference, batch-major)
+ *   wa_h      H rows of ld_wa floats = attn.attn.weight[:, :H];  v [H] = attn.v
+ *   wordtab   [V][H]      = word_linear(embedding.weight)  (row w = the embedded previous symbol w)
+ *   w_ih [3H][2H+E], b_ih [3H], w_hh [3H][H], b_hh [3H] = decoder.rnn (GRUCell, gates r, z, n);  w_out [V][H], b_out [V] = decoder.out
+ * Output pred [N][S] (argmax per step, int32; the reference's early exit is applied by the caller) and, if prob != NULL, the per-step
+ * softmax [N][S][V].  workspace >= mr_attn_decode_workspace_bytes(N, H, E), 256-byte aligned.  mr_attn_decode_status reads back the
+ * error word (non-zero: a grid barrier timed out and the results are invalid). */
+int64_t mr_attn_decode_workspace_bytes(int64_t N, int64_t H, int64_t E);
+int mr_attn_decode_f32(const float *projected, const float *memory, const float *wa_h, int64_t ld_wa, const float *v,
+                       const float *wordtab, const float *w_ih, const float *b_ih, const float *w_hh, const float *b_hh,
+                       const float *w_out, const float *b_out, int *pred, float *prob, void *workspace, int64_t workspace_bytes,
+                       int N, int L, int H, int E, int V, int S, int blank, void *stream);
+int mr_attn_decode_status(const void *workspace, int64_t N, int64_t H, int64_t E, void *stream, int *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,9 @@ _SIGS = {
     "mr_dcn_fused_workspace_bytes": [c_i64] * 7,
     "mr_dcn_forward_fused_f32": [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64] + [c_int] * 15 + [c_p],
     "mr_dcn_forward_f32": [c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_i64] + [c_int] * 15 + [c_p],
+    "mr_attn_decode_workspace_bytes": [c_i64] * 3,
+    "mr_attn_decode_f32": [c_p] * 3 + [c_i64] + [c_p] * 11 + [c_i64] + [c_int] * 7 + [c_p],
+    "mr_attn_decode_status": [c_p, c_i64, c_i64, c_i64, c_p, c_p],
     "mr_dcn_fused_wgrad_workspace_bytes": [c_i64] * 7,
     "mr_dcn_fused_backward_workspace_bytes": [c_i64] * 9,
     "mr_dcn_backward_fused_f32": [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_f32,
@@ -85,6 +88,7 @@ _RESTYPES = {
     "mr_dcn_workspace_bytes": c_i64,
     "mr_dcn_fused_workspace_bytes": c_i64,
     "mr_dcn_fused_wgrad_workspace_bytes": c_i64,
+    "mr_attn_decode_workspace_bytes": c_i64,
     "mr_dcn_fused_backward_workspace_bytes": c_i64,
     "mr_status_string": ctypes.c_char_p,
     "mr_last_cuda_error": ctypes.c_char_p,

@@ -286,11 +286,11 @@ struct DcnWArgs {
 struct DcnWSmem {
     static constexpr int B_BYTES = BM * BK * 2;               // produced tile, one of (hi, lo): [128 pixels][64 kc]
     static constexpr int A_BYTES = BM * BM * 2;               // go tile, one of (hi, lo): [128 co][128 pixels] = two 64-pixel atoms
-    static constexpr int STAGE_BYTES = 2 * B_BYTES + 2 * A_BYTES;     // 96 KB
-    static constexpr int STAGES = 2;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int STAGES = 2;                          // of the produced operand; the TMA operand has ONE buffer: its load for tile
+    static constexpr int A_OFF = STAGES * 2 * B_BYTES;        // i + 1 is issued when the MMAs of tile i retire and lands while tile i + 1
+    static constexpr int BAR_OFF = A_OFF + 2 * A_BYTES;       // is being gathered -- 64 KB less shared memory = 64 KB more L1 for the gathers
     static constexpr int TAP_OFF = BAR_OFF + 128;
-    static constexpr int TOTAL = TAP_OFF + STAGES * BM * 24 + 1024;   // one tap-table row set per stage
+    static constexpr int TOTAL = TAP_OFF + 2 * BM * 24 + 1024;   // one tap-table row set per tile parity
 };
 
 __global__ void __launch_bounds__(kDcnThreads, 1)
@@ -299,9 +299,10 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
     constexpr int STAGES = L::STAGES;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);
+    uint64_t *full = (uint64_t *)(smem + L::BAR_OFF);         // produced operand: full (512 producer arrivals) / empty (MMA commit)
     uint64_t *empty = full + STAGES;
-    uint64_t *tmem_full = empty + STAGES;
+    uint64_t *a_full = empty + STAGES, *a_empty = a_full + 1;  // TMA operand, single buffer
+    uint64_t *tmem_full = a_empty + 1;
     uint32_t *tmem_slot = (uint32_t *)(tmem_full + 1);
     float4 *tapw_all = (float4 *)(smem + L::TAP_OFF);         // [STAGES][128]
     uint2 *tapc_all = (uint2 *)(tapw_all + STAGES * BM);      // [STAGES][128]
@@ -315,7 +316,8 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmGh);
         tma_prefetch_desc(&tmGl);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1 + kProducerThreads); mbar_init(empty + s, 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, kProducerThreads); mbar_init(empty + s, 1); }
+        mbar_init(a_full, 1); mbar_init(a_empty, 1);
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
@@ -328,16 +330,15 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
     if (warp == 0) {
         if (elect_one()) {
             for (int i = 0; i < nt; ++i) {
-                const int s = i % STAGES;
                 const int gt = (int)blockIdx.y + i * a.splits;
-                mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
-                unsigned char *st = smem + s * L::STAGE_BYTES + 2 * L::B_BYTES;
-                mbar_expect_tx(full + s, 2 * L::A_BYTES);
+                mbar_wait(a_empty, (i & 1) ^ 1);
+                unsigned char *st = smem + L::A_OFF;
+                mbar_expect_tx(a_full, 2 * L::A_BYTES);
                 const int row = gt * a.Cout + co0;                        // rows of the re-tiled grad_output: (tile, co)
-                tma_load_2d(&tmGh, full + s, st, 0, row);
-                tma_load_2d(&tmGh, full + s, st + BM * 128, 64, row);
-                tma_load_2d(&tmGl, full + s, st + L::A_BYTES, 0, row);
-                tma_load_2d(&tmGl, full + s, st + L::A_BYTES + BM * 128, 64, row);
+                tma_load_2d(&tmGh, a_full, st, 0, row);
+                tma_load_2d(&tmGh, a_full, st + BM * 128, 64, row);
+                tma_load_2d(&tmGl, a_full, st + L::A_BYTES, 0, row);
+                tma_load_2d(&tmGl, a_full, st + L::A_BYTES + BM * 128, 64, row);
             }
         }
     } else if (warp == 1) {
@@ -345,11 +346,12 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
         for (int i = 0; i < nt; ++i) {
             const int s = i % STAGES;
             mbar_wait(full + s, (i / STAGES) & 1);
+            mbar_wait(a_full, i & 1);
             tc_fence_after();
             if (elect_one()) {
-                const uint32_t bh = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint32_t bh = smem_u32(smem + s * 2 * L::B_BYTES);
                 const uint32_t bl = bh + L::B_BYTES;
-                const uint32_t ah = bl + L::B_BYTES;
+                const uint32_t ah = smem_u32(smem + L::A_OFF);
                 const uint32_t al = ah + L::A_BYTES;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
@@ -360,6 +362,7 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                                   make_desc(bb + j * 2048, BM * 128, 1024), idesc, (i | pass | j) != 0);
                 }
                 umma_commit(empty + s);
+                umma_commit(a_empty);
                 if (i == nt - 1) umma_commit(tmem_full);
             }
             __syncwarp();
@@ -372,41 +375,54 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
 #pragma unroll
         for (int u = 0; u < 2; ++u) rrow[u] = pwp * 8 + u * 4 + sub;
         const int ti = k / a.kw, tj = k - ti * a.kw;
+        // tap table of one pixel tile (128 rows, this CTA's tap): raw offset / mask loads and the derived weights / corners are split so
+        // that the loads of tile i + 1 are in flight while tile i is gathered
+        auto tap_load = [&](int gt, float &oh, float &ow, float &m) {
+            const int bb = gt / a.tiles_per_sample, tile = gt - bb * a.tiles_per_sample;
+            const int r = ptid;
+            const int py = (tile / a.tiles_x) * 8 + (r >> 4), px = (tile % a.tiles_x) * 16 + (r & 15);
+            const bool rok = py < a.Ho && px < a.Wo;
+            const int pc = (rok ? py : a.Ho - 1) * a.Wo + (rok ? px : a.Wo - 1);
+            const float *offb = a.off + (int64_t)bb * a.off_bs;
+            oh = __ldg(offb + (int64_t)(2 * k) * a.P + pc);
+            ow = __ldg(offb + (int64_t)(2 * k + 1) * a.P + pc);
+            m = a.msk ? __ldg(a.msk + (int64_t)bb * a.mask_bs + (int64_t)k * a.P + pc) : 1.f;
+        };
+        auto tap_store = [&](int gt, int slot, float oh, float ow, float m) {
+            const int bb = gt / a.tiles_per_sample, tile = gt - bb * a.tiles_per_sample;
+            const int r = ptid;
+            const int py = (tile / a.tiles_x) * 8 + (r >> 4), px = (tile % a.tiles_x) * 16 + (r & 15);
+            const bool rok = py < a.Ho && px < a.Wo;
+            const int ho = rok ? py : a.Ho - 1, wo = rok ? px : a.Wo - 1;
+            const float hy = (float)(ho * a.sh - a.ph + ti * a.dh) + oh;
+            const float wx = (float)(wo * a.sw - a.pw + tj * a.dw) + ow;
+            const bool inside = rok && hy > -1.f && wx > -1.f && hy < (float)a.H && wx < (float)a.W;
+            const int hl = (int)floorf(hy), wl = (int)floorf(wx);
+            const int hh = hl + 1, wh = wl + 1;
+            const float lh = hy - hl, lw = wx - wl, uh = 1.f - lh, uw = 1.f - lw;
+            const bool m1 = inside && hl >= 0 && wl >= 0, m2 = inside && hl >= 0 && wh <= a.W - 1;
+            const bool m3 = inside && hh <= a.H - 1 && wl >= 0, m4 = inside && hh <= a.H - 1 && wh <= a.W - 1;
+            tapw_all[slot * BM + r] = make_float4(m1 ? uh * uw * m : 0.f, m2 ? uh * lw * m : 0.f, m3 ? lh * uw * m : 0.f, m4 ? lh * lw * m : 0.f);
+            const int y0 = min(max(hl, 0), a.H - 1), y1 = min(max(hh, 0), a.H - 1);
+            const int x0 = min(max(wl, 0), a.W - 1), x1 = min(max(wh, 0), a.W - 1);
+            tapc_all[slot * BM + r] = make_uint2((unsigned)y0 | ((unsigned)y1 << 16), (unsigned)x0 | ((unsigned)x1 << 16));
+        };
+        if (ptid < BM && nt > 0) {
+            float oh, ow, m;
+            tap_load((int)blockIdx.y, oh, ow, m);
+            tap_store((int)blockIdx.y, 0, oh, ow, m);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
         for (int i = 0; i < nt; ++i) {
             const int s = i % STAGES;
             const int gt = (int)blockIdx.y + i * a.splits;
             const int b = gt / a.tiles_per_sample;
-            const int tile = gt - b * a.tiles_per_sample;
-            const int ty0 = (tile / a.tiles_x) * 8, tx0 = (tile % a.tiles_x) * 16;
-            float4 *tapw = tapw_all + s * BM;
-            uint2 *tapc = tapc_all + s * BM;
-            // the stage's previous tile (i - STAGES) has been consumed by every producer before anybody reached this point:
-            // its readers passed the named barrier of tile i - 1 ... but not necessarily of this stage; wait for the slot first
+            const float4 *tapw = tapw_all + (i & 1) * BM;
+            const uint2 *tapc = tapc_all + (i & 1) * BM;
+            const bool prep = ptid < BM && i + 1 < nt;
+            float noh = 0.f, now = 0.f, nm = 0.f;
+            if (prep) tap_load(gt + a.splits, noh, now, nm);
             mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
-            if (ptid < BM) {
-                const int r = ptid;
-                const int py = ty0 + (r >> 4), px = tx0 + (r & 15);
-                const bool rok = py < a.Ho && px < a.Wo;
-                const int ho = rok ? py : a.Ho - 1, wo = rok ? px : a.Wo - 1;
-                const int pc = ho * a.Wo + wo;
-                const float *offb = a.off + (int64_t)b * a.off_bs;
-                const float oh = __ldg(offb + (int64_t)(2 * k) * a.P + pc);
-                const float ow = __ldg(offb + (int64_t)(2 * k + 1) * a.P + pc);
-                const float m = a.msk ? __ldg(a.msk + (int64_t)b * a.mask_bs + (int64_t)k * a.P + pc) : 1.f;
-                const float hy = (float)(ho * a.sh - a.ph + ti * a.dh) + oh;
-                const float wx = (float)(wo * a.sw - a.pw + tj * a.dw) + ow;
-                const bool inside = rok && hy > -1.f && wx > -1.f && hy < (float)a.H && wx < (float)a.W;
-                const int hl = (int)floorf(hy), wl = (int)floorf(wx);
-                const int hh = hl + 1, wh = wl + 1;
-                const float lh = hy - hl, lw = wx - wl, uh = 1.f - lh, uw = 1.f - lw;
-                const bool m1 = inside && hl >= 0 && wl >= 0, m2 = inside && hl >= 0 && wh <= a.W - 1;
-                const bool m3 = inside && hh <= a.H - 1 && wl >= 0, m4 = inside && hh <= a.H - 1 && wh <= a.W - 1;
-                tapw[r] = make_float4(m1 ? uh * uw * m : 0.f, m2 ? uh * lw * m : 0.f, m3 ? lh * uw * m : 0.f, m4 ? lh * lw * m : 0.f);
-                const int y0 = min(max(hl, 0), a.H - 1), y1 = min(max(hh, 0), a.H - 1);
-                const int x0 = min(max(wl, 0), a.W - 1), x1 = min(max(wh, 0), a.W - 1);
-                tapc[r] = make_uint2((unsigned)y0 | ((unsigned)y1 << 16), (unsigned)x0 | ((unsigned)x1 << 16));
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
             const float *xb = a.xh + (int64_t)b * a.H * a.W * a.C + j * 4;
             const int c4 = cc * (BK / 4);
             float4 x1[2][2], x2[2][2], x3[2][2], x4[2][2];
@@ -427,7 +443,7 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                     x3[u][e] = __ldg(q3 + c4 + e * 8); x4[u][e] = __ldg(q4 + c4 + e * 8);
                 }
             }
-            const uint32_t bh_s = smem_u32(smem + s * L::STAGE_BYTES);
+            const uint32_t bh_s = smem_u32(smem + s * 2 * L::B_BYTES);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const uint32_t row_off = (uint32_t)rrow[u] * 128u, sw = (uint32_t)(rrow[u] & 7);
@@ -452,6 +468,8 @@ dcn_wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
             }
             fence_proxy_async();
             mbar_arrive_cta(full + s);
+            if (prep) tap_store(gt + a.splits, (i + 1) & 1, noh, now, nm);
+            asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
         }
         // ---- epilogue: D[co][kc] -> gw[co][c][k] (fp32 atomics; 4 warps per TMEM quarter, 16 columns each)
         const int q = warp & 3, part = (warp - 2) >> 2;
@@ -495,24 +513,67 @@ struct DcnDArgs {
     float *goff, *gmask;       // reference layouts (flat (Ho, Wo) strides inside per-sample slabs); either may be nullptr
     int64_t off_bs, mask_bs, goff_bs, gmask_bs;
     int B, C, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, Ho, Wo, P;
-    int tiles_per_sample, tiles_x, nch, nkk, tap_splits;     // nch = C / 128 channel chunks, nkk = Cout / 64 K blocks
+    int tiles_per_sample, tiles_x, nch, nkk, tap_splits;     // nch = C / 128 channel chunks, nkk = Cout / 32 K blocks
 };
 
 struct DcnDSmem {
     static constexpr int BN = 128;
-    static constexpr int OP_BYTES = BK * 128 * 2;             // one operand tile, one of (hi, lo): [64 co][128 (pixels | kc)] = 16 KB
+    static constexpr int KB = 32;                             // output channels (the reduction dimension) per pipeline stage
+    static constexpr int OP_BYTES = KB * 128 * 2;             // one operand tile, one of (hi, lo): [32 co][128 (pixels | kc)] = 8 KB
     static constexpr int STAGE_BYTES = 4 * OP_BYTES;          // A hi, A lo, B hi, B lo
-    static constexpr int STAGES = 2;
+    static constexpr int STAGES = 2;                          // small on purpose: the epilogue's gathers want the rest of the SM's L1
     static constexpr int STG_OFF = STAGES * STAGE_BYTES;      // fp32 staging tile [128 pixels][128 channels], 16-byte chunks XOR-swizzled
     static constexpr int STG_BYTES = BM * BN * 4;
     static constexpr int BAR_OFF = STG_OFF + STG_BYTES;
     static constexpr int TAB_OFF = BAR_OFF + 128;
-    static constexpr int TAB_BYTES = BM * (3 * 16 + 8 + 4);
+    static constexpr int TAB_BYTES = 2 * BM * (3 * 16 + 8 + 4);          // tap tables, double-buffered by tap parity
     static constexpr int TOTAL = TAB_OFF + TAB_BYTES + 1024;
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// per-(pixel row, tap) sampling data of the data-gradient epilogue (dmcn_im2col_bilinear / dmcn_get_coordinate_weight,
+// deform_conv_cuda_kernel.cu:466-567, evaluated once per row instead of once per channel)
+struct DcnDTab {
+    float4 *w, *h, *v;      // bilinear weights of the valid corners; mask * d/dh and mask * d/dw coefficients of the four corner values
+    uint2 *c;               // clamped corner rows / columns
+    float *m;               // modulation mask
+};
+struct DcnDRaw { float oh, ow, m; };
+__device__ __forceinline__ DcnDRaw dcn_dgrad_load_row(const DcnDArgs &a, int b, int kk, int r, int ty0, int tx0) {
+    const int py = ty0 + (r >> 4), px = tx0 + (r & 15);
+    const bool rok = py < a.Ho && px < a.Wo;
+    const int pc = (rok ? py : a.Ho - 1) * a.Wo + (rok ? px : a.Wo - 1);
+    const float *offb = a.off + (int64_t)b * a.off_bs;
+    DcnDRaw v;
+    v.oh = __ldg(offb + (int64_t)(2 * kk) * a.P + pc);
+    v.ow = __ldg(offb + (int64_t)(2 * kk + 1) * a.P + pc);
+    v.m = a.msk ? __ldg(a.msk + (int64_t)b * a.mask_bs + (int64_t)kk * a.P + pc) : 1.f;
+    return v;
+}
+__device__ __forceinline__ void dcn_dgrad_store_row(const DcnDArgs &a, const DcnDTab &t, const DcnDRaw &v, int kk, int r, int ty0, int tx0) {
+    const int ti = kk / a.kw, tj = kk - ti * a.kw;
+    const int py = ty0 + (r >> 4), px = tx0 + (r & 15);
+    const bool rok = py < a.Ho && px < a.Wo;
+    const int ho = rok ? py : a.Ho - 1, wo = rok ? px : a.Wo - 1;
+    const float m = v.m;
+    const float hy = (float)(ho * a.sh - a.ph + ti * a.dh) + v.oh;
+    const float wx = (float)(wo * a.sw - a.pw + tj * a.dw) + v.ow;
+    const bool inside = rok && hy > -1.f && wx > -1.f && hy < (float)a.H && wx < (float)a.W;
+    const int hl = (int)floorf(hy), wl = (int)floorf(wx);
+    const int hh = hl + 1, wh = wl + 1;
+    const float lh = hy - hl, lw = wx - wl, uh = 1.f - lh, uw = 1.f - lw;
+    const float f1 = (inside && hl >= 0 && wl >= 0) ? 1.f : 0.f, f2 = (inside && hl >= 0 && wh <= a.W - 1) ? 1.f : 0.f;
+    const float f3 = (inside && hh <= a.H - 1 && wl >= 0) ? 1.f : 0.f, f4 = (inside && hh <= a.H - 1 && wh <= a.W - 1) ? 1.f : 0.f;
+    t.w[r] = make_float4(f1 * uh * uw, f2 * uh * lw, f3 * lh * uw, f4 * lh * lw);
+    t.h[r] = make_float4(-m * uw * f1, -m * lw * f2, m * uw * f3, m * lw * f4);
+    t.v[r] = make_float4(-m * uh * f1, m * uh * f2, -m * lh * f3, m * lh * f4);
+    const int y0 = min(max(hl, 0), a.H - 1), y1 = min(max(hh, 0), a.H - 1);
+    const int x0 = min(max(wl, 0), a.W - 1), x1 = min(max(wh, 0), a.W - 1);
+    t.c[r] = make_uint2((unsigned)y0 | ((unsigned)y1 << 16), (unsigned)x0 | ((unsigned)x1 << 16));
+    t.m[r] = m;
 }
 
 __global__ void __launch_bounds__(kDcnThreads, 1)
@@ -528,11 +589,13 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
     uint64_t *acc_full = empty + STAGES;
     uint64_t *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = (uint32_t *)(acc_empty + 2);
-    float4 *tabw = (float4 *)(smem + L::TAB_OFF);      // bilinear weights of the valid corners (no mask)
-    float4 *tabh = tabw + BM;                          // mask * d/dh coefficients of the four corner values
-    float4 *tabv = tabh + BM;                          // mask * d/dw coefficients
-    uint2 *tabc = (uint2 *)(tabv + BM);                // clamped corner rows / columns
-    float *tabm = (float *)(tabc + BM);                // modulation mask of the (pixel, tap)
+    auto tab_of = [&](int tb) {
+        DcnDTab t;
+        unsigned char *base = smem + L::TAB_OFF + tb * (L::TAB_BYTES / 2);
+        t.w = (float4 *)base; t.h = t.w + BM; t.v = t.h + BM;
+        t.c = (uint2 *)(t.v + BM); t.m = (float *)(t.c + BM);
+        return t;
+    };
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gt = blockIdx.x;
     const int b = gt / a.tiles_per_sample;
@@ -543,7 +606,7 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmGh); tma_prefetch_desc(&tmGl); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
         for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kProducerThreads / 32); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
@@ -562,16 +625,16 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                         mbar_wait(empty + s, ((i / STAGES) & 1) ^ 1);
                         unsigned char *st = smem + s * L::STAGE_BYTES;
                         mbar_expect_tx(full + s, L::STAGE_BYTES);
-                        const int grow = gt * a.Cout + kb * BK;                          // (tile, co) rows of the re-tiled grad_output
+                        const int grow = gt * a.Cout + kb * L::KB;                         // (tile, co) rows of the re-tiled grad_output
                         tma_load_2d(&tmGh, full + s, st, 0, grow);
-                        tma_load_2d(&tmGh, full + s, st + BK * 128, 64, grow);
+                        tma_load_2d(&tmGh, full + s, st + L::KB * 128, 64, grow);
                         tma_load_2d(&tmGl, full + s, st + L::OP_BYTES, 0, grow);
-                        tma_load_2d(&tmGl, full + s, st + L::OP_BYTES + BK * 128, 64, grow);
+                        tma_load_2d(&tmGl, full + s, st + L::OP_BYTES + L::KB * 128, 64, grow);
                         const int kc0 = ((2 * h) * K + kk) * BK, kc1 = ((2 * h + 1) * K + kk) * BK;   // the chunk's two channel blocks
-                        tma_load_2d(&tmWh, full + s, st + 2 * L::OP_BYTES, kc0, kb * BK);
-                        tma_load_2d(&tmWh, full + s, st + 2 * L::OP_BYTES + BK * 128, kc1, kb * BK);
-                        tma_load_2d(&tmWl, full + s, st + 3 * L::OP_BYTES, kc0, kb * BK);
-                        tma_load_2d(&tmWl, full + s, st + 3 * L::OP_BYTES + BK * 128, kc1, kb * BK);
+                        tma_load_2d(&tmWh, full + s, st + 2 * L::OP_BYTES, kc0, kb * L::KB);
+                        tma_load_2d(&tmWh, full + s, st + 2 * L::OP_BYTES + L::KB * 128, kc1, kb * L::KB);
+                        tma_load_2d(&tmWl, full + s, st + 3 * L::OP_BYTES, kc0, kb * L::KB);
+                        tma_load_2d(&tmWl, full + s, st + 3 * L::OP_BYTES + L::KB * 128, kc1, kb * L::KB);
                     }
         }
     } else if (warp == 1) {
@@ -593,9 +656,9 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                         for (int pass = 0; pass < 3; ++pass) {
                             const uint32_t aa = pass == 2 ? al : ah, bb = pass == 1 ? bl : bh;
 #pragma unroll
-                            for (int k4 = 0; k4 < BK / UMMA_K; ++k4)
-                                umma_bf16(tmem_base + buf * BN, make_desc(aa + k4 * 2048, BK * 128, 1024),
-                                          make_desc(bb + k4 * 2048, BK * 128, 1024), idesc, (kb | pass | k4) != 0);
+                            for (int k4 = 0; k4 < L::KB / UMMA_K; ++k4)
+                                umma_bf16(tmem_base + buf * BN, make_desc(aa + k4 * 2048, L::KB * 128, 1024),
+                                          make_desc(bb + k4 * 2048, L::KB * 128, 1024), idesc, (kb | pass | k4) != 0);
                         }
                         umma_commit(empty + s);
                         if (kb == a.nkk - 1) umma_commit(acc_full + buf);
@@ -604,45 +667,26 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                 }
             }
     } else {
+        // Epilogue warp = (TMEM quarter q, slice `part`).  It drains 32 channels of its quarter's 32 pixel rows into the shared staging tile
+        // and then owns 8 of those rows for all 128 channels (8 lanes per row, 2 rows per lane: the forward's gather mapping), so the sums
+        // over channels stay in registers.  Only the four warps of a quarter synchronise (named barriers 1 + q and 5 + q); the quarters
+        // drift apart, which overlaps one quarter's gather latency with another's arithmetic.
         const int pwp = warp - 2;
+        const int q = warp & 3, part = pwp >> 2;
         const int sub = lane >> 3, j = lane & 7;
-        const int ptid = threadIdx.x - 64;
-        const int q = warp & 3, part = pwp >> 2;                  // TMEM quarter of this warp, 32-column slice it drains
-        int rrow[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) rrow[u] = pwp * 8 + u * 4 + sub;
         const uint32_t stg = smem_u32(smem + L::STG_OFF);
         const float *xb = a.xh + (int64_t)b * a.H * a.W * a.C + j * 4;
         float *gxb = a.gxh ? a.gxh + (int64_t)b * a.H * a.W * a.C + j * 4 : nullptr;
-        int n = 0;
-        for (int kk = blockIdx.y; kk < K; kk += a.tap_splits) {
-            if (ptid < BM) {
-                const int r = ptid;
-                const int ti = kk / a.kw, tj = kk - ti * a.kw;
-                const int py = ty0 + (r >> 4), px = tx0 + (r & 15);
-                const bool rok = py < a.Ho && px < a.Wo;
-                const int ho = rok ? py : a.Ho - 1, wo = rok ? px : a.Wo - 1;
-                const int pc = ho * a.Wo + wo;
-                const float *offb = a.off + (int64_t)b * a.off_bs;
-                const float oh = __ldg(offb + (int64_t)(2 * kk) * a.P + pc);
-                const float ow = __ldg(offb + (int64_t)(2 * kk + 1) * a.P + pc);
-                const float m = a.msk ? __ldg(a.msk + (int64_t)b * a.mask_bs + (int64_t)kk * a.P + pc) : 1.f;
-                const float hy = (float)(ho * a.sh - a.ph + ti * a.dh) + oh;
-                const float wx = (float)(wo * a.sw - a.pw + tj * a.dw) + ow;
-                const bool inside = rok && hy > -1.f && wx > -1.f && hy < (float)a.H && wx < (float)a.W;
-                const int hl = (int)floorf(hy), wl = (int)floorf(wx);
-                const int hh = hl + 1, wh = wl + 1;
-                const float lh = hy - hl, lw = wx - wl, uh = 1.f - lh, uw = 1.f - lw;
-                const float f1 = (inside && hl >= 0 && wl >= 0) ? 1.f : 0.f, f2 = (inside && hl >= 0 && wh <= a.W - 1) ? 1.f : 0.f;
-                const float f3 = (inside && hh <= a.H - 1 && wl >= 0) ? 1.f : 0.f, f4 = (inside && hh <= a.H - 1 && wh <= a.W - 1) ? 1.f : 0.f;
-                tabw[r] = make_float4(f1 * uh * uw, f2 * uh * lw, f3 * lh * uw, f4 * lh * lw);
-                tabh[r] = make_float4(-m * uw * f1, -m * lw * f2, m * uw * f3, m * lw * f4);      // dmcn_get_coordinate_weight :527-567
-                tabv[r] = make_float4(-m * uh * f1, m * uh * f2, -m * lh * f3, m * lh * f4);
-                const int y0 = min(max(hl, 0), a.H - 1), y1 = min(max(hh, 0), a.H - 1);
-                const int x0 = min(max(wl, 0), a.W - 1), x1 = min(max(wh, 0), a.W - 1);
-                tabc[r] = make_uint2((unsigned)y0 | ((unsigned)y1 << 16), (unsigned)x0 | ((unsigned)x1 << 16));
-                tabm[r] = m;
-            }
+        const int R0 = q * 32;
+        int rrow[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) rrow[u] = R0 + part * 8 + u * 4 + sub;
+        if (part == 0 && (int)blockIdx.y < K)
+            dcn_dgrad_store_row(a, tab_of(0), dcn_dgrad_load_row(a, b, blockIdx.y, R0 + lane, ty0, tx0), blockIdx.y, R0 + lane, ty0, tx0);
+        int n = 0, t = 0;
+        for (int kk = blockIdx.y; kk < K; kk += a.tap_splits, ++t) {
+            const int tb = t & 1;
+            const DcnDTab T = tab_of(tb);
             float vh[2] = {0.f, 0.f}, vw[2] = {0.f, 0.f}, vm[2] = {0.f, 0.f};
             for (int h = 0; h < a.nch; ++h, ++n) {
                 const int buf = n & 1;
@@ -651,7 +695,7 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                 {
                     uint32_t rr[32];
                     tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(part * 32), rr);
-                    const int r = q * 32 + lane;
+                    const int r = R0 + lane;
                     const uint32_t rb = stg + (uint32_t)r * 512u;
 #pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4)
@@ -659,18 +703,22 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                                      "r"(rr[4 * c4]), "r"(rr[4 * c4 + 1]), "r"(rr[4 * c4 + 2]), "r"(rr[4 * c4 + 3]) : "memory");
                 }
                 tc_fence_before();
-                asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");
-                if (ptid == 0) mbar_arrive_cta(acc_empty + buf);
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+                if (lane == 0) mbar_arrive_cta(acc_empty + buf);
+                // the next tap's table: its three global loads are issued now and consumed after this N block's work
+                const bool prep = part == 0 && h == 0 && kk + a.tap_splits < K;
+                DcnDRaw raw = {0.f, 0.f, 0.f};
+                if (prep) raw = dcn_dgrad_load_row(a, b, kk + a.tap_splits, R0 + lane, ty0, tx0);
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int r = rrow[u];
-                    const float4 w = tabw[r], ch = tabh[r], cv = tabv[r];
-                    const uint2 cc = tabc[r];
+                    const float4 w = T.w[r], ch = T.h[r], cv = T.v[r];
+                    const uint2 cc = T.c[r];
+                    const float mk = T.m[r];               // ch / cv carry the mask already; the scatter needs it separately
                     const int y0 = (int)(cc.x & 0xffffu) * a.W, y1 = (int)(cc.x >> 16) * a.W;
                     const int x0 = (int)(cc.y & 0xffffu), x1 = (int)(cc.y >> 16);
                     const int64_t o1 = (int64_t)(y0 + x0) * a.C + h * 128, o2 = (int64_t)(y0 + x1) * a.C + h * 128;
                     const int64_t o3 = (int64_t)(y1 + x0) * a.C + h * 128, o4 = (int64_t)(y1 + x1) * a.C + h * 128;
-                    const float mk = tabm[r];          // ch / cv carry the mask already; the scatter needs it separately
 #pragma unroll 1
                     for (int eh = 0; eh < 4; eh += 2) {         // two 16-byte channel chunks at a time (register budget: 96)
                         float4 g[2], v1[2], v2[2], v3[2], v4[2];
@@ -705,7 +753,8 @@ dcn_dgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap tmGh, const __grid_
                         }
                     }
                 }
-                asm volatile("bar.sync 2, %0;" ::"n"(kProducerThreads) : "memory");
+                if (prep) dcn_dgrad_store_row(a, tab_of(tb ^ 1), raw, kk + a.tap_splits, R0 + lane, ty0, tx0);
+                asm volatile("bar.sync %0, 128;" ::"r"(5 + q) : "memory");
             }
             // the tap is complete: fold the 8 channel lanes of each pixel row and write its three gradients
 #pragma unroll
@@ -757,19 +806,40 @@ __global__ void __launch_bounds__(256) dcn_nhwc_to_nchw_add_kernel(const float *
 // grad_output [B][Cout][P] fp32 -> hi / lo bf16 [B * tiles][Cout][128] in the 8 x 16 tile order of the kernels (0 outside the map)
 __global__ void dcn_go_retile_kernel(const float *__restrict__ go, int B, int Cout, int Ho, int Wo, int tiles_x, int tiles_per_sample,
                                      bf16 *__restrict__ hi, bf16 *__restrict__ lo) {
-    const int64_t n = (int64_t)B * tiles_per_sample * Cout * BM;
+    // one thread = one 16-pixel tile row of one channel: 64 contiguous bytes in, 32 + 32 contiguous bytes out
+    const int64_t n = (int64_t)B * tiles_per_sample * Cout * 8;
+    const bool vec = (Wo & 3) == 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i % BM);
-        int64_t t = i / BM;
+        const int gr = (int)(i & 7);
+        int64_t t = i >> 3;
         const int co = (int)(t % Cout); t /= Cout;
         const int tile = (int)(t % tiles_per_sample);
         const int b = (int)(t / tiles_per_sample);
-        const int py = (tile / tiles_x) * 8 + (r >> 4), px = (tile % tiles_x) * 16 + (r & 15);
-        float v = 0.f;
-        if (py < Ho && px < Wo) v = go[((int64_t)b * Cout + co) * Ho * Wo + (int64_t)py * Wo + px];
-        const bf16 h = __float2bfloat16_rn(v);
-        hi[i] = h;
-        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+        const int py = (tile / tiles_x) * 8 + gr, px0 = (tile % tiles_x) * 16;
+        float v[16];
+        const float *src = go + ((int64_t)b * Cout + co) * Ho * Wo + (int64_t)py * Wo + px0;
+        if (py < Ho && vec && px0 + 16 <= Wo) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 f = __ldg(reinterpret_cast<const float4 *>(src) + e);
+                v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = (py < Ho && px0 + e < Wo) ? __ldg(src + e) : 0.f;
+        }
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            const float2 f = __bfloat1622float2(h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * e] - f.x, v[2 * e + 1] - f.y);
+            ph[e] = *reinterpret_cast<const uint32_t *>(&h2);
+            pl[e] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        uint4 *dh = reinterpret_cast<uint4 *>(hi + i * 16), *dl = reinterpret_cast<uint4 *>(lo + i * 16);
+        dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+        dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
     }
 }
 
@@ -819,10 +889,17 @@ int launch_dcn_wgrad(DcnWArgs &a, const bf16 *ghi, const bf16 *glo, cudaStream_t
     if (rc) return rc;
     rc = make_map(&tl, glo, BM, (int64_t)a.ntiles * a.Cout, BM, BK, BM);
     if (rc) return rc;
+    // split-K over the pixel tiles: whole waves of CTAs (one CTA per SM), the fewest (rounds x tiles per CTA + per-CTA overhead)
     const int ctas_fixed = a.nkb * (a.Cout / BM);
-    int splits = (int)ceil_div(2 * sm_count(), ctas_fixed);
-    if (splits > a.ntiles) splits = a.ntiles;
-    if (splits < 1) splits = 1;
+    int splits = 1;
+    int64_t best = -1;
+    for (int waves = 1; waves <= 4; ++waves) {
+        int sp = (int)((int64_t)waves * sm_count() / ctas_fixed);
+        sp = sp < 1 ? 1 : (sp > a.ntiles ? a.ntiles : sp);
+        const int64_t rounds = ceil_div((int64_t)ctas_fixed * sp, sm_count());
+        const int64_t cost = rounds * (ceil_div(a.ntiles, sp) + 3);
+        if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
     a.splits = splits;
     { int rc_attr = ensure_dyn_smem((const void *)dcn_wgrad_tcgen05_kernel, DcnWSmem::TOTAL, "dcn_wgrad_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
     dim3 grid((unsigned)a.nkb, (unsigned)splits, (unsigned)(a.Cout / BM));
@@ -941,7 +1018,7 @@ int mr_dcn_backward_fused_f32(const float *input, const float *weight, const flo
     }
     int rc = check_launch("dcn_nchw_to_nhwc_kernel");
     if (rc) return rc;
-    const int64_t ng = (int64_t)ntiles * Cout * BM;
+    const int64_t ng = (int64_t)ntiles * Cout * 8;
     dcn_go_retile_kernel<<<(unsigned)std::min<int64_t>(ceil_div(ng, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(
         grad_output, B, Cout, Ho, Wo, tiles_x, tiles_per_sample, ghi, glo);
     rc = check_launch("dcn_go_retile_kernel");
@@ -963,20 +1040,25 @@ int mr_dcn_backward_fused_f32(const float *input, const float *weight, const flo
         if (grad_input) MR_CUDA_TRY(cudaMemsetAsync(gxh, 0, (size_t)B * H * W * C * 4, st), "cudaMemsetAsync(dcn grad_input scratch)");
         DcnDArgs a;
         a.B = B; a.C = C; a.H = H; a.W = W; a.Cout = Cout; a.kh = kh; a.kw = kw; a.sh = sh; a.sw = sw; a.ph = ph; a.pw = pw; a.dh = dh; a.dw = dw;
-        a.Ho = Ho; a.Wo = Wo; a.P = Ho * Wo; a.tiles_x = tiles_x; a.tiles_per_sample = tiles_per_sample; a.nch = C / 128; a.nkk = Cout / BK;
+        a.Ho = Ho; a.Wo = Wo; a.P = Ho * Wo; a.tiles_x = tiles_x; a.tiles_per_sample = tiles_per_sample; a.nch = C / 128; a.nkk = Cout / DcnDSmem::KB;
         a.xh = xh; a.off = offset; a.msk = mask; a.gxh = grad_input ? gxh : nullptr; a.goff = grad_offset; a.gmask = grad_mask;
         a.off_bs = offset_bstride; a.mask_bs = mask_bstride; a.goff_bs = grad_offset_bstride; a.gmask_bs = grad_mask_bstride;
         const int K = kh * kw;
-        int splits = 1;                                   // taps are spread over grid.y until the grid covers the SMs
-        while (splits < K && (int64_t)ntiles * splits < sm_count()) ++splits;
-        while (K % splits) ++splits;
+        // taps are spread over grid.y (a divisor of the tap count): the fewest (rounds of CTAs x N blocks per CTA + per-CTA overhead)
+        int splits = 1;
+        int64_t best = -1;
+        for (int sp = 1; sp <= K; ++sp) {
+            if (K % sp) continue;
+            const int64_t cost = ceil_div((int64_t)ntiles * sp, sm_count()) * ((int64_t)(K / sp) * a.nch + 1);
+            if (best < 0 || cost < best) { best = cost; splits = sp; }
+        }
         a.tap_splits = splits;
         CUtensorMap gh, gl, wh, wl;
         const int64_t Kt = (int64_t)K * C;
-        if ((rc = make_map(&gh, ghi, BM, (int64_t)ntiles * Cout, BM, BK, BK))) return rc;
-        if ((rc = make_map(&gl, glo, BM, (int64_t)ntiles * Cout, BM, BK, BK))) return rc;
-        if ((rc = make_map(&wh, whi, Kt, Cout, Kt, BK, BK))) return rc;
-        if ((rc = make_map(&wl, wlo, Kt, Cout, Kt, BK, BK))) return rc;
+        if ((rc = make_map(&gh, ghi, BM, (int64_t)ntiles * Cout, BM, BK, DcnDSmem::KB))) return rc;
+        if ((rc = make_map(&gl, glo, BM, (int64_t)ntiles * Cout, BM, BK, DcnDSmem::KB))) return rc;
+        if ((rc = make_map(&wh, whi, Kt, Cout, Kt, BK, DcnDSmem::KB))) return rc;
+        if ((rc = make_map(&wl, wlo, Kt, Cout, Kt, BK, DcnDSmem::KB))) return rc;
         { int rc_attr = ensure_dyn_smem((const void *)dcn_dgrad_tcgen05_kernel, DcnDSmem::TOTAL, "dcn_dgrad_tcgen05 smem attr"); if (rc_attr) return rc_attr; }
         dim3 grid((unsigned)ntiles, (unsigned)splits);
         dcn_dgrad_tcgen05_kernel<<<grid, kDcnThreads, DcnDSmem::TOTAL, st>>>(gh, gl, wh, wl, a);
@@ -1030,7 +1112,7 @@ int mr_dcn_wgrad_fused_f32(const float *input, const float *offset, int64_t offs
     }
     int rc = check_launch("dcn_nchw_to_nhwc_kernel");
     if (rc) return rc;
-    const int64_t ng = (int64_t)a.ntiles * Cout * BM;
+    const int64_t ng = (int64_t)a.ntiles * Cout * 8;
     dcn_go_retile_kernel<<<(unsigned)std::min<int64_t>(ceil_div(ng, 256), (int64_t)sm_count() * 16), 256, 0, st>>>(
         grad_output, B, Cout, a.Ho, a.Wo, a.tiles_x, a.tiles_per_sample, ghi, glo);
     rc = check_launch("dcn_go_retile_kernel");

@@ -128,6 +128,40 @@ class AttentionDecoder(nn.Module):
         ex = self.onehot_embedding_x(xs).permute(2, 0, 1)
         return torch.cat([ey, ex], 0).unsqueeze(0).expand(batch, -1, -1, -1)
 
+    def _decode_cuda(self, memory_bt, projected, want_prob=False):
+        """The eval loop on the GPU: one persistent kernel for all max_size steps (csrc/attn_decode.cu).  memory_bt (N,L,H+E),
+        projected (N,L,H) -> pred (N,max_size) int32 [, per-step softmax (N,max_size,V)]."""
+        from megreader_b200 import _lib
+        cell = self.decoder
+        n, L, _ = memory_bt.shape
+        H, E, V, S = self.inner_channels, self.max_size + self.height, len(self.charset), self.max_size
+        dev = memory_bt.device
+        f32 = lambda t: t.detach().float().contiguous()  # noqa: E731
+        memory_bt, projected = f32(memory_bt), f32(projected)
+        wa = f32(cell.attn.attn.weight)                                   # (H, 2H+E); the kernel reads [:, :H] through the row stride
+        wordtab = f32(cell.word_linear(cell.embedding.weight))           # (V, H): row w = word_linear(embedding(w))
+        params = [f32(t) for t in (cell.attn.v, cell.rnn.weight_ih, cell.rnn.bias_ih, cell.rnn.weight_hh, cell.rnn.bias_hh,
+                                   cell.out.weight, cell.out.bias)]
+        pred = torch.empty(n, S, dtype=torch.int32, device=dev)
+        prob = torch.empty(n, S, V, dtype=torch.float32, device=dev) if want_prob else None
+        lib = _lib.lib()
+        ws_bytes = int(lib.mr_attn_decode_workspace_bytes(n, H, E))
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(lib.mr_attn_decode_f32(
+                projected.data_ptr(), memory_bt.data_ptr(), wa.data_ptr(), wa.stride(0), params[0].data_ptr(), wordtab.data_ptr(),
+                params[1].data_ptr(), params[2].data_ptr(), params[3].data_ptr(), params[4].data_ptr(), params[5].data_ptr(),
+                params[6].data_ptr(), pred.data_ptr(), prob.data_ptr() if prob is not None else None, ws.data_ptr(), ws_bytes,
+                n, L, H, E, V, S, int(self.charset.blank), stream), "attn_decode")
+            if not torch.cuda.is_current_stream_capturing():
+                import ctypes
+                status = ctypes.c_int(0)
+                _lib.check(lib.mr_attn_decode_status(ws.data_ptr(), n, H, E, stream, ctypes.byref(status)), "attn_decode_status")
+                if status.value:
+                    raise RuntimeError("megreader_b200 attn_decode: grid barrier timed out (error word %d)" % status.value)
+        return (pred, prob) if want_prob else pred
+
     def forward(self, feature, targets=None, lengths=None, train=False):
         device = feature.device
         n = feature.shape[0]
@@ -158,11 +192,24 @@ class AttentionDecoder(nn.Module):
                 word = word.to(device) * (1 - swap) + noise * swap
             return loss, torch.cat(attention, 1).view(n, -1, self.height, self.max_size)
 
-        steps = []
+        if feature.is_cuda:
+            pred = self._decode_cuda(memory_bt, projected)
+            finished = (pred == blank).all(dim=0).long().cummax(0).values.bool()
+            return pred.masked_fill(finished.unsqueeze(0), blank)
+        pred = self._decode_aten(memory, memory_bt, projected)
+        finished = (pred == blank).all(dim=0).long().cummax(0).values.bool()   # step t or an earlier one was all-blank
+        return pred.masked_fill(finished.unsqueeze(0), blank).to(torch.int32)
+
+    def _decode_aten(self, memory, memory_bt, projected, want_prob=False):
+        """The eval loop as a framework composition (CPU tensors; the comparison arm of tests/test_attention_decode_gpu.py)."""
+        n = memory_bt.shape[0]
+        hidden = memory_bt.new_zeros(n, self.inner_channels)
+        word = torch.full((n,), self.charset.blank, dtype=torch.long, device=memory_bt.device)
+        steps, probs = [], []
         for t in range(self.max_size):
             prob, hidden, _ = self.decoder(word, hidden, memory, False, projected, memory_bt)
             word = prob.argmax(dim=1)
             steps.append(word)
+            probs.append(prob)
         pred = torch.stack(steps, 1)                                             # (N, max_size)
-        finished = (pred == blank).all(dim=0).long().cummax(0).values.bool()   # step t or an earlier one was all-blank
-        return pred.masked_fill(finished.unsqueeze(0), blank).to(torch.int32)
+        return (pred, torch.stack(probs, 1)) if want_prob else pred
