@@ -185,20 +185,43 @@ def run(args, peaks, ClockSampler, emit_json):
     batch = args.batch or (8 if cfg == 5 else 32)           # BASELINE.json: 256 (cfg 3/4) and 64 (cfg 5) over 8 GPUs
     net, n_engine = build(cfg, dev)
     params = [p for p in net.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
+    # N > 1: gradients as views of one flat buffer, ONE in-place NCCL all-reduce (AVG) between the two graphs (megreader_b200/dp.py)
+    fg = dp.FlatGrads(params) if world > 1 else None
     host = []
     for i in range(3):
         hb = make_batch(cfg, 100 * rank + i, batch)
         host.append(tuple(_map(t, lambda v: v.pin_memory()) for t in hb))
     dev_batches = [tuple(_map(t, lambda v: v.to(dev)) for t in hb) for hb in host]
+    static = tuple(_map(t, lambda v: torch.empty_like(v)) for t in dev_batches[0])
+    # config 4: the attention head's per-step random draws (teacher-forcing coin, step dropout) are made on the host before every
+    # step in the reference's order and copied into static device tensors the captured forward reads (decoder.feedback_static)
+    attn = net.decoder if cfg == 4 else None
+    fb_static = None
+    if attn is not None:
+        fb_static = tuple(t.to(dev) for t in attn.draw_feedback(batch))
+        attn.feedback_static = fb_static
 
-    def step(x, y, l):
-        opt.zero_grad(set_to_none=True)
+    def refresh_feedback():
+        if attn is not None:
+            for dst, src in zip(fb_static, attn.draw_feedback(batch)):
+                dst.copy_(src.pin_memory(), non_blocking=True)
+
+    def fwd_bwd(x, y, l):
+        if fg is not None:
+            fg.zero()
+        else:
+            opt.zero_grad(set_to_none=True)
         loss, _ = net(x, y, l)
         loss = loss.mean()
         loss.backward()
-        if world > 1:
-            dp.allreduce_mean_grads_(params)
+        return loss
+
+    def eager_step(x, y, l):
+        refresh_feedback()
+        loss = fwd_bwd(x, y, l)
+        if fg is not None:
+            fg.allreduce_()
         opt.step()
         return loss
 
@@ -206,13 +229,66 @@ def run(args, peaks, ClockSampler, emit_json):
         if world > 1:
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(3):
+            eager_step(*dev_batches[i % 3])
+    torch.cuda.current_stream().wait_stream(side)
+    barrier()
+    _lib.reset_launch_count()
+    eager_step(*dev_batches[0])
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count()
+    # the step as CUDA graphs (graph A = zero + forward + backward [+ Adam when N = 1]; N > 1: NCCL all-reduce, then graph B = Adam):
+    # ~4,000 launches per step are otherwise bound by the host.  MR_BENCH_EAGER=1 keeps the eager launch mode; a capture that fails
+    # (every rank decides together) falls back to it and says so -- the kernels are the same either way.
+    graph_a = graph_b = static_loss = None
+    launch_mode = "eager (MR_BENCH_EAGER=1)"
+    if not os.environ.get("MR_BENCH_EAGER"):
+        ok = torch.ones(1, device=dev)
+        try:
+            graph_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_a):
+                static_loss = fwd_bwd(*static)
+                if world == 1:
+                    opt.step()
+            if world > 1:
+                graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_b, pool=graph_a.pool()):
+                    opt.step()
+            launch_mode = "step captured in CUDA graph(s)" + ("; the NCCL all-reduce runs between two graphs" if world > 1 else "")
+        except Exception as e:                         # launch mode only: the eager step runs the same kernels
+            ok.zero_()
+            launch_mode = "eager (CUDA-graph capture failed: %s)" % str(e).replace("\n", " ")[:160]
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            graph_a = graph_b = None
+            if not launch_mode.startswith("eager"):
+                launch_mode = "eager (CUDA-graph capture failed on another rank)"
+
+    def step(x, y, l):
+        if graph_a is None:
+            return eager_step(x, y, l)
+        refresh_feedback()
+        for dst, src in zip(static, (x, y, l)):
+            if dst is None:
+                continue
+            if isinstance(dst, dict):
+                for k in dst:
+                    dst[k].copy_(src[k], non_blocking=True)
+            else:
+                dst.copy_(src, non_blocking=True)
+        graph_a.replay()
+        if graph_b is not None:
+            fg.allreduce_()
+            graph_b.replay()
+        return static_loss
     for i in range(max(3, args.warmup)):
         step(*dev_batches[i % 3])
     barrier()
-    _lib.reset_launch_count()
-    step(*dev_batches[0])
-    torch.cuda.synchronize()
-    launches_per_step = _lib.launch_count()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -279,8 +355,8 @@ def run(args, peaks, ClockSampler, emit_json):
                          "head": ("megreader_b200 fused 2D-CTC epilogue + DP kernels" if cfg == 3 else
                                   "attention decoder: library (ATen) per-step arithmetic, hoisted encoder projection" if cfg == 4 else
                                   "EAST head: 3x3 / 1x1 convolutions on the conv engine, transposed convolutions + losses library; "
-                                  "DCNv2 units: fused tcgen05 forward (csrc/dcn_tcgen05.cu), round-1 backward kernels + cuBLAS"),
-                         "Adam": "library (torch fused)", "launch": "eager (no CUDA graph for these configurations)"}
+                                  "DCNv2 units: fused tcgen05 forward / weight-gradient / data-gradient kernels (csrc/dcn_tcgen05.cu)"),
+                         "Adam": "library (torch fused, capturable)", "launch": launch_mode}
         emit_json(out)
     if world > 1:
         dist.destroy_process_group()

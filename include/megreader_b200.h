@@ -357,6 +357,36 @@ int mr_attn_decode_f32(const float *projected, const float *memory, const float 
                        int N, int L, int H, int E, int V, int S, int blank, void *stream);
 int mr_attn_decode_status(const void *workspace, int64_t N, int64_t H, int64_t E, void *stream, int *status);
 
+/* ---- attention recogniser head: the TRAINING loop (decoders/attention_decoder.py:96-117 around AttentionRNNCell.forward :187-231) as
+ * one persistent cooperative kernel per direction (csrc/attn_decode.cu).  Inputs as for mr_attn_decode_f32, plus
+ *   targets [N][S] int32, lengths [N] int32 (the per-step NLL counts while step <= lengths[n], attention_decoder.py:104)
+ *   coin [S] int32 (1: the target is fed back, 0: the step's own argmax -- the reference's `gt_as_output` draw, :51-54, :107-110)
+ *   swap, noise [S][N] int32 (step dropout, :111-116: where swap is 1 the fed-back symbol is replaced by noise)
+ * The caller makes the random draws on the host in the reference's order.  Outputs: loss [N] (sum over the steps), attn [N][S][L]
+ * (the attention maps the reference returns) and the per-step state the backward needs:
+ *   h_all [S+1][N][H] (slice t = hidden state after t steps), fh_all [S][N][H] (= Wa_h . h), x_all [S][N][2H+E] (GRU inputs),
+ *   gates [S][N][4][H] (r, z, n, W_hn h + b_hn), logp [S][N][V] (log-softmax of the step outputs), word [S][N] (symbol fed into step t).
+ * sync: 2 x uint32 scratch (arrival counter, error word: mr_attn_sync_status). */
+int mr_attn_train_fwd_f32(const float *projected, const float *memory, const float *wa_h, int64_t ld_wa, const float *v,
+                          const float *wordtab, const float *w_ih, const float *b_ih, const float *w_hh, const float *b_hh,
+                          const float *w_out, const float *b_out, const int *targets, const int *lengths, const int *coin,
+                          const int *swap, const int *noise, float *h_all, float *fh_all, float *x_all, float *gates, float *logp,
+                          float *attn, int *word, float *loss, void *sync, int N, int L, int H, int E, int V, int S, int blank,
+                          void *stream);
+/* Backward through time of the loop above for the upstream gradient grad_loss [N] of `loss`.  Written (zero-filled here first):
+ *   dprojected [N][L][H], dmemory [N][L][H+E], dv [H], dwordtab [V][H]                  -- complete gradients
+ *   dlogits [S][N][V], dgi / dgh [S][N][3H], dfh [S][N][H]                              -- per-step pre-activation gradients; the weight
+ *       gradients are plain dense products over the S*N rows, left to the caller:  dW_out = dlogits^T . h_all[1:],  dW_ih = dgi^T . x_all,
+ *       dW_hh = dgh^T . h_all[:-1],  dWa_h = dfh^T . h_all[:-1],  the bias gradients are the column sums of dlogits / dgi / dgh
+ *   dx [N][2H+E], dh [N][H]                                                              -- scratch */
+int mr_attn_train_bwd_f32(const float *projected, const float *memory, const float *wa_h, int64_t ld_wa, const float *v,
+                          const float *w_ih, const float *w_hh, const float *w_out, const float *h_all, const float *fh_all,
+                          const float *gates, const float *logp, const float *attn, const int *word, const int *targets,
+                          const int *lengths, const float *grad_loss, float *dlogits, float *dgi, float *dgh, float *dfh, float *dx,
+                          float *dh, float *dprojected, float *dmemory, float *dv, float *dwordtab, void *sync, int N, int L, int H,
+                          int E, int V, int S, void *stream);
+int mr_attn_sync_status(const void *sync, void *stream, int *status);
+
 #ifdef __cplusplus
 }
 #endif

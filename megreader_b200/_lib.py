@@ -76,6 +76,9 @@ _SIGS = {
     "mr_attn_decode_workspace_bytes": [c_i64] * 3,
     "mr_attn_decode_f32": [c_p] * 3 + [c_i64] + [c_p] * 11 + [c_i64] + [c_int] * 7 + [c_p],
     "mr_attn_decode_status": [c_p, c_i64, c_i64, c_i64, c_p, c_p],
+    "mr_attn_train_fwd_f32": [c_p] * 3 + [c_i64] + [c_p] * 22 + [c_int] * 7 + [c_p],
+    "mr_attn_train_bwd_f32": [c_p] * 3 + [c_i64] + [c_p] * 24 + [c_int] * 6 + [c_p],
+    "mr_attn_sync_status": [c_p, c_p, c_p],
     "mr_dcn_fused_wgrad_workspace_bytes": [c_i64] * 7,
     "mr_dcn_fused_backward_workspace_bytes": [c_i64] * 9,
     "mr_dcn_backward_fused_f32": [c_p, c_p, c_p, c_i64, c_p, c_i64, c_p, c_p, c_p, c_p, c_i64, c_p, c_i64, c_f32,

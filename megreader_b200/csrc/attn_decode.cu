@@ -1,27 +1,43 @@
-// Greedy decoding loop of the attention recogniser head as ONE persistent kernel (round 2).
+// The recurrent loop of the attention recogniser head as persistent cooperative kernels.
 //
-//   reference: decoders/attention_decoder.py:119-131 (the eval loop: max_size steps of AttentionRNNCell.forward, :187-231, each of
-//   them ~15 framework kernels: embedding, Linear, cat + Linear + tanh + bmm for the energies (:160-171), softmax, bmm for the
-//   context, GRUCell, Linear, softmax, argmax).
+//   reference: decoders/attention_decoder.py:96-131 (training loop with teacher forcing / step dropout, eval loop) around
+//   AttentionRNNCell.forward (:187-231): per step ~15 framework kernels forward (embedding, Linear, cat + Linear + tanh + bmm for the
+//   energies (:160-171), softmax, bmm for the context, GRUCell, Linear, (log-)softmax, NLL / argmax) and ~40 backward.
 //
-// Per step t (h_0 = 0, word_0 = blank):
+//   attn_fwd_kernel<false>   eval: greedy decoding, max_size steps, pred (+ per-step softmax)
+//   attn_fwd_kernel<true>    training forward: fed-back symbol = target / own argmax / dropout noise from caller-made draws, masked
+//                            NLL summed over the steps, attention maps; keeps per-step state for the backward
+//   attn_bwd_kernel          training backward through time: gradients w.r.t. `projected`, `memory`, v, the word table; per-step
+//                            pre-activation gradients for the weight-gradient GEMMs (which are plain dense GEMMs over S*N rows and
+//                            are left to the caller)
+//
+// Forward, per step t (h_0 = 0, word_0 = blank):
 //   P1  fh[n, :]    = Wa_h . h[n]                                    (the hidden half of the additive-attention Linear; the encoder
 //                                                                      half `projected` is step-invariant and computed once by the caller)
-//   P2  word[n]     = argmax_v (Wout . h[n] + bout)                   (output of the PREVIOUS step; t = 0: blank)     -> pred[n, t-1]
+//   P2  logits[n]   = Wout . h[n] + bout  -> output of the PREVIOUS step (eval: argmax -> pred[n, t-1]; training: log-softmax, NLL, and
+//                     the symbol fed back)
 //       score[l]    = v . tanh(projected[n, l] + fh[n]);  a = softmax_l(score);  context = sum_l a[l] memory[n, l]
 //       x[n]        = [wordtab[word[n]] ; context]
 //   P3  h'[n, j]    = GRU(x[n], h[n])_j                               (gi = W_ih x + b_ih, gh = W_hh h + b_hh, r, z, n gates)
 // and one more P2 head after the last step.  P1 / P3 are parallel over output columns / hidden units: every CTA owns ceil(H / grid)
 // of them and keeps ITS rows of Wa_h, W_ih, W_hh in shared memory for the whole loop (weights are read from HBM once per call, not
-// once per step); P2 is parallel over samples.  The three phases are separated by grid-wide barriers (monotonic arrival counter,
-// cooperative launch so that co-residency is guaranteed; every wait is bounded and raises an error word instead of hanging).
-// All arithmetic is fp32 with accurate tanhf / expf: the results match the framework composition to rounding, and the decoded
+// once per step); a warp multiplies them with the activation rows of FOUR samples at a time (lane = k index; 4 units x 4 samples x
+// 4 gate sums = 64 accumulators per lane, reduced with a 64-shuffle butterfly instead of 320 xor-shuffles), so that one shared-memory
+// weight load feeds four FMAs.  P2 is parallel over samples.  The phases are separated by grid-wide barriers (monotonic arrival
+// counter, cooperative launch so that co-residency is guaranteed; every wait is bounded and raises an error word instead of hanging).
+// The backward runs the same structure in reverse with TRANSPOSED weight slices stationary in shared memory (see attn_bwd_kernel).
+// All arithmetic is fp32 with accurate tanhf / expf / logf: the results match the framework composition to rounding, and the decoded
 // strings are identical on the committed goldens.
 #include "common.cuh"
 #include <math.h>
 
 namespace {
 using namespace mr;
+
+constexpr int kAttnThreads = 512;
+constexpr int kTS = 4;            // samples per warp tile
+constexpr int kUC = 4;            // weight rows (hidden units / output columns) per warp tile
+constexpr unsigned kFull = 0xffffffffu;
 
 struct AttnArgs {
     const float *projected;   // [N][L][H]   Wa_enc . memory + b   (bias included)
@@ -33,12 +49,23 @@ struct AttnArgs {
     const float *w_ih, *b_ih; // [3H][H + D], [3H]
     const float *w_hh, *b_hh; // [3H][H],     [3H]
     const float *w_out, *b_out;   // [V][H], [V]
-    float *h0, *h1;           // [N][H] ping-pong hidden state (h0 zero-filled by the caller)
-    float *fh;                // [N][H]
-    float *x;                 // [N][H + D]
-    int *word;                // [N]
+    // state.  eval: h [2][N][H] ping-pong, fh [N][H], x [N][X].  training: one slice per step, h [S+1][N][H], fh [S][N][H], x [S][N][X]
+    float *h, *fh, *x;
+    int64_t h_stride;         // floats between two hidden-state slices
+    // eval outputs
     int *pred;                // [N][S]
     float *prob;              // [N][S][V] softmax of the logits (the reference's per-step output), or nullptr
+    // training inputs / outputs
+    const int *targets;       // [N][S]
+    const int *lengths;       // [N]
+    const int *coin;          // [S]     1: feed the target back, 0: the step's own argmax
+    const int *swap;          // [S][N]  1: replace the fed-back symbol by noise
+    const int *noise;         // [S][N]
+    float *gates;             // [S][N][4][H]  r, z, n, W_hn h + b_hn
+    float *logp;              // [S][N][V]
+    float *attn;              // [N][S][L]
+    int *word;                // [S][N]  symbol fed into step t
+    float *loss;              // [N], zeroed by the entry point
     unsigned *sync;           // [2]: arrival counter (zeroed), error word
     int N, L, H, D, V, S, blank, upc;   // upc = hidden units (and Wa_h columns) per CTA
 };
@@ -68,15 +95,76 @@ __device__ __forceinline__ void grid_barrier(unsigned *sync, unsigned idx) {
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(kFull, v, s);
     return v;
 }
 
-constexpr int kAttnThreads = 512;
+// Warp-wide sums of 16*Q per-lane partials in 16*Q - Q + Q shuffles: v[pair * Q + q], pair = 0..15.  Every stage folds the upper half
+// of the index range onto the lanes whose bit is set and the lower half onto the others; afterwards lanes 2p and 2p+1 both hold the
+// complete sums of pair p in v[0..Q).
+template <int Q>
+__device__ __forceinline__ void reduce_pairs(float (&v)[16 * Q], int lane) {
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8 * Q; ++i) {
+            const float a = v[i], b = v[i + 8 * Q];
+            v[i] = (up ? b : a) + __shfl_xor_sync(kFull, up ? a : b, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4 * Q; ++i) {
+            const float a = v[i], b = v[i + 4 * Q];
+            v[i] = (up ? b : a) + __shfl_xor_sync(kFull, up ? a : b, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2 * Q; ++i) {
+            const float a = v[i], b = v[i + 2 * Q];
+            v[i] = (up ? b : a) + __shfl_xor_sync(kFull, up ? a : b, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const float a = v[i], b = v[i + Q];
+            v[i] = (up ? b : a) + __shfl_xor_sync(kFull, up ? a : b, 2);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) v[i] += __shfl_xor_sync(kFull, v[i], 1);
+}
 
-__global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(AttnArgs a) {
+// acc[c * kTS + s] += sum_k w[c][k] * act[s][k] for the lane's k (k = lane, lane + 32, ...): up to kUC weight rows in shared memory
+// (`nrows` valid, the others repeat the last one), kTS activation rows in global memory written by other CTAs before the last grid
+// barrier (read past L1).
+__device__ __forceinline__ void tile_dot(float (&acc)[kUC * kTS], const float *s_w, int ldw, int nrows, const float *const (&arow)[kTS],
+                                         int K, int lane) {
+    const float *wr[kUC];
+#pragma unroll
+    for (int c = 0; c < kUC; ++c) wr[c] = s_w + (size_t)min(c, nrows - 1) * ldw;
+    for (int k = lane; k < K; k += 32) {
+        float xv[kTS];
+#pragma unroll
+        for (int s = 0; s < kTS; ++s) xv[s] = __ldcg(arow[s] + k);
+#pragma unroll
+        for (int c = 0; c < kUC; ++c) {
+            const float w = wr[c][k];
+#pragma unroll
+            for (int s = 0; s < kTS; ++s) acc[c * kTS + s] = fmaf(w, xv[s], acc[c * kTS + s]);
+        }
+    }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(AttnArgs a) {
     extern __shared__ float sm[];
-    const int H = a.H, D = a.D, X = a.H + a.D, V = a.V, L = a.L, N = a.N;
+    const int H = a.H, D = a.D, X = a.H + a.D, V = a.V, L = a.L, N = a.N, S = a.S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kAttnThreads / 32;
     // hidden units / Wa_h columns of this CTA
     const int j0 = min((int)blockIdx.x * a.upc, H), j1 = min(j0 + a.upc, H), nj = j1 - j0;
@@ -94,26 +182,28 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(AttnArgs a
     float *s_row = s_p2, *s_score = s_p2 + H, *s_logit = s_score + L;
     __shared__ int s_word;
     unsigned bar = 0;
-    const float *h = a.h0;
-    float *hn = a.h1;
+    const int64_t NH = (int64_t)N * H, NX = (int64_t)N * X;
+    const int pair = lane >> 1, pc = pair / kTS, ps = pair % kTS;      // the (unit, sample) pair whose sums this lane holds after reduce_pairs
 
-    for (int t = 0; t <= a.S; ++t) {
+    for (int t = 0; t <= S; ++t) {
+        const float *h = a.h + (TRAIN ? t : (t & 1)) * a.h_stride;     // hidden state after t steps
+        float *hn = a.h + (TRAIN ? t + 1 : ((t + 1) & 1)) * a.h_stride;
+        float *fh = a.fh + (TRAIN ? t : 0) * NH;
+        float *x = a.x + (TRAIN ? t : 0) * NX;
         // ---------------- P1: fh = Wa_h . h (columns j0..j1 of every sample); skipped after the last step
-        if (t < a.S) {
-            for (int n = warp; n < N; n += nwarps) {
-                const float *hr = h + (int64_t)n * H;
-                for (int cb = 0; cb < nj; cb += 4) {                  // four columns at a time share the loads of h
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                    for (int k = lane; k < H; k += 32) {
-                        const float hv = hr[k];
+        if (t < S) {
+            for (int g = warp; g * kTS < N; g += nwarps) {
+                const int n0 = g * kTS;
+                const float *hr[kTS];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[c] = fmaf(s_wa[min(cb + c, nj - 1) * H + k], hv, acc[c]);
-                    }
+                for (int s = 0; s < kTS; ++s) hr[s] = h + (int64_t)min(n0 + s, N - 1) * H;
+                for (int cb = 0; cb < nj; cb += kUC) {
+                    float acc[kUC * kTS];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float r = warp_sum(acc[c]);
-                        if (lane == 0 && cb + c < nj) a.fh[(int64_t)n * H + j0 + cb + c] = r;
-                    }
+                    for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
+                    tile_dot(acc, s_wa + (size_t)cb * H, H, nj - cb, hr, H, lane);
+                    reduce_pairs<1>(acc, lane);
+                    if (!(lane & 1) && cb + pc < nj && n0 + ps < N) fh[(int64_t)(n0 + ps) * H + j0 + cb + pc] = acc[0];
                 }
             }
             grid_barrier(a.sync, bar++);
@@ -121,12 +211,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(AttnArgs a
         // ---------------- P2: per sample -- previous step's output symbol, attention, context, GRU input
         for (int n = blockIdx.x; n < N; n += gridDim.x) {
             __syncthreads();
-            for (int i = threadIdx.x; i < H; i += kAttnThreads) s_row[i] = h[(int64_t)n * H + i];
+            for (int i = threadIdx.x; i < H; i += kAttnThreads) s_row[i] = __ldcg(h + (int64_t)n * H + i);
             __syncthreads();
             if (t > 0) {
                 for (int vv = warp; vv < V; vv += nwarps) {
                     float acc = 0.f;
-                    for (int k = lane; k < H; k += 32) acc = fmaf(a.w_out[(int64_t)vv * H + k], s_row[k], acc);
+                    for (int k = lane; k < H; k += 32) acc = fmaf(__ldg(a.w_out + (int64_t)vv * H + k), s_row[k], acc);
                     acc = warp_sum(acc);
                     if (lane == 0) s_logit[vv] = acc + a.b_out[vv];
                 }
@@ -138,24 +228,37 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(AttnArgs a
                         if (s_logit[vv] > best) { best = s_logit[vv]; bi = vv; }
 #pragma unroll
                     for (int s = 16; s > 0; s >>= 1) {
-                        const float ob = __shfl_xor_sync(0xffffffffu, best, s);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+                        const float ob = __shfl_xor_sync(kFull, best, s);
+                        const int oi = __shfl_xor_sync(kFull, bi, s);
                         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }       // first maximum, like torch.argmax
                     }
-                    if (lane == 0) { s_word = bi; a.pred[(int64_t)n * a.S + t - 1] = bi; a.word[n] = bi; }
-                    if (a.prob) {
-                        float den = 0.f;
-                        for (int vv = lane; vv < V; vv += 32) den += expf(s_logit[vv] - best);
-                        den = warp_sum(den);
-                        for (int vv = lane; vv < V; vv += 32) a.prob[((int64_t)n * a.S + t - 1) * V + vv] = expf(s_logit[vv] - best) / den;
+                    float den = 0.f;
+                    for (int vv = lane; vv < V; vv += 32) den += expf(s_logit[vv] - best);
+                    den = warp_sum(den);
+                    if (TRAIN) {
+                        const float lden = logf(den);
+                        float *lp = a.logp + ((int64_t)(t - 1) * N + n) * V;
+                        for (int vv = lane; vv < V; vv += 32) lp[vv] = (s_logit[vv] - best) - lden;
+                        if (lane == 0) {
+                            const int tgt = min(max(a.targets[(int64_t)n * S + t - 1], 0), V - 1);
+                            if (t - 1 <= a.lengths[n]) a.loss[n] -= (s_logit[tgt] - best) - lden;      // NLLLoss * (t <= lengths)
+                            int w = a.coin[t - 1] ? tgt : bi;
+                            if (a.swap[(int64_t)(t - 1) * N + n]) w = min(max(a.noise[(int64_t)(t - 1) * N + n], 0), V - 1);
+                            s_word = w;
+                        }
+                    } else {
+                        if (lane == 0) { s_word = bi; a.pred[(int64_t)n * S + t - 1] = bi; }
+                        if (a.prob)
+                            for (int vv = lane; vv < V; vv += 32) a.prob[((int64_t)n * S + t - 1) * V + vv] = expf(s_logit[vv] - best) / den;
                     }
                 }
             } else if (threadIdx.x == 0) {
                 s_word = a.blank;
             }
-            if (t == a.S) continue;
+            if (t == S) continue;
             __syncthreads();
-            for (int i = threadIdx.x; i < H; i += kAttnThreads) s_row[i] = a.fh[(int64_t)n * H + i];
+            if (TRAIN && threadIdx.x == 0) a.word[(int64_t)t * N + n] = s_word;
+            for (int i = threadIdx.x; i < H; i += kAttnThreads) s_row[i] = __ldcg(fh + (int64_t)n * H + i);
             __syncthreads();
             const float *pj = a.projected + (int64_t)n * L * H;
             for (int l = warp; l < L; l += nwarps) {
@@ -169,15 +272,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(AttnArgs a
                 float mx = -INFINITY;
                 for (int l = lane; l < L; l += 32) mx = fmaxf(mx, s_score[l]);
 #pragma unroll
-                for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+                for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, s));
                 float den = 0.f;
                 for (int l = lane; l < L; l += 32) den += expf(s_score[l] - mx);
                 den = warp_sum(den);
-                for (int l = lane; l < L; l += 32) s_score[l] = expf(s_score[l] - mx) / den;
+                for (int l = lane; l < L; l += 32) {
+                    const float w = expf(s_score[l] - mx) / den;
+                    s_score[l] = w;
+                    if (TRAIN) a.attn[((int64_t)n * S + t) * L + l] = w;
+                }
             }
             __syncthreads();
             const float *mem = a.memory + (int64_t)n * L * D;
-            float *xr = a.x + (int64_t)n * X;
+            float *xr = x + (int64_t)n * X;
             for (int d = threadIdx.x; d < D; d += kAttnThreads) {
                 float acc = 0.f;
                 for (int l = 0; l < L; ++l) acc = fmaf(s_score[l], mem[(int64_t)l * D + d], acc);
@@ -186,49 +293,254 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_decode_kernel(AttnArgs a
             const float *wt = a.wordtab + (int64_t)s_word * H;
             for (int i = threadIdx.x; i < H; i += kAttnThreads) xr[i] = wt[i];
         }
-        if (t == a.S) break;
+        if (t == S) break;
         grid_barrier(a.sync, bar++);
         // ---------------- P3: GRU cell for hidden units j0..j1 of every sample (torch.nn.GRUCell gate order r, z, n)
-        for (int n = warp; n < N; n += nwarps) {
-            const float *xr = a.x + (int64_t)n * X, *hr = h + (int64_t)n * H;
-            for (int cb = 0; cb < nj; cb += 4) {                      // four hidden units (12 gate rows) share the loads of x and h
-                float ai[3][4], ah[3][4];
+        for (int g = warp; g * kTS < N; g += nwarps) {
+            const int n0 = g * kTS;
+            const float *xr[kTS], *hr[kTS];
 #pragma unroll
-                for (int g = 0; g < 3; ++g)
+            for (int s = 0; s < kTS; ++s) {
+                xr[s] = x + (int64_t)min(n0 + s, N - 1) * X;
+                hr[s] = h + (int64_t)min(n0 + s, N - 1) * H;
+            }
+            for (int cb = 0; cb < nj; cb += kUC) {
+                // per (unit c, sample s): q = 0 r-gate sum (input + hidden), 1 z-gate sum, 2 n-gate input part, 3 n-gate hidden part
+                float acc[kUC * kTS * 4];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) ai[g][c] = ah[g][c] = 0.f;
+                for (int i = 0; i < kUC * kTS * 4; ++i) acc[i] = 0.f;
+                const float *wi[kUC], *wh[kUC];
+#pragma unroll
+                for (int c = 0; c < kUC; ++c) {
+                    wi[c] = s_wih + (size_t)min(cb + c, nj - 1) * X;
+                    wh[c] = s_whh + (size_t)min(cb + c, nj - 1) * H;
+                }
+                const size_t gx = (size_t)a.upc * X, gh = (size_t)a.upc * H;      // gate stride inside the shared-memory slices
                 for (int k = lane; k < X; k += 32) {
-                    const float xv = xr[k];
+                    float xv[kTS];
 #pragma unroll
-                    for (int g = 0; g < 3; ++g)
+                    for (int s = 0; s < kTS; ++s) xv[s] = __ldcg(xr[s] + k);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) ai[g][c] = fmaf(s_wih[(size_t)(g * a.upc + min(cb + c, nj - 1)) * X + k], xv, ai[g][c]);
+                    for (int c = 0; c < kUC; ++c) {
+                        const float w0 = wi[c][k], w1 = wi[c][gx + k], w2 = wi[c][2 * gx + k];
+#pragma unroll
+                        for (int s = 0; s < kTS; ++s) {
+                            float *q = acc + (c * kTS + s) * 4;
+                            q[0] = fmaf(w0, xv[s], q[0]);
+                            q[1] = fmaf(w1, xv[s], q[1]);
+                            q[2] = fmaf(w2, xv[s], q[2]);
+                        }
+                    }
                 }
                 for (int k = lane; k < H; k += 32) {
-                    const float hv = hr[k];
+                    float hv[kTS];
 #pragma unroll
-                    for (int g = 0; g < 3; ++g)
+                    for (int s = 0; s < kTS; ++s) hv[s] = __ldcg(hr[s] + k);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) ah[g][c] = fmaf(s_whh[(size_t)(g * a.upc + min(cb + c, nj - 1)) * H + k], hv, ah[g][c]);
+                    for (int c = 0; c < kUC; ++c) {
+                        const float w0 = wh[c][k], w1 = wh[c][gh + k], w2 = wh[c][2 * gh + k];
+#pragma unroll
+                        for (int s = 0; s < kTS; ++s) {
+                            float *q = acc + (c * kTS + s) * 4;
+                            q[0] = fmaf(w0, hv[s], q[0]);
+                            q[1] = fmaf(w1, hv[s], q[1]);
+                            q[3] = fmaf(w2, hv[s], q[3]);
+                        }
+                    }
                 }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float gi[3], gh[3];
-#pragma unroll
-                    for (int g = 0; g < 3; ++g) { gi[g] = warp_sum(ai[g][c]); gh[g] = warp_sum(ah[g][c]); }
-                    if (lane == 0 && cb + c < nj) {
-                        const int j = j0 + cb + c;
-                        const float r = 1.f / (1.f + expf(-(gi[0] + a.b_ih[j] + gh[0] + a.b_hh[j])));
-                        const float z = 1.f / (1.f + expf(-(gi[1] + a.b_ih[H + j] + gh[1] + a.b_hh[H + j])));
-                        const float nn = tanhf(gi[2] + a.b_ih[2 * H + j] + r * (gh[2] + a.b_hh[2 * H + j]));
-                        hn[(int64_t)n * H + j] = (1.f - z) * nn + z * hr[j];
+                reduce_pairs<4>(acc, lane);
+                if (!(lane & 1) && cb + pc < nj && n0 + ps < N) {
+                    const int j = j0 + cb + pc, n = n0 + ps;
+                    const float r = 1.f / (1.f + expf(-(acc[0] + a.b_ih[j] + a.b_hh[j])));
+                    const float z = 1.f / (1.f + expf(-(acc[1] + a.b_ih[H + j] + a.b_hh[H + j])));
+                    const float ghn = acc[3] + a.b_hh[2 * H + j];
+                    const float nn = tanhf(acc[2] + a.b_ih[2 * H + j] + r * ghn);
+                    hn[(int64_t)n * H + j] = (1.f - z) * nn + z * __ldcg(h + (int64_t)n * H + j);
+                    if (TRAIN) {
+                        float *gt = a.gates + ((int64_t)t * N + n) * 4 * H + j;
+                        gt[0] = r; gt[H] = z; gt[2 * H] = nn; gt[3 * H] = ghn;
                     }
                 }
             }
         }
         grid_barrier(a.sync, bar++);
-        const float *tmp = h; h = hn; hn = const_cast<float *>(tmp);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------ backward
+// Reverse loop over the steps with dh = d loss / d h_t carried in global memory.  Per step:
+//   B1 (per sample)   dlogits = (softmax - onehot(target)) * mask * grad_loss;  dh += dlogits . Wout;  GRU cell derivative ->
+//                     dgi, dgh (pre-activation gradients of the two gate products), dh <- dh * z (direct path to h_{t-1})
+//   B2 (per column)   dx = dgi . W_ih (GRU input gradient: word part + context part), dh += dgh . W_hh        [transposed slices]
+//   B3 (per sample)   context / softmax / energy derivative: dmemory += a (x) dctx, dprojected += dpre, dv += ds . e, dfh = sum_l dpre;
+//                     word-table rows += dx[:H]
+//   B4 (per column)   dh += dfh . Wa_h                                                                           [transposed slice]
+// Every CTA owns cx columns of W_ih (as rows of W_ih^T), ch columns of W_hh and of Wa_h, stationary in shared memory.
+struct AttnBwdArgs {
+    const float *projected, *memory, *wa_h;
+    int64_t ld_wa;
+    const float *v, *w_ih, *w_hh, *w_out;
+    const float *h, *fh, *gates, *logp, *attn;     // saved by the forward
+    const int *word, *targets, *lengths;
+    const float *gloss;       // [N] upstream gradient of the per-sample loss
+    float *dlogits;           // [S][N][V]
+    float *dgi, *dgh;         // [S][N][3H]
+    float *dfh;               // [S][N][H]
+    float *dx;                // [N][X] scratch
+    float *dh;                // [N][H], zeroed by the entry point
+    float *dP, *dM;           // [N][L][H], [N][L][D], zeroed
+    float *dv;                // [H], zeroed
+    float *dwordtab;          // [V][H], zeroed
+    unsigned *sync;
+    int N, L, H, D, V, S, cx, ch;
+};
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(AttnBwdArgs a) {
+    extern __shared__ float sm[];
+    const int H = a.H, D = a.D, X = a.H + a.D, V = a.V, L = a.L, N = a.N, S = a.S, H3 = 3 * a.H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kAttnThreads / 32;
+    const int kx0 = min((int)blockIdx.x * a.cx, X), ncx = min(kx0 + a.cx, X) - kx0;       // columns of W_ih
+    const int kh0 = min((int)blockIdx.x * a.ch, H), nch = min(kh0 + a.ch, H) - kh0;       // columns of W_hh / Wa_h
+    float *s_wihT = sm;                                   // [cx][3H]
+    float *s_whhT = s_wihT + (size_t)a.cx * H3;           // [ch][3H]
+    float *s_waT = s_whhT + (size_t)a.ch * H3;            // [ch][H]
+    float *s_dv = s_waT + (size_t)a.ch * H;               // [H]
+    float *s_dctx = s_dv + H;                             // [D]
+    float *s_a = s_dctx + D, *s_da = s_a + L, *s_ds = s_da + L;   // [L] each
+    float *s_dlogit = s_ds + L;                           // [V]
+    for (int i = threadIdx.x; i < ncx * H3; i += kAttnThreads) s_wihT[i] = a.w_ih[(int64_t)(i % H3) * X + kx0 + i / H3];
+    for (int i = threadIdx.x; i < nch * H3; i += kAttnThreads) s_whhT[i] = a.w_hh[(int64_t)(i % H3) * H + kh0 + i / H3];
+    for (int i = threadIdx.x; i < nch * H; i += kAttnThreads) s_waT[i] = a.wa_h[(int64_t)(i % H) * a.ld_wa + kh0 + i / H];
+    for (int i = threadIdx.x; i < H; i += kAttnThreads) s_dv[i] = 0.f;
+    __syncthreads();
+    unsigned bar = 0;
+    const int pair = lane >> 1, pc = pair / kTS, ps = pair % kTS;
+
+    for (int t = S - 1; t >= 0; --t) {
+        const int64_t tN = (int64_t)t * N;
+        // ---------------- B1: output layer + GRU cell derivative, per sample
+        for (int n = blockIdx.x; n < N; n += gridDim.x) {
+            __syncthreads();
+            const int tgt = min(max(a.targets[(int64_t)n * S + t], 0), V - 1);
+            const float m = (t <= a.lengths[n]) ? a.gloss[n] : 0.f;
+            for (int vv = threadIdx.x; vv < V; vv += kAttnThreads) {
+                const float g = (expf(a.logp[(tN + n) * V + vv]) - (vv == tgt ? 1.f : 0.f)) * m;
+                s_dlogit[vv] = g;
+                a.dlogits[(tN + n) * V + vv] = g;
+            }
+            __syncthreads();
+            const float *gt = a.gates + (tN + n) * 4 * H;
+            const float *hp = a.h + (tN + n) * H;                     // h_{t-1} = slice t
+            for (int k = threadIdx.x; k < H; k += kAttnThreads) {
+                float d = __ldcg(a.dh + (int64_t)n * H + k);
+                for (int vv = 0; vv < V; ++vv) d = fmaf(s_dlogit[vv], __ldg(a.w_out + (int64_t)vv * H + k), d);
+                const float r = gt[k], z = gt[H + k], nn = gt[2 * H + k], ghn = gt[3 * H + k];
+                const float dn_pre = d * (1.f - z) * (1.f - nn * nn);
+                const float dz_pre = d * (hp[k] - nn) * z * (1.f - z);
+                const float dr_pre = dn_pre * ghn * r * (1.f - r);
+                float *gi = a.dgi + (tN + n) * H3, *gh = a.dgh + (tN + n) * H3;
+                gi[k] = dr_pre; gi[H + k] = dz_pre; gi[2 * H + k] = dn_pre;
+                gh[k] = dr_pre; gh[H + k] = dz_pre; gh[2 * H + k] = dn_pre * r;
+                a.dh[(int64_t)n * H + k] = d * z;
+            }
+        }
+        grid_barrier(a.sync, bar++);
+        // ---------------- B2: dx = dgi . W_ih (columns kx0..), dh += dgh . W_hh (columns kh0..)
+        for (int g = warp; g * kTS < N; g += nwarps) {
+            const int n0 = g * kTS;
+            const float *gi[kTS], *gh[kTS];
+#pragma unroll
+            for (int s = 0; s < kTS; ++s) {
+                gi[s] = a.dgi + (tN + min(n0 + s, N - 1)) * H3;
+                gh[s] = a.dgh + (tN + min(n0 + s, N - 1)) * H3;
+            }
+            for (int cb = 0; cb < ncx; cb += kUC) {
+                float acc[kUC * kTS];
+#pragma unroll
+                for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
+                tile_dot(acc, s_wihT + (size_t)cb * H3, H3, ncx - cb, gi, H3, lane);
+                reduce_pairs<1>(acc, lane);
+                if (!(lane & 1) && cb + pc < ncx && n0 + ps < N) a.dx[(int64_t)(n0 + ps) * X + kx0 + cb + pc] = acc[0];
+            }
+            for (int cb = 0; cb < nch; cb += kUC) {
+                float acc[kUC * kTS];
+#pragma unroll
+                for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
+                tile_dot(acc, s_whhT + (size_t)cb * H3, H3, nch - cb, gh, H3, lane);
+                reduce_pairs<1>(acc, lane);
+                if (!(lane & 1) && cb + pc < nch && n0 + ps < N) {
+                    float *p = a.dh + (int64_t)(n0 + ps) * H + kh0 + cb + pc;
+                    *p = __ldcg(p) + acc[0];
+                }
+            }
+        }
+        grid_barrier(a.sync, bar++);
+        // ---------------- B3: attention derivative, per sample
+        for (int n = blockIdx.x; n < N; n += gridDim.x) {
+            __syncthreads();
+            for (int d = threadIdx.x; d < D; d += kAttnThreads) s_dctx[d] = __ldcg(a.dx + (int64_t)n * X + H + d);
+            for (int l = threadIdx.x; l < L; l += kAttnThreads) s_a[l] = a.attn[((int64_t)n * S + t) * L + l];
+            {
+                float *row = a.dwordtab + (int64_t)a.word[tN + n] * H;
+                for (int k = threadIdx.x; k < H; k += kAttnThreads) atomicAdd(row + k, __ldcg(a.dx + (int64_t)n * X + k));
+            }
+            __syncthreads();
+            const float *mem = a.memory + (int64_t)n * L * D;
+            for (int l = warp; l < L; l += nwarps) {
+                float acc = 0.f;
+                for (int d = lane; d < D; d += 32) acc = fmaf(s_dctx[d], mem[(int64_t)l * D + d], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) s_da[l] = acc;
+            }
+            __syncthreads();
+            for (int l = threadIdx.x; l < L; l += kAttnThreads) {
+                float dot = 0.f;
+                for (int i = 0; i < L; ++i) dot = fmaf(s_a[i], s_da[i], dot);
+                s_ds[l] = s_a[l] * (s_da[l] - dot);
+            }
+            float *dm = a.dM + (int64_t)n * L * D;
+            for (int i = threadIdx.x; i < L * D; i += kAttnThreads) dm[i] += s_a[i / D] * s_dctx[i % D];
+            __syncthreads();
+            const float *pj = a.projected + (int64_t)n * L * H;
+            float *dp = a.dP + (int64_t)n * L * H;
+            for (int k = threadIdx.x; k < H; k += kAttnThreads) {
+                const float fhk = a.fh[(tN + n) * H + k], vk = a.v[k];
+                float dvk = 0.f, dfhk = 0.f;
+                for (int l = 0; l < L; ++l) {
+                    const float e = tanhf(pj[(int64_t)l * H + k] + fhk);
+                    dvk = fmaf(s_ds[l], e, dvk);
+                    const float dpre = s_ds[l] * vk * (1.f - e * e);
+                    dp[(int64_t)l * H + k] += dpre;
+                    dfhk += dpre;
+                }
+                a.dfh[(tN + n) * H + k] = dfhk;
+                s_dv[k] += dvk;
+            }
+        }
+        grid_barrier(a.sync, bar++);
+        // ---------------- B4: dh += dfh . Wa_h (columns kh0..)
+        for (int g = warp; g * kTS < N; g += nwarps) {
+            const int n0 = g * kTS;
+            const float *fr[kTS];
+#pragma unroll
+            for (int s = 0; s < kTS; ++s) fr[s] = a.dfh + (tN + min(n0 + s, N - 1)) * H;
+            for (int cb = 0; cb < nch; cb += kUC) {
+                float acc[kUC * kTS];
+#pragma unroll
+                for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
+                tile_dot(acc, s_waT + (size_t)cb * H, H, nch - cb, fr, H, lane);
+                reduce_pairs<1>(acc, lane);
+                if (!(lane & 1) && cb + pc < nch && n0 + ps < N) {
+                    float *p = a.dh + (int64_t)(n0 + ps) * H + kh0 + cb + pc;
+                    *p = __ldcg(p) + acc[0];
+                }
+            }
+        }
+        grid_barrier(a.sync, bar++);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < H; k += kAttnThreads)
+        if (s_dv[k] != 0.f) atomicAdd(a.dv + k, s_dv[k]);
 }
 
 template <typename... Args>
@@ -240,6 +552,24 @@ cudaError_t launch_coop(void (*kern)(Args...), dim3 grid, int threads, size_t sm
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+constexpr size_t kAttnSmemMax = 220 * 1024;
+
+template <bool TRAIN>
+int launch_fwd(AttnArgs &a, cudaStream_t st) {
+    const int X = a.H + a.D;
+    const int grid = sm_count();
+    a.upc = (int)ceil_div(a.H, grid);
+    const size_t smem = ((size_t)a.upc * a.H + (size_t)3 * a.upc * X + (size_t)3 * a.upc * a.H + a.H + a.L + a.V) * sizeof(float);
+    if (smem > kAttnSmemMax) return MR_ERR_UNSUPPORTED;
+    int rc = ensure_dyn_smem((const void *)attn_fwd_kernel<TRAIN>, smem, "attn_fwd smem attr");
+    if (rc) return rc;
+    int max_blocks = 0;
+    MR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, attn_fwd_kernel<TRAIN>, kAttnThreads, smem), "attn_fwd occupancy");
+    if (max_blocks < 1) return MR_ERR_UNSUPPORTED;
+    MR_CUDA_TRY(launch_coop(attn_fwd_kernel<TRAIN>, dim3((unsigned)grid), kAttnThreads, smem, st, a), "attn_fwd_kernel");
+    return check_launch("attn_fwd_kernel");
 }
 
 }  // namespace
@@ -262,30 +592,17 @@ int mr_attn_decode_f32(const float *projected, const float *memory, const float 
         return MR_ERR_NULL_POINTER;
     if (workspace_bytes < mr_attn_decode_workspace_bytes(N, H, E) || ((uintptr_t)workspace % 256)) return MR_ERR_BAD_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
-    AttnArgs a;
+    AttnArgs a = {};
     a.projected = projected; a.memory = memory; a.wa_h = wa_h; a.ld_wa = ld_wa; a.v = v; a.wordtab = wordtab;
     a.w_ih = w_ih; a.b_ih = b_ih; a.w_hh = w_hh; a.b_hh = b_hh; a.w_out = w_out; a.b_out = b_out;
     a.N = N; a.L = L; a.H = H; a.D = H + E; a.V = V; a.S = S; a.blank = blank; a.pred = pred; a.prob = prob;
     unsigned char *ws = (unsigned char *)workspace;
     const int64_t hb = round_up((int64_t)N * H * 4, 256), xb = round_up((int64_t)N * (2 * H + E) * 4, 256), wb = round_up((int64_t)N * 4, 256);
-    a.h0 = (float *)ws; a.h1 = (float *)(ws + hb); a.fh = (float *)(ws + 2 * hb); a.x = (float *)(ws + 3 * hb);
-    a.word = (int *)(ws + 3 * hb + xb); a.sync = (unsigned *)(ws + 3 * hb + xb + wb);
-    MR_CUDA_TRY(cudaMemsetAsync(a.h0, 0, (size_t)N * H * 4, st), "cudaMemsetAsync(attn h0)");
+    a.h = (float *)ws; a.h_stride = hb / 4; a.fh = (float *)(ws + 2 * hb); a.x = (float *)(ws + 3 * hb);
+    a.sync = (unsigned *)(ws + 3 * hb + xb + wb);
+    MR_CUDA_TRY(cudaMemsetAsync(a.h, 0, (size_t)N * H * 4, st), "cudaMemsetAsync(attn h0)");
     MR_CUDA_TRY(cudaMemsetAsync(a.sync, 0, 256, st), "cudaMemsetAsync(attn sync)");
-    const int X = 2 * H + E;
-    int grid = sm_count();
-    int upc = (int)ceil_div(H, grid);
-    auto smem_of = [&](int u) { return ((size_t)u * H + (size_t)3 * u * X + (size_t)3 * u * H + H + L + V) * sizeof(float); };
-    if (smem_of(upc) > 220 * 1024) return MR_ERR_UNSUPPORTED;
-    const size_t smem = smem_of(upc);
-    a.upc = upc;
-    int rc = ensure_dyn_smem((const void *)attn_decode_kernel, (int)smem, "attn_decode smem attr");
-    if (rc) return rc;
-    int max_blocks = 0;
-    MR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, attn_decode_kernel, kAttnThreads, smem), "attn_decode occupancy");
-    if (max_blocks < 1) return MR_ERR_UNSUPPORTED;
-    MR_CUDA_TRY(launch_coop(attn_decode_kernel, dim3((unsigned)grid), kAttnThreads, smem, st, a), "attn_decode_kernel");
-    return check_launch("attn_decode_kernel");
+    return launch_fwd<false>(a, st);
 }
 
 /* error word of the last decode on this workspace (0 = fine, 1 = a grid barrier timed out); synchronises the stream */
@@ -296,6 +613,83 @@ int mr_attn_decode_status(const void *workspace, int64_t N, int64_t H, int64_t E
     unsigned words[2] = {0, 0};
     MR_CUDA_TRY(cudaMemcpyAsync(words, ws + 3 * hb + xb + wb, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "cudaMemcpyAsync(attn status)");
     MR_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize(attn status)");
+    *status = (int)words[1];
+    return MR_OK;
+}
+
+/* Training forward of the attention head's loop (decoders/attention_decoder.py:96-117).  See include/megreader_b200.h. */
+int mr_attn_train_fwd_f32(const float *projected, const float *memory, const float *wa_h, int64_t ld_wa, const float *v,
+                          const float *wordtab, const float *w_ih, const float *b_ih, const float *w_hh, const float *b_hh,
+                          const float *w_out, const float *b_out, const int *targets, const int *lengths, const int *coin,
+                          const int *swap, const int *noise, float *h_all, float *fh_all, float *x_all, float *gates, float *logp,
+                          float *attn, int *word, float *loss, void *sync, int N, int L, int H, int E, int V, int S, int blank,
+                          void *stream) {
+    if (N < 0 || L <= 0 || H <= 0 || E < 0 || V <= 0 || S <= 0 || blank < 0 || blank >= V) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!projected || !memory || !wa_h || !v || !wordtab || !w_ih || !b_ih || !w_hh || !b_hh || !w_out || !b_out || !targets || !lengths ||
+        !coin || !swap || !noise || !h_all || !fh_all || !x_all || !gates || !logp || !attn || !word || !loss || !sync)
+        return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    AttnArgs a = {};
+    a.projected = projected; a.memory = memory; a.wa_h = wa_h; a.ld_wa = ld_wa; a.v = v; a.wordtab = wordtab;
+    a.w_ih = w_ih; a.b_ih = b_ih; a.w_hh = w_hh; a.b_hh = b_hh; a.w_out = w_out; a.b_out = b_out;
+    a.N = N; a.L = L; a.H = H; a.D = H + E; a.V = V; a.S = S; a.blank = blank;
+    a.targets = targets; a.lengths = lengths; a.coin = coin; a.swap = swap; a.noise = noise;
+    a.h = h_all; a.h_stride = (int64_t)N * H; a.fh = fh_all; a.x = x_all; a.gates = gates; a.logp = logp; a.attn = attn; a.word = word; a.loss = loss;
+    a.sync = (unsigned *)sync;
+    MR_CUDA_TRY(cudaMemsetAsync(h_all, 0, (size_t)N * H * 4, st), "cudaMemsetAsync(attn h0)");
+    MR_CUDA_TRY(cudaMemsetAsync(loss, 0, (size_t)N * 4, st), "cudaMemsetAsync(attn loss)");
+    MR_CUDA_TRY(cudaMemsetAsync(sync, 0, 8, st), "cudaMemsetAsync(attn sync)");
+    return launch_fwd<true>(a, st);
+}
+
+/* Training backward of the attention head's loop.  See include/megreader_b200.h. */
+int mr_attn_train_bwd_f32(const float *projected, const float *memory, const float *wa_h, int64_t ld_wa, const float *v,
+                          const float *w_ih, const float *w_hh, const float *w_out, const float *h_all, const float *fh_all,
+                          const float *gates, const float *logp, const float *attn, const int *word, const int *targets,
+                          const int *lengths, const float *grad_loss, float *dlogits, float *dgi, float *dgh, float *dfh, float *dx,
+                          float *dh, float *dprojected, float *dmemory, float *dv, float *dwordtab, void *sync, int N, int L, int H,
+                          int E, int V, int S, void *stream) {
+    if (N < 0 || L <= 0 || H <= 0 || E < 0 || V <= 0 || S <= 0) return MR_ERR_BAD_SHAPE;
+    if (N == 0) return MR_OK;
+    if (!projected || !memory || !wa_h || !v || !w_ih || !w_hh || !w_out || !h_all || !fh_all || !gates || !logp || !attn || !word ||
+        !targets || !lengths || !grad_loss || !dlogits || !dgi || !dgh || !dfh || !dx || !dh || !dprojected || !dmemory || !dv || !dwordtab ||
+        !sync)
+        return MR_ERR_NULL_POINTER;
+    cudaStream_t st = (cudaStream_t)stream;
+    AttnBwdArgs a = {};
+    a.projected = projected; a.memory = memory; a.wa_h = wa_h; a.ld_wa = ld_wa; a.v = v; a.w_ih = w_ih; a.w_hh = w_hh; a.w_out = w_out;
+    a.h = h_all; a.fh = fh_all; a.gates = gates; a.logp = logp; a.attn = attn; a.word = word; a.targets = targets; a.lengths = lengths;
+    a.gloss = grad_loss; a.dlogits = dlogits; a.dgi = dgi; a.dgh = dgh; a.dfh = dfh; a.dx = dx; a.dh = dh; a.dP = dprojected;
+    a.dM = dmemory; a.dv = dv; a.dwordtab = dwordtab; a.sync = (unsigned *)sync;
+    a.N = N; a.L = L; a.H = H; a.D = H + E; a.V = V; a.S = S;
+    const int X = 2 * H + E, D = H + E;
+    const int grid = sm_count();
+    a.cx = (int)ceil_div(X, grid);
+    a.ch = (int)ceil_div(H, grid);
+    const size_t smem = ((size_t)a.cx * 3 * H + (size_t)a.ch * 3 * H + (size_t)a.ch * H + H + D + 3 * (size_t)L + V) * sizeof(float);
+    if (smem > kAttnSmemMax) return MR_ERR_UNSUPPORTED;
+    MR_CUDA_TRY(cudaMemsetAsync(dh, 0, (size_t)N * H * 4, st), "cudaMemsetAsync(attn dh)");
+    MR_CUDA_TRY(cudaMemsetAsync(dprojected, 0, (size_t)N * L * H * 4, st), "cudaMemsetAsync(attn dprojected)");
+    MR_CUDA_TRY(cudaMemsetAsync(dmemory, 0, (size_t)N * L * D * 4, st), "cudaMemsetAsync(attn dmemory)");
+    MR_CUDA_TRY(cudaMemsetAsync(dv, 0, (size_t)H * 4, st), "cudaMemsetAsync(attn dv)");
+    MR_CUDA_TRY(cudaMemsetAsync(dwordtab, 0, (size_t)V * H * 4, st), "cudaMemsetAsync(attn dwordtab)");
+    MR_CUDA_TRY(cudaMemsetAsync(sync, 0, 8, st), "cudaMemsetAsync(attn sync)");
+    int rc = ensure_dyn_smem((const void *)attn_bwd_kernel, smem, "attn_bwd smem attr");
+    if (rc) return rc;
+    int max_blocks = 0;
+    MR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, attn_bwd_kernel, kAttnThreads, smem), "attn_bwd occupancy");
+    if (max_blocks < 1) return MR_ERR_UNSUPPORTED;
+    MR_CUDA_TRY(launch_coop(attn_bwd_kernel, dim3((unsigned)grid), kAttnThreads, smem, st, a), "attn_bwd_kernel");
+    return check_launch("attn_bwd_kernel");
+}
+
+/* error word of a training forward / backward (sync[1]; 0 = fine, 1 = a grid barrier timed out); synchronises the stream */
+int mr_attn_sync_status(const void *sync, void *stream, int *status) {
+    if (!sync || !status) return MR_ERR_NULL_POINTER;
+    unsigned words[2] = {0, 0};
+    MR_CUDA_TRY(cudaMemcpyAsync(words, sync, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "cudaMemcpyAsync(attn sync)");
+    MR_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize(attn sync)");
     *status = (int)words[1];
     return MR_OK;
 }

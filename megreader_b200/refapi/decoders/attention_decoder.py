@@ -10,11 +10,14 @@ What is done differently (same numbers up to fp32 re-association):
     does not depend on the step, so it is computed ONCE per call ((N,L,E)x(E,H)) and each step only adds the
     (N,H) hidden half — the reference rebuilds the (N,L,2H+E) concatenation and redoes the full product on each
     of its 32 steps (attention_decoder.py:152-169);
+  * on CUDA tensors the recurrent loop -- training (with its backward through time) and greedy decoding -- runs as persistent
+    cooperative kernels (megreader_b200/attn.py, csrc/attn_decode.cu); the framework composition below is what they are tested against;
   * the eval loop issues all steps without a host round-trip and applies the reference's early exit
     ("stop once every sample emitted blank", attention_decoder.py:129-130) afterwards on the device: columns
     after the first all-blank step are blank, which is exactly what the break leaves behind.
 Random draws during training (teacher-forcing coin, step dropout) consume numpy / torch CPU generators in the
-reference's order (attention_decoder.py:106-114), so seeded runs line up.
+reference's order (attention_decoder.py:106-114), so seeded runs line up; they are made before the loop (draw_feedback) and
+applied on the device (torch.where), so the loop has no host-dependent control flow and can be replayed from a CUDA graph.
 """
 import math
 
@@ -101,6 +104,8 @@ class AttentionDecoder(nn.Module):
         self.onehot_embedding_y = nn.Embedding(height, height)
         self.onehot_embedding_y.weight.data = torch.eye(height)
         self.gt_as_output = gt_as_output
+        self.feedback_static = None       # (coin, swap, noise) device tensors of a CUDA-graph caller, see forward()
+        self.loop_kernels = True          # CUDA tensors: the recurrent loop runs on csrc/attn_decode.cu (False: framework composition)
         self.loss_function = nn.NLLLoss(reduction='none')
 
     def conv_bn_relu(self, input_channels, output_channels, kernel_size=3, stride=1, padding=1):
@@ -119,6 +124,18 @@ class AttentionDecoder(nn.Module):
         if self.gt_as_output is not None:
             return self.gt_as_output
         return np.random.rand() < 0.5
+
+    def draw_feedback(self, batch):
+        """The random draws of one training forward, made on the host in the reference's order (per step: the numpy teacher-forcing
+        coin, then torch.rand and torch.randint of the step dropout; attention_decoder.py:106-114):
+        coin (max_size,) bool, swap (max_size, batch) int64 in {0, 1}, noise (max_size, batch) int64 class indices."""
+        vocab = len(self.charset)
+        coin, swap, noise = [], [], []
+        for _ in range(self.max_size):
+            coin.append(bool(self._get_gt_as_output()))
+            swap.append((torch.rand(batch) < self.step_dropout).long())
+            noise.append(torch.randint(high=vocab, size=(batch,)))
+        return torch.tensor(coin, dtype=torch.bool), torch.stack(swap), torch.stack(noise)
 
     def _positions(self, batch, device):
         """(N, height+max_size, height, max_size): one-hot row then column coordinates of every cell."""
@@ -180,16 +197,25 @@ class AttentionDecoder(nn.Module):
             lengths = lengths.to(device)
             loss = None
             attention = []
+            # the step's random draws (teacher-forcing coin, step dropout) as device tensors: either handed in by a caller that
+            # replays this forward from a CUDA graph (`feedback_static`, refreshed from draw_feedback() before every replay) or
+            # drawn here, on the host, in the reference's order (attention_decoder.py:106-114)
+            coin, swap, noise = self.feedback_static if self.feedback_static is not None else \
+                tuple(t.to(device) for t in self.draw_feedback(n))
+            if feature.is_cuda and self.loop_kernels:
+                # the whole loop (and its backward through time) on the persistent kernels of csrc/attn_decode.cu
+                from megreader_b200 import attn as attn_kernels
+                loss, maps = attn_kernels.attention_loop_loss(projected, memory_bt, self.decoder, targets, lengths,
+                                                              (coin, swap, noise), blank)
+                return loss, maps.view(n, -1, self.height, self.max_size)
             for t in range(self.max_size):
                 logp, hidden, weights = self.decoder(word, hidden, memory, True, projected, memory_bt)
                 step = self.loss_function(logp, targets[:, t]) * (t <= lengths).float()
                 loss = step if loss is None else loss + step
                 attention.append(weights)
-                word = targets[:, t] if self._get_gt_as_output() else logp.argmax(dim=1).detach()
+                word = torch.where(coin[t], targets[:, t], logp.argmax(dim=1).detach())
                 # step dropout: a random class replaces the fed-back symbol with probability step_dropout
-                swap = (torch.rand(*word.shape) < self.step_dropout).long().to(device)
-                noise = torch.randint(high=vocab, size=word.shape).to(device)
-                word = word.to(device) * (1 - swap) + noise * swap
+                word = word * (1 - swap[t]) + noise[t] * swap[t]
             return loss, torch.cat(attention, 1).view(n, -1, self.height, self.max_size)
 
         if feature.is_cuda:
