@@ -298,7 +298,14 @@ def run_ours(args):
             out["parity"] = bench_parity(dev, lambda: net)
         except Exception as e:
             out["parity"] = {"error": str(e)[:200]}
-        out["cpu_baseline"] = cpu_arm(steps=3, warmup=1, sample_n=16)
+        if os.environ.get("MR_BENCH_SKIP_CPU"):                 # profiling runs (ncu launch lists) skip the host-core arms
+            out["cpu_baseline"] = {"skipped": "MR_BENCH_SKIP_CPU"}
+        else:
+            out["cpu_baseline"] = cpu_arm(steps=3, warmup=1, sample_n=16)
+            try:
+                out["cpu_baselines_other"] = cpu_side_baselines()
+            except Exception as e:
+                out["cpu_baselines_other"] = {"error": str(e)[:200]}
         out["stages"] = {"conv": "megreader_b200 tcgen05 implicit-GEMM kernels (fprop, dgrad, wgrad); conv0 (Cin=3): im2col kernel + cuBLAS",
                          "bias+ReLU+MaxPool, BatchNorm": "megreader_b200 CUDA (fused NHWC kernels)",
                          "BiLSTM+Linear": "recurrence: megreader_b200 persistent tcgen05 kernels (one launch per layer and pass, mode '%s'); "
@@ -610,6 +617,64 @@ def cpu_arm(steps, warmup, sample_n, budget_s=25.0):
     return {"value": sample_n * steps / dt, "unit": "lines/s", "cores": cores, "kind": "port",
             "sample": "%d steps of a %d-line batch (3x32x256 fp32) of the same train step, torch CPU fp32, %d threads"
                       % (steps, sample_n, torch.get_num_threads()), "ms_per_step": dt / steps * 1e3}
+
+
+def cpu_side_baselines():
+    """BASELINE.md section 3's remaining CPU figures, on this box's host cores (single thread for the C restatements):
+    cfg 1 exactly (CRNN + BiLSTM + 1D CTC, N = 4, 3x32x100, fwd + bwd + Adam) through the oracle port; the fp64 C restatement of the
+    2D-CTC kernels (K1 + K2 + K3) at the cfg-3 shape, N in {32, 256}; the fp64 C restatement of DCNv2 forward / backward at the three
+    bench shapes for ONE sample (the GPU figures in roofline_dcn are for B = 8)."""
+    import statistics
+    from oracle import capi, crnn_port
+    from tests.cases import ctc2d_case
+    from tests.weights import crnn_batch, fill_state_dict
+    out = {"cores_c_restatements": 1}
+    # cfg 1
+    cores = usable_cores()
+    torch.set_num_threads(cores)
+    bb = fill_state_dict(crnn_port.CRNNBackbonePort(), "bb.").train()
+    dec = fill_state_dict(crnn_port.CRNNDecoderPort(), "dec.").train()
+    opt = torch.optim.Adam(list(bb.parameters()) + list(dec.parameters()), lr=1e-3)
+    x, y, l = (torch.from_numpy(a) for a in crnn_batch(0, 4, 100, 8, 26))
+    ts = []
+    for i in range(7):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, _ = dec(bb(x), y, l, train=True)
+        loss.mean().backward()
+        opt.step()
+        if i >= 2:
+            ts.append(time.perf_counter() - t0)
+    out["cfg1_crnn_ctc_n4_32x100"] = {"lines_per_s_median": 4 / statistics.median(ts), "lines_per_s_best": 4 / min(ts), "threads": cores,
+                                       "kind": "port", "timed_steps": len(ts)}
+    # 2D-CTC, fp64 restatement of the reference kernels
+    c2 = {}
+    for N in (32, 256):
+        lp, tg, il, tl = ctc2d_case(3, 32, 8, N, 38, 32, 12)
+        go, lp64 = (1.0 / tl).astype(np.float64), lp.astype(np.float64)
+        ts = []
+        for i in range(3 if N == 32 else 2):
+            t0 = time.perf_counter()
+            capi.ctc2d_fwd_bwd(go, lp64, tg, il, tl)
+            ts.append(time.perf_counter() - t0)
+        c2[str(N)] = {"fwd_bwd_ms_best": min(ts) * 1e3, "samples_per_s": N / min(ts)}
+    out["ctc2d_oracle_f64_T32_H8_C38_S32"] = c2
+    # DCNv2, fp64 restatement, one sample
+    rng = np.random.RandomState(0)
+    dc = {}
+    for C, H in ((128, 64), (256, 32), (512, 16)):
+        x = rng.standard_normal((1, C, H, H))
+        w = rng.standard_normal((C, C, 3, 3)) / (3 * C ** 0.5)
+        off = 2 * rng.standard_normal((1, 18, H, H))
+        m = 1 / (1 + np.exp(-rng.standard_normal((1, 9, H, H))))
+        t0 = time.perf_counter()
+        o = capi.dcn_forward(x, w, None, off, m)
+        t1 = time.perf_counter()
+        capi.dcn_backward(x, w, None, off, m, rng.standard_normal(o.shape))
+        t2 = time.perf_counter()
+        dc["C%d@%dx%d" % (C, H, H)] = {"fwd_ms_per_sample": (t1 - t0) * 1e3, "bwd_ms_per_sample": (t2 - t1) * 1e3}
+    out["dcn_oracle_f64_one_sample"] = dc
+    return out
 
 
 def run_reference(args):

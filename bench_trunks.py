@@ -5,8 +5,9 @@
 
 One "step" = forward + backward + Adam on one synthetic batch (per-GPU batch 32 = BASELINE's 256 over 8 GPUs; --batch overrides).
 bf16 compute on the repo's kernels: every convolution of trunk and head runs on the tcgen05 implicit-GEMM kernels
-(megreader_b200.conv_engine), the 2D-CTC head epilogue + loss on csrc/ctc2d_head.cu + csrc/ctc2d.cu; BatchNorm / ReLU / pooling /
-interpolation and the attention decoder's per-step arithmetic are library (ATen) kernels.
+(megreader_b200.conv_engine), the 2D-CTC head epilogue + loss on csrc/ctc2d_head.cu + csrc/ctc2d.cu, the attention decoder's recurrent
+loop on csrc/attn_decode.cu, the deformable units on csrc/dcn_tcgen05.cu; BatchNorm / ReLU / pooling / interpolation are library (ATen)
+kernels.  The step is captured in CUDA graphs (MR_BENCH_EAGER=1: eager launches).
 """
 import os
 import time
@@ -353,7 +354,7 @@ def run(args, peaks, ClockSampler, emit_json):
         out["stages"] = {"convolutions (trunk + head, %d layers)" % n_engine: "megreader_b200 tcgen05 implicit-GEMM kernels (fprop, dgrad, wgrad)",
                          "BatchNorm / ReLU / pooling / interpolation": "library (ATen, channels_last bf16)",
                          "head": ("megreader_b200 fused 2D-CTC epilogue + DP kernels" if cfg == 3 else
-                                  "attention decoder: library (ATen) per-step arithmetic, hoisted encoder projection" if cfg == 4 else
+                                  "attention decoder: the 32-step loop and its backward through time = megreader_b200 persistent cooperative kernels (csrc/attn_decode.cu), hoisted encoder projection; weight-gradient products over the saved rows: library GEMMs" if cfg == 4 else
                                   "EAST head: 3x3 / 1x1 convolutions on the conv engine, transposed convolutions + losses library; "
                                   "DCNv2 units: fused tcgen05 forward / weight-gradient / data-gradient kernels (csrc/dcn_tcgen05.cu)"),
                          "Adam": "library (torch fused, capturable)", "launch": launch_mode}
