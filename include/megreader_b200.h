@@ -364,7 +364,8 @@ int mr_attn_decode_status(const void *workspace, int64_t N, int64_t H, int64_t E
  *   swap, noise [S][N] int32 (step dropout, :111-116: where swap is 1 the fed-back symbol is replaced by noise)
  * The caller makes the random draws on the host in the reference's order.  Outputs: loss [N] (sum over the steps), attn [N][S][L]
  * (the attention maps the reference returns) and the per-step state the backward needs:
- *   h_all [S+1][N][H] (slice t = hidden state after t steps), fh_all [S][N][H] (= Wa_h . h), x_all [S][N][2H+E] (GRU inputs),
+ *   h_all [S+1][N][H] (slice t = hidden state after t steps), fh_all [S][N][H] (= Wa_h . h), x_all [S][N][Xp] (GRU inputs, row stride
+ *   Xp = 2H+E rounded up to a multiple of 4 floats; H % 4 == 0 is required),
  *   gates [S][N][4][H] (r, z, n, W_hn h + b_hn), logp [S][N][V] (log-softmax of the step outputs), word [S][N] (symbol fed into step t).
  * sync: 2 x uint32 scratch (arrival counter, error word: mr_attn_sync_status). */
 int mr_attn_train_fwd_f32(const float *projected, const float *memory, const float *wa_h, int64_t ld_wa, const float *v,
@@ -376,7 +377,7 @@ int mr_attn_train_fwd_f32(const float *projected, const float *memory, const flo
 /* Backward through time of the loop above for the upstream gradient grad_loss [N] of `loss`.  Written (zero-filled here first):
  *   dprojected [N][L][H], dmemory [N][L][H+E], dv [H], dwordtab [V][H]                  -- complete gradients
  *   dlogits [S][N][V], dgi / dgh [S][N][3H], dfh [S][N][H]                              -- per-step pre-activation gradients; the weight
- *       gradients are plain dense products over the S*N rows, left to the caller:  dW_out = dlogits^T . h_all[1:],  dW_ih = dgi^T . x_all,
+ *       gradients are plain dense products over the S*N rows, left to the caller:  dW_out = dlogits^T . h_all[1:],  dW_ih = dgi^T . x_all[:, :, :2H+E],
  *       dW_hh = dgh^T . h_all[:-1],  dWa_h = dfh^T . h_all[:-1],  the bias gradients are the column sums of dlogits / dgi / dgh
  *   dx [N][2H+E], dh [N][H]                                                              -- scratch */
 int mr_attn_train_bwd_f32(const float *projected, const float *memory, const float *wa_h, int64_t ld_wa, const float *v,

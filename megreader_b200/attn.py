@@ -58,7 +58,8 @@ class _AttnLoopFn(torch.autograd.Function):
         if wa.stride(1) != 1:
             wa = wa.contiguous()
         f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
-        h_all, fh_all, x_all, gates = f(S + 1, N, H), f(S, N, H), f(S, N, X), f(S, N, 4, H)
+        Xp = -(-X // 4) * 4                                   # GRU-input rows padded to 16 bytes (cp.async staging in the kernel)
+        h_all, fh_all, x_all, gates = f(S + 1, N, H), f(S, N, H), f(S, N, Xp), f(S, N, 4, H)
         logp, attn, loss = f(S, N, V), f(N, S, L), f(N)
         word = torch.empty((S, N), dtype=torch.int32, device=dev)
         sync = torch.empty(2, dtype=torch.int32, device=dev)
@@ -103,7 +104,7 @@ class _AttnLoopFn(torch.autograd.Function):
         dl2, gi2, gh2, fh2 = dlogits.view(S * N, V), dgi.view(S * N, 3 * H), dgh.view(S * N, 3 * H), dfh.view(S * N, H)
         need = ctx.needs_input_grad
         d_wa = fh2.t().mm(h_prev) if need[2] else None
-        d_wih = gi2.t().mm(x_all.view(S * N, X)) if need[5] else None
+        d_wih = gi2.t().mm(x_all.view(S * N, -1)[:, :X]) if need[5] else None
         d_bih = gi2.sum(0) if need[6] else None
         d_whh = gh2.t().mm(h_prev) if need[7] else None
         d_bhh = gh2.sum(0) if need[8] else None

@@ -23,7 +23,10 @@
 // of them and keeps ITS rows of Wa_h, W_ih, W_hh in shared memory for the whole loop (weights are read from HBM once per call, not
 // once per step); a warp multiplies them with the activation rows of FOUR samples at a time (lane = k index; 4 units x 4 samples x
 // 4 gate sums = 64 accumulators per lane, reduced with a 64-shuffle butterfly instead of 320 xor-shuffles), so that one shared-memory
-// weight load feeds four FMAs.  P2 is parallel over samples.  The phases are separated by grid-wide barriers (monotonic arrival
+// weight load feeds four FMAs.  The activation rows (written by the other CTAs in the previous phase) stream L2 -> shared memory
+// through a warp-private 4-stage cp.async ring: the first version loaded them into registers inside the k loop and was bound by the
+// bytes in flight (12 B/clk/SM at N = 256; one L2 round trip per iteration at N = 32).  With fewer sample groups than warps the
+// reduction range is split over 2 or 4 warps and summed through shared memory.  P2 is parallel over samples.  The phases are separated by grid-wide barriers (monotonic arrival
 // counter, cooperative launch so that co-residency is guaranteed; every wait is bounded and raises an error word instead of hanging).
 // The backward runs the same structure in reverse with TRANSPOSED weight slices stationary in shared memory (see attn_bwd_kernel).
 // All arithmetic is fp32 with accurate tanhf / expf / logf: the results match the framework composition to rounding, and the decoded
@@ -68,6 +71,7 @@ struct AttnArgs {
     float *loss;              // [N], zeroed by the entry point
     unsigned *sync;           // [2]: arrival counter (zeroed), error word
     int N, L, H, D, V, S, blank, upc;   // upc = hidden units (and Wa_h columns) per CTA
+    int Xp;                   // floats between two rows of x: 2H + E rounded up to a multiple of 4
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
@@ -140,24 +144,98 @@ __device__ __forceinline__ void reduce_pairs(float (&v)[16 * Q], int lane) {
     for (int i = 0; i < Q; ++i) v[i] += __shfl_xor_sync(kFull, v[i], 1);
 }
 
-// acc[c * kTS + s] += sum_k w[c][k] * act[s][k] for the lane's k (k = lane, lane + 32, ...): up to kUC weight rows in shared memory
-// (`nrows` valid, the others repeat the last one), kTS activation rows in global memory written by other CTAs before the last grid
-// barrier (read past L1).
-__device__ __forceinline__ void tile_dot(float (&acc)[kUC * kTS], const float *s_w, int ldw, int nrows, const float *const (&arow)[kTS],
-                                         int K, int lane) {
-    const float *wr[kUC];
+// Streams kTS activation rows (global memory written by OTHER CTAs before the last grid barrier: rows base + min(n0 + s, N - 1) * ld,
+// 16-byte aligned, readable up to round_up(k1, 4)) over k in [k0, k1) through a warp-private cp.async ring (L2 -> shared memory, no
+// register staging: kStages - 1 chunks of kTS x kChunk floats are in flight per warp whatever the register budget) and calls
+// body(k, xv[kTS]) for this lane's k values (k = k0 + lane, + 32, ...).  k0 must be a multiple of 4.
+constexpr int kChunk = 64;        // floats of k per stage and row
+constexpr int kStages = 4;
+constexpr int kStageFloats = kStages * kTS * kChunk;     // per warp: 4 KB
+
+template <typename Body>
+__device__ __forceinline__ void staged_rows(float *stage, const float *base, int64_t ld, int n0, int N, int k0, int k1, int lane, Body &&body) {
+    const int nch = (k1 - k0 + kChunk - 1) / kChunk;
+    auto issue = [&](int c) {
+        if (c < nch) {
+            const int kc = k0 + c * kChunk;
+            float *dst = stage + (c % kStages) * (kTS * kChunk);
 #pragma unroll
-    for (int c = 0; c < kUC; ++c) wr[c] = s_w + (size_t)min(c, nrows - 1) * ldw;
-    for (int k = lane; k < K; k += 32) {
-        float xv[kTS];
-#pragma unroll
-        for (int s = 0; s < kTS; ++s) xv[s] = __ldcg(arow[s] + k);
-#pragma unroll
-        for (int c = 0; c < kUC; ++c) {
-            const float w = wr[c][k];
-#pragma unroll
-            for (int s = 0; s < kTS; ++s) acc[c * kTS + s] = fmaf(w, xv[s], acc[c * kTS + s]);
+            for (int j = 0; j < (kTS * kChunk / 4) / 32; ++j) {
+                const int p = lane + 32 * j, row = p / (kChunk / 4), f4 = p % (kChunk / 4);
+                const int k = kc + 4 * f4;
+                if (k < k1) cp_async16(dst + row * kChunk + 4 * f4, base + (int64_t)min(n0 + row, N - 1) * ld + k);
+            }
         }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int c = 0; c < kStages - 1; ++c) issue(c);
+    for (int c = 0; c < nch; ++c) {
+        issue(c + kStages - 1);
+        cp_async_wait<kStages - 1>();
+        __syncwarp();
+        const float *src = stage + (c % kStages) * (kTS * kChunk);
+        const int kc = k0 + c * kChunk;
+#pragma unroll
+        for (int u = 0; u < kChunk / 32; ++u) {
+            const int kk = lane + 32 * u, k = kc + kk;
+            if (k < k1) {
+                float xv[kTS];
+#pragma unroll
+                for (int s = 0; s < kTS; ++s) xv[s] = src[s * kChunk + kk];
+                body(k, xv);
+            }
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+}
+
+__device__ __forceinline__ float *align16(float *p) { return (float *)(((uintptr_t)p + 15) & ~(uintptr_t)15); }
+constexpr size_t kRoundsSmemBytes = (kAttnThreads / 32) * 64 * sizeof(float) + 16 + (kAttnThreads / 32) * kStageFloats * sizeof(float);
+
+// k-slices per sample group: with fewer groups than warps the reduction range is split over 2 or 4 warps
+__device__ __forceinline__ int k_slices(int N) {
+    const int ngroups = (N + kTS - 1) / kTS, nwarps = kAttnThreads / 32;
+    return ngroups * 2 > nwarps ? 1 : (ngroups * 4 > nwarps ? 2 : 4);
+}
+__device__ __forceinline__ int slice_len(int K, int KS) { return ((K + KS - 1) / KS + kChunk - 1) / kChunk * kChunk; }
+
+// One pass over all samples for one chunk of kUC weight rows: the work items (sample group g, k-slice ks) go round-robin to the
+// warps; compute(g, ks, acc) accumulates the lane partials acc[(c * kTS + s) * Q + q]; the warp sums go to shared memory and
+// finish(n, c, sums[Q]) runs once per (sample, weight row) on the total over the k-slices.  Called by all threads of the CTA.
+template <int Q, typename Compute, typename Finish>
+__device__ __forceinline__ void tile_rounds(float *s_part, int N, int KS, Compute &&compute, Finish &&finish) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = kAttnThreads / 32;
+    const int ngroups = (N + kTS - 1) / kTS, nitems = ngroups * KS;
+    for (int base = 0; base < nitems; base += nwarps) {
+        const int item = base + warp;
+        if (item < nitems) {
+            float acc[16 * Q];
+#pragma unroll
+            for (int i = 0; i < 16 * Q; ++i) acc[i] = 0.f;
+            compute(item / KS, item % KS, acc);
+            reduce_pairs<Q>(acc, lane);
+            if (!(lane & 1)) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) s_part[(warp * 16 + (lane >> 1)) * Q + q] = acc[q];
+            }
+        }
+        __syncthreads();
+        const int g0 = base / KS, ng = min(nwarps / KS, ngroups - g0);
+        for (int idx = threadIdx.x; idx < ng * 16; idx += kAttnThreads) {
+            const int gl = idx >> 4, pr = idx & 15;
+            float sums[Q];
+#pragma unroll
+            for (int q = 0; q < Q; ++q) sums[q] = 0.f;
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q) sums[q] += s_part[((gl * KS + ks) * 16 + pr) * Q + q];
+            }
+            const int n = (g0 + gl) * kTS + pr % kTS;
+            if (n < N) finish(n, pr / kTS, sums);
+        }
+        __syncthreads();
     }
 }
 
@@ -173,6 +251,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(AttnArgs a) {
     float *s_wih = s_wa + (size_t)a.upc * H;
     float *s_whh = s_wih + (size_t)3 * a.upc * X;
     float *s_p2 = s_whh + (size_t)3 * a.upc * H;       // fh / h row (H), scores (L), logits (V)
+    float *s_part = s_p2 + H + L + V;                   // [warps][16 pairs][4] warp sums of a round
+    float *s_stage = align16(s_part + (kAttnThreads / 32) * 64) + (size_t)warp * kStageFloats;   // this warp's cp.async ring
     for (int i = threadIdx.x; i < nj * H; i += kAttnThreads) s_wa[i] = a.wa_h[(int64_t)(j0 + i / H) * a.ld_wa + i % H];
     for (int g = 0; g < 3; ++g) {
         for (int i = threadIdx.x; i < nj * X; i += kAttnThreads) s_wih[(size_t)(g * a.upc) * X + i] = a.w_ih[((int64_t)g * H + j0) * X + i];
@@ -182,8 +262,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(AttnArgs a) {
     float *s_row = s_p2, *s_score = s_p2 + H, *s_logit = s_score + L;
     __shared__ int s_word;
     unsigned bar = 0;
-    const int64_t NH = (int64_t)N * H, NX = (int64_t)N * X;
-    const int pair = lane >> 1, pc = pair / kTS, ps = pair % kTS;      // the (unit, sample) pair whose sums this lane holds after reduce_pairs
+    const int Xp = a.Xp;                                  // row stride of x (X rounded up to 4 floats: 16-byte rows for cp.async)
+    const int64_t NH = (int64_t)N * H, NX = (int64_t)N * Xp;
+    const int KS = k_slices(N), slx = slice_len(X, KS), slh = slice_len(H, KS);
 
     for (int t = 0; t <= S; ++t) {
         const float *h = a.h + (TRAIN ? t : (t & 1)) * a.h_stride;     // hidden state after t steps
@@ -192,19 +273,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(AttnArgs a) {
         float *x = a.x + (TRAIN ? t : 0) * NX;
         // ---------------- P1: fh = Wa_h . h (columns j0..j1 of every sample); skipped after the last step
         if (t < S) {
-            for (int g = warp; g * kTS < N; g += nwarps) {
-                const int n0 = g * kTS;
-                const float *hr[kTS];
+            for (int cb = 0; cb < nj; cb += kUC) {
+                const float *wr[kUC];
 #pragma unroll
-                for (int s = 0; s < kTS; ++s) hr[s] = h + (int64_t)min(n0 + s, N - 1) * H;
-                for (int cb = 0; cb < nj; cb += kUC) {
-                    float acc[kUC * kTS];
+                for (int c = 0; c < kUC; ++c) wr[c] = s_wa + (size_t)min(cb + c, nj - 1) * H;
+                tile_rounds<1>(s_part, N, KS,
+                    [&](int g, int ks, float (&acc)[16]) {
+                        staged_rows(s_stage, h, H, g * kTS, N, ks * slh, min(H, (ks + 1) * slh), lane, [&](int k, const float (&xv)[kTS]) {
 #pragma unroll
-                    for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
-                    tile_dot(acc, s_wa + (size_t)cb * H, H, nj - cb, hr, H, lane);
-                    reduce_pairs<1>(acc, lane);
-                    if (!(lane & 1) && cb + pc < nj && n0 + ps < N) fh[(int64_t)(n0 + ps) * H + j0 + cb + pc] = acc[0];
-                }
+                            for (int c = 0; c < kUC; ++c) {
+                                const float w = wr[c][k];
+#pragma unroll
+                                for (int s = 0; s < kTS; ++s) acc[c * kTS + s] = fmaf(w, xv[s], acc[c * kTS + s]);
+                            }
+                        });
+                    },
+                    [&](int n, int c, const float (&sums)[1]) {
+                        if (cb + c < nj) fh[(int64_t)n * H + j0 + cb + c] = sums[0];
+                    });
             }
             grid_barrier(a.sync, bar++);
         }
@@ -284,7 +370,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(AttnArgs a) {
             }
             __syncthreads();
             const float *mem = a.memory + (int64_t)n * L * D;
-            float *xr = x + (int64_t)n * X;
+            float *xr = x + (int64_t)n * Xp;
             for (int d = threadIdx.x; d < D; d += kAttnThreads) {
                 float acc = 0.f;
                 for (int l = 0; l < L; ++l) acc = fmaf(s_score[l], mem[(int64_t)l * D + d], acc);
@@ -296,72 +382,57 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_fwd_kernel(AttnArgs a) {
         if (t == S) break;
         grid_barrier(a.sync, bar++);
         // ---------------- P3: GRU cell for hidden units j0..j1 of every sample (torch.nn.GRUCell gate order r, z, n)
-        for (int g = warp; g * kTS < N; g += nwarps) {
-            const int n0 = g * kTS;
-            const float *xr[kTS], *hr[kTS];
+        for (int cb = 0; cb < nj; cb += kUC) {
+            // per (unit c, sample s): q = 0 r-gate sum (input + hidden), 1 z-gate sum, 2 n-gate input part, 3 n-gate hidden part
+            const float *wi[kUC], *wh[kUC];
 #pragma unroll
-            for (int s = 0; s < kTS; ++s) {
-                xr[s] = x + (int64_t)min(n0 + s, N - 1) * X;
-                hr[s] = h + (int64_t)min(n0 + s, N - 1) * H;
+            for (int c = 0; c < kUC; ++c) {
+                wi[c] = s_wih + (size_t)min(cb + c, nj - 1) * X;
+                wh[c] = s_whh + (size_t)min(cb + c, nj - 1) * H;
             }
-            for (int cb = 0; cb < nj; cb += kUC) {
-                // per (unit c, sample s): q = 0 r-gate sum (input + hidden), 1 z-gate sum, 2 n-gate input part, 3 n-gate hidden part
-                float acc[kUC * kTS * 4];
+            const size_t gx = (size_t)a.upc * X, gh = (size_t)a.upc * H;      // gate stride inside the shared-memory slices
+            tile_rounds<4>(s_part, N, KS,
+                [&](int g, int ks, float (&acc)[64]) {
+                    staged_rows(s_stage, x, Xp, g * kTS, N, ks * slx, min(X, (ks + 1) * slx), lane, [&](int k, const float (&xv)[kTS]) {
 #pragma unroll
-                for (int i = 0; i < kUC * kTS * 4; ++i) acc[i] = 0.f;
-                const float *wi[kUC], *wh[kUC];
+                        for (int c = 0; c < kUC; ++c) {
+                            const float w0 = wi[c][k], w1 = wi[c][gx + k], w2 = wi[c][2 * gx + k];
 #pragma unroll
-                for (int c = 0; c < kUC; ++c) {
-                    wi[c] = s_wih + (size_t)min(cb + c, nj - 1) * X;
-                    wh[c] = s_whh + (size_t)min(cb + c, nj - 1) * H;
-                }
-                const size_t gx = (size_t)a.upc * X, gh = (size_t)a.upc * H;      // gate stride inside the shared-memory slices
-                for (int k = lane; k < X; k += 32) {
-                    float xv[kTS];
-#pragma unroll
-                    for (int s = 0; s < kTS; ++s) xv[s] = __ldcg(xr[s] + k);
-#pragma unroll
-                    for (int c = 0; c < kUC; ++c) {
-                        const float w0 = wi[c][k], w1 = wi[c][gx + k], w2 = wi[c][2 * gx + k];
-#pragma unroll
-                        for (int s = 0; s < kTS; ++s) {
-                            float *q = acc + (c * kTS + s) * 4;
-                            q[0] = fmaf(w0, xv[s], q[0]);
-                            q[1] = fmaf(w1, xv[s], q[1]);
-                            q[2] = fmaf(w2, xv[s], q[2]);
+                            for (int s = 0; s < kTS; ++s) {
+                                float *q = acc + (c * kTS + s) * 4;
+                                q[0] = fmaf(w0, xv[s], q[0]);
+                                q[1] = fmaf(w1, xv[s], q[1]);
+                                q[2] = fmaf(w2, xv[s], q[2]);
+                            }
                         }
-                    }
-                }
-                for (int k = lane; k < H; k += 32) {
-                    float hv[kTS];
+                    });
+                    staged_rows(s_stage, h, H, g * kTS, N, ks * slh, min(H, (ks + 1) * slh), lane, [&](int k, const float (&hv)[kTS]) {
 #pragma unroll
-                    for (int s = 0; s < kTS; ++s) hv[s] = __ldcg(hr[s] + k);
+                        for (int c = 0; c < kUC; ++c) {
+                            const float w0 = wh[c][k], w1 = wh[c][gh + k], w2 = wh[c][2 * gh + k];
 #pragma unroll
-                    for (int c = 0; c < kUC; ++c) {
-                        const float w0 = wh[c][k], w1 = wh[c][gh + k], w2 = wh[c][2 * gh + k];
-#pragma unroll
-                        for (int s = 0; s < kTS; ++s) {
-                            float *q = acc + (c * kTS + s) * 4;
-                            q[0] = fmaf(w0, hv[s], q[0]);
-                            q[1] = fmaf(w1, hv[s], q[1]);
-                            q[3] = fmaf(w2, hv[s], q[3]);
+                            for (int s = 0; s < kTS; ++s) {
+                                float *q = acc + (c * kTS + s) * 4;
+                                q[0] = fmaf(w0, hv[s], q[0]);
+                                q[1] = fmaf(w1, hv[s], q[1]);
+                                q[3] = fmaf(w2, hv[s], q[3]);
+                            }
                         }
-                    }
-                }
-                reduce_pairs<4>(acc, lane);
-                if (!(lane & 1) && cb + pc < nj && n0 + ps < N) {
-                    const int j = j0 + cb + pc, n = n0 + ps;
-                    const float r = 1.f / (1.f + expf(-(acc[0] + a.b_ih[j] + a.b_hh[j])));
-                    const float z = 1.f / (1.f + expf(-(acc[1] + a.b_ih[H + j] + a.b_hh[H + j])));
-                    const float ghn = acc[3] + a.b_hh[2 * H + j];
-                    const float nn = tanhf(acc[2] + a.b_ih[2 * H + j] + r * ghn);
+                    });
+                },
+                [&](int n, int c, const float (&sums)[4]) {
+                    if (cb + c >= nj) return;
+                    const int j = j0 + cb + c;
+                    const float r = 1.f / (1.f + expf(-(sums[0] + a.b_ih[j] + a.b_hh[j])));
+                    const float z = 1.f / (1.f + expf(-(sums[1] + a.b_ih[H + j] + a.b_hh[H + j])));
+                    const float ghn = sums[3] + a.b_hh[2 * H + j];
+                    const float nn = tanhf(sums[2] + a.b_ih[2 * H + j] + r * ghn);
                     hn[(int64_t)n * H + j] = (1.f - z) * nn + z * __ldcg(h + (int64_t)n * H + j);
                     if (TRAIN) {
                         float *gt = a.gates + ((int64_t)t * N + n) * 4 * H + j;
                         gt[0] = r; gt[H] = z; gt[2 * H] = nn; gt[3 * H] = ghn;
                     }
-                }
-            }
+                });
         }
         grid_barrier(a.sync, bar++);
     }
@@ -408,13 +479,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(AttnBwdArgs a
     float *s_dctx = s_dv + H;                             // [D]
     float *s_a = s_dctx + D, *s_da = s_a + L, *s_ds = s_da + L;   // [L] each
     float *s_dlogit = s_ds + L;                           // [V]
+    float *s_part = s_dlogit + V;                         // [warps][16 pairs] warp sums of a round
+    float *s_stage = align16(s_part + (kAttnThreads / 32) * 64) + (size_t)warp * kStageFloats;   // this warp's cp.async ring
     for (int i = threadIdx.x; i < ncx * H3; i += kAttnThreads) s_wihT[i] = a.w_ih[(int64_t)(i % H3) * X + kx0 + i / H3];
     for (int i = threadIdx.x; i < nch * H3; i += kAttnThreads) s_whhT[i] = a.w_hh[(int64_t)(i % H3) * H + kh0 + i / H3];
     for (int i = threadIdx.x; i < nch * H; i += kAttnThreads) s_waT[i] = a.wa_h[(int64_t)(i % H) * a.ld_wa + kh0 + i / H];
     for (int i = threadIdx.x; i < H; i += kAttnThreads) s_dv[i] = 0.f;
     __syncthreads();
     unsigned bar = 0;
-    const int pair = lane >> 1, pc = pair / kTS, ps = pair % kTS;
+    const int KS = k_slices(N), sl3 = slice_len(H3, KS), slh = slice_len(H, KS);
 
     for (int t = S - 1; t >= 0; --t) {
         const int64_t tN = (int64_t)t * N;
@@ -446,32 +519,34 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(AttnBwdArgs a
         }
         grid_barrier(a.sync, bar++);
         // ---------------- B2: dx = dgi . W_ih (columns kx0..), dh += dgh . W_hh (columns kh0..)
-        for (int g = warp; g * kTS < N; g += nwarps) {
-            const int n0 = g * kTS;
-            const float *gi[kTS], *gh[kTS];
+        for (int pass = 0; pass < 2; ++pass) {               // 0: dx from dgi and W_ih^T, 1: dh from dgh and W_hh^T
+            const int ncol = pass ? nch : ncx;
+            const float *sw = pass ? s_whhT : s_wihT;
+            const float *act = (pass ? a.dgh : a.dgi) + tN * H3;
+            for (int cb = 0; cb < ncol; cb += kUC) {
+                const float *wr[kUC];
 #pragma unroll
-            for (int s = 0; s < kTS; ++s) {
-                gi[s] = a.dgi + (tN + min(n0 + s, N - 1)) * H3;
-                gh[s] = a.dgh + (tN + min(n0 + s, N - 1)) * H3;
-            }
-            for (int cb = 0; cb < ncx; cb += kUC) {
-                float acc[kUC * kTS];
+                for (int c = 0; c < kUC; ++c) wr[c] = sw + (size_t)min(cb + c, ncol - 1) * H3;
+                tile_rounds<1>(s_part, N, KS,
+                    [&](int g, int ks, float (&acc)[16]) {
+                        staged_rows(s_stage, act, H3, g * kTS, N, ks * sl3, min(H3, (ks + 1) * sl3), lane, [&](int k, const float (&xv)[kTS]) {
 #pragma unroll
-                for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
-                tile_dot(acc, s_wihT + (size_t)cb * H3, H3, ncx - cb, gi, H3, lane);
-                reduce_pairs<1>(acc, lane);
-                if (!(lane & 1) && cb + pc < ncx && n0 + ps < N) a.dx[(int64_t)(n0 + ps) * X + kx0 + cb + pc] = acc[0];
-            }
-            for (int cb = 0; cb < nch; cb += kUC) {
-                float acc[kUC * kTS];
+                            for (int c = 0; c < kUC; ++c) {
+                                const float w = wr[c][k];
 #pragma unroll
-                for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
-                tile_dot(acc, s_whhT + (size_t)cb * H3, H3, nch - cb, gh, H3, lane);
-                reduce_pairs<1>(acc, lane);
-                if (!(lane & 1) && cb + pc < nch && n0 + ps < N) {
-                    float *p = a.dh + (int64_t)(n0 + ps) * H + kh0 + cb + pc;
-                    *p = __ldcg(p) + acc[0];
-                }
+                                for (int s = 0; s < kTS; ++s) acc[c * kTS + s] = fmaf(w, xv[s], acc[c * kTS + s]);
+                            }
+                        });
+                    },
+                    [&](int n, int c, const float (&sums)[1]) {
+                        if (cb + c >= ncol) return;
+                        if (pass == 0) {
+                            a.dx[(int64_t)n * X + kx0 + cb + c] = sums[0];
+                        } else {
+                            float *p = a.dh + (int64_t)n * H + kh0 + cb + c;
+                            *p = __ldcg(p) + sums[0];
+                        }
+                    });
             }
         }
         grid_barrier(a.sync, bar++);
@@ -506,12 +581,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(AttnBwdArgs a
             for (int k = threadIdx.x; k < H; k += kAttnThreads) {
                 const float fhk = a.fh[(tN + n) * H + k], vk = a.v[k];
                 float dvk = 0.f, dfhk = 0.f;
-                for (int l = 0; l < L; ++l) {
-                    const float e = tanhf(pj[(int64_t)l * H + k] + fhk);
-                    dvk = fmaf(s_ds[l], e, dvk);
-                    const float dpre = s_ds[l] * vk * (1.f - e * e);
-                    dp[(int64_t)l * H + k] += dpre;
-                    dfhk += dpre;
+                for (int l0 = 0; l0 < L; l0 += 8) {               // eight rows at a time: all loads issued before the first store
+                    float pv[8], dq[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int l = min(l0 + u, L - 1);
+                        pv[u] = __ldg(pj + (int64_t)l * H + k);
+                        dq[u] = dp[(int64_t)l * H + k];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (l0 + u < L) {
+                            const float e = tanhf(pv[u] + fhk);
+                            dvk = fmaf(s_ds[l0 + u], e, dvk);
+                            const float dpre = s_ds[l0 + u] * vk * (1.f - e * e);
+                            dp[(int64_t)(l0 + u) * H + k] = dq[u] + dpre;
+                            dfhk += dpre;
+                        }
+                    }
                 }
                 a.dfh[(tN + n) * H + k] = dfhk;
                 s_dv[k] += dvk;
@@ -519,22 +606,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_bwd_kernel(AttnBwdArgs a
         }
         grid_barrier(a.sync, bar++);
         // ---------------- B4: dh += dfh . Wa_h (columns kh0..)
-        for (int g = warp; g * kTS < N; g += nwarps) {
-            const int n0 = g * kTS;
-            const float *fr[kTS];
+        for (int cb = 0; cb < nch; cb += kUC) {
+            const float *wr[kUC];
 #pragma unroll
-            for (int s = 0; s < kTS; ++s) fr[s] = a.dfh + (tN + min(n0 + s, N - 1)) * H;
-            for (int cb = 0; cb < nch; cb += kUC) {
-                float acc[kUC * kTS];
+            for (int c = 0; c < kUC; ++c) wr[c] = s_waT + (size_t)min(cb + c, nch - 1) * H;
+            const float *act = a.dfh + tN * H;
+            tile_rounds<1>(s_part, N, KS,
+                [&](int g, int ks, float (&acc)[16]) {
+                    staged_rows(s_stage, act, H, g * kTS, N, ks * slh, min(H, (ks + 1) * slh), lane, [&](int k, const float (&xv)[kTS]) {
 #pragma unroll
-                for (int i = 0; i < kUC * kTS; ++i) acc[i] = 0.f;
-                tile_dot(acc, s_waT + (size_t)cb * H, H, nch - cb, fr, H, lane);
-                reduce_pairs<1>(acc, lane);
-                if (!(lane & 1) && cb + pc < nch && n0 + ps < N) {
-                    float *p = a.dh + (int64_t)(n0 + ps) * H + kh0 + cb + pc;
-                    *p = __ldcg(p) + acc[0];
-                }
-            }
+                        for (int c = 0; c < kUC; ++c) {
+                            const float w = wr[c][k];
+#pragma unroll
+                            for (int s = 0; s < kTS; ++s) acc[c * kTS + s] = fmaf(w, xv[s], acc[c * kTS + s]);
+                        }
+                    });
+                },
+                [&](int n, int c, const float (&sums)[1]) {
+                    if (cb + c >= nch) return;
+                    float *p = a.dh + (int64_t)n * H + kh0 + cb + c;
+                    *p = __ldcg(p) + sums[0];
+                });
         }
         grid_barrier(a.sync, bar++);
     }
@@ -561,7 +653,8 @@ int launch_fwd(AttnArgs &a, cudaStream_t st) {
     const int X = a.H + a.D;
     const int grid = sm_count();
     a.upc = (int)ceil_div(a.H, grid);
-    const size_t smem = ((size_t)a.upc * a.H + (size_t)3 * a.upc * X + (size_t)3 * a.upc * a.H + a.H + a.L + a.V) * sizeof(float);
+    const size_t smem = ((size_t)a.upc * a.H + (size_t)3 * a.upc * X + (size_t)3 * a.upc * a.H + a.H + a.L + a.V) * sizeof(float) + kRoundsSmemBytes;
+    if (a.H % 4) return MR_ERR_UNSUPPORTED;               // 16-byte activation rows
     if (smem > kAttnSmemMax) return MR_ERR_UNSUPPORTED;
     int rc = ensure_dyn_smem((const void *)attn_fwd_kernel<TRAIN>, smem, "attn_fwd smem attr");
     if (rc) return rc;
@@ -578,7 +671,7 @@ extern "C" {
 
 /* floats of scratch the decode loop needs: h (2 x N x H), fh (N x H), x (N x (2H + E)), word (N ints), sync (2 words, 256 B) */
 int64_t mr_attn_decode_workspace_bytes(int64_t N, int64_t H, int64_t E) {
-    return round_up(N * H * 4, 256) * 3 + round_up(N * (2 * H + E) * 4, 256) + round_up(N * 4, 256) + 256;
+    return round_up(N * H * 4, 256) * 3 + round_up(N * round_up(2 * H + E, 4) * 4, 256) + round_up(N * 4, 256) + 256;
 }
 
 /* Greedy decoding loop of AttentionDecoder.forward (eval branch, decoders/attention_decoder.py:119-131).  See the header. */
@@ -597,7 +690,8 @@ int mr_attn_decode_f32(const float *projected, const float *memory, const float 
     a.w_ih = w_ih; a.b_ih = b_ih; a.w_hh = w_hh; a.b_hh = b_hh; a.w_out = w_out; a.b_out = b_out;
     a.N = N; a.L = L; a.H = H; a.D = H + E; a.V = V; a.S = S; a.blank = blank; a.pred = pred; a.prob = prob;
     unsigned char *ws = (unsigned char *)workspace;
-    const int64_t hb = round_up((int64_t)N * H * 4, 256), xb = round_up((int64_t)N * (2 * H + E) * 4, 256), wb = round_up((int64_t)N * 4, 256);
+    const int64_t hb = round_up((int64_t)N * H * 4, 256), xb = round_up((int64_t)N * round_up(2 * H + E, 4) * 4, 256), wb = round_up((int64_t)N * 4, 256);
+    a.Xp = (int)round_up(2 * H + E, 4);
     a.h = (float *)ws; a.h_stride = hb / 4; a.fh = (float *)(ws + 2 * hb); a.x = (float *)(ws + 3 * hb);
     a.sync = (unsigned *)(ws + 3 * hb + xb + wb);
     MR_CUDA_TRY(cudaMemsetAsync(a.h, 0, (size_t)N * H * 4, st), "cudaMemsetAsync(attn h0)");
@@ -609,7 +703,7 @@ int mr_attn_decode_f32(const float *projected, const float *memory, const float 
 int mr_attn_decode_status(const void *workspace, int64_t N, int64_t H, int64_t E, void *stream, int *status) {
     if (!workspace || !status) return MR_ERR_NULL_POINTER;
     const unsigned char *ws = (const unsigned char *)workspace;
-    const int64_t hb = round_up(N * H * 4, 256), xb = round_up(N * (2 * H + E) * 4, 256), wb = round_up(N * 4, 256);
+    const int64_t hb = round_up(N * H * 4, 256), xb = round_up(N * round_up(2 * H + E, 4) * 4, 256), wb = round_up(N * 4, 256);
     unsigned words[2] = {0, 0};
     MR_CUDA_TRY(cudaMemcpyAsync(words, ws + 3 * hb + xb + wb, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream), "cudaMemcpyAsync(attn status)");
     MR_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize(attn status)");
@@ -635,6 +729,7 @@ int mr_attn_train_fwd_f32(const float *projected, const float *memory, const flo
     a.w_ih = w_ih; a.b_ih = b_ih; a.w_hh = w_hh; a.b_hh = b_hh; a.w_out = w_out; a.b_out = b_out;
     a.N = N; a.L = L; a.H = H; a.D = H + E; a.V = V; a.S = S; a.blank = blank;
     a.targets = targets; a.lengths = lengths; a.coin = coin; a.swap = swap; a.noise = noise;
+    a.Xp = (int)round_up(2 * H + E, 4);
     a.h = h_all; a.h_stride = (int64_t)N * H; a.fh = fh_all; a.x = x_all; a.gates = gates; a.logp = logp; a.attn = attn; a.word = word; a.loss = loss;
     a.sync = (unsigned *)sync;
     MR_CUDA_TRY(cudaMemsetAsync(h_all, 0, (size_t)N * H * 4, st), "cudaMemsetAsync(attn h0)");
@@ -667,7 +762,8 @@ int mr_attn_train_bwd_f32(const float *projected, const float *memory, const flo
     const int grid = sm_count();
     a.cx = (int)ceil_div(X, grid);
     a.ch = (int)ceil_div(H, grid);
-    const size_t smem = ((size_t)a.cx * 3 * H + (size_t)a.ch * 3 * H + (size_t)a.ch * H + H + D + 3 * (size_t)L + V) * sizeof(float);
+    const size_t smem = ((size_t)a.cx * 3 * H + (size_t)a.ch * 3 * H + (size_t)a.ch * H + H + D + 3 * (size_t)L + V) * sizeof(float) + kRoundsSmemBytes;
+    if (H % 4) return MR_ERR_UNSUPPORTED;
     if (smem > kAttnSmemMax) return MR_ERR_UNSUPPORTED;
     MR_CUDA_TRY(cudaMemsetAsync(dh, 0, (size_t)N * H * 4, st), "cudaMemsetAsync(attn dh)");
     MR_CUDA_TRY(cudaMemsetAsync(dprojected, 0, (size_t)N * L * H * 4, st), "cudaMemsetAsync(attn dprojected)");
