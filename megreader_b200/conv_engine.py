@@ -3,7 +3,8 @@ swap that puts the reference-named trunks on it.
 
     conv2d(x, weight, bias, stride, padding, dilation)            x, result: (N, C, H, W) bf16 in channels_last memory
     EngineConv2d                                                   nn.Conv2d subclass (same parameters / state-dict keys)
-    use_engine_convs(module)                                       swaps every eligible nn.Conv2d of a trunk in place
+    EngineBatchNorm2d                                              nn.BatchNorm2d subclass on the NHWC row kernels of the CRNN engine
+    use_engine_convs(module)                                       swaps every eligible nn.Conv2d / nn.BatchNorm2d of a trunk in place
 
 Covers what the ResNet-50 / dilated / PPM / FPN trunks and the 2D-CTC head branches use (backbones/resnet.py:110-256,
 resnet_dilated.py:50-69, ppm.py:6-44, fpn_top_down.py:6-30, decoders/ctc_decoder2d.py:16-27): 1x1 and 3x3 kernels, stride 1 / 2,
@@ -70,15 +71,16 @@ class _Conv2dFn(torch.autograd.Function):
             db = dz.view(-1, Cp)[:, :Cout].float().sum(0)
         if ctx.needs_input_grad[0]:
             # dgrad = stride-1 convolution of (zero-upsampled) dz with the flipped, transposed weights, padding d*(k-1) - p
-            w = weight.detach().float()
-            Wd = w.flip(2, 3).permute(1, 2, 3, 0)               # [Cin, kh, kw, Cout]
-            if Cp != Cout:
-                Wd = F.pad(Wd, (0, Cp - Cout))
             Kp = _pad_to(Cp, 64)                                # the forward kernel wants its channel count % 64 == 0
-            if Kp != Cp:
-                Wd = F.pad(Wd, (0, Kp - Cp))
+            if Kp == Cout:
+                # one launch: [Cin][(flipped tap) * Cout + co] bf16 straight from the fp32 master weights
+                Wd = ops.conv_weight_pack(weight.detach().float().contiguous(), Cin, kh * kw * Cin, torch.bfloat16, 1)
+            else:                                               # few-channel heads (Cout = 1, 38): pad through the framework
+                w = weight.detach().float()
+                Wd = w.flip(2, 3).permute(1, 2, 3, 0)           # [Cin, kh, kw, Cout]
+                Wd = F.pad(Wd, (0, Kp - Cout))
                 dz = F.pad(dz, (0, Kp - Cp))
-            Wd = Wd.reshape(Cin, kh * kw * Kp).to(torch.bfloat16).contiguous()
+                Wd = Wd.reshape(Cin, kh * kw * Kp).to(torch.bfloat16).contiguous()
             if sh > 1 or sw > 1:
                 Hu, Wu = (Ho - 1) * sh + 1, (Wo - 1) * sw + 1
                 up = torch.zeros((N, Hu, Wu, Kp), dtype=torch.bfloat16, device=dz.device)
@@ -133,7 +135,14 @@ class _StemFn(torch.autograd.Function):
         (A,) = ctx.saved_tensors
         Cout, Cin, kh, kw, K, has_bias, wdtype = ctx.geo
         dz = dy.permute(0, 2, 3, 1).reshape(-1, Cout).to(torch.bfloat16).contiguous()
-        dWm = ops.gemm_tc(dz, A, transA=True, transB=False, out_dtype=torch.float32)  # [Cout, Kp] = dz^T A
+        # [Cout, Kp] = dz^T A: a tiny output over a reduction as long as the batch has pixels (524,288 rows at 8 x 512 x 512) --
+        # split-K over up to 128 CTAs, fp32 atomics into the zero-filled result (one CTA took 1.8 ms there, profiles/r2_cfg5_launch_top.txt)
+        splits = max(1, min(128, dz.size(0) // 4096))
+        if splits > 1:
+            dWm = torch.zeros((Cout, A.size(1)), dtype=torch.float32, device=dz.device)
+            ops.gemm_tc(dz, A, transA=True, transB=False, out=dWm, beta=1.0, splits=splits)
+        else:
+            dWm = ops.gemm_tc(dz, A, transA=True, transB=False, out_dtype=torch.float32)
         dw_ = dWm[:, :K].reshape(Cout, Cin, kh, kw).to(wdtype)
         db = dz.float().sum(0) if has_bias else None
         return None, dw_, db, None, None, None
@@ -150,6 +159,63 @@ class EngineConv2d(nn.Conv2d):
         return _StemFn.apply(x, self.weight, self.bias, self.stride, self.padding, self.dilation)
 
 
+class _BatchNormFn(torch.autograd.Function):
+    """nn.BatchNorm2d on the NHWC row kernels of csrc/nn_kernels.cu (the CRNN engine's: column statistics through block partials,
+    row-tiled normalisation, fused backward): x (N, C, H, W) in channels_last memory, bf16 or fp32, C % 8 == 0."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, batch_stats):
+        N, C, H, W = x.shape
+        rows = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(N * H * W, C)
+        g, b = gamma.detach().float(), beta.detach().float()
+        # the result is a fresh channels_last tensor (not a view made inside the Function: an in-place ReLU may follow); the kernels
+        # write its NHWC rows
+        out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        out_rows = out.permute(0, 2, 3, 1).reshape(N * H * W, C)
+        assert out_rows.data_ptr() == out.data_ptr() and rows.is_contiguous()
+        if batch_stats:
+            _, mean, invstd = ops.bn_train_fwd(rows, None, g, b, running_mean, running_var, momentum, eps, out=out_rows)
+        else:
+            mean = running_mean.float()
+            invstd = torch.rsqrt(running_var.float() + eps)
+            ops.bn_apply(rows, None, mean, invstd, g, b, out=out_rows)
+        ctx.save_for_backward(rows, mean, invstd, g)
+        ctx.batch_stats = batch_stats
+        ctx.shape = (N, C, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        rows, mean, invstd, g = ctx.saved_tensors
+        N, C, H, W = ctx.shape
+        dyr = dy.to(rows.dtype).contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(N * H * W, C)
+        dx = torch.empty((N, C, H, W), dtype=rows.dtype, device=rows.device, memory_format=torch.channels_last)
+        dx_rows = dx.permute(0, 2, 3, 1).reshape(N * H * W, C)
+        if ctx.batch_stats:
+            _, dgamma, dbeta, _ = ops.bn_train_bwd(dyr, rows, None, mean, invstd, g, want_dbias=False, out=dx_rows)
+        else:                                                   # frozen statistics: an affine map per channel
+            d32 = dyr.float()
+            dbeta = d32.sum(0)
+            dgamma = (d32 * ((rows.float() - mean) * invstd)).sum(0)
+            dx_rows.copy_(d32 * (g * invstd))
+        return dx, dgamma, dbeta, None, None, None, None, None
+
+
+class EngineBatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d whose arithmetic runs on megreader_b200's NHWC kernels (same parameters / buffers / state-dict keys).
+    Configurations the kernels do not cover (no affine parameters, no running statistics, cumulative momentum, C % 8 != 0,
+    CPU tensors) go through the framework implementation unchanged."""
+
+    def forward(self, x):
+        if (not x.is_cuda or x.dim() != 4 or not self.affine or not self.track_running_stats or self.momentum is None
+                or self.num_features % 8 or x.dtype not in (torch.float32, torch.bfloat16) or x.numel() == 0):
+            return super().forward(x)
+        if self.training:
+            self.num_batches_tracked.add_(1)
+        return _BatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, float(self.momentum),
+                                  float(self.eps), bool(self.training))
+
+
 def eligible(m):
     return (type(m) is nn.Conv2d and m.groups == 1 and m.padding_mode == "zeros" and not isinstance(m.padding, str)
             and (m.in_channels % 64 == 0 or m.in_channels <= 4))
@@ -162,15 +228,17 @@ def _cast_input_hook(mod, args):
     return None
 
 
-def use_engine_convs(module):
-    """Re-class every eligible nn.Conv2d below `module` to EngineConv2d (parameters stay the same objects).  Returns the
-    number of layers switched.  Undo with restore_library_convs().  The layers that stay with the library (transposed and grouped
+def use_engine_convs(module, batchnorm=True):
+    """Re-class every eligible nn.Conv2d below `module` to EngineConv2d and (batchnorm=True) every nn.BatchNorm2d to
+    EngineBatchNorm2d (parameters and buffers stay the same objects).  Returns the number of convolutions switched.  Undo with restore_library_convs().  The layers that stay with the library (transposed and grouped
     convolutions, Linear) get a pre-hook that casts the bf16 activations arriving from engine layers to their weights' dtype."""
     n = 0
     for m in module.modules():
         if eligible(m):
             m.__class__ = EngineConv2d
             n += 1
+        elif batchnorm and type(m) is nn.BatchNorm2d:
+            m.__class__ = EngineBatchNorm2d
         elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)) and type(m) is not EngineConv2d \
                 and not hasattr(m, "_mr_cast_hook"):
             m._mr_cast_hook = m.register_forward_pre_hook(_cast_input_hook)
@@ -183,6 +251,8 @@ def restore_library_convs(module):
         if type(m) is EngineConv2d:
             m.__class__ = nn.Conv2d
             n += 1
+        if type(m) is EngineBatchNorm2d:
+            m.__class__ = nn.BatchNorm2d
         if hasattr(m, "_mr_cast_hook"):
             m._mr_cast_hook.remove()
             del m._mr_cast_hook

@@ -127,7 +127,7 @@ partials_finalize_kernel(const float *__restrict__ part, int nb, int ncols, doub
 }
 
 constexpr int kMaxPartialBlocks = 148 * 8;
-constexpr int kMaxPartialCols = 2048;
+constexpr int kMaxPartialCols = 4096;     // 2 * C columns of statistics for C up to 2048 (ResNet-50 layer4)
 // Library-owned scratch for the block partial sums (stream-ordered use on one stream at a time).  Allocated on first
 // use, which must not happen inside a CUDA-graph capture: callers run one eager step before capturing (as they must
 // for cuBLAS anyway).  NULL when the allocation is impossible -> the fp64-atomic path is used instead.

@@ -90,9 +90,9 @@ def _sums(C, dev):
     return torch.empty((2 * C,), dtype=torch.float64, device=dev)
 
 
-def bn_train_fwd(z, bias, gamma, beta, running_mean, running_var, momentum, eps):
+def bn_train_fwd(z, bias, gamma, beta, running_mean, running_var, momentum, eps, out=None):
     rows, C = z.shape
-    y = torch.empty_like(z)
+    y = out if out is not None else torch.empty_like(z)
     mean = torch.empty((C,), dtype=torch.float32, device=z.device)
     invstd = torch.empty_like(mean)
     _chk(_lib.lib().mr_bn_train_fwd(_p(z), _p(bias), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
@@ -101,20 +101,20 @@ def bn_train_fwd(z, bias, gamma, beta, running_mean, running_var, momentum, eps)
     return y, mean, invstd
 
 
-def bn_apply(z, bias, mean, invstd, gamma, beta):
+def bn_apply(z, bias, mean, invstd, gamma, beta, out=None):
     rows, C = z.shape
-    y = torch.empty_like(z)
+    y = out if out is not None else torch.empty_like(z)
     _chk(_lib.lib().mr_bn_apply(_p(z), _p(bias), _p(mean), _p(invstd), _p(gamma), _p(beta), rows, C, code(z.dtype), _p(y),
                                 _st()), "bn_apply")
     return y
 
 
-def bn_train_bwd(dy, z, bias, mean, invstd, gamma):
+def bn_train_bwd(dy, z, bias, mean, invstd, gamma, want_dbias=True, out=None):
     rows, C = z.shape
-    dx = torch.empty_like(z)
+    dx = out if out is not None else torch.empty_like(z)
     dgamma = torch.empty((C,), dtype=torch.float32, device=z.device)
     dbeta = torch.empty_like(dgamma)
-    dbias = torch.empty_like(dgamma)
+    dbias = torch.empty_like(dgamma) if want_dbias else None
     sums = torch.empty((3 * C,), dtype=torch.float64, device=z.device)
     _chk(_lib.lib().mr_bn_train_bwd(_p(dy), _p(z), _p(bias), _p(mean), _p(invstd), _p(gamma), rows, C, code(z.dtype),
                                     _p(dx), _p(dgamma), _p(dbeta), _p(dbias), _p(sums), _st()), "bn_train_bwd")

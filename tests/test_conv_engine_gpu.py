@@ -21,6 +21,7 @@ CASES = [
     (128, 128, 3, 2, 1, 1, 2, 15, 33, False),    # odd sizes under stride 2
     (64, 64, 3, 1, 1, 1, 2, 12, 65, True),       # width with a 1-wide TMA segment
     (3, 64, 7, 2, 3, 1, 2, 64, 96, False),       # stem (unfold + GEMM)
+    (3, 64, 7, 2, 3, 1, 4, 128, 256, False),     # stem with enough pixels for the split-K weight gradient
 ]
 
 
@@ -65,3 +66,54 @@ def test_trunk_switch_counts_and_restores(cuda):
     assert conv_engine.restore_library_convs(m) == 3
     with pytest.raises(NotImplementedError):
         conv_engine.conv2d(torch.zeros(1, 64, 4, 4), torch.zeros(64, 64, 1, 1))
+
+
+BN_CASES = [
+    # C, N, H, W, dtype, training
+    (64, 4, 16, 64, torch.float32, True),
+    (256, 4, 16, 64, torch.bfloat16, True),
+    (2048, 8, 8, 32, torch.bfloat16, True),       # layer4 of the dilated trunk: 2 * C = 4096 statistic columns
+    (1024, 3, 7, 9, torch.float32, True),         # odd row count
+    (512, 4, 8, 32, torch.bfloat16, False),       # frozen statistics (eval with gradients)
+]
+
+
+@pytest.mark.parametrize("case", BN_CASES, ids=[str(i) for i in range(len(BN_CASES))])
+def test_batchnorm_forward_backward(cuda, case):
+    """EngineBatchNorm2d (NHWC row kernels) against nn.BatchNorm2d in fp32 on the same (dtype-rounded) input: output, running
+    statistics, input / weight / bias gradients"""
+    from megreader_b200 import conv_engine
+    C, N, H, W, dtype, training = case
+    torch.manual_seed(C + N)
+    x = (torch.randn(N, C, H, W, device=cuda) * 1.7 + 0.3).to(dtype).float()
+    go = torch.randn(N, C, H, W, device=cuda).to(dtype).float()
+    ref = torch.nn.BatchNorm2d(C).to(cuda)
+    with torch.no_grad():
+        ref.weight.copy_(torch.rand(C, device=cuda) + 0.5)
+        ref.bias.copy_(torch.randn(C, device=cuda))
+        ref.running_mean.copy_(0.1 * torch.randn(C, device=cuda))
+        ref.running_var.copy_(torch.rand(C, device=cuda) + 0.5)
+    eng = torch.nn.BatchNorm2d(C).to(cuda)
+    eng.load_state_dict(ref.state_dict())
+    wrap = torch.nn.Sequential(eng)
+    conv_engine.use_engine_convs(wrap)
+    assert type(wrap[0]) is conv_engine.EngineBatchNorm2d
+    ref.train(training)
+    wrap.train(training)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(go)
+    xe = x.to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ye = wrap(xe)
+    assert ye.dtype == dtype and tuple(ye.shape) == (N, C, H, W)
+    ye.backward(go.to(dtype))
+    tol = 2e-5 if dtype == torch.float32 else 6e-3
+
+    def rel(a, r):
+        return float((a.float() - r).norm() / (r.norm() + 1e-12))
+    assert rel(ye, yr) < tol, rel(ye, yr)
+    assert rel(xe.grad, xr.grad) < 2 * tol, rel(xe.grad, xr.grad)
+    assert rel(eng.weight.grad, ref.weight.grad) < 2 * tol and rel(eng.bias.grad, ref.bias.grad) < 2 * tol
+    assert rel(eng.running_mean, ref.running_mean) < 1e-5 and rel(eng.running_var, ref.running_var) < 1e-5
+    assert int(eng.num_batches_tracked) == int(ref.num_batches_tracked)
+    assert conv_engine.restore_library_convs(wrap) == 0 and type(wrap[0]) is torch.nn.BatchNorm2d
