@@ -6,8 +6,8 @@
 One "step" = forward + backward + Adam on one synthetic batch (per-GPU batch 32 = BASELINE's 256 over 8 GPUs; --batch overrides).
 bf16 compute on the repo's kernels: every convolution of trunk and head runs on the tcgen05 implicit-GEMM kernels
 (megreader_b200.conv_engine), the 2D-CTC head epilogue + loss on csrc/ctc2d_head.cu + csrc/ctc2d.cu, the attention decoder's recurrent
-loop on csrc/attn_decode.cu, the deformable units on csrc/dcn_tcgen05.cu; BatchNorm / ReLU / pooling / interpolation are library (ATen)
-kernels.  The step is captured in CUDA graphs (MR_BENCH_EAGER=1: eager launches).
+loop on csrc/attn_decode.cu, the deformable units on csrc/dcn_tcgen05.cu, BatchNorm on the NHWC row kernels of csrc/nn_kernels.cu;
+ReLU / residual adds / pooling / interpolation are library (ATen) kernels.  The step is captured in CUDA graphs (MR_BENCH_EAGER=1: eager launches).
 """
 import os
 import time
@@ -352,10 +352,12 @@ def run(args, peaks, ClockSampler, emit_json):
         out["roofline"] = conv_roofline(dev, peaks, cfg)
         out["cpu_baseline"] = cpu_arm(cfg, 2, 3)
         out["stages"] = {"convolutions (trunk + head, %d layers)" % n_engine: "megreader_b200 tcgen05 implicit-GEMM kernels (fprop, dgrad, wgrad)",
-                         "BatchNorm / ReLU / pooling / interpolation": "library (ATen, channels_last bf16)",
+                         "BatchNorm": "megreader_b200 NHWC row kernels (conv_engine.EngineBatchNorm2d: column statistics through block partials, "
+                                      "row-tiled normalisation, fused backward)",
+                         "ReLU / residual add / pooling / interpolation": "library (ATen, channels_last bf16)",
                          "head": ("megreader_b200 fused 2D-CTC epilogue + DP kernels" if cfg == 3 else
                                   "attention decoder: the 32-step loop and its backward through time = megreader_b200 persistent cooperative kernels (csrc/attn_decode.cu), hoisted encoder projection; weight-gradient products over the saved rows: library GEMMs" if cfg == 4 else
-                                  "EAST head: 3x3 / 1x1 convolutions on the conv engine, transposed convolutions + losses library; "
+                                  "EAST head: 3x3 / 1x1 convolutions and the 2x2 stride-2 transposed convolutions (as 1x1 convolutions + depth-to-space) on the conv engine, losses library; "
                                   "DCNv2 units: fused tcgen05 forward / weight-gradient / data-gradient kernels (csrc/dcn_tcgen05.cu)"),
                          "Adam": "library (torch fused, capturable)", "launch": launch_mode}
         emit_json(out)

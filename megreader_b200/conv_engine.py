@@ -216,6 +216,29 @@ class EngineBatchNorm2d(nn.BatchNorm2d):
                                   float(self.eps), bool(self.training))
 
 
+class EngineConvTranspose2d(nn.ConvTranspose2d):
+    """nn.ConvTranspose2d with kernel = stride = 2 x 2 (the up-sampling layers of decoders/east.py:20-21) on the tcgen05 convolution
+    kernels: such a layer is a 1 x 1 convolution to 4 * C_out channels -- one output channel block per (row, column) offset inside the
+    2 x 2 cell -- followed by a depth-to-space rearrangement.  The weight re-layout and the rearrangement are framework views / copies,
+    so autograd carries the gradients back to the reference-shaped parameters.  Other geometries use the library implementation."""
+
+    def _engine_ok(self, x):
+        return (x.is_cuda and x.dim() == 4 and tuple(self.kernel_size) == (2, 2) and tuple(self.stride) == (2, 2)
+                and tuple(self.padding) == (0, 0) and tuple(self.output_padding) == (0, 0) and tuple(self.dilation) == (1, 1)
+                and self.groups == 1 and self.in_channels % 64 == 0)
+
+    def forward(self, x, output_size=None):
+        if output_size is not None or not self._engine_ok(x):
+            return super().forward(x, output_size)
+        cin, cout = self.in_channels, self.out_channels
+        n, _, h, w = x.shape
+        w_eq = self.weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)        # row (a * 2 + b) * C_out + co  <-  W[ci, co, a, b]
+        b_eq = self.bias.repeat(4) if self.bias is not None else None
+        y = conv2d(x, w_eq, b_eq)                                                    # (N, 4 C_out, H, W)
+        y = y.reshape(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2)                 # (N, C_out, H, a, W, b)
+        return y.reshape(n, cout, 2 * h, 2 * w).contiguous(memory_format=torch.channels_last)
+
+
 def eligible(m):
     return (type(m) is nn.Conv2d and m.groups == 1 and m.padding_mode == "zeros" and not isinstance(m.padding, str)
             and (m.in_channels % 64 == 0 or m.in_channels <= 4))
@@ -239,6 +262,8 @@ def use_engine_convs(module, batchnorm=True):
             n += 1
         elif batchnorm and type(m) is nn.BatchNorm2d:
             m.__class__ = EngineBatchNorm2d
+        elif type(m) is nn.ConvTranspose2d and tuple(m.kernel_size) == (2, 2) and tuple(m.stride) == (2, 2) and m.in_channels % 64 == 0:
+            m.__class__ = EngineConvTranspose2d
         elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)) and type(m) is not EngineConv2d \
                 and not hasattr(m, "_mr_cast_hook"):
             m._mr_cast_hook = m.register_forward_pre_hook(_cast_input_hook)
@@ -253,6 +278,8 @@ def restore_library_convs(module):
             n += 1
         if type(m) is EngineBatchNorm2d:
             m.__class__ = nn.BatchNorm2d
+        if type(m) is EngineConvTranspose2d:
+            m.__class__ = nn.ConvTranspose2d
         if hasattr(m, "_mr_cast_hook"):
             m._mr_cast_hook.remove()
             del m._mr_cast_hook

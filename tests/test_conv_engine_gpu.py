@@ -75,6 +75,7 @@ BN_CASES = [
     (2048, 8, 8, 32, torch.bfloat16, True),       # layer4 of the dilated trunk: 2 * C = 4096 statistic columns
     (1024, 3, 7, 9, torch.float32, True),         # odd row count
     (512, 4, 8, 32, torch.bfloat16, False),       # frozen statistics (eval with gradients)
+    (64, 8, 128, 128, torch.bfloat16, True),      # 131,072 rows (the 512 x 512 scenes of the EAST configuration)
 ]
 
 
@@ -117,3 +118,37 @@ def test_batchnorm_forward_backward(cuda, case):
     assert rel(eng.running_mean, ref.running_mean) < 1e-5 and rel(eng.running_var, ref.running_var) < 1e-5
     assert int(eng.num_batches_tracked) == int(ref.num_batches_tracked)
     assert conv_engine.restore_library_convs(wrap) == 0 and type(wrap[0]) is torch.nn.BatchNorm2d
+
+
+@pytest.mark.parametrize("case", [(256, 128, 2, 16, 24, True), (128, 64, 1, 9, 7, False)], ids=["256-128", "128-64-odd"])
+def test_conv_transpose_2x2(cuda, case):
+    """EngineConvTranspose2d (kernel = stride = 2: a 1x1 engine convolution to 4 C_out channels + depth-to-space) against
+    F.conv_transpose2d in fp32 on the same bf16-rounded operands (decoders/east.py:20-21)"""
+    from megreader_b200 import conv_engine
+    cin, cout, n, h, w, with_bias = case
+    torch.manual_seed(cin + cout)
+    x = torch.randn(n, cin, h, w, device=cuda).bfloat16().float()
+    m = torch.nn.ConvTranspose2d(cin, cout, 2, 2, bias=with_bias).to(cuda)
+    m.weight.data = m.weight.data.bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    ref = F.conv_transpose2d(xr, m.weight, m.bias, 2)
+    go = torch.randn_like(ref).bfloat16().float()
+    gw_ref, gb_ref = torch.autograd.grad(ref, [m.weight] + ([m.bias] if with_bias else []), go, retain_graph=True) if with_bias else \
+        (torch.autograd.grad(ref, [m.weight], go, retain_graph=True)[0], None)
+    gx_ref = torch.autograd.grad(ref, xr, go)[0]
+    wrap = torch.nn.Sequential(m)
+    conv_engine.use_engine_convs(wrap)
+    assert type(wrap[0]) is conv_engine.EngineConvTranspose2d
+    xe = x.clone().requires_grad_(True)
+    out = wrap(xe)
+    assert tuple(out.shape) == tuple(ref.shape)
+    out.backward(go.to(out.dtype))
+
+    def rel(a, r):
+        return float((a.float() - r).norm() / (r.norm() + 1e-12))
+    assert rel(out, ref) < 6e-3, rel(out, ref)
+    assert rel(xe.grad, gx_ref) < 1e-2 and rel(m.weight.grad, gw_ref) < 1e-2
+    if with_bias:
+        assert rel(m.bias.grad, gb_ref) < 1e-2
+    conv_engine.restore_library_convs(wrap)
+    assert type(wrap[0]) is torch.nn.ConvTranspose2d
