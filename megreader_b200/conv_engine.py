@@ -12,6 +12,8 @@ any dilation, groups = 1, C_in % 64 == 0; the stem (C_in = 3, 7x7 stride 2) is a
 bf16 operands, fp32 accumulation, fp32 master weights.  Forward = implicit GEMM; input gradient = implicit GEMM of dz with the
 flipped / transposed weights (stride 2: over the zero-upsampled dz); weight gradient = implicit GEMM over pixels (split-K).
 CUDA only -- there is no CPU fallback."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -234,9 +236,10 @@ class EngineConvTranspose2d(nn.ConvTranspose2d):
         n, _, h, w = x.shape
         w_eq = self.weight.permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)        # row (a * 2 + b) * C_out + co  <-  W[ci, co, a, b]
         b_eq = self.bias.repeat(4) if self.bias is not None else None
-        y = conv2d(x, w_eq, b_eq)                                                    # (N, 4 C_out, H, W)
-        y = y.reshape(n, 2, 2, cout, h, w).permute(0, 3, 4, 1, 5, 2)                 # (N, C_out, H, a, W, b)
-        return y.reshape(n, cout, 2 * h, 2 * w).contiguous(memory_format=torch.channels_last)
+        y = conv2d(x, w_eq, b_eq)                                                    # (N, 4 C_out, H, W), NHWC memory
+        yh = y.permute(0, 2, 3, 1).reshape(n, h, w, 2, 2, cout)                      # (N, H, W, a, b, C_out): still a view
+        out = yh.permute(0, 1, 3, 2, 4, 5).reshape(n, 2 * h, 2 * w, cout)            # (N, 2H, 2W, C_out): the one copy
+        return out.permute(0, 3, 1, 2)                                               # channels_last view
 
 
 def eligible(m):
@@ -262,7 +265,8 @@ def use_engine_convs(module, batchnorm=True):
             n += 1
         elif batchnorm and type(m) is nn.BatchNorm2d:
             m.__class__ = EngineBatchNorm2d
-        elif type(m) is nn.ConvTranspose2d and tuple(m.kernel_size) == (2, 2) and tuple(m.stride) == (2, 2) and m.in_channels % 64 == 0:
+        elif type(m) is nn.ConvTranspose2d and tuple(m.kernel_size) == (2, 2) and tuple(m.stride) == (2, 2) and m.in_channels % 64 == 0 \
+                and not os.environ.get("MR_NO_ENGINE_CONVT"):
             m.__class__ = EngineConvTranspose2d
         elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d, nn.Linear)) and type(m) is not EngineConv2d \
                 and not hasattr(m, "_mr_cast_hook"):
