@@ -1,5 +1,7 @@
 """Thin torch-tensor wrappers over the C-ABI building blocks (include/megreader_b200.h, csrc/nn_kernels.cu,
 csrc/gemm.cu).  No arithmetic happens in Python; these only allocate outputs and pass pointers."""
+import os
+
 import torch
 
 from . import _lib
@@ -281,6 +283,11 @@ def conv2d_fprop_tc(x, Wm, kh, kw, sh, sw, ph, pw, dh, dw, out_dtype=torch.bfloa
     return y, Ho, Wo
 
 
+# minimum 64-pixel k-blocks per split of conv2d_wgrad_tc.  Measured on the ResNet50-PPM step (bench.py --config 3, ms per step):
+# 1: 14.06, 8: 13.41, 16: 12.46, 32: 12.78, 64: 13.03
+_WGRAD_MIN_KB = max(1, int(os.environ.get("MR_WGRAD_MIN_KB", "16")))
+
+
 def conv2d_wgrad_tc(dz, x, kh, kw, sh, sw, ph, pw, dh, dw, splits=0, out=None):
     """dWm [Cout, kh*kw*C] fp32 from dz [N,Ho,Wo,Cout] and x [N,H,W,C] (NHWC bf16), stride / dilation as the forward."""
     N, H, W, C = x.shape
@@ -290,6 +297,10 @@ def conv2d_wgrad_tc(dz, x, kh, kw, sh, sw, ph, pw, dh, dw, splits=0, out=None):
     if splits <= 0:
         tiles = ((Cout + 127) // 128) * ((K + 255) // 256)
         splits = max(1, -(-288 // tiles))
+        # a split should own enough 64-pixel k-blocks to amortise its fixed cost (TMEM / pipeline set-up and the fp32 atomic
+        # epilogue of a whole output tile): small weights over many pixels (layer1 of a ResNet) otherwise spend their time in atomics
+        kb_total = dz.size(0) * dz.size(1) * -(-dz.size(2) // 64)
+        splits = max(1, min(splits, kb_total // _WGRAD_MIN_KB))
     _chk(_lib.lib().mr_conv2d_wgrad_tcgen05(_p(dz), _p(x), _p(dWm), N, H, W, C, Cout, kh, kw, sh, sw, ph, pw, dh, dw,
                                             int(splits), _st()), "conv2d_wgrad_tcgen05")
     return dWm
