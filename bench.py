@@ -483,6 +483,8 @@ def bench_dcn(dev, iters=10):
     return {"kernel": "dcn_fwd_tcgen05_kernel (bilinear gather = A-operand producer, bf16 hi/lo split: 3 MMAs per K block); backward = "
                       "dcn_wgrad_tcgen05_kernel + dcn_dgrad_tcgen05_kernel (no column matrices in HBM)",
             "bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops"], "peak_source": pk["source"], "B": 8, "shapes": out,
+            "traffic_bwd_C128@64x64": {"dcn_dgrad_tcgen05_kernel": _measured("dcn_dgrad_c128", "dram_bytes_per_launch"),
+                                       "dcn_wgrad_tcgen05_kernel": _measured("dcn_wgrad_c128", "dram_bytes_per_launch")},
             "round1_fwd_us": {"C128@64x64": 319.2, "C256@32x32": 264.5, "C512@16x16": 215.3},
             "round1_fwd_bwd_us": {"C128@64x64": 1611.0, "C256@32x32": 1115.3, "C512@16x16": 944.9}}
 

@@ -205,11 +205,14 @@ class _BatchNormFn(torch.autograd.Function):
 
 class EngineBatchNorm2d(nn.BatchNorm2d):
     """nn.BatchNorm2d whose arithmetic runs on megreader_b200's NHWC kernels (same parameters / buffers / state-dict keys).
-    Configurations the kernels do not cover (no affine parameters, no running statistics, cumulative momentum, C % 8 != 0,
-    CPU tensors) go through the framework implementation unchanged."""
+    Configurations the kernels do not cover (no affine parameters, no running statistics, cumulative momentum, C % 8 != 0) go
+    through the framework's CUDA implementation; CPU tensors raise."""
 
     def forward(self, x):
-        if (not x.is_cuda or x.dim() != 4 or not self.affine or not self.track_running_stats or self.momentum is None
+        if not x.is_cuda:
+            raise NotImplementedError("megreader_b200.conv_engine: CUDA tensors only (no CPU fallback); restore_library_convs() "
+                                      "gives the framework modules back")
+        if (x.dim() != 4 or not self.affine or not self.track_running_stats or self.momentum is None
                 or self.num_features % 8 or x.dtype not in (torch.float32, torch.bfloat16) or x.numel() == 0):
             return super().forward(x)
         if self.training:
@@ -225,7 +228,10 @@ class EngineConvTranspose2d(nn.ConvTranspose2d):
     so autograd carries the gradients back to the reference-shaped parameters.  Other geometries use the library implementation."""
 
     def _engine_ok(self, x):
-        return (x.is_cuda and x.dim() == 4 and tuple(self.kernel_size) == (2, 2) and tuple(self.stride) == (2, 2)
+        if not x.is_cuda:
+            raise NotImplementedError("megreader_b200.conv_engine: CUDA tensors only (no CPU fallback); restore_library_convs() "
+                                      "gives the framework modules back")
+        return (x.dim() == 4 and tuple(self.kernel_size) == (2, 2) and tuple(self.stride) == (2, 2)
                 and tuple(self.padding) == (0, 0) and tuple(self.output_padding) == (0, 0) and tuple(self.dilation) == (1, 1)
                 and self.groups == 1 and self.in_channels % 64 == 0)
 

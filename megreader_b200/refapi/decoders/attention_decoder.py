@@ -105,7 +105,10 @@ class AttentionDecoder(nn.Module):
         self.onehot_embedding_y.weight.data = torch.eye(height)
         self.gt_as_output = gt_as_output
         self.feedback_static = None       # (coin, swap, noise) device tensors of a CUDA-graph caller, see forward()
-        self.loop_kernels = True          # CUDA tensors: the recurrent loop runs on csrc/attn_decode.cu (False: framework composition)
+        # CUDA tensors: the recurrent loop (training and greedy decoding) runs on csrc/attn_decode.cu.  False = the framework
+        # composition (what the kernels are tested against; also the way out for hidden sizes whose weight slices do not fit in
+        # shared memory, inner_channels > ~640, which the kernels refuse with MR_ERR_UNSUPPORTED)
+        self.loop_kernels = True
         self.loss_function = nn.NLLLoss(reduction='none')
 
     def conv_bn_relu(self, input_channels, output_channels, kernel_size=3, stride=1, padding=1):
@@ -218,7 +221,7 @@ class AttentionDecoder(nn.Module):
                 word = word * (1 - swap[t]) + noise[t] * swap[t]
             return loss, torch.cat(attention, 1).view(n, -1, self.height, self.max_size)
 
-        if feature.is_cuda:
+        if feature.is_cuda and self.loop_kernels:
             pred = self._decode_cuda(memory_bt, projected)
             finished = (pred == blank).all(dim=0).long().cummax(0).values.bool()
             return pred.masked_fill(finished.unsqueeze(0), blank)

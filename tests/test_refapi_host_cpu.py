@@ -74,3 +74,23 @@ def test_public_names_match_the_reference_inits(api):
     assert sorted(dcn.__all__) == sorted(['DeformConv', 'DeformConvPack', 'ModulatedDeformConv', 'ModulatedDeformConvPack',
                                           'DeformRoIPooling', 'DeformRoIPoolingPack', 'ModulatedDeformRoIPoolingPack',
                                           'deform_conv', 'modulated_deform_conv', 'deform_roi_pooling'])
+
+
+def test_engine_modules_refuse_cpu_tensors():
+    """the modules use_engine_convs() installs have no CPU fallback: they raise on CPU tensors, and restore_library_convs() gives the
+    framework modules back (same parameter objects)"""
+    import pytest
+    import torch
+    from megreader_b200 import conv_engine
+    m = torch.nn.Sequential(torch.nn.Conv2d(64, 64, 1), torch.nn.BatchNorm2d(64), torch.nn.ConvTranspose2d(64, 32, 2, 2))
+    params = [id(p) for p in m.parameters()]
+    assert conv_engine.use_engine_convs(m) == 1
+    assert [type(x) for x in m] == [conv_engine.EngineConv2d, conv_engine.EngineBatchNorm2d, conv_engine.EngineConvTranspose2d]
+    x = torch.zeros(1, 64, 4, 4)
+    for layer in m:
+        with pytest.raises(NotImplementedError):
+            layer(x)
+    assert conv_engine.restore_library_convs(m) == 1
+    assert [type(x) for x in m] == [torch.nn.Conv2d, torch.nn.BatchNorm2d, torch.nn.ConvTranspose2d]
+    assert [id(p) for p in m.parameters()] == params
+    assert tuple(m(x).shape) == (1, 32, 8, 8)
