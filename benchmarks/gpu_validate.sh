@@ -1,4 +1,6 @@
 #!/bin/bash
+# one gpurun call that validates a revision: all GPU tests, smoke(), the bench line of every configuration (outputs under gpurun_out/)
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- "bash benchmarks/gpu_validate.sh"
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/s3f_gputests.log 2>&1; echo "rc=$?" >> gpurun_out/s3f_gputests.log
 timeout 150 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/s3f_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/s3f_smoke.log
