@@ -94,3 +94,27 @@ def test_engine_modules_refuse_cpu_tensors():
     assert [type(x) for x in m] == [torch.nn.Conv2d, torch.nn.BatchNorm2d, torch.nn.ConvTranspose2d]
     assert [id(p) for p in m.parameters()] == params
     assert tuple(m(x).shape) == (1, 32, 8, 8)
+
+
+def test_attention_feedback_draws_follow_the_reference_order():
+    """AttentionDecoder.draw_feedback makes the training loop's random draws before the loop: per step the numpy teacher-forcing coin
+    (attention_decoder.py:51-54, :107), then torch.rand and torch.randint of the step dropout (:112-116) -- the same generators in the
+    same order as the reference's in-loop draws, so seeded runs line up"""
+    import numpy as np
+    import torch
+    import megreader_b200.refapi.decoders as md
+    m = md.AttentionDecoder(32, inner_channels=64, max_size=8, height=1, step_dropout=0.3)
+    n, vocab = 5, len(m.charset)
+    np.random.seed(11)
+    torch.manual_seed(11)
+    coin, swap, noise = m.draw_feedback(n)
+    np.random.seed(11)
+    torch.manual_seed(11)
+    for t in range(m.max_size):                      # the reference's loop body, draws only
+        c = np.random.rand() < 0.5
+        f = (torch.rand(n) < 0.3).long()
+        r = torch.randint(high=vocab, size=(n,))
+        assert bool(coin[t]) == bool(c) and torch.equal(swap[t], f) and torch.equal(noise[t], r)
+    assert coin.dtype == torch.bool and tuple(swap.shape) == (8, n) == tuple(noise.shape)
+    m2 = md.AttentionDecoder(32, inner_channels=64, max_size=8, height=1, gt_as_output=True)
+    assert bool(m2.draw_feedback(3)[0].all()) and int(m2.draw_feedback(3)[1].sum()) == 0
