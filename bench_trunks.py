@@ -359,6 +359,8 @@ def run(args, peaks, ClockSampler, emit_json):
                                   "attention decoder: the 32-step loop and its backward through time = megreader_b200 persistent cooperative kernels (csrc/attn_decode.cu), hoisted encoder projection; weight-gradient products over the saved rows: library GEMMs" if cfg == 4 else
                                   "EAST head: 3x3 / 1x1 convolutions and the 2x2 stride-2 transposed convolutions (as 1x1 convolutions + depth-to-space) on the conv engine, losses library; "
                                   "DCNv2 units: fused tcgen05 forward / weight-gradient / data-gradient kernels (csrc/dcn_tcgen05.cu)"),
+                         "conv weight gradients": "side stream, joined at the end of the backward pass (conv_engine.WGRAD_SIDE_STREAM)"
+                                                  if world == 1 else "main stream (the gradients accumulate into the flat all-reduce buffer)",
                          "Adam": "library (torch fused, capturable)", "launch": launch_mode}
         emit_json(out)
     if world > 1:

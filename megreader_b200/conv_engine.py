@@ -25,6 +25,35 @@ def _pad_to(n, m):
     return -(-n // m) * m
 
 
+# Weight gradients off the critical path.  A convolution's weight gradient depends only on dz and the saved input, and nothing in
+# the backward pass consumes it (the parameter's .grad is read after backward() returns), while the input gradient feeds the next
+# layer's BatchNorm / ReLU / convolution chain -- small dependent kernels that leave most SMs idle at the configured batches.  So the
+# weight-gradient kernels of leaf parameters whose .grad is still unset run on a side stream (forked from the backward's stream, one
+# per device) and are joined by a callback the autograd engine runs at the end of the backward pass: transparent to the caller, and
+# captured as a parallel branch when the step is recorded into a CUDA graph.  MR_CONV_WGRAD_SIDE_STREAM=0 keeps everything on one stream.
+WGRAD_SIDE_STREAM = os.environ.get("MR_CONV_WGRAD_SIDE_STREAM", "1") != "0"
+_side_streams = {}
+_pending = {}
+
+
+def _side_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+        _pending[key] = []
+    return key, _side_streams[key]
+
+
+def _join_side_streams():
+    """end-of-backward callback: the stream that ran backward() waits for every weight gradient still in flight"""
+    for key, events in _pending.items():
+        if events:
+            cur = torch.cuda.current_stream(key)
+            for ev in events:
+                cur.wait_event(ev)
+            events.clear()
+
+
 class _Conv2dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, dilation):
@@ -67,8 +96,26 @@ class _Conv2dFn(torch.autograd.Function):
         dz = dz.contiguous()                                    # [N, Ho, Wo, Cp]
         dx = dw_ = db = None
         if ctx.needs_input_grad[1]:
-            dWm = ops.conv2d_wgrad_tc(dz, xh, kh, kw, sh, sw, ph, pw, dh, dw)               # [Cp, kh*kw*Cin] fp32
-            dw_ = dWm[:Cout].view(Cout, kh, kw, Cin).permute(0, 3, 1, 2).contiguous().to(weight.dtype)
+            def wgrad():
+                dWm = ops.conv2d_wgrad_tc(dz, xh, kh, kw, sh, sw, ph, pw, dh, dw)           # [Cp, kh*kw*Cin] fp32
+                return dWm[:Cout].view(Cout, kh, kw, Cin).permute(0, 3, 1, 2).contiguous().to(weight.dtype)
+            if WGRAD_SIDE_STREAM and weight.is_leaf and weight.grad is None and not torch.is_grad_enabled():
+                cur = torch.cuda.current_stream(dz.device)
+                key, side = _side_stream(dz.device)
+                side.wait_stream(cur)                           # dz and the saved input are complete on `cur` here
+                with torch.cuda.stream(side):
+                    dw_ = wgrad()
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                for t in (dz, xh):
+                    t.record_stream(side)                       # the allocator must not hand their memory out before `side` is done
+                dw_.record_stream(cur)                          # allocated on `side`, consumed on `cur` after the join
+                _pending[key].append(ev)
+                # one callback per weight gradient (the first to run joins them all): nothing is left behind if an earlier backward
+                # pass died before its callback ran
+                torch.autograd.Variable._execution_engine.queue_callback(_join_side_streams)
+            else:
+                dw_ = wgrad()
         if has_bias and ctx.needs_input_grad[2]:
             db = dz.view(-1, Cp)[:, :Cout].float().sum(0)
         if ctx.needs_input_grad[0]:
