@@ -70,7 +70,7 @@ def make_batch(cfg, seed, n):
     return synth(seed, n, c["hw"], c["l_max"])
 
 
-def build(cfg, device, engine=True):
+def build(cfg, device, engine=True, wgrad_side_stream=None):
     import megreader_b200
     megreader_b200.install_reference_api()
     import backbones
@@ -101,7 +101,7 @@ def build(cfg, device, engine=True):
     n_engine = 0
     if engine:
         from megreader_b200 import conv_engine
-        n_engine = conv_engine.use_engine_convs(net)
+        n_engine = conv_engine.use_engine_convs(net, wgrad_side_stream=wgrad_side_stream)
     return net, n_engine
 
 
@@ -184,7 +184,10 @@ def run(args, peaks, ClockSampler, emit_json):
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     batch = args.batch or (8 if cfg == 5 else 32)           # BASELINE.json: 256 (cfg 3/4) and 64 (cfg 5) over 8 GPUs
-    net, n_engine = build(cfg, dev)
+    # one GPU: the convolutions' weight gradients run on a side stream (nothing reads a gradient before backward() returns here);
+    # N > 1: they accumulate into the flat all-reduce buffer on the backward's stream.  MR_CONV_WGRAD_SIDE_STREAM=0 switches it off.
+    side_wgrad = world == 1 and os.environ.get("MR_CONV_WGRAD_SIDE_STREAM", "1") != "0"
+    net, n_engine = build(cfg, dev, wgrad_side_stream=side_wgrad)
     params = [p for p in net.parameters() if p.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
     # N > 1: gradients as views of one flat buffer, ONE in-place NCCL all-reduce (AVG) between the two graphs (megreader_b200/dp.py)
@@ -360,7 +363,7 @@ def run(args, peaks, ClockSampler, emit_json):
                                   "EAST head: 3x3 / 1x1 convolutions and the 2x2 stride-2 transposed convolutions (as 1x1 convolutions + depth-to-space) on the conv engine, losses library; "
                                   "DCNv2 units: fused tcgen05 forward / weight-gradient / data-gradient kernels (csrc/dcn_tcgen05.cu)"),
                          "conv weight gradients": "side stream, joined at the end of the backward pass (conv_engine.WGRAD_SIDE_STREAM)"
-                                                  if world == 1 else "main stream (the gradients accumulate into the flat all-reduce buffer)",
+                                                  if side_wgrad else "the backward's stream",
                          "Adam": "library (torch fused, capturable)", "launch": launch_mode}
         emit_json(out)
     if world > 1:

@@ -30,8 +30,11 @@ def _pad_to(n, m):
 # layer's BatchNorm / ReLU / convolution chain -- small dependent kernels that leave most SMs idle at the configured batches.  So the
 # weight-gradient kernels of leaf parameters whose .grad is still unset run on a side stream (forked from the backward's stream, one
 # per device) and are joined by a callback the autograd engine runs at the end of the backward pass: transparent to the caller, and
-# captured as a parallel branch when the step is recorded into a CUDA graph.  MR_CONV_WGRAD_SIDE_STREAM=0 keeps everything on one stream.
-WGRAD_SIDE_STREAM = os.environ.get("MR_CONV_WGRAD_SIDE_STREAM", "1") != "0"
+# captured as a parallel branch when the step is recorded into a CUDA graph.  OFF by default: code that reads a gradient INSIDE the
+# backward pass on the backward's stream (parameter hooks, e.g. a bucketing DistributedDataParallel wrapper) would read it before
+# the join.  A training loop that only touches gradients after backward() returns switches it on with
+# use_engine_convs(model, wgrad_side_stream=True) (bench_trunks.py does) or MR_CONV_WGRAD_SIDE_STREAM=1.
+WGRAD_SIDE_STREAM = os.environ.get("MR_CONV_WGRAD_SIDE_STREAM", "0") == "1"
 _side_streams = {}
 _pending = {}
 
@@ -307,10 +310,14 @@ def _cast_input_hook(mod, args):
     return None
 
 
-def use_engine_convs(module, batchnorm=True):
+def use_engine_convs(module, batchnorm=True, wgrad_side_stream=None):
     """Re-class every eligible nn.Conv2d below `module` to EngineConv2d and (batchnorm=True) every nn.BatchNorm2d to
-    EngineBatchNorm2d (parameters and buffers stay the same objects).  Returns the number of convolutions switched.  Undo with restore_library_convs().  The layers that stay with the library (transposed and grouped
+    EngineBatchNorm2d (parameters and buffers stay the same objects).  Returns the number of convolutions switched.
+    wgrad_side_stream=True / False sets the process-wide WGRAD_SIDE_STREAM switch (weight gradients off the critical path).  Undo with restore_library_convs().  The layers that stay with the library (transposed and grouped
     convolutions, Linear) get a pre-hook that casts the bf16 activations arriving from engine layers to their weights' dtype."""
+    if wgrad_side_stream is not None:                       # process-wide switch, see WGRAD_SIDE_STREAM above
+        global WGRAD_SIDE_STREAM
+        WGRAD_SIDE_STREAM = bool(wgrad_side_stream)
     n = 0
     for m in module.modules():
         if eligible(m):

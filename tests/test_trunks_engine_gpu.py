@@ -36,8 +36,12 @@ def test_trunk_step_engine_vs_library(cuda, cfg):
         net.load_state_dict(state)                        # BatchNorm running statistics
         return float(loss), g
     loss_ref, g_ref = run()
-    assert conv_engine.use_engine_convs(net) > 40
-    loss_eng, g_eng = run()
+    # weight gradients on the side stream (what bench.py --config 3 / 4 runs; tests/test_conv_engine_gpu.py covers the one-stream path)
+    assert conv_engine.use_engine_convs(net, wgrad_side_stream=True) > 40
+    try:
+        loss_eng, g_eng = run()
+    finally:
+        conv_engine.WGRAD_SIDE_STREAM = False
     assert abs(loss_eng - loss_ref) / abs(loss_ref) < 5e-2, (loss_eng, loss_ref)
     assert all(torch.isfinite(v).all() for v in g_eng.values())
     assert set(g_eng) == set(g_ref)
