@@ -266,6 +266,8 @@ class EngineBatchNorm2d(nn.BatchNorm2d):
                 or self.num_features % 8 or x.dtype not in (torch.float32, torch.bfloat16) or x.numel() == 0):
             return super().forward(x)
         if self.training:
+            if x.numel() // x.size(1) <= 1:                     # same refusal as torch.nn.functional.batch_norm
+                raise ValueError("Expected more than 1 value per channel when training, got input size %s" % (tuple(x.shape),))
             self.num_batches_tracked.add_(1)
         return _BatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, float(self.momentum),
                                   float(self.eps), bool(self.training))
